@@ -1,0 +1,391 @@
+// C ABI of the B200-native Allsteps-v0 MDP step (include/allsteps_b200.h): argument checking, launch geometry,
+// and nothing else.  All arithmetic lives in the kernels (as_step_kernel.cuh, as_aux_kernels.cuh).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "as_aux_kernels.cuh"
+
+using namespace as;
+
+struct AsHandle {
+  AsParams params;
+  int64_t num_envs;
+  int64_t env_id_offset;
+  int device;
+  int sm_count;
+  Workspace ws;
+  int64_t launches;
+  MirrorTable mirror_obs, mirror_act;
+  bool pass1_done;
+  bool pending_valid;   // a fused step was launched and still needs as_finish_step
+  StepArgs pending;     // its arguments: the conditional fix-up re-reads the same inputs
+};
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return AS_ERR_CUDA;
+}
+#define AS_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t _e = (call);                            \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+  } while (0)
+#define AS_REQUIRE(cond, msg) \
+  do {                        \
+    if (!(cond)) return fail(AS_ERR_INVALID, msg); \
+  } while (0)
+
+int check_launch(AsHandle* h, const char* what) {
+  h->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  return AS_OK;
+}
+
+int num_tiles(int64_t n) { return static_cast<int>((n + kTile - 1) / kTile); }
+
+int validate_state_in(const AsStateIn* in, bool need_origins) {
+  AS_REQUIRE(in != nullptr, "AsStateIn is null");
+  AS_REQUIRE(in->root_pos && in->root_quat && in->root_lin_vel, "root state pointers must be set");
+  AS_REQUIRE(in->body_pos, "body_pos must be set");
+  AS_REQUIRE(in->joint_pos && in->joint_vel, "joint state pointers must be set");
+  AS_REQUIRE(in->contact_right && in->contact_left, "contact matrices must be set");
+  AS_REQUIRE(in->root_pos_stride >= 3 && in->root_quat_stride >= 4 && in->root_lin_vel_stride >= 3,
+             "root strides too small");
+  AS_REQUIRE(in->joint_pos_stride >= kJ && in->joint_vel_stride >= kJ, "joint strides too small");
+  AS_REQUIRE(in->contact_right_stride >= kS * 3 && in->contact_left_stride >= kS * 3, "contact strides too small");
+  AS_REQUIRE(in->body_row_stride >= 3 && in->body_env_stride >= 3, "body strides too small");
+  AS_REQUIRE(in->right_foot_row >= 0 && in->left_foot_row >= 0 && in->torso_row >= 0, "negative body row");
+  if (need_origins) AS_REQUIRE(in->env_origins != nullptr, "env_origins must be set for the fused step");
+  return AS_OK;
+}
+
+void build_mirror_tables(AsHandle* h) {
+  // ENV:574-584: swap right/left joint columns (+ their velocity columns and the two contact flags), negate
+  // roll, v_y, the negation joints (pos and vel) and the y of the three stone targets.
+  const AsParams& P = h->params;
+  MirrorTable& o = h->mirror_obs;
+  o.dim = kObs;
+  for (int c = 0; c < kObs; ++c) {
+    o.src[c] = c;
+    o.sign[c] = 1.0f;
+  }
+  MirrorTable& a = h->mirror_act;
+  a.dim = kJ;
+  for (int c = 0; c < kObs; ++c) {
+    a.src[c] = c < kJ ? c : 0;
+    a.sign[c] = 1.0f;
+  }
+  for (int j = 0; j < kJ; ++j) {
+    const int s = P.mirror_src[j];
+    a.src[j] = s;
+    a.sign[j] = P.mirror_sign[j];
+    o.src[6 + j] = 6 + s;
+    o.src[6 + kJ + j] = 6 + kJ + s;
+    o.sign[6 + j] = P.mirror_sign[j];
+    o.sign[6 + kJ + j] = P.mirror_sign[j];
+  }
+  o.src[48] = 49;
+  o.src[49] = 48;
+  o.sign[1] = -1.0f;
+  o.sign[4] = -1.0f;
+  o.sign[51] = o.sign[54] = o.sign[57] = -1.0f;
+}
+
+StepArgs make_step_args(AsHandle* h, const AsStateIn* in, const float* actions, int64_t actions_stride,
+                        const AsStepOut* out) {
+  StepArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.P = h->params;
+  if (in) a.in = *in;
+  a.actions = actions;
+  a.actions_stride = actions_stride;
+  if (out) a.out = *out;
+  a.ws = h->ws;
+  a.num_envs = h->num_envs;
+  a.env_id_offset = h->env_id_offset;
+  a.num_tiles = num_tiles(h->num_envs);
+  return a;
+}
+
+ResetArgs make_reset_args(AsHandle* h, const float* env_origins) {
+  ResetArgs r;
+  std::memset(&r, 0, sizeof(r));
+  r.P = h->params;
+  r.ws = h->ws;
+  r.env_origins = env_origins;
+  r.num_envs = h->num_envs;
+  r.env_id_offset = h->env_id_offset;
+  return r;
+}
+
+int grid_for(int64_t items, int per_block, int sm_count, int max_waves) {
+  int64_t blocks = (items + per_block - 1) / per_block;
+  const int64_t cap = static_cast<int64_t>(sm_count) * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+
+extern "C" {
+
+int as_abi_version(void) { return AS_ABI_VERSION; }
+
+const char* as_last_error(void) { return g_error.c_str(); }
+
+int64_t as_workspace_bytes(int64_t num_envs) {
+  if (num_envs <= 0) return 0;
+  return workspace_layout(num_envs).total;
+}
+
+int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, int device, void* workspace,
+              int64_t workspace_bytes, void* stream, AsHandle** out) {
+  AS_REQUIRE(params && out, "params/out is null");
+  AS_REQUIRE(num_envs > 0 && num_envs < (1ll << 31), "num_envs out of range");
+  AS_REQUIRE(env_id_offset >= 0 && env_id_offset + num_envs <= (1ll << 32), "global env ids must fit 32 bits");
+  AS_REQUIRE(params->stop_frames >= 1 && params->stop_frames <= 3, "stop_frames must be in 1..3");
+  AS_REQUIRE(params->max_level >= 0 && params->max_level < AS_NUM_LEVELS, "max_level out of range");
+  AS_REQUIRE(params->max_episode_length > 1 && params->max_episode_length < kMaxEpisodeLength,
+             "max_episode_length out of range");
+  AS_REQUIRE(params->step_dt > 0.0f, "step_dt must be positive");
+  for (int j = 0; j < kJ; ++j) {
+    AS_REQUIRE(params->joint_upper[j] > params->joint_lower[j], "joint limits must satisfy lower < upper");
+    AS_REQUIRE(params->mirror_src[j] >= 0 && params->mirror_src[j] < kJ, "mirror_src out of range");
+  }
+  const WorkspaceLayout l = workspace_layout(num_envs);
+  AS_REQUIRE(workspace != nullptr && workspace_bytes >= l.total, "workspace too small (see as_workspace_bytes)");
+  AS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+  AS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  AS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    return fail(AS_ERR_CUDA, "this library contains sm_100a code only; device is sm_" + std::to_string(prop.major) +
+                                 std::to_string(prop.minor));
+  }
+  AsHandle* h = new (std::nothrow) AsHandle();
+  AS_REQUIRE(h != nullptr, "out of host memory");
+  h->params = *params;
+  h->num_envs = num_envs;
+  h->env_id_offset = env_id_offset;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->launches = 0;
+  h->pass1_done = false;
+  h->pending_valid = false;
+  unsigned char* base = static_cast<unsigned char*>(workspace);
+  h->ws.ctrl = reinterpret_cast<Ctrl*>(base + l.ctrl_off);
+  h->ws.state[0] = reinterpret_cast<uint2*>(base + l.state0_off);
+  h->ws.state[1] = reinterpret_cast<uint2*>(base + l.state1_off);
+  h->ws.stones = reinterpret_cast<float4*>(base + l.stones_off);
+  h->ws.reset_ids = reinterpret_cast<int32_t*>(base + l.reset_ids_off);
+  h->ws.regen_ids = reinterpret_cast<int32_t*>(base + l.regen_ids_off);
+  build_mirror_tables(h);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(l.total), s);
+  if (e != cudaSuccess) {
+    delete h;
+    return cuda_fail(e, "cudaMemsetAsync(workspace)");
+  }
+  // initial MDP state of AllstepsEnv.__init__ (ENV:74-78): index 1, right leg swings, everything else zero
+  AsMdpState none;
+  std::memset(&none, 0, sizeof(none));
+  *out = h;
+  // state words: idx = 1
+  {
+    // a zeroed word has idx 0; write idx 1 through the import kernel with a constant source is overkill --
+    // fill both buffers with the packed constant instead (low 32 bits of each 8-byte word).
+    const uint32_t word = pack_state(1, 0, 0, 0, 0);
+    e = cudaMemset2DAsync(h->ws.state[0], 8, static_cast<int>(word & 0xFFu), 1, static_cast<size_t>(num_envs), s);
+    if (e == cudaSuccess)
+      e = cudaMemset2DAsync(h->ws.state[1], 8, static_cast<int>(word & 0xFFu), 1, static_cast<size_t>(num_envs), s);
+    if (e != cudaSuccess) {
+      delete h;
+      *out = nullptr;
+      return cuda_fail(e, "cudaMemset2DAsync(state)");
+    }
+  }
+  return AS_OK;
+}
+
+void as_destroy(AsHandle* h) { delete h; }
+
+int as_generate_stones(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids,
+                       const float* uniforms, void* stream) {
+  AS_REQUIRE(h && env_origins, "handle/env_origins is null");
+  AS_REQUIRE(env_ids == nullptr || n_ids >= 0, "negative id count");
+  ResetArgs r = make_reset_args(h, env_origins);
+  r.env_ids = env_ids;
+  r.n_ids = n_ids;
+  r.stone_uniforms = uniforms;
+  const int64_t n = env_ids ? n_ids : h->num_envs;
+  if (n == 0) return AS_OK;
+  const int grid = grid_for(n, 8, h->sm_count, 8);
+  k_generate_stones<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(r);
+  return check_launch(h, "k_generate_stones");
+}
+
+int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_t actions_stride,
+                  const AsStepOut* out, const AsResetOut* reset_out, void* stream) {
+  AS_REQUIRE(h && out && actions, "handle/out/actions is null");
+  if (int rc = validate_state_in(in, true)) return rc;
+  AS_REQUIRE(actions_stride >= kJ, "actions stride too small");
+  AS_REQUIRE(out->obs && out->reward && out->terminated && out->time_out, "step outputs must be set");
+  if (h->pending_valid) return fail(AS_ERR_STATE, "previous fused step was not closed with as_finish_step");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StepArgs a = make_step_args(h, in, actions, actions_stride, out);
+  const bool want_rows = reset_out && (reset_out->root_state || reset_out->joint_pos || reset_out->joint_vel ||
+                                       reset_out->reset_ids || reset_out->n_reset);
+  const bool regen_enabled = (h->params.flags & AS_FLAG_INTENDED_REGEN) != 0;
+  a.want_reset_list = want_rows ? 1 : 0;
+  k_step<kModeFused><<<a.num_tiles, kTile, kSmemBytes, s>>>(a);
+  if (int rc = check_launch(h, "k_step<fused>")) return rc;
+  if (want_rows || regen_enabled) {
+    ResetArgs r = make_reset_args(h, in->env_origins);
+    if (reset_out) r.out = *reset_out;
+    r.fused = 1;
+    const int grid = grid_for(h->num_envs, 64, h->sm_count, 4);
+    k_reset_rows<<<grid, 256, 0, s>>>(r);
+    if (int rc = check_launch(h, "k_reset_rows")) return rc;
+  }
+  h->pending = a;
+  h->pending_valid = true;
+  return AS_OK;
+}
+
+int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream) {
+  AS_REQUIRE(h, "handle is null");
+  if (!h->pending_valid) return fail(AS_ERR_STATE, "as_finish_step without a preceding as_step_fused");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StepArgs a = h->pending;  // the fix-up re-reads the inputs of the step it closes
+  a.global_stats = global_stats;
+  const int grid = grid_for(a.num_tiles, 1, h->sm_count, 4);
+  k_fixup_finish<<<grid, kTile, kSmemBytes, s>>>(a);
+  h->pending_valid = false;
+  return check_launch(h, "k_fixup_finish");
+}
+
+int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_t actions_stride,
+                  const int64_t* episode_length, const AsStepOut* out, void* stream) {
+  AS_REQUIRE(h && out && actions, "handle/out/actions is null");
+  if (int rc = validate_state_in(in, false)) return rc;
+  AS_REQUIRE(actions_stride >= kJ, "actions stride too small");
+  AS_REQUIRE(out->obs && out->reward && out->terminated && out->time_out, "step outputs must be set");
+  if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
+  StepArgs a = make_step_args(h, in, actions, actions_stride, out);
+  a.ext_episode_length = episode_length;
+  k_step<kModePass1><<<a.num_tiles, kTile, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
+  h->pass1_done = true;
+  return check_launch(h, "k_step<pass1>");
+}
+
+int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids, int64_t* episode_length,
+             const AsResetOut* compact_out, void* stream) {
+  AS_REQUIRE(h && env_origins && env_ids, "handle/env_origins/env_ids is null");
+  AS_REQUIRE(n_ids >= 0 && n_ids <= h->num_envs, "id count out of range");
+  if (n_ids == 0) return AS_OK;  // DRL:360: `_reset_idx` is not entered
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  k_decide_promotion<<<1, 32, 0, s>>>(h->params, h->ws.ctrl, nullptr, 1);
+  if (int rc = check_launch(h, "k_decide_promotion")) return rc;
+  ResetArgs r = make_reset_args(h, env_origins);
+  if (compact_out) r.out = *compact_out;
+  r.env_ids = env_ids;
+  r.n_ids = n_ids;
+  r.ext_episode_length = episode_length;
+  r.fused = 0;
+  const int grid = grid_for(n_ids, 8, h->sm_count, 4);
+  k_reset_rows<<<grid, 256, 0, s>>>(r);
+  return check_launch(h, "k_reset_rows");
+}
+
+int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
+  AS_REQUIRE(h && obs, "handle/obs is null");
+  if (int rc = validate_state_in(in, false)) return rc;
+  if (!h->pass1_done) return fail(AS_ERR_STATE, "as_step_pass2 without a preceding as_step_pass1");
+  AsStepOut out;
+  std::memset(&out, 0, sizeof(out));
+  out.obs = obs;
+  StepArgs a = make_step_args(h, in, nullptr, 0, &out);
+  k_step<kModePass2><<<a.num_tiles, kTile, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch(h, "k_step<pass2>");
+}
+
+int as_apply_action(AsHandle* h, const float* actions, int64_t actions_stride, float* efforts, void* stream) {
+  AS_REQUIRE(h && actions && efforts, "null argument");
+  AS_REQUIRE(actions_stride >= kJ, "actions stride too small");
+  const int grid = grid_for(h->num_envs * kJ, 256 * 4, h->sm_count, 8);
+  k_apply_action<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->params, h->ws, actions, actions_stride,
+                                                                       efforts, h->num_envs);
+  return check_launch(h, "k_apply_action");
+}
+
+int as_mirror_rows(AsHandle* h, const float* in, float* out, int64_t rows, int32_t kind, void* stream) {
+  AS_REQUIRE(h && in && out, "null argument");
+  AS_REQUIRE(rows >= 0, "negative row count");
+  AS_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (observations) or 1 (actions)");
+  if (rows == 0) return AS_OK;
+  const MirrorTable& t = kind == 0 ? h->mirror_obs : h->mirror_act;
+  const int grid = grid_for(rows * t.dim, 256 * 4, h->sm_count, 8);
+  k_mirror_rows<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, in, out, rows);
+  return check_launch(h, "k_mirror_rows");
+}
+
+int as_export_state(AsHandle* h, const AsMdpState* dst, void* stream) {
+  AS_REQUIRE(h && dst, "null argument");
+  if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
+  const int grid = grid_for(h->num_envs, 256, h->sm_count, 8);
+  k_export<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->params, h->ws, *dst, h->num_envs);
+  return check_launch(h, "k_export");
+}
+
+int as_import_state(AsHandle* h, const AsMdpState* src, void* stream) {
+  AS_REQUIRE(h && src, "null argument");
+  if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(h->num_envs, 256, h->sm_count, 8);
+  k_import<<<grid, 256, 0, s>>>(h->params, h->ws, *src, h->num_envs);
+  if (int rc = check_launch(h, "k_import")) return rc;
+  k_clear_promotion<<<1, 32, 0, s>>>(h->ws.ctrl);
+  return check_launch(h, "k_clear_promotion");
+}
+
+int64_t as_launch_count(const AsHandle* h) { return h ? h->launches : 0; }
+
+int64_t as_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(AsParams);
+    case 1: return sizeof(AsStateIn);
+    case 2: return sizeof(AsStepOut);
+    case 3: return sizeof(AsResetOut);
+    case 4: return sizeof(AsStats);
+    case 5: return sizeof(AsMdpState);
+    default: return -1;
+  }
+}
+
+int as_stats_device_ptr(AsHandle* h, AsStats** device_stats) {
+  AS_REQUIRE(h && device_stats, "null argument");
+  *device_stats = &h->ws.ctrl->stats;
+  return AS_OK;
+}
+
+int as_read_stats(AsHandle* h, AsStats* host_out, void* stream) {
+  AS_REQUIRE(h && host_out, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  AS_CUDA(cudaMemcpyAsync(host_out, &h->ws.ctrl->stats, sizeof(AsStats), cudaMemcpyDeviceToHost, s));
+  AS_CUDA(cudaStreamSynchronize(s));
+  return AS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,288 @@
+// Kernels (b) and (c) plus the small adapters around the fused step:
+//   k_reset_rows      warp-per-env reset: start-pose rows for PhysX (ENV:505-565) from the same Philox draws the
+//                     step kernel used, and stone-sequence regeneration (ENV:106-174) for the compacted id lists
+//   k_generate_stones stone sequences for all / listed envs (init, ENV:71)
+//   k_apply_action    ENV:257-274
+//   k_mirror_rows     ENV:570-660 (mirror-symmetry augmentation)
+//   k_export / k_import  packed state <-> the reference's int64/fp32 buffers
+#pragma once
+#include "as_internal.cuh"
+#include "as_math.cuh"
+#include "philox.cuh"
+#include "as_step_kernel.cuh"
+
+namespace as {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// Sequential inclusive scan over the first kS lanes, accumulated in double exactly like torch.cumsum on CPU
+// (acc_type<float> is double there) -- a log-step warp scan would re-associate the additions.
+__device__ __forceinline__ float warp_cumsum_sequential(float x, int lane) {
+  double acc = 0.0;
+  float mine = 0.0f;
+#pragma unroll
+  for (int s = 0; s < kS; ++s) {
+    const float vs = __shfl_sync(kFullMask, x, s);
+    acc += static_cast<double>(vs);
+    if (lane == s) mine = static_cast<float>(acc);
+  }
+  return mine;
+}
+
+// ENV:125-174 for one env, one stone per lane (lanes >= kS idle).  `u_dr/u_dphi/u_dtheta` are this lane's draws.
+__device__ __forceinline__ void generate_stones_warp(const AsParams& P, int lane, int level, const Vec3& origin,
+                                                     float u_dr, float u_dphi, float u_dtheta, float4* out_row) {
+  const float deg2rad = 0.017453292519943295f;  // torch.deg2rad multiplies by float32(pi/180)
+  const float half_pi = 1.5707963705062866f;
+  level = min(level, P.max_level);                                                   // ENV:126
+  const float ratio = static_cast<float>(level) / static_cast<float>(P.max_level);   // ENV:127
+  const float yaw_lo = (P.yaw_range_deg[0] * ratio) * deg2rad, yaw_hi = (P.yaw_range_deg[1] * ratio) * deg2rad;
+  const float pit_lo = (P.pitch_range_deg[0] * ratio) * deg2rad + half_pi;           // ENV:132
+  const float pit_hi = (P.pitch_range_deg[1] * ratio) * deg2rad + half_pi;
+  float dr = torch_lerp(P.dist_lower, P.dist_upper[level], u_dr);                    // ENV:137
+  float dphi = torch_lerp(yaw_lo, yaw_hi, u_dphi);                                   // ENV:138
+  float dth = torch_lerp(pit_lo, pit_hi, u_dtheta);                                  // ENV:139
+  if (lane == 0) {                                                                   // ENV:144-146
+    dr = 0.0f; dphi = 0.0f; dth = half_pi;
+  } else if (lane <= 2) {                                                            // ENV:148-150
+    dr = P.init_step_separation; dphi = 0.0f; dth = half_pi;
+  }
+  if (lane >= kS) { dr = 0.0f; dphi = 0.0f; dth = half_pi; }
+  const float phi = warp_cumsum_sequential(dphi, lane);                              // ENV:155
+  const float st = sinf(dth), ct = cosf(dth);
+  const float dx = (dr * st) * cosf(phi);                                            // ENV:157
+  const float dy = (dr * st) * sinf(phi);                                            // ENV:158
+  const float dz = dr * ct;                                                          // ENV:159
+  const float x = warp_cumsum_sequential(dx, lane);                                  // ENV:165-167
+  const float y = warp_cumsum_sequential(dy, lane);
+  const float z = warp_cumsum_sequential(dz, lane);
+  if (lane < kS) out_row[lane] = make_float4(x + origin.x, y + origin.y, z + origin.z, phi);  // ENV:111
+}
+
+__device__ __forceinline__ void stone_draws(const ResetArgs& a, unsigned long long step, int64_t e, uint32_t gid,
+                                            int lane, float& u_dr, float& u_dphi, float& u_dth) {
+  u_dr = u_dphi = u_dth = 0.0f;
+  if (lane >= kS) return;
+  if (a.stone_uniforms) {  // explicit (5,N,S) tables indexed by local env id
+    const int64_t plane = a.num_envs * kS;
+    u_dr = a.stone_uniforms[0 * plane + e * kS + lane];
+    u_dphi = a.stone_uniforms[1 * plane + e * kS + lane];
+    u_dth = a.stone_uniforms[2 * plane + e * kS + lane];
+  } else {
+    u_dr = philox_uniform(a.P.seed, step, kStreamStones, gid, 0 * kS + lane);
+    u_dphi = philox_uniform(a.P.seed, step, kStreamStones, gid, 1 * kS + lane);
+    u_dth = philox_uniform(a.P.seed, step, kStreamStones, gid, 2 * kS + lane);
+  }
+}
+
+// Kernel (b).  One warp per listed env.
+//   fused = 1: lists were compacted by the step kernel (ws.reset_ids / ws.regen_ids), MDP words already reset;
+//              PhysX rows are written at the env's own row of full-size buffers.
+//   fused = 0: explicit `env_ids` (3-call path): also resets the MDP word and the DirectRLEnv episode counter,
+//              decides regeneration, writes compact rows.
+__global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ ResetArgs a) {
+  const AsParams& P = a.P;
+  Ctrl* ctrl = a.ws.ctrl;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const unsigned long long step = ctrl->step_counter;
+  const int64_t n_reset = a.fused ? static_cast<int64_t>(ctrl->n_reset_list) : a.n_ids;
+  // promotion decided in THIS step is already in force when stones are regenerated (ENV:471 precedes ENV:500)
+  // (3-call path: as_reset ran k_decide_promotion first and left the decision in promote_cur)
+  const AsStats* g = a.global_stats ? a.global_stats : &ctrl->stats;
+  const int promote_now = a.fused ? static_cast<int>(promotion_decision(P, *g)) : static_cast<int>(ctrl->promote_cur);
+  const uint32_t parity = ctrl->parity;
+  uint2* st_cur = a.fused ? a.ws.state[parity ^ 1u] : a.ws.state[parity];  // fused: the step wrote the other buffer
+
+  for (int64_t w = warp; w < n_reset; w += n_warps) {
+    const int64_t e = a.fused ? a.ws.reset_ids[w] : a.env_ids[w];
+    const int64_t row = a.fused ? e : w;
+    const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
+    const uint4 b0 = philox_block(P.seed, step, kStreamReset, gid, 0);
+    const bool mirror = u32_to_unit(b0.x) > 0.5f;  // ENV:518
+    const float ox = a.env_origins[e * 3], oy = a.env_origins[e * 3 + 1], oz = a.env_origins[e * 3 + 2];
+    if (lane < kJ) {
+      const float u = philox_uniform(P.seed, step, kStreamReset, gid, 1 + lane);
+      if (a.out.joint_pos) a.out.joint_pos[row * kJ + lane] = reset_joint_value(P, lane, mirror, u);
+      if (a.out.joint_vel) a.out.joint_vel[row * kJ + lane] = mirror ? 0.0f * P.mirror_sign[lane] : 0.0f;
+    }
+    if (a.out.root_state && lane < AS_ROOT_STATE_DIM) {
+      const float z = mirror ? -0.0f : 0.0f;
+      float val = 0.0f;
+      if (lane == 0) val = P.default_root_pos[0] + ox;
+      else if (lane == 1) val = P.default_root_pos[1] + oy;
+      else if (lane == 2) val = P.default_root_pos[2] + oz;
+      else if (lane == 3) val = 1.0f;
+      else if (lane <= 6) val = z;
+      a.out.root_state[row * AS_ROOT_STATE_DIM + lane] = val;
+    }
+    if (a.out.reset_ids && lane == 0) a.out.reset_ids[w] = static_cast<int32_t>(e);
+    if (!a.fused) {
+      uint32_t word = st_cur[e].x;  // same address for all lanes: broadcast
+      const int level = min(state_level(word) + promote_now, P.max_level);
+      const bool regen = (P.flags & AS_FLAG_INTENDED_REGEN) && state_idx(word) > kS / 2;
+      __syncwarp();
+      if (lane == 0) {
+        uint2 sw;
+        sw.x = pack_state(1, mirror ? 1 : 0, 0, state_level(word), 0);  // ENV:487-494,538; DRL:584
+        sw.y = __float_as_uint(0.0f);
+        st_cur[e] = sw;
+        if (a.ext_episode_length) a.ext_episode_length[e] = 0;
+      }
+      if (regen) {
+        float u0, u1, u2;
+        stone_draws(a, step, e, gid, lane, u0, u1, u2);
+        generate_stones_warp(P, lane, level, Vec3{ox, oy, oz}, u0, u1, u2, a.ws.stones + e * kS);
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->stats.n_regenerated), 1ull);
+      }
+    }
+  }
+  if (a.fused) {
+    const int64_t n_regen = ctrl->n_regen_list;
+    for (int64_t w = warp; w < n_regen; w += n_warps) {
+      const int64_t e = a.ws.regen_ids[w];
+      const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
+      const int level = min(state_level(st_cur[e].x) + promote_now, P.max_level);
+      const Vec3 origin{a.env_origins[e * 3], a.env_origins[e * 3 + 1], a.env_origins[e * 3 + 2]};
+      float u0, u1, u2;
+      stone_draws(a, step, e, gid, lane, u0, u1, u2);
+      generate_stones_warp(P, lane, level, origin, u0, u1, u2, a.ws.stones + e * kS);
+    }
+  }
+  if (a.out.n_reset && blockIdx.x == 0 && threadIdx.x == 0) *a.out.n_reset = static_cast<int32_t>(n_reset);
+}
+
+// Stone sequences for all envs (env_ids == null) or a list; level from the packed word (+ pending promotion).
+__global__ void __launch_bounds__(256) k_generate_stones(const __grid_constant__ ResetArgs a) {
+  Ctrl* ctrl = a.ws.ctrl;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t n = a.env_ids ? a.n_ids : a.num_envs;
+  const unsigned long long step = ctrl->step_counter;
+  const uint2* st = a.ws.state[ctrl->parity];
+  const int pending = static_cast<int>(ctrl->promote_cur);
+  for (int64_t w = warp; w < n; w += n_warps) {
+    const int64_t e = a.env_ids ? a.env_ids[w] : w;
+    const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
+    const int level = min(state_level(st[e].x) + pending, a.P.max_level);
+    const Vec3 origin{a.env_origins[e * 3], a.env_origins[e * 3 + 1], a.env_origins[e * 3 + 2]};
+    float u0, u1, u2;
+    stone_draws(a, step, e, gid, lane, u0, u1, u2);
+    generate_stones_warp(a.P, lane, level, origin, u0, u1, u2, a.ws.stones + e * kS);
+  }
+}
+
+// 3-call path: `_reset_idx` opens with the promotion rule (ENV:471-479) on the statistics pass 1 folded.
+__global__ void k_decide_promotion(const __grid_constant__ AsParams P, Ctrl* ctrl, const AsStats* global_stats,
+                                   int force_any_reset) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    AsStats s = global_stats ? *global_stats : ctrl->stats;
+    if (force_any_reset) s.n_reset = s.n_reset > 0 ? s.n_reset : 1;
+    ctrl->promote_cur = promotion_decision(P, s);
+  }
+}
+
+// ENV:257-274: efforts = gain[level] * gear * clamp(action)
+__global__ void __launch_bounds__(256) k_apply_action(const __grid_constant__ AsParams P, Workspace ws,
+                                                      const float* __restrict__ actions, int64_t stride,
+                                                      float* __restrict__ efforts, int64_t num_envs) {
+  const int64_t total = num_envs * kJ;
+  const uint2* st = ws.state[ws.ctrl->parity];
+  const int pending = static_cast<int>(ws.ctrl->promote_cur);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e = i / kJ;
+    const int j = static_cast<int>(i - e * kJ);
+    const int level = min(state_level(st[e].x) + pending, P.max_level);
+    const float act = fminf(fmaxf(actions[e * stride + j], -1.0f), 1.0f);
+    efforts[i] = (P.applied_gain[level] * P.joint_gears[j]) * act;
+  }
+}
+
+struct MirrorTable {
+  int32_t src[AS_OBS_DIM];
+  float sign[AS_OBS_DIM];
+  int32_t dim;
+};
+
+// ENV:570-660: rows [0,R) copy, rows [R,2R) = sign[c] * in[r][src[c]]
+__global__ void __launch_bounds__(256) k_mirror_rows(const __grid_constant__ MirrorTable t,
+                                                     const float* __restrict__ in, float* __restrict__ out,
+                                                     int64_t rows) {
+  const int64_t total = rows * t.dim;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / t.dim;
+    const int c = static_cast<int>(i - r * t.dim);
+    out[i] = in[i];
+    out[total + i] = t.sign[c] * in[r * t.dim + t.src[c]];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_export(const __grid_constant__ AsParams P, Workspace ws, AsMdpState dst,
+                                                int64_t num_envs) {
+  const uint2* st = ws.state[ws.ctrl->parity];
+  const int pending = static_cast<int>(ws.ctrl->promote_cur);
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < num_envs;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint2 sw = st[e];
+    if (dst.curr_target_index) dst.curr_target_index[e] = state_idx(sw.x);
+    if (dst.swing_leg) dst.swing_leg[e] = state_leg(sw.x);
+    if (dst.target_reach_count) dst.target_reach_count[e] = state_count(sw.x);
+    if (dst.episode_length) dst.episode_length[e] = state_ep(sw.x);
+    if (dst.curriculum) dst.curriculum[e] = min(state_level(sw.x) + pending, P.max_level);
+    if (dst.potentials) dst.potentials[e] = __uint_as_float(sw.y);
+    if (dst.steps_pos || dst.steps_dphi) {
+      for (int s = 0; s < kS; ++s) {
+        const float4 v = ws.stones[e * kS + s];
+        if (dst.steps_pos) {
+          dst.steps_pos[(e * kS + s) * 3 + 0] = v.x;
+          dst.steps_pos[(e * kS + s) * 3 + 1] = v.y;
+          dst.steps_pos[(e * kS + s) * 3 + 2] = v.z;
+        }
+        if (dst.steps_dphi) dst.steps_dphi[e * kS + s] = v.w;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_import(const __grid_constant__ AsParams P, Workspace ws, AsMdpState src,
+                                                int64_t num_envs) {
+  uint2* st = ws.state[ws.ctrl->parity];
+  const int pending = static_cast<int>(ws.ctrl->promote_cur);
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < num_envs;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    uint2 sw = st[e];
+    int idx = state_idx(sw.x), leg = state_leg(sw.x), cnt = state_count(sw.x), lvl = state_level(sw.x),
+        ep = state_ep(sw.x);
+    if (src.curr_target_index) idx = static_cast<int>(min(max(src.curr_target_index[e], (int64_t)0), (int64_t)(kS - 1)));
+    if (src.swing_leg) leg = static_cast<int>(src.swing_leg[e] & 1);
+    if (src.target_reach_count) cnt = static_cast<int>(min(max(src.target_reach_count[e], (int64_t)0), (int64_t)3));
+    if (src.episode_length) ep = static_cast<int>(min(max(src.episode_length[e], (int64_t)0), (int64_t)kMaxEpisodeLength));
+    if (src.curriculum) lvl = static_cast<int>(min(max(src.curriculum[e], (int64_t)0), (int64_t)P.max_level));
+    else lvl = min(lvl + pending, P.max_level);  // a pending promotion is folded in, the flag is cleared below
+    sw.x = pack_state(idx, leg, cnt, lvl, ep);
+    if (src.potentials) sw.y = __float_as_uint(src.potentials[e]);
+    st[e] = sw;
+    if (src.steps_pos || src.steps_dphi) {
+      for (int s = 0; s < kS; ++s) {
+        float4 v = ws.stones[e * kS + s];
+        if (src.steps_pos) {
+          v.x = src.steps_pos[(e * kS + s) * 3 + 0];
+          v.y = src.steps_pos[(e * kS + s) * 3 + 1];
+          v.z = src.steps_pos[(e * kS + s) * 3 + 2];
+        }
+        if (src.steps_dphi) v.w = src.steps_dphi[e * kS + s];
+        ws.stones[e * kS + s] = v;
+      }
+    }
+  }
+}
+
+__global__ void k_clear_promotion(Ctrl* ctrl) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) ctrl->promote_cur = 0;
+}
+
+}  // namespace as

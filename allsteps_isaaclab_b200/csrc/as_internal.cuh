@@ -1,0 +1,128 @@
+// Internal layout shared by the Allsteps kernels and the C-ABI glue (not part of the public header).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/allsteps_b200.h"
+
+namespace as {
+
+constexpr int kJ = AS_NUM_JOINTS;
+constexpr int kS = AS_NUM_STONES;
+constexpr int kObs = AS_OBS_DIM;
+constexpr int kTile = AS_TILE_ENVS;  // envs per CTA == threads per CTA
+constexpr int kSlots = 32;           // replicated statistic accumulators (spreads same-address atomics)
+
+// Per-step counters accumulated by the step kernels (index into Ctrl::slots[slot][]).
+enum Counter {
+  kCntReset = 0,
+  kCntTerminated,
+  kCntTimeOut,
+  kCntFell,
+  kCntSoFast,
+  kCntDied,
+  kCntAdvanced1,  // index advances in pass 1
+  kCntAdvanced2,  // index advances in pass 2 (void when the fix-up discards pass 2)
+  kCntSumIndex,   // sum of curr_target_index after pass 1 (numerator of ENV:471)
+  kCntRegen,
+  kNumCounters = 12
+};
+
+// Packed per-env MDP state word (state.x); state.y holds the bits of `potentials`.
+//   [0:5) curr_target_index   [5] swing_leg   [6:8) target_reach_count   [8:12) curriculum level
+//   [12:32) episode_length
+// prev/next target index are always clamp(curr -/+ 1) in the reference (ENV:76-77,446-456,493-494), so they are
+// derived, not stored.  old_potentials is dead between passes (overwritten at ENV:415 before it is read).
+__host__ __device__ inline uint32_t pack_state(int idx, int leg, int count, int level, int ep) {
+  return static_cast<uint32_t>(idx) | (static_cast<uint32_t>(leg) << 5) | (static_cast<uint32_t>(count) << 6) |
+         (static_cast<uint32_t>(level) << 8) | (static_cast<uint32_t>(ep) << 12);
+}
+__host__ __device__ inline int state_idx(uint32_t w) { return static_cast<int>(w & 31u); }
+__host__ __device__ inline int state_leg(uint32_t w) { return static_cast<int>((w >> 5) & 1u); }
+__host__ __device__ inline int state_count(uint32_t w) { return static_cast<int>((w >> 6) & 3u); }
+__host__ __device__ inline int state_level(uint32_t w) { return static_cast<int>((w >> 8) & 15u); }
+__host__ __device__ inline int state_ep(uint32_t w) { return static_cast<int>(w >> 12); }
+constexpr int kMaxEpisodeLength = (1 << 20) - 2;
+
+// Device control block at the head of the workspace.
+struct Ctrl {
+  uint32_t parity;        // state buffer holding the CURRENT MDP state (fused path ping-pongs)
+  uint32_t promote_cur;   // level promotion decided last step, applied when the state word is next read
+  uint32_t blocks_done;   // ticket counter for "last block folds the statistics"
+  uint32_t blocks_done2;  // same, for the fix-up / finish kernel
+  uint32_t n_reset_list;  // entries of reset_ids written this step
+  uint32_t n_regen_list;  // entries of regen_ids written this step
+  uint32_t fixup_ran;     // diagnostics: how many steps needed the no-reset fix-up
+  uint32_t last_adv2;     // pass-2 index advances of the last step (discarded again if the fix-up runs)
+  unsigned long long step_counter;
+  AsStats stats;          // folded statistics of the last step (this shard)
+  unsigned int slots[kSlots][kNumCounters];
+  float slot_reward[kSlots];
+};
+
+struct Workspace {
+  Ctrl* ctrl;
+  uint2* state[2];    // (N) packed state / potentials, ping-pong
+  float4* stones;     // (N,S) x,y,z (world frame), cumulative yaw
+  int32_t* reset_ids; // (N)
+  int32_t* regen_ids; // (N)
+};
+
+struct WorkspaceLayout {
+  int64_t ctrl_off, state0_off, state1_off, stones_off, reset_ids_off, regen_ids_off, total;
+};
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+inline WorkspaceLayout workspace_layout(int64_t n) {
+  WorkspaceLayout l;
+  int64_t off = 0;
+  l.ctrl_off = off;
+  off = align_up(off + static_cast<int64_t>(sizeof(Ctrl)), 256);
+  l.state0_off = off;
+  off = align_up(off + n * 8, 256);
+  l.state1_off = off;
+  off = align_up(off + n * 8, 256);
+  l.stones_off = off;
+  off = align_up(off + n * kS * 16, 256);
+  l.reset_ids_off = off;
+  off = align_up(off + n * 4, 256);
+  l.regen_ids_off = off;
+  off = align_up(off + n * 4, 256);
+  l.total = off;
+  return l;
+}
+
+enum StepMode { kModeFused = 0, kModeFixup = 1, kModePass1 = 2, kModePass2 = 3 };
+
+struct StepArgs {
+  AsParams P;
+  AsStateIn in;
+  const float* actions;
+  int64_t actions_stride;
+  AsStepOut out;
+  Workspace ws;
+  const int64_t* ext_episode_length;  // 3-call path: DirectRLEnv-owned counter (already incremented), or null
+  const AsStats* global_stats;        // fix-up/finish: statistics summed over ranks, or null
+  int64_t num_envs;
+  int64_t env_id_offset;
+  int32_t num_tiles;
+  int32_t want_reset_list;            // fused: append reset env ids to ws.reset_ids
+};
+
+struct ResetArgs {
+  AsParams P;
+  Workspace ws;
+  AsResetOut out;
+  const float* env_origins;
+  const int32_t* env_ids;   // 3-call path: explicit list; fused path: null (uses ws.reset_ids / ws.regen_ids)
+  int64_t n_ids;
+  int64_t* ext_episode_length;
+  const AsStats* global_stats;
+  const float* stone_uniforms;  // optional explicit draws (5,N,S)
+  int64_t num_envs;
+  int64_t env_id_offset;
+  int32_t fused;                // 1: state words were already reset by the step kernel, rows go to env's own row
+};
+
+}  // namespace as

@@ -1,0 +1,674 @@
+// Kernel (a): the fused Allsteps-v0 MDP step for sm_100a.
+//
+// One CTA of 128 threads owns a tile of 128 consecutive envs, one thread per env.
+//
+//   HBM -> SMEM   the row-major PhysX views of the tile (joint_pos/joint_vel/actions (128,21), root pos/quat/vel,
+//                 feet+torso positions) are contiguous byte ranges, so one elected thread moves each of them with a
+//                 single TMA bulk copy (cp.async.bulk.shared.global, completion on an mbarrier).  A thread then
+//                 reads ITS row from shared memory: row strides 21, 3, 9 are odd => bank-conflict free, and the
+//                 global side is perfectly coalesced although the layout is array-of-structs.
+//   gathers       the packed 8-byte MDP state word is a coalesced load; the two 12-byte contact-force vectors of
+//                 the current stone and the three 16-byte stones are data-dependent gathers issued before the
+//                 mbarrier wait so their latency overlaps the bulk copies.
+//   compute       pass 1 -> dones -> rewards -> masked reset (Philox) -> pass 2 -> observations, all in registers.
+//   SMEM -> HBM   the (128,59) observation tile is assembled in shared memory (row stride 59, odd) on top of the
+//                 consumed input tiles and leaves with one TMA bulk store; reward / flags / state word are
+//                 coalesced per-thread stores.
+//
+// Reference semantics reproduced (ENV = allsteps_env.py, DRL = direct_rl_env.py of the reference):
+//   DRL:351 episode counter, ENV:276-324 pass, ENV:396-405 dones, ENV:347-394 rewards, ENV:469-567 reset + pass 2
+//   for ALL envs when any env resets, ENV:326-345 observations.
+#pragma once
+#include "as_internal.cuh"
+#include "as_math.cuh"
+#include "philox.cuh"
+
+namespace as {
+
+// ------------------------------------------------------------------------------------------------ SMEM plan
+constexpr int kOffJp = 0;
+constexpr int kOffJv = kOffJp + kTile * kJ * 4;
+constexpr int kOffAct = kOffJv + kTile * kJ * 4;
+constexpr int kOffRp = kOffAct + kTile * kJ * 4;
+constexpr int kOffRq = kOffRp + kTile * 3 * 4;
+constexpr int kOffRv = kOffRq + kTile * 4 * 4;
+constexpr int kOffBody = kOffRv + kTile * 3 * 4;
+constexpr int kOffMisc = kOffBody + kTile * 9 * 4;
+constexpr int kSmemBytes = kOffMisc + 256;
+static_assert(kTile * kObs * 4 <= kOffRp, "observation tile must fit over the joint/action tiles it aliases");
+static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffRq % 16 == 0 &&
+                  kOffRv % 16 == 0 && kOffBody % 16 == 0 && kOffMisc % 16 == 0,
+              "bulk copies need 16-byte aligned shared addresses");
+
+struct Misc {  // lives at kOffMisc, never aliased
+  unsigned long long mbar;
+  unsigned int cnt[kNumCounters];
+  float reward_sum;
+  unsigned int is_last;
+  unsigned int fold[kNumCounters];
+};
+static_assert(sizeof(Misc) <= 256, "misc block");
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// TMA 1-D bulk copy shared -> global.
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ staging
+template <int W>
+__device__ __forceinline__ bool bulk_ok(const float* base, int64_t stride, int64_t env0, int n_valid) {
+  return stride == W && ((reinterpret_cast<uintptr_t>(base + env0 * W) & 15u) == 0) && (((n_valid * W) & 3) == 0);
+}
+template <int W>
+__device__ __forceinline__ void coop_load(float* dst, const float* base, int64_t stride, int64_t env0, int n_valid) {
+  for (int i = threadIdx.x; i < n_valid * W; i += kTile) {
+    const int r = i / W;
+    const int c = i - r * W;
+    dst[i] = __ldg(base + (env0 + r) * stride + c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ one pass
+struct Mdp {
+  int idx, leg, count;
+  float pot;
+};
+struct PassOut {
+  float contact_r, contact_l;  // foot_contact (right, left) as 0/1 floats, ENV:426
+  float d_swing;               // foot_to_target_dist_xy[n, swing_leg] with the POST-update leg, ENV:371
+  float body_dist;             // ENV:410
+  float old_pot;               // ENV:415
+  bool reached, advanced;
+  Vec3 tb0, tb1, tb2;          // targets_b rows (prev, curr, next), ENV:302-316
+};
+
+// ENV:418-467 + ENV:302-316 + ENV:407-416.  `force_r/l` are the contact-force norms of the CURRENT stone,
+// (s_prev, s_curr, s_next) the stones at clamp(idx-1), idx, clamp(idx+1); `stone(i)` gathers stone i.
+template <class StoneFn>
+__device__ __forceinline__ void mdp_pass(const AsParams& P, const Vec3& p, const Quat& q, const Vec3& rf,
+                                         const Vec3& lf, float force_r, float force_l, float4& s_prev,
+                                         float4& s_curr, float4& s_next, StoneFn&& stone, Mdp& m, PassOut& o) {
+  const bool press_r = force_r > P.contact_epsilon;
+  const bool press_l = force_l > P.contact_epsilon;
+  o.contact_r = press_r ? 1.0f : 0.0f;
+  o.contact_l = press_l ? 1.0f : 0.0f;
+  const float d_r = norm2(rf.x - s_curr.x, rf.y - s_curr.y);
+  const float d_l = norm2(lf.x - s_curr.x, lf.y - s_curr.y);
+  o.reached = m.leg ? (press_l && d_l < P.step_radius) : (press_r && d_r < P.step_radius);
+  m.count += o.reached ? 1 : 0;
+  o.advanced = m.count >= P.stop_frames;
+  if (o.advanced) {
+    m.leg ^= 1;
+    const int nidx = min(m.idx + 1, kS - 1);
+    if (nidx != m.idx) {
+      s_prev = s_curr;
+      s_curr = s_next;
+      s_next = stone(min(nidx + 1, kS - 1));
+    }
+    m.idx = nidx;
+    m.count = 0;
+  }
+  o.d_swing = m.leg ? d_l : d_r;
+  const Quat inv = quat_inverse(q);
+  o.tb0 = point_in_frame(p, inv, Vec3{s_prev.x, s_prev.y, s_prev.z});
+  o.tb1 = point_in_frame(p, inv, Vec3{s_curr.x, s_curr.y, s_curr.z});
+  o.tb2 = point_in_frame(p, inv, Vec3{s_next.x, s_next.y, s_next.z});
+  o.body_dist = norm2(s_next.x - p.x, s_next.y - p.y);
+  o.old_pot = m.pot;
+  m.pot = (-o.body_dist) / P.step_dt;
+}
+
+// First three stones of ANY generated sequence are fixed (ENV:144-150): the pass after a regeneration needs
+// only these, so the step kernel does not wait for the regeneration kernel.
+__device__ __forceinline__ void first_three_stones(const AsParams& P, const Vec3& origin, float4& s0, float4& s1,
+                                                   float4& s2) {
+  const float half_pi = 1.5707963705062866f;
+  const float st = sinf(half_pi), ct = cosf(half_pi);
+  const float dx = (P.init_step_separation * st) * cosf(0.0f);
+  const float dy = (P.init_step_separation * st) * sinf(0.0f);
+  const float dz = P.init_step_separation * ct;
+  double x = 0.0, y = 0.0, z = 0.0;  // torch.cumsum on CPU accumulates fp32 inputs in double
+  s0 = make_float4(static_cast<float>(x) + origin.x, static_cast<float>(y) + origin.y,
+                   static_cast<float>(z) + origin.z, 0.0f);
+  x += dx; y += dy; z += dz;
+  s1 = make_float4(static_cast<float>(x) + origin.x, static_cast<float>(y) + origin.y,
+                   static_cast<float>(z) + origin.z, 0.0f);
+  x += dx; y += dy; z += dz;
+  s2 = make_float4(static_cast<float>(x) + origin.x, static_cast<float>(y) + origin.y,
+                   static_cast<float>(z) + origin.z, 0.0f);
+}
+
+// Start-pose joint value of a reset env (ENV:505-560): running-start pose, optional mirror, uniform noise, clip.
+__device__ __forceinline__ float reset_joint_value(const AsParams& P, int j, bool mirror, float u) {
+  const int src = mirror ? P.mirror_src[j] : j;
+  const float base = mirror ? P.reset_pose[src] * P.mirror_sign[j] : P.reset_pose[src];
+  const float noisy = base + (u * P.noise_span + P.noise_lower);
+  float unit = scale_to_unit(noisy, P.joint_lower[j], P.joint_upper[j]);
+  unit = fminf(fmaxf(unit, P.clip_lower), P.clip_upper);
+  return unscale_from_unit(unit, P.joint_lower[j], P.joint_upper[j]);
+}
+
+// ------------------------------------------------------------------------------------------------ statistics
+__device__ __forceinline__ void fold_stats(Ctrl* ctrl, Misc* misc, const StepArgs& a) {
+  const int t = threadIdx.x;
+  if (t < kNumCounters) {
+    unsigned int acc = 0;
+    if (t == 10) {
+      for (int s = 0; s < kSlots; ++s) acc = max(acc, atomicExch(&ctrl->slots[s][t], 0u));
+    } else {
+      for (int s = 0; s < kSlots; ++s) acc += atomicExch(&ctrl->slots[s][t], 0u);
+    }
+    misc->fold[t] = acc;
+  }
+  float rsum = 0.0f;
+  if (t == 32) {
+    for (int s = 0; s < kSlots; ++s) rsum += atomicExch(&ctrl->slot_reward[s], 0.0f);
+  }
+  __syncthreads();
+  if (t == 0) {
+    AsStats& st = ctrl->stats;
+    st.n_envs = a.num_envs;
+    st.n_reset = misc->fold[kCntReset];
+    st.n_terminated = misc->fold[kCntTerminated];
+    st.n_time_out = misc->fold[kCntTimeOut];
+    st.n_fell = misc->fold[kCntFell];
+    st.n_so_fast = misc->fold[kCntSoFast];
+    st.n_died = misc->fold[kCntDied];
+    st.n_advanced = static_cast<int64_t>(misc->fold[kCntAdvanced1]) + misc->fold[kCntAdvanced2];
+    st.sum_target_index = misc->fold[kCntSumIndex];
+    st.n_regenerated = misc->fold[kCntRegen];
+    st.level = misc->fold[10];
+    st.step_counter = static_cast<int64_t>(ctrl->step_counter);
+    ctrl->last_adv2 = misc->fold[kCntAdvanced2];
+    ctrl->blocks_done = 0;
+  }
+  if (t == 32) ctrl->stats.sum_reward = static_cast<double>(rsum);
+}
+
+// ------------------------------------------------------------------------------------------------ the tile
+template <int MODE>
+__device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32_t& phase, unsigned char* smem) {
+  const AsParams& P = a.P;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int64_t env0 = static_cast<int64_t>(tile) * kTile;
+  const int64_t rem = a.num_envs - env0;
+  const int n_valid = rem < kTile ? static_cast<int>(rem) : kTile;
+  const bool active = tid < n_valid;
+  const int64_t e = env0 + tid;
+
+  float* s_jp = reinterpret_cast<float*>(smem + kOffJp);
+  float* s_jv = reinterpret_cast<float*>(smem + kOffJv);
+  float* s_act = reinterpret_cast<float*>(smem + kOffAct);
+  float* s_rp = reinterpret_cast<float*>(smem + kOffRp);
+  float* s_rq = reinterpret_cast<float*>(smem + kOffRq);
+  float* s_rv = reinterpret_cast<float*>(smem + kOffRv);
+  float* s_body = reinterpret_cast<float*>(smem + kOffBody);
+  float* s_obs = reinterpret_cast<float*>(smem);
+  Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
+  const uint32_t bar = smem_u32(&misc->mbar);
+  Ctrl* ctrl = a.ws.ctrl;
+
+  constexpr bool kNeedActions = MODE != kModePass2;
+  constexpr bool kPingPong = MODE == kModeFused || MODE == kModeFixup;
+
+  // ---------------------------------------------------------------- HBM -> SMEM (TMA bulk where the view allows)
+  const bool body_compact = a.in.body_row_stride == 3 && a.in.body_env_stride == 9 && a.in.right_foot_row == 0 &&
+                            a.in.left_foot_row == 1 && a.in.torso_row == 2;
+  const bool b_jp = bulk_ok<kJ>(a.in.joint_pos, a.in.joint_pos_stride, env0, n_valid);
+  const bool b_jv = bulk_ok<kJ>(a.in.joint_vel, a.in.joint_vel_stride, env0, n_valid);
+  const bool b_act = kNeedActions && bulk_ok<kJ>(a.actions, a.actions_stride, env0, n_valid);
+  const bool b_rp = bulk_ok<3>(a.in.root_pos, a.in.root_pos_stride, env0, n_valid);
+  const bool b_rq = bulk_ok<4>(a.in.root_quat, a.in.root_quat_stride, env0, n_valid);
+  const bool b_rv = bulk_ok<3>(a.in.root_lin_vel, a.in.root_lin_vel_stride, env0, n_valid);
+  const bool b_body = body_compact && bulk_ok<9>(a.in.body_pos, 9, env0, n_valid);
+  const bool any_bulk = b_jp || b_jv || b_act || b_rp || b_rq || b_rv || b_body;
+  if (tid == 0 && any_bulk) {
+    const uint32_t nv = static_cast<uint32_t>(n_valid);
+    const uint32_t tx = (b_jp ? nv * kJ * 4 : 0) + (b_jv ? nv * kJ * 4 : 0) + (b_act ? nv * kJ * 4 : 0) +
+                        (b_rp ? nv * 12 : 0) + (b_rq ? nv * 16 : 0) + (b_rv ? nv * 12 : 0) + (b_body ? nv * 36 : 0);
+    mbar_arrive_expect_tx(bar, tx);
+    if (b_jp) bulk_g2s(smem_u32(s_jp), a.in.joint_pos + env0 * kJ, nv * kJ * 4, bar);
+    if (b_jv) bulk_g2s(smem_u32(s_jv), a.in.joint_vel + env0 * kJ, nv * kJ * 4, bar);
+    if (b_act) bulk_g2s(smem_u32(s_act), a.actions + env0 * kJ, nv * kJ * 4, bar);
+    if (b_rp) bulk_g2s(smem_u32(s_rp), a.in.root_pos + env0 * 3, nv * 12, bar);
+    if (b_rq) bulk_g2s(smem_u32(s_rq), a.in.root_quat + env0 * 4, nv * 16, bar);
+    if (b_rv) bulk_g2s(smem_u32(s_rv), a.in.root_lin_vel + env0 * 3, nv * 12, bar);
+    if (b_body) bulk_g2s(smem_u32(s_body), a.in.body_pos + env0 * 9, nv * 36, bar);
+  }
+
+  // ---------------------------------------------------------------- per-env state word + dependent gathers
+  const uint32_t parity = ctrl->parity;
+  const uint2* st_in = a.ws.state[parity];
+  uint2* st_out = kPingPong ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
+  const float4* stones = a.ws.stones + e * kS;
+  auto stone_at = [&](int i) -> float4 { return __ldg(stones + i); };
+
+  Mdp m{1, 0, 0, 0.0f};
+  int level = 0, ep = 0;
+  float4 s_prev = make_float4(0, 0, 0, 0), s_curr = s_prev, s_next = s_prev;
+  float f_r = 0.0f, f_l = 0.0f;
+  const float* cr_row = nullptr;
+  const float* cl_row = nullptr;
+  if (active) {
+    const uint2 sw = st_in[e];
+    m.idx = state_idx(sw.x);
+    m.leg = state_leg(sw.x);
+    m.count = state_count(sw.x);
+    level = state_level(sw.x);
+    ep = state_ep(sw.x);
+    m.pot = __uint_as_float(sw.y);
+    if (MODE != kModePass2) level = min(level + static_cast<int>(ctrl->promote_cur), P.max_level);
+    if (kPingPong) ep = min(ep + 1, kMaxEpisodeLength);  // DRL:351
+    if (MODE == kModePass1) {
+      ep = a.ext_episode_length ? static_cast<int>(min(a.ext_episode_length[e], (int64_t)kMaxEpisodeLength))
+                                : min(ep + 1, kMaxEpisodeLength);
+    }
+    cr_row = a.in.contact_right + e * a.in.contact_right_stride;
+    cl_row = a.in.contact_left + e * a.in.contact_left_stride;
+    const float* fr = cr_row + m.idx * 3;
+    const float* fl = cl_row + m.idx * 3;
+    const float frx = __ldg(fr), fry = __ldg(fr + 1), frz = __ldg(fr + 2);
+    const float flx = __ldg(fl), fly = __ldg(fl + 1), flz = __ldg(fl + 2);
+    s_prev = stone_at(max(m.idx - 1, 0));
+    s_curr = stone_at(m.idx);
+    s_next = stone_at(min(m.idx + 1, kS - 1));
+    f_r = norm3(frx, fry, frz);  // ENV:421-424
+    f_l = norm3(flx, fly, flz);
+  }
+
+  // views the bulk path cannot take (strided (N,13) root_state_w slices, full (N,B,3/13) body tensor, ragged tail)
+  if (!b_jp) coop_load<kJ>(s_jp, a.in.joint_pos, a.in.joint_pos_stride, env0, n_valid);
+  if (!b_jv) coop_load<kJ>(s_jv, a.in.joint_vel, a.in.joint_vel_stride, env0, n_valid);
+  if (kNeedActions && !b_act) coop_load<kJ>(s_act, a.actions, a.actions_stride, env0, n_valid);
+  if (!b_rp) coop_load<3>(s_rp, a.in.root_pos, a.in.root_pos_stride, env0, n_valid);
+  if (!b_rq) coop_load<4>(s_rq, a.in.root_quat, a.in.root_quat_stride, env0, n_valid);
+  if (!b_rv) coop_load<3>(s_rv, a.in.root_lin_vel, a.in.root_lin_vel_stride, env0, n_valid);
+  if (!b_body) {
+    for (int i = tid; i < n_valid * 9; i += kTile) {
+      const int r = i / 9;
+      const int c = i - r * 9;
+      const int b = c / 3;
+      const int k = c - b * 3;
+      const int row = b == 0 ? a.in.right_foot_row : (b == 1 ? a.in.left_foot_row : a.in.torso_row);
+      s_body[i] = __ldg(a.in.body_pos + (env0 + r) * a.in.body_env_stride + row * a.in.body_row_stride + k);
+    }
+  }
+  __syncthreads();
+  if (any_bulk) {
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+  }
+
+  // ---------------------------------------------------------------- compute (registers)
+  Vec3 p{0, 0, 0}, v{0, 0, 0}, rf{0, 0, 0}, lf{0, 0, 0};
+  Quat q{1, 0, 0, 0};
+  float torso_z = 0.0f;
+  if (active) {
+    p = Vec3{s_rp[tid * 3], s_rp[tid * 3 + 1], s_rp[tid * 3 + 2]};
+    const float4 q4 = *reinterpret_cast<const float4*>(s_rq + tid * 4);
+    q = Quat{q4.x, q4.y, q4.z, q4.w};
+    v = Vec3{s_rv[tid * 3], s_rv[tid * 3 + 1], s_rv[tid * 3 + 2]};
+    rf = Vec3{s_body[tid * 9 + 0], s_body[tid * 9 + 1], s_body[tid * 9 + 2]};
+    lf = Vec3{s_body[tid * 9 + 3], s_body[tid * 9 + 4], s_body[tid * 9 + 5]};
+    torso_z = s_body[tid * 9 + 8];
+  }
+
+  // head of the observation row; refreshed by whichever pass ran last
+  float h = 0.0f, roll = 0.0f, pitch = 0.0f;
+  Vec3 vb{0, 0, 0};
+  PassOut po{};
+  bool terminated = false, time_out = false, is_reset = false, mirror = false, regen = false;
+  bool fell = false, so_fast = false, died = false, adv1 = false, adv2 = false;
+  float r_progress = 0.0f, r_roll = 0.0f, r_pitch = 0.0f, r_speed = 0.0f, r_step = 0.0f, r_bonus = 0.0f;
+  int idx_after_pass1 = 0;
+  uint4 rblk = make_uint4(0, 0, 0, 0);
+  const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
+  const unsigned long long step_now = ctrl->step_counter;
+
+  if (active) {
+    h = torso_z - fminf(lf.z, rf.z);  // ENV:281-283
+    euler_roll_pitch(q, roll, pitch);  // ENV:285
+    vb = rotate_by_inverse(q, v);      // ENV:293
+    mdp_pass(P, p, q, rf, lf, f_r, f_l, s_prev, s_curr, s_next, stone_at, m, po);
+    adv1 = po.advanced;
+    idx_after_pass1 = m.idx;
+  }
+
+  if (MODE != kModePass2 && active) {
+    // ---- dones, ENV:396-405
+    time_out = ep >= P.max_episode_length - 1;
+    fell = h < P.termination_height[level];
+    const float speed = norm3(v.x, v.y, v.z);
+    so_fast = speed > P.max_root_speed;
+    died = p.z < P.termination_height_absolute;
+    terminated = fell || so_fast || died;
+    is_reset = terminated || time_out;
+    // ---- reward terms that do not need the joint loop, ENV:350-375
+    r_progress = m.pot - po.old_pot;
+    r_roll = (roll > 0.4f || roll < -0.4f) ? fabsf(roll) : 0.0f;
+    r_pitch = (pitch > 0.4f || pitch < -0.2f) ? fabsf(pitch) : 0.0f;
+    r_speed = speed > 1.6f ? speed - 1.6f : 0.0f;
+    const bool pays_step = po.reached && m.count == 1 && m.idx < kS - 1;
+    r_step = pays_step ? 50.0f * expf((-po.d_swing) / 0.25f) : 0.0f;
+    r_bonus = (m.idx == kS - 1 && po.body_dist < 0.15f) ? 10.0f : 0.0f;
+  }
+
+  if (MODE == kModeFused) {
+    // ---- masked reset, ENV:487-538 (rows for PhysX are produced by the reset kernel from the same draws)
+    if (active && is_reset) {
+      regen = (P.flags & AS_FLAG_INTENDED_REGEN) && m.idx > kS / 2;
+      rblk = philox_block(P.seed, step_now, kStreamReset, gid, 0);
+      mirror = u32_to_unit(rblk.x) > 0.5f;  // ENV:518
+      const float ox = __ldg(a.in.env_origins + e * 3), oy = __ldg(a.in.env_origins + e * 3 + 1),
+                  oz = __ldg(a.in.env_origins + e * 3 + 2);
+      p = Vec3{P.default_root_pos[0] + ox, P.default_root_pos[1] + oy, P.default_root_pos[2] + oz};
+      const float z = mirror ? -0.0f : 0.0f;  // ENV:535 flips the sign of the (zero) vector part
+      q = Quat{1.0f, z, z, z};
+      v = Vec3{0, 0, 0};
+      m.pot = 0.0f;
+      m.count = 0;
+      m.leg = mirror ? 1 : 0;  // ENV:491,538
+      m.idx = 1;
+      ep = 0;  // DRL:584
+      f_r = 0.0f;  // scene.reset zeroes the contact rows, contact_sensor.py:155
+      f_l = 0.0f;
+      if (regen) {
+        first_three_stones(P, Vec3{ox, oy, oz}, s_prev, s_curr, s_next);
+      } else {
+        s_prev = stone_at(0);
+        s_curr = stone_at(1);
+        s_next = stone_at(2);
+      }
+      // root-frame quantities are recomputed on the post-reset state; body positions are stale (unchanged)
+      euler_roll_pitch(q, roll, pitch);
+      vb = rotate_by_inverse(q, v);
+    }
+    // ---- pass 2 over ALL envs, ENV:567; assumed to happen, the fix-up kernel undoes the assumption
+    const bool run_pass2 = active && (is_reset || !(P.flags & AS_FLAG_SKIP_PASS2));
+    if (run_pass2) {
+      if (!is_reset && adv1) {  // the current stone changed in pass 1: its contact column is a new gather
+        const float* fr = cr_row + m.idx * 3;
+        const float* fl = cl_row + m.idx * 3;
+        f_r = norm3(__ldg(fr), __ldg(fr + 1), __ldg(fr + 2));
+        f_l = norm3(__ldg(fl), __ldg(fl + 1), __ldg(fl + 2));
+      }
+      auto stone_after = [&](int i) -> float4 {
+        if (regen) {  // stone 3 of a regenerated sequence is not known here; unreachable (count restarts at 0)
+          return s_next;
+        }
+        return stone_at(i);
+      };
+      mdp_pass(P, p, q, rf, lf, f_r, f_l, s_prev, s_curr, s_next, stone_after, m, po);
+      adv2 = po.advanced;
+    }
+  }
+
+  // ---------------------------------------------------------------- joint loop: reward sums + observation body
+  float o_jp[kJ], o_jv[kJ];
+  float energy = 0.0f, act_sq = 0.0f;
+  int at_limit = 0;
+  if (active) {
+    const float* my_jp = s_jp + tid * kJ;
+    const float* my_jv = s_jv + tid * kJ;
+    const float* my_act = s_act + tid * kJ;
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+      const float jp = my_jp[j];
+      float jv = my_jv[j];
+      float sc = scale_to_unit(jp, P.joint_lower[j], P.joint_upper[j]);  // ENV:287-291
+      if (kNeedActions) {
+        const float act = fminf(fmaxf(my_act[j], -1.0f), 1.0f);  // ENV:268
+        at_limit += fabsf(sc) > 0.99f ? 1 : 0;                   // ENV:367
+        energy += fabsf(jv * act);                               // ENV:365
+        act_sq = fmaf(act, act, act_sq);                         // ENV:364
+      }
+      if (MODE == kModeFused) {
+        if (((1 + j) & 3) == 0 && is_reset) rblk = philox_block(P.seed, step_now, kStreamReset, gid, (1 + j) >> 2);
+        if (is_reset) {
+          const float u = u32_to_unit(lane_of(rblk, (1 + j) & 3));
+          sc = scale_to_unit(reset_joint_value(P, j, mirror, u), P.joint_lower[j], P.joint_upper[j]);
+          jv = mirror ? 0.0f * P.mirror_sign[j] : 0.0f;  // default_joint_vel is all zeros, ENV:513,528-532
+        }
+      }
+      o_jp[j] = sc;
+      o_jv[j] = fminf(fmaxf(jv * P.dof_vel_scale, -5.0f), 5.0f);  // ENV:337
+    }
+  }
+
+  // ---------------------------------------------------------------- reward, ENV:377-394
+  float reward = 0.0f;
+  if (MODE != kModePass2 && active) {
+    const float r_energy = P.energy_cost_scale * energy;
+    const float r_action = P.actions_cost_scale * sqrtf(act_sq);
+    const float r_limit = static_cast<float>(at_limit) * P.joint_at_limit_cost_scale;
+    float total = P.alive_reward_scale + r_progress;
+    total = total - r_roll;
+    total = total - r_pitch;
+    total = total - r_speed;
+    total = total - r_energy;
+    total = total - r_action;
+    total = total - r_limit;
+    total = total + r_step;
+    total = total + r_bonus;
+    reward = terminated ? P.death_cost : total;
+    a.out.reward[e] = reward;
+    a.out.terminated[e] = terminated ? 1 : 0;
+    a.out.time_out[e] = time_out ? 1 : 0;
+    if (a.out.reward_terms) {
+      float* rt = a.out.reward_terms + e * AS_NUM_REWARD_TERMS;
+      rt[0] = P.alive_reward_scale; rt[1] = r_progress; rt[2] = r_roll; rt[3] = r_pitch; rt[4] = r_speed;
+      rt[5] = r_energy; rt[6] = r_action; rt[7] = r_limit; rt[8] = r_step; rt[9] = r_bonus;
+    }
+  }
+  if (active) {
+    uint2 sw;
+    sw.x = pack_state(m.idx, m.leg, m.count, level, ep);
+    sw.y = __float_as_uint(m.pot);
+    st_out[e] = sw;
+  }
+
+  // ---------------------------------------------------------------- reset / regeneration lists (warp ballots)
+  if (MODE == kModeFused) {
+    const unsigned rmask = __ballot_sync(0xffffffffu, is_reset);
+    if (rmask && a.want_reset_list) {
+      const int leader = __ffs(rmask) - 1;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(&ctrl->n_reset_list, __popc(rmask));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (is_reset) a.ws.reset_ids[base + __popc(rmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
+    }
+    const unsigned gmask = __ballot_sync(0xffffffffu, regen);
+    if (gmask) {
+      const int leader = __ffs(gmask) - 1;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(&ctrl->n_regen_list, __popc(gmask));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (regen) a.ws.regen_ids[base + __popc(gmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
+    }
+  }
+
+  // ---------------------------------------------------------------- statistics (warp -> CTA)
+  if (MODE == kModeFused || MODE == kModePass1) {
+    auto count_into = [&](int which, bool flag) {
+      const unsigned bm = __ballot_sync(0xffffffffu, flag);
+      if (lane == 0 && bm) atomicAdd(&misc->cnt[which], __popc(bm));
+    };
+    count_into(kCntReset, is_reset);
+    count_into(kCntTerminated, terminated);
+    count_into(kCntTimeOut, time_out);
+    count_into(kCntFell, fell);
+    count_into(kCntSoFast, so_fast);
+    count_into(kCntDied, died);
+    count_into(kCntAdvanced1, adv1);
+    count_into(kCntAdvanced2, adv2);
+    count_into(kCntRegen, regen);
+    const unsigned sidx = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(active ? idx_after_pass1 : 0));
+    const unsigned lmax = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(active ? level : 0));
+    float rs = active ? reward : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (lane == 0) {
+      atomicAdd(&misc->cnt[kCntSumIndex], sidx);
+      atomicMax(&misc->cnt[10], lmax);
+      atomicAdd(&misc->reward_sum, rs);
+    }
+  }
+
+  // ---------------------------------------------------------------- observation tile -> HBM, ENV:326-345
+  __syncthreads();  // every thread has consumed its input rows: the tile may be overwritten
+  if (active) {
+    float* row = s_obs + tid * kObs;
+    row[0] = h;
+    row[1] = roll;
+    row[2] = pitch;
+    row[3] = vb.x;
+    row[4] = vb.y;
+    row[5] = vb.z;
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+      row[6 + j] = o_jp[j];
+      row[6 + kJ + j] = o_jv[j];
+    }
+    row[48] = po.contact_r;
+    row[49] = po.contact_l;
+    row[50] = po.tb0.x; row[51] = po.tb0.y; row[52] = po.tb0.z;
+    row[53] = po.tb1.x; row[54] = po.tb1.y; row[55] = po.tb1.z;
+    row[56] = po.tb2.x; row[57] = po.tb2.y; row[58] = po.tb2.z;
+  }
+  float* obs_dst = a.out.obs + env0 * kObs;
+  const bool b_obs = ((reinterpret_cast<uintptr_t>(obs_dst) & 15u) == 0) && (((n_valid * kObs) & 3) == 0);
+  if (b_obs) {
+    fence_proxy_async_smem();  // make the generic-proxy writes visible to the TMA engine
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(obs_dst, smem_u32(s_obs), static_cast<uint32_t>(n_valid) * kObs * 4);
+      bulk_commit();
+    }
+  } else {
+    __syncthreads();
+    for (int i = tid; i < n_valid * kObs; i += kTile) obs_dst[i] = s_obs[i];
+  }
+  if (tid == 0 && b_obs) bulk_wait_read_all();  // shared memory must stay intact until the engine has read it
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+template <int MODE>
+__global__ void __launch_bounds__(kTile, 4) k_step(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(smem_u32(&misc->mbar), 1);
+  if (tid < kNumCounters) misc->cnt[tid] = 0;
+  if (tid == 0) misc->reward_sum = 0.0f;
+  __syncthreads();
+  uint32_t phase = 0;
+  process_tile<MODE>(a, blockIdx.x, phase, smem);
+
+  if (MODE == kModeFused || MODE == kModePass1) {
+    Ctrl* ctrl = a.ws.ctrl;
+    __syncthreads();
+    const int slot = blockIdx.x & (kSlots - 1);
+    if (tid < kNumCounters && misc->cnt[tid]) {
+      if (tid == 10) atomicMax(&ctrl->slots[slot][tid], misc->cnt[tid]);
+      else atomicAdd(&ctrl->slots[slot][tid], misc->cnt[tid]);
+    }
+    if (tid == 32) atomicAdd(&ctrl->slot_reward[slot], misc->reward_sum);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned t = atomicAdd(&ctrl->blocks_done, 1u);
+      misc->is_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (misc->is_last) {
+      __threadfence();
+      fold_stats(ctrl, misc, a);
+      if (MODE == kModePass1 && tid == 0) {
+        ctrl->promote_cur = 0;       // applied by every CTA above; consumed
+        ctrl->step_counter += 1ull;  // 3-call path: a reset that follows draws at the advanced counter
+      }
+    }
+  }
+}
+
+// ENV:471-472 promotion rule on folded statistics (this shard's, or summed over ranks).
+__device__ __forceinline__ uint32_t promotion_decision(const AsParams& P, const AsStats& s) {
+  if (s.n_reset <= 0 || s.n_envs <= 0) return 0u;  // `_reset_idx` is only entered when an env resets, DRL:360
+  const float mean = static_cast<float>(s.sum_target_index) / static_cast<float>(s.n_envs);
+  return mean > P.progress_threshold ? 1u : 0u;
+}
+
+// Fix-up + finish.  If NO env of this shard reset, the reference never runs pass 2 (DRL:360): redo every tile
+// without it from the untouched pre-step state buffer (rare: needs zero resets among all envs).  The last CTA
+// then publishes next step's promotion, flips the state parity and advances the Philox step counter.
+__global__ void __launch_bounds__(kTile, 4) k_fixup_finish(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
+  Ctrl* ctrl = a.ws.ctrl;
+  const int tid = threadIdx.x;
+  const bool need_fixup = ctrl->stats.n_reset == 0 && !(a.P.flags & AS_FLAG_SKIP_PASS2);
+  if (need_fixup) {
+    if (tid == 0) mbar_init(smem_u32(&misc->mbar), 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      process_tile<kModeFixup>(a, tile, phase, smem);
+      __syncthreads();
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(&ctrl->blocks_done2, 1u);
+    if (t == gridDim.x - 1) {
+      __threadfence();
+      const AsStats* g = a.global_stats ? a.global_stats : &ctrl->stats;
+      ctrl->promote_cur = promotion_decision(a.P, *g);
+      ctrl->parity ^= 1u;
+      ctrl->step_counter += 1ull;
+      ctrl->n_reset_list = 0;
+      ctrl->n_regen_list = 0;
+      ctrl->blocks_done2 = 0;
+      if (need_fixup) {
+        ctrl->fixup_ran += 1;
+        ctrl->stats.n_advanced -= ctrl->last_adv2;  // pass-2 advances were discarded with pass 2
+      }
+    }
+  }
+}
+
+}  // namespace as

@@ -1,0 +1,292 @@
+"""`AllstepsMDP` -- host-side owner of the Allsteps-v0 MDP state on one GPU.
+
+It holds what `AllstepsEnv.__init__` allocates in the reference (ENV:41-96) -- but as one packed device
+workspace -- and exposes the step of direct_rl_env.py:351-375 as `step()` (one fused launch) or as
+`pass1() / reset() / pass2()` for hosts that run PhysX in between.  PyTorch is used for device memory and
+streams only; every number is produced by the CUDA library behind include/allsteps_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _cabi
+from .config import AllstepsCfg, NUM_JOINTS, NUM_STONES, OBS_DIM
+from .params import make_params
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require(t: torch.Tensor, dtype, device, name: str):
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.device != device:
+        raise ValueError(f"{name}: expected device {device}, got {t.device}")
+
+
+class PhysicsViews:
+    """Device views of the PhysX-side tensors of one step, in the layouts Isaac Lab publishes them.
+
+    Accepts the tensors the reference reads (`robot.data.root_pos_w`, ..., `sensor_left.data.force_matrix_w`);
+    strided views such as slices of `root_state_w (N,13)` / `body_state_w (N,B,13)` are taken as they are.
+    """
+
+    def __init__(self, *, root_pos_w, root_quat_w, root_lin_vel_w, body_pos_w, joint_pos, joint_vel,
+                 force_matrix_right, force_matrix_left, env_origins, body_rows=(0, 1, 2)):
+        self.tensors = dict(root_pos_w=root_pos_w, root_quat_w=root_quat_w, root_lin_vel_w=root_lin_vel_w,
+                            body_pos_w=body_pos_w, joint_pos=joint_pos, joint_vel=joint_vel,
+                            force_matrix_right=force_matrix_right, force_matrix_left=force_matrix_left,
+                            env_origins=env_origins)
+        N = root_pos_w.shape[0]
+        s = _cabi.AsStateIn()
+
+        def rows(t, width, name):
+            if t.dtype != torch.float32:
+                raise TypeError(f"{name} must be float32")
+            if t.dim() != 2 or t.shape[0] != N or t.shape[1] != width or (N > 1 and t.stride(1) != 1):
+                raise ValueError(f"{name} must be a (N,{width}) view with unit inner stride, got {tuple(t.shape)}")
+            return t.data_ptr(), (t.stride(0) if N > 1 else width)
+
+        s.root_pos, s.root_pos_stride = rows(root_pos_w, 3, "root_pos_w")
+        s.root_quat, s.root_quat_stride = rows(root_quat_w, 4, "root_quat_w")
+        s.root_lin_vel, s.root_lin_vel_stride = rows(root_lin_vel_w, 3, "root_lin_vel_w")
+        s.joint_pos, s.joint_pos_stride = rows(joint_pos, NUM_JOINTS, "joint_pos")
+        s.joint_vel, s.joint_vel_stride = rows(joint_vel, NUM_JOINTS, "joint_vel")
+        if body_pos_w.dim() != 3 or body_pos_w.shape[0] != N or body_pos_w.shape[2] != 3 or body_pos_w.stride(2) != 1:
+            raise ValueError("body_pos_w must be a (N,B,3) view with unit inner stride")
+        B = body_pos_w.shape[1]
+        s.body_pos = body_pos_w.data_ptr()
+        s.body_env_stride = body_pos_w.stride(0) if N > 1 else B * 3
+        s.body_row_stride = body_pos_w.stride(1) if B > 1 else 3
+        s.right_foot_row, s.left_foot_row, s.torso_row = (int(b) for b in body_rows)
+        if max(body_rows) >= B:
+            raise ValueError("body row index out of range")
+        for name, t in (("force_matrix_right", force_matrix_right), ("force_matrix_left", force_matrix_left)):
+            if t.dtype != torch.float32 or t.shape[0] != N or t.shape[-1] != 3 or t.shape[-2] != NUM_STONES:
+                raise ValueError(f"{name} must be float32 (N,1,{NUM_STONES},3)")
+            if not t[0].is_contiguous():
+                raise ValueError(f"{name}: the per-env (1,S,3) block must be contiguous")
+        s.contact_right = force_matrix_right.data_ptr()
+        s.contact_right_stride = force_matrix_right.stride(0) if N > 1 else NUM_STONES * 3
+        s.contact_left = force_matrix_left.data_ptr()
+        s.contact_left_stride = force_matrix_left.stride(0) if N > 1 else NUM_STONES * 3
+        if env_origins is not None:
+            if env_origins.dtype != torch.float32 or tuple(env_origins.shape) != (N, 3) or not env_origins.is_contiguous():
+                raise ValueError("env_origins must be contiguous float32 (N,3)")
+            s.env_origins = env_origins.data_ptr()
+        self.struct = s
+        self.num_envs = N
+        self.device = root_pos_w.device
+
+    @classmethod
+    def from_dict(cls, d: Dict[str, torch.Tensor], env_origins, body_rows=(0, 1, 2)) -> "PhysicsViews":
+        return cls(root_pos_w=d["root_pos_w"], root_quat_w=d["root_quat_w"], root_lin_vel_w=d["root_lin_vel_w"],
+                   body_pos_w=d["body_pos_w"], joint_pos=d["joint_pos"], joint_vel=d["joint_vel"],
+                   force_matrix_right=d["force_matrix_right"], force_matrix_left=d["force_matrix_left"],
+                   env_origins=env_origins, body_rows=body_rows)
+
+
+class StepBuffers:
+    """Output tensors of a step; allocated once, overwritten every step (the caller clones what it keeps)."""
+
+    def __init__(self, num_envs: int, device, reward_terms: bool = False, reset_rows: bool = True):
+        kw = dict(device=device)
+        self.obs = torch.empty(num_envs, OBS_DIM, dtype=torch.float32, **kw)
+        self.reward = torch.empty(num_envs, dtype=torch.float32, **kw)
+        self.terminated = torch.zeros(num_envs, dtype=torch.bool, **kw)
+        self.time_out = torch.zeros(num_envs, dtype=torch.bool, **kw)
+        self.reward_terms = (torch.empty(num_envs, _cabi.NUM_REWARD_TERMS, dtype=torch.float32, **kw)
+                             if reward_terms else None)
+        self.reset_root_state = self.reset_joint_pos = self.reset_joint_vel = None
+        self.reset_ids = self.n_reset = None
+        if reset_rows:
+            self.reset_root_state = torch.zeros(num_envs, _cabi.ROOT_STATE_DIM, dtype=torch.float32, **kw)
+            self.reset_joint_pos = torch.zeros(num_envs, NUM_JOINTS, dtype=torch.float32, **kw)
+            self.reset_joint_vel = torch.zeros(num_envs, NUM_JOINTS, dtype=torch.float32, **kw)
+            self.reset_ids = torch.zeros(num_envs, dtype=torch.int32, **kw)
+            self.n_reset = torch.zeros(1, dtype=torch.int32, **kw)
+        self.step_out = _cabi.AsStepOut(_ptr(self.obs), _ptr(self.reward), _ptr(self.terminated),
+                                        _ptr(self.time_out), _ptr(self.reward_terms))
+        self.reset_out = _cabi.AsResetOut(_ptr(self.reset_root_state), _ptr(self.reset_joint_pos),
+                                          _ptr(self.reset_joint_vel), _ptr(self.reset_ids), _ptr(self.n_reset))
+
+
+class AllstepsMDP:
+    def __init__(self, num_envs: int, device="cuda:0", cfg: Optional[AllstepsCfg] = None, seed: int = 0,
+                 env_id_offset: int = 0, intended_regen: bool = False, skip_pass2: bool = False):
+        self.lib = _cabi.load()  # raises if the CUDA library was not built: there is no fallback
+        self.cfg = cfg or AllstepsCfg()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _cabi.AllstepsLibraryError("AllstepsMDP runs on a CUDA device only (sm_100a); no CPU path exists")
+        self.num_envs = int(num_envs)
+        self.env_id_offset = int(env_id_offset)
+        flags = (_cabi.FLAG_INTENDED_REGEN if intended_regen else 0) | (_cabi.FLAG_SKIP_PASS2 if skip_pass2 else 0)
+        self.params = make_params(self.cfg, seed=seed, flags=flags)
+        nbytes = self.lib.as_workspace_bytes(self.num_envs)
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            assert self.workspace.data_ptr() % 256 == 0
+            handle = C.c_void_p()
+            _cabi.check(self.lib.as_create(C.byref(self.params), self.num_envs, self.env_id_offset,
+                                           self.device.index or 0, self.workspace.data_ptr(), nbytes,
+                                           self._stream(), C.byref(handle)), "as_create")
+        self.handle = handle
+        stats_ptr = C.c_void_p()
+        _cabi.check(self.lib.as_stats_device_ptr(self.handle, C.byref(stats_ptr)), "as_stats_device_ptr")
+        off = stats_ptr.value - self.workspace.data_ptr()
+        # device view of the folded step statistics (int64 fields; see _cabi.AsStats)
+        self.stats_tensor = self.workspace[off: off + C.sizeof(_cabi.AsStats)].view(torch.int64)
+        self._keepalive = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            self.lib.as_destroy(h)
+            self.handle = None
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.as_launch_count(self.handle))
+
+    # ------------------------------------------------------------------ stones (ENV:106-174)
+    def generate_stones(self, env_origins: torch.Tensor, env_ids: Optional[torch.Tensor] = None,
+                        uniforms: Optional[torch.Tensor] = None):
+        _require(env_origins, torch.float32, self.device, "env_origins")
+        ids_ptr, n_ids = None, 0
+        if env_ids is not None:
+            env_ids = env_ids.to(device=self.device, dtype=torch.int32).contiguous()
+            ids_ptr, n_ids = env_ids.data_ptr(), env_ids.numel()
+        if uniforms is not None:
+            _require(uniforms, torch.float32, self.device, "uniforms")
+            if tuple(uniforms.shape) != (5, self.num_envs, NUM_STONES) and tuple(uniforms.shape) != (
+                    3, self.num_envs, NUM_STONES):
+                raise ValueError("uniforms must be (5|3, N, S)")
+            uniforms = uniforms.contiguous()
+        _cabi.check(self.lib.as_generate_stones(self.handle, env_origins.data_ptr(), ids_ptr, n_ids,
+                                                _ptr(uniforms), self._stream()), "as_generate_stones")
+
+    # ------------------------------------------------------------------ fused step (DRL:351-375)
+    def step(self, views: PhysicsViews, actions: torch.Tensor, out: StepBuffers,
+             global_stats: Optional[torch.Tensor] = None, finish: bool = True):
+        """One MDP step in one fused launch. Results land in `out`; nothing is synchronised."""
+        if views.num_envs != self.num_envs:
+            raise ValueError("views belong to a different number of envs")
+        _require(actions, torch.float32, self.device, "actions")
+        if actions.dim() != 2 or actions.shape != (self.num_envs, NUM_JOINTS) or actions.stride(1) != 1:
+            raise ValueError("actions must be (N,21) with unit inner stride")
+        stride = actions.stride(0) if self.num_envs > 1 else NUM_JOINTS
+        _cabi.check(self.lib.as_step_fused(self.handle, C.byref(views.struct), actions.data_ptr(), stride,
+                                           C.byref(out.step_out), C.byref(out.reset_out), self._stream()),
+                    "as_step_fused")
+        self._keepalive = (views, actions, out)
+        if finish:
+            self.finish_step(global_stats)
+
+    def finish_step(self, global_stats: Optional[torch.Tensor] = None):
+        """Close the fused step: conditional no-reset fix-up, promotion rule (ENV:471-479), counters."""
+        _cabi.check(self.lib.as_finish_step(self.handle, _ptr(global_stats), self._stream()), "as_finish_step")
+
+    # ------------------------------------------------------------------ 3-call path
+    def pass1(self, views: PhysicsViews, actions: torch.Tensor, out: StepBuffers,
+              episode_length: Optional[torch.Tensor] = None):
+        _require(actions, torch.float32, self.device, "actions")
+        stride = actions.stride(0) if self.num_envs > 1 else NUM_JOINTS
+        if episode_length is not None:
+            _require(episode_length, torch.int64, self.device, "episode_length")
+        _cabi.check(self.lib.as_step_pass1(self.handle, C.byref(views.struct), actions.data_ptr(), stride,
+                                           _ptr(episode_length), C.byref(out.step_out), self._stream()),
+                    "as_step_pass1")
+
+    def reset(self, env_origins: torch.Tensor, env_ids: torch.Tensor, out: StepBuffers,
+              episode_length: Optional[torch.Tensor] = None):
+        ids = env_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        _cabi.check(self.lib.as_reset(self.handle, env_origins.data_ptr(), ids.data_ptr(), ids.numel(),
+                                      _ptr(episode_length), C.byref(out.reset_out), self._stream()), "as_reset")
+        self._keepalive = (ids, env_origins)
+
+    def pass2(self, views: PhysicsViews, out: StepBuffers):
+        _cabi.check(self.lib.as_step_pass2(self.handle, C.byref(views.struct), out.obs.data_ptr(), self._stream()),
+                    "as_step_pass2")
+
+    # ------------------------------------------------------------------ action path / symmetry
+    def apply_action(self, actions: torch.Tensor, efforts: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _require(actions, torch.float32, self.device, "actions")
+        if efforts is None:
+            efforts = torch.empty(self.num_envs, NUM_JOINTS, dtype=torch.float32, device=self.device)
+        stride = actions.stride(0) if self.num_envs > 1 else NUM_JOINTS
+        _cabi.check(self.lib.as_apply_action(self.handle, actions.data_ptr(), stride, efforts.data_ptr(),
+                                             self._stream()), "as_apply_action")
+        return efforts
+
+    def mirror_rows(self, rows: torch.Tensor, kind: str) -> torch.Tensor:
+        """ENV:570-660: returns vstack((rows, mirrored(rows))). kind: 'obs' (dim 59) or 'actions' (dim 21)."""
+        _require(rows, torch.float32, self.device, "rows")
+        k = {"obs": 0, "actions": 1}[kind]
+        dim = OBS_DIM if k == 0 else NUM_JOINTS
+        if rows.dim() != 2 or rows.shape[1] != dim or not rows.is_contiguous():
+            raise ValueError(f"rows must be contiguous (R,{dim})")
+        out = torch.empty(2 * rows.shape[0], dim, dtype=torch.float32, device=self.device)
+        _cabi.check(self.lib.as_mirror_rows(self.handle, rows.data_ptr(), out.data_ptr(), rows.shape[0], k,
+                                            self._stream()), "as_mirror_rows")
+        return out
+
+    # ------------------------------------------------------------------ state in the reference's layouts
+    def export_state(self) -> Dict[str, torch.Tensor]:
+        N, dev = self.num_envs, self.device
+        i64 = lambda: torch.empty(N, dtype=torch.int64, device=dev)  # noqa: E731
+        d = {
+            "curr_target_index": i64(), "swing_leg": i64(), "target_reach_count": i64(),
+            "episode_length_buf": i64(), "curriculum": i64(),
+            "potentials": torch.empty(N, dtype=torch.float32, device=dev),
+            "steps_pos": torch.empty(N, NUM_STONES, 3, dtype=torch.float32, device=dev),
+            "steps_dphi": torch.empty(N, NUM_STONES, dtype=torch.float32, device=dev),
+        }
+        st = _cabi.AsMdpState(_ptr(d["curr_target_index"]), _ptr(d["swing_leg"]), _ptr(d["target_reach_count"]),
+                              _ptr(d["episode_length_buf"]), _ptr(d["curriculum"]), _ptr(d["potentials"]),
+                              _ptr(d["steps_pos"]), _ptr(d["steps_dphi"]))
+        _cabi.check(self.lib.as_export_state(self.handle, C.byref(st), self._stream()), "as_export_state")
+        d["prev_target_index"] = torch.clamp(d["curr_target_index"] - 1, 0, NUM_STONES - 1)  # ENV:76
+        d["next_target_index"] = torch.clamp(d["curr_target_index"] + 1, 0, NUM_STONES - 1)  # ENV:77
+        return d
+
+    def import_state(self, state: Dict[str, torch.Tensor]):
+        keep = {}
+
+        def get(name, dtype, shape):
+            t = state.get(name)
+            if t is None:
+                return None
+            t = t.to(device=self.device, dtype=dtype).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{name}: expected shape {shape}, got {tuple(t.shape)}")
+            keep[name] = t
+            return t.data_ptr()
+
+        N = self.num_envs
+        st = _cabi.AsMdpState(
+            get("curr_target_index", torch.int64, (N,)), get("swing_leg", torch.int64, (N,)),
+            get("target_reach_count", torch.int64, (N,)), get("episode_length_buf", torch.int64, (N,)),
+            get("curriculum", torch.int64, (N,)), get("potentials", torch.float32, (N,)),
+            get("steps_pos", torch.float32, (N, NUM_STONES, 3)), get("steps_dphi", torch.float32, (N, NUM_STONES)))
+        _cabi.check(self.lib.as_import_state(self.handle, C.byref(st), self._stream()), "as_import_state")
+        self._keepalive = keep
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Checkpoint: MDP buffers + the Philox position (seed is in the params, step counter in the stats)."""
+        d = {k: v.cpu() for k, v in self.export_state().items()}
+        d["step_counter"] = torch.tensor(self.read_stats()["step_counter"], dtype=torch.int64)
+        return d
+
+    def read_stats(self) -> Dict[str, float]:
+        s = _cabi.AsStats()
+        _cabi.check(self.lib.as_read_stats(self.handle, C.byref(s), self._stream()), "as_read_stats")
+        return s.as_dict()

@@ -1,0 +1,228 @@
+/*
+ * allsteps_b200.h -- C ABI of the B200-native Allsteps-v0 batched MDP step.
+ *
+ * The reference (xindonglin99/allsteps_isaaclab) has no FFI layer: the path is six Python hook methods of
+ * `AllstepsEnv(DirectRLEnv)`.  This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md; allsteps_isaaclab_b200/_cabi.py is that stub).  Every entry point names the reference code
+ * it replaces:  ENV = source/isaaclab_tasks/isaaclab_tasks/direct/allsteps/allsteps_env.py,
+ *               DRL = source/isaaclab/isaaclab/envs/direct_rl_env.py,  CFG = .../allsteps/allsteps_env_cfg.py.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, POD structs.  No torch / CUDA types; a stream is passed as `void*`
+ *    (a `cudaStream_t`, e.g. `torch.cuda.current_stream().cuda_stream`).
+ *  - every pointer inside AsStateIn / AsStepOut / AsResetOut is a DEVICE pointer owned by the caller.
+ *  - the library never allocates device memory and never synchronises the stream or the device on the step path
+ *    (only the *_export_* / as_read_stats helpers, which return host data, synchronise the given stream).
+ *  - return value: 0 on success, negative AS_ERR_* otherwise; text via as_last_error() (thread local).
+ *  - built only for sm_100a.  There is no CPU fallback: on a machine without a usable device every compute
+ *    entry point returns AS_ERR_CUDA.
+ */
+#ifndef ALLSTEPS_B200_H_
+#define ALLSTEPS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AS_ABI_VERSION 1
+
+#define AS_NUM_JOINTS 21  /* CFG:57  action_space            */
+#define AS_NUM_STONES 20  /* CFG:90  num_steps               */
+#define AS_OBS_DIM 59     /* CFG:58  observation_space       */
+#define AS_NUM_LEVELS 10  /* ENV:45  max_curriculum + 1      */
+#define AS_ROOT_STATE_DIM 13
+#define AS_NUM_REWARD_TERMS 10
+#define AS_TILE_ENVS 128  /* envs handled by one CTA; sharded slices should start on a multiple of 4 envs */
+
+enum {
+  AS_OK = 0,
+  AS_ERR_INVALID = -1, /* bad argument (null pointer, bad size, unsupported stride ...) */
+  AS_ERR_CUDA = -2,    /* a CUDA runtime call failed; as_last_error() has the CUDA message  */
+  AS_ERR_STATE = -3    /* call sequence violated (e.g. pass2 without pass1)                */
+};
+
+/* AsParams.flags */
+enum {
+  AS_FLAG_INTENDED_REGEN = 1u << 0, /* extension: regenerate stones of a reset env whose index had passed
+                                       num_steps/2 BEFORE the index reset.  Off = reference-exact: the test at
+                                       ENV:497 runs after ENV:492 and is never true.            */
+  AS_FLAG_SKIP_PASS2 = 1u << 1,     /* extension: never run the second `_compute_useful_values` pass
+                                       (ENV:567) for envs that did not reset.  Off = reference. */
+  AS_FLAG_GRID_CURRICULUM = 1u << 2 /* extension: pitch x yaw difficulty grid sampling at regeneration.   */
+};
+
+/* Constants of the task: CFG:52-235 plus the values hard-coded in ENV:41-59.  Tables that the reference builds
+ * with torch (linspace) are filled in by the host with torch so that they are bit-identical. */
+typedef struct AsParams {
+  float step_dt;                   /* sim.dt * decimation, DRL step_dt                                  */
+  int32_t max_episode_length;      /* DRL:248-250 -> 900                                                */
+  float step_radius;               /* CFG:97                                                            */
+  float dist_lower;                /* ENV:41 dist_range[0]                                              */
+  float dist_upper[AS_NUM_LEVELS]; /* linspace(dist_range, 10), ENV:129                                 */
+  float yaw_range_deg[2];          /* ENV:43                                                            */
+  float pitch_range_deg[2];        /* ENV:42                                                            */
+  float init_step_separation;      /* ENV:50                                                            */
+  int32_t max_level;               /* ENV:45                                                            */
+  float termination_height[AS_NUM_LEVELS]; /* linspace(0.75, 0.45, 10), ENV:46                          */
+  float applied_gain[AS_NUM_LEVELS];       /* linspace(1.2, 1.2, 10),  ENV:47                           */
+  float progress_threshold;        /* ENV:53 (12)                                                       */
+  float contact_epsilon;           /* ENV:32                                                            */
+  int32_t stop_frames;             /* ENV:56 (<= 3)                                                     */
+  float energy_cost_scale, actions_cost_scale, alive_reward_scale, dof_vel_scale;   /* CFG:222-225      */
+  float joint_at_limit_cost_scale, death_cost;                                      /* CFG:226-227      */
+  float termination_height_absolute; /* CFG:228                                                         */
+  float max_root_speed;            /* ENV:402 (5.0)                                                     */
+  float noise_span, noise_lower;   /* (hi - lo) and lo of CFG:232, as MATH:1331 evaluates them          */
+  float clip_lower, clip_upper;    /* CFG:233                                                           */
+  float default_root_pos[3];       /* walker3d.py:36                                                    */
+  float joint_lower[AS_NUM_JOINTS], joint_upper[AS_NUM_JOINTS]; /* robot.data.joint_pos_limits[0]       */
+  float joint_gears[AS_NUM_JOINTS];/* CFG:133-155                                                       */
+  float reset_pose[AS_NUM_JOINTS]; /* ENV:505-511                                                       */
+  int32_t mirror_src[AS_NUM_JOINTS]; /* ENV:522-526: joint j takes the value of joint mirror_src[j] ... */
+  float mirror_sign[AS_NUM_JOINTS];  /* ... times mirror_sign[j]                                        */
+  uint32_t flags;
+  uint32_t grid_bins;              /* AS_FLAG_GRID_CURRICULUM: bins per axis (<= 16), else 0            */
+  uint64_t seed;                   /* Philox key                                                        */
+} AsParams;
+
+/* Device views of what PhysX publishes after `scene.update` (DRL:347).  Row strides are in ELEMENTS (floats);
+ * a stride equal to the row width with a 16-byte aligned base takes the TMA-staged fast path, anything else
+ * (e.g. the (N,13) `root_state_w` views Isaac Lab hands out) takes the strided path. */
+typedef struct AsStateIn {
+  const float* root_pos;      int64_t root_pos_stride;     /* robot.data.root_pos_w      (N,3)              */
+  const float* root_quat;     int64_t root_quat_stride;    /* robot.data.root_quat_w     (N,4) w,x,y,z      */
+  const float* root_lin_vel;  int64_t root_lin_vel_stride; /* robot.data.root_lin_vel_w  (N,3)              */
+  const float* body_pos;      int64_t body_env_stride;     /* robot.data.body_pos_w      (N,B,3)            */
+  int64_t body_row_stride;                                  /* floats between bodies of one env (3 or 13)    */
+  int32_t right_foot_row, left_foot_row, torso_row;         /* ENV:87-88                                     */
+  int32_t _pad0;
+  const float* joint_pos;     int64_t joint_pos_stride;    /* robot.data.joint_pos       (N,21)             */
+  const float* joint_vel;     int64_t joint_vel_stride;    /* robot.data.joint_vel       (N,21)             */
+  const float* contact_right; int64_t contact_right_stride;/* sensor_right.data.force_matrix_w (N,1,S,3)    */
+  const float* contact_left;  int64_t contact_left_stride; /* sensor_left.data.force_matrix_w  (N,1,S,3)    */
+  const float* env_origins;                                 /* scene.env_origins (N,3) contiguous            */
+} AsStateIn;
+
+/* Results of one step, the tuple DRL:383 returns.  `terminated` / `time_out` are 1-byte 0/1 (torch.bool). */
+typedef struct AsStepOut {
+  float* obs;            /* (N,59)  ENV:326-345                                                            */
+  float* reward;         /* (N)     ENV:347-394                                                            */
+  uint8_t* terminated;   /* (N)     ENV:405 fell | so_fast | died                                          */
+  uint8_t* time_out;     /* (N)     ENV:399                                                                */
+  float* reward_terms;   /* optional (N,10): alive, progress, roll, pitch, speed, energy, action, limit,
+                            step, bonus (costs positive) -- for per-term manager logging; NULL to skip     */
+} AsStepOut;
+
+/* What `_reset_idx` hands to PhysX (ENV:563-565).  Rows are written AT THE ENV'S OWN ROW (full-size buffers),
+ * only for envs that reset; `reset_ids[0 .. *n_reset)` lists them (unordered).  All optional. */
+typedef struct AsResetOut {
+  float* root_state;     /* (N,13) pos, quat wxyz, lin vel, ang vel                                        */
+  float* joint_pos;      /* (N,21)                                                                         */
+  float* joint_vel;      /* (N,21)                                                                         */
+  int32_t* reset_ids;    /* (N)                                                                            */
+  int32_t* n_reset;      /* (1)                                                                            */
+} AsResetOut;
+
+/* Step statistics, accumulated on the device and summed over ranks by the caller (NCCL) when sharded. */
+typedef struct AsStats {
+  int64_t n_envs;        /* envs that contributed                                                          */
+  int64_t n_reset, n_terminated, n_time_out, n_fell, n_so_fast, n_died;
+  int64_t n_advanced;    /* stones reached (index advances) in this step, both passes                      */
+  int64_t sum_target_index; /* sum of curr_target_index after pass 1: numerator of ENV:471                 */
+  int64_t n_regenerated;
+  int64_t level;         /* current curriculum level (max over envs when per-env levels are in use)        */
+  int64_t step_counter;
+  double sum_reward;
+} AsStats;
+
+typedef struct AsHandle AsHandle;
+
+/* ---- lifetime --------------------------------------------------------------------------------------- */
+int as_abi_version(void);
+const char* as_last_error(void);
+/* Bytes of device workspace needed for `num_envs` envs (MDP state: stones, packed state, control block). */
+int64_t as_workspace_bytes(int64_t num_envs);
+/* `workspace`: device memory of as_workspace_bytes() bytes, 256-byte aligned, zero-initialised by this call.
+ * `env_id_offset`: global id of local env 0 (env-id sharding; Philox is keyed by global id).
+ * Replaces AllstepsEnv.__init__ buffer allocation, ENV:41-96. */
+int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, int device,
+              void* workspace, int64_t workspace_bytes, void* stream, AsHandle** out);
+void as_destroy(AsHandle* h);
+
+/* ---- stones: ENV:106-174 `_generate_foot_steps` -------------------------------------------------------
+ * env_ids: NULL = all envs, else `n_ids` local ids (device, int32).  uniforms: NULL = in-kernel Philox at the
+ * current step counter, else device (5,N,S) floats indexed by LOCAL env id (replay of external draws).
+ * levels are taken from the per-env state. */
+int as_generate_stones(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids,
+                       const float* uniforms, void* stream);
+
+/* ---- the fused step: DRL:351-375 in one launch (+ a device-side conditional fix-up launch) -------------
+ * episode counter += 1, pass 1 (ENV:276-324), dones (ENV:396-405), rewards (ENV:347-394), masked reset
+ * (ENV:469-565), pass 2 (ENV:567) and observations (ENV:326-345).  `actions` (N,21) raw policy output, clamped
+ * to [-1,1] inside (ENV:267-268).  For envs that reset, pass 2 sees the root / joint rows this call generates,
+ * zero contacts and unchanged body positions (what `robot.data` holds between the PhysX writes and the next
+ * physics step). */
+int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_t actions_stride,
+                  const AsStepOut* out, const AsResetOut* reset_out, void* stream);
+
+/* ---- the same step as three calls, for hosts that run PhysX between them --------------------------------
+ * pass1:  `_get_dones` + `_get_rewards` (+ observations as they are when nothing resets).
+ *         episode_length: optional device int64 (N) owned by DirectRLEnv (already incremented, DRL:351);
+ *         NULL = the library keeps and increments its own counter.
+ * reset:  `_reset_idx(env_ids)` minus the PhysX writes: promotion rule, MDP state reset, start pose rows.
+ *         Compact outputs: row i of the AsResetOut buffers belongs to env_ids[i].
+ * pass2:  the second `_compute_useful_values` over ALL envs + `_get_observations`, on the post-write state. */
+int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_t actions_stride,
+                  const int64_t* episode_length, const AsStepOut* out, void* stream);
+int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids,
+             int64_t* episode_length, const AsResetOut* compact_out, void* stream);
+int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream);
+
+/* ---- curriculum: ENV:470-479 -----------------------------------------------------------------------------
+ * The step kernels leave per-step statistics in the control block; as_finish_step folds them, applies the
+ * promotion rule (mean(curr_target_index) > 12 and at least one reset => level+1) for the NEXT step and clears
+ * the accumulators.  When envs are sharded, pass `global_stats` = device AsStats summed over ranks (NCCL) to
+ * promote on the global mean; NULL = promote on this shard's own envs (what `--distributed` replicas do). */
+int as_stats_device_ptr(AsHandle* h, AsStats** device_stats);
+/* Closes the step opened by as_step_fused (required once per fused step, on the same stream; the buffers given
+ * to as_step_fused must stay alive until then because the conditional no-reset fix-up re-reads them). */
+int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream);
+int as_read_stats(AsHandle* h, AsStats* host_out, void* stream); /* synchronises `stream` */
+
+/* ---- action path: ENV:257-274 `_pre_physics_step` + `_apply_action` --------------------------------------
+ * efforts[n,j] = applied_gain[level[n]] * joint_gears[j] * clamp(actions[n,j], -1, 1) */
+int as_apply_action(AsHandle* h, const float* actions, int64_t actions_stride, float* efforts, void* stream);
+
+/* ---- mirror-symmetry augmentation: ENV:570-660 `get_symmetric_states_*` ----------------------------------
+ * out (2*rows, dim): rows [0,rows) = copy of `in`, rows [rows, 2*rows) = mirrored.  kind: 0 = observations
+ * (dim 59), 1 = actions / mus (dim 21). */
+int as_mirror_rows(AsHandle* h, const float* in, float* out, int64_t rows, int32_t kind, void* stream);
+
+/* ---- state exchange in the reference's own layouts (checkpoint / replay / tests) -------------------------
+ * All pointers device, optional (NULL = skip).  int64 arrays as in ENV:48,74-78 and DRL:179. */
+typedef struct AsMdpState {
+  int64_t* curr_target_index; /* (N) */
+  int64_t* swing_leg;         /* (N) */
+  int64_t* target_reach_count;/* (N) */
+  int64_t* episode_length;    /* (N) */
+  int64_t* curriculum;        /* (N) */
+  float* potentials;          /* (N) */
+  float* steps_pos;           /* (N,S,3) */
+  float* steps_dphi;          /* (N,S)   */
+} AsMdpState;
+int as_export_state(AsHandle* h, const AsMdpState* dst, void* stream);
+int as_import_state(AsHandle* h, const AsMdpState* src, void* stream);
+
+/* Host-side introspection used by the tests: number of kernel launches issued by this handle so far, and
+ * sizeof() of the public structs (0 AsParams, 1 AsStateIn, 2 AsStepOut, 3 AsResetOut, 4 AsStats, 5 AsMdpState)
+ * so that a foreign-language binding can verify its struct layout. */
+int64_t as_launch_count(const AsHandle* h);
+int64_t as_sizeof(int32_t which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALLSTEPS_B200_H_ */

@@ -1,0 +1,326 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical replayed state.
+
+Bar (BASELINE.json north_star): integer / index / mask outputs bit-exact; fp32 observations and rewards within
+1e-5 relative (|a-b| <= 1e-5 * max(1, |b|)).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from scenario import Scenario, install_mdp_state
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def close(a: torch.Tensor, b: torch.Tensor, what: str, rtol: float = RTOL):
+    a = a.detach().cpu().double()
+    b = b.detach().cpu().double()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    err = (a - b).abs() / b.abs().clamp(min=1.0)
+    worst = err.max().item() if err.numel() else 0.0
+    assert worst <= rtol, f"{what}: max relative error {worst:.3e} > {rtol:.1e} at {int(err.argmax())}"
+    return worst
+
+
+def close_obs(a: torch.Tensor, b: torch.Tensor, what: str):
+    """Observation compare; columns 1,2 are angles wrapped to [0, 2*pi): compare them on the circle."""
+    a = a.detach().cpu().double().clone()
+    b = b.detach().cpu().double().clone()
+    for c in (1, 2):
+        d = (a[:, c] - b[:, c]).abs()
+        wrapped = torch.minimum(d, 2 * math.pi - d)
+        a[:, c] = b[:, c] + wrapped
+    return close(a, b, what)
+
+
+def exact(a: torch.Tensor, b: torch.Tensor, what: str):
+    a = a.detach().cpu()
+    b = b.detach().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    bad = (a != b).nonzero()
+    assert bad.numel() == 0, f"{what}: {bad.shape[0]} mismatches, first at {bad[0].tolist()}"
+
+
+def make_cuda(num_envs, seed, **kw):
+    from allsteps_isaaclab_b200.mdp import AllstepsMDP
+
+    return AllstepsMDP(num_envs, device="cuda:0", seed=seed, **kw)
+
+
+def to_views(phys, env_origins_cuda, body_rows, layout="contiguous"):
+    """Move one synthetic physics dict to the GPU in a chosen memory layout."""
+    from allsteps_isaaclab_b200.mdp import PhysicsViews
+
+    d = {k: v.cuda() for k, v in phys.items()}
+    if layout == "isaac":
+        # what Isaac Lab really hands out: slices of root_state_w (N,13) and body_state_w (N,B,13)
+        N = d["root_pos_w"].shape[0]
+        root_state = torch.zeros(N, 13, device="cuda")
+        root_state[:, 0:3] = d["root_pos_w"]
+        root_state[:, 3:7] = d["root_quat_w"]
+        root_state[:, 7:10] = d["root_lin_vel_w"]
+        root_state[:, 10:13] = d["root_ang_vel_w"]
+        B = d["body_pos_w"].shape[1]
+        body_state = torch.zeros(N, B, 13, device="cuda")
+        body_state[..., 0:3] = d["body_pos_w"]
+        d["root_pos_w"], d["root_quat_w"], d["root_lin_vel_w"] = root_state[:, 0:3], root_state[:, 3:7], root_state[:, 7:10]
+        d["body_pos_w"] = body_state[..., 0:3]
+        d["_keep"] = (root_state, body_state)
+    return PhysicsViews.from_dict(d, env_origins_cuda, body_rows), d
+
+
+def compare_state(mdp, orc, what):
+    st = mdp.export_state()
+    exact(st["curr_target_index"], orc.curr_target_index, f"{what} curr_target_index")
+    exact(st["prev_target_index"], orc.prev_target_index, f"{what} prev_target_index")
+    exact(st["next_target_index"], orc.next_target_index, f"{what} next_target_index")
+    exact(st["swing_leg"], orc.swing_leg, f"{what} swing_leg")
+    exact(st["target_reach_count"], orc.target_reach_count, f"{what} target_reach_count")
+    exact(st["episode_length_buf"], orc.episode_length_buf, f"{what} episode_length_buf")
+    exact(st["curriculum"], orc.curriculum, f"{what} curriculum")
+    close(st["potentials"], orc.potentials, f"{what} potentials")
+    return st
+
+
+def run_replay(num_envs, steps, seed, full_bodies=False, layout="contiguous", fall_fraction=0.02,
+               high_index=False, per_env_levels=False, intended_regen=False, env_id_offset=0):
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+    from oracle import allsteps_oracle as ao
+
+    sc = Scenario(num_envs, seed=seed, full_bodies=full_bodies, fall_fraction=fall_fraction,
+                  env_id_offset=env_id_offset)
+    st0 = sc.initial_mdp_state(per_env_levels=per_env_levels)
+    if high_index:
+        st0["curr_target_index"] = torch.randint(11, 20, (num_envs,), generator=sc.gen)
+    orc = ao.AllstepsOracle(sc.cfg, num_envs, sc.env_origins, sc.joint_limits, sc.body_indices,
+                            sc.stone_uniforms(0), intended_regen=intended_regen)
+    mdp = make_cuda(num_envs, seed, intended_regen=intended_regen, env_id_offset=env_id_offset)
+    origins = sc.env_origins.cuda()
+    if per_env_levels:
+        # levels first, then stones at those levels (oracle: set curriculum, regenerate)
+        orc.curriculum[:] = st0["curriculum"]
+        orc.regenerate_stones(torch.arange(num_envs), sc.stone_uniforms(0))
+        mdp.import_state({"curriculum": st0["curriculum"]})
+    mdp.generate_stones(origins)  # in-kernel Philox at step counter 0
+    install_mdp_state(orc, st0)
+    mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                          "episode_length_buf", "potentials")})
+    st = compare_state(mdp, orc, "initial")
+    close(st["steps_pos"], orc.steps_pos, "initial steps_pos")
+    close(st["steps_dphi"], orc.steps_dphi, "initial steps_dphi")
+    # from here on both sides use the SAME stones, so that fp noise in sin/cos cannot flip a later mask
+    mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
+
+    out = StepBuffers(num_envs, "cuda:0", reward_terms=True)
+    totals = dict(resets=0, advanced=0, promoted=0, fixups=0, regen=0)
+    worst_obs = worst_rew = 0.0
+    for step in range(steps):
+        phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+        mirror_u, noise_u = sc.reset_uniforms(step)
+        level_before = orc.curriculum.clone()
+        o_obs, o_rew, o_term, o_to, o_ids = orc.step(phys, phys["actions"], mirror_u, noise_u,
+                                                     sc.stone_uniforms(step))
+        views, keep = to_views(phys, origins, sc.body_indices, layout)
+        mdp.step(views, keep["actions"], out)
+        torch.cuda.synchronize()
+        exact(out.terminated, o_term, f"step {step} terminated")
+        exact(out.time_out, o_to, f"step {step} time_out")
+        worst_rew = max(worst_rew, close(out.reward, o_rew, f"step {step} reward"))
+        worst_obs = max(worst_obs, close_obs(out.obs, o_obs, f"step {step} obs"))
+        rt = out.reward_terms.cpu()
+        total = rt[:, 0] + rt[:, 1] - rt[:, 2:8].sum(-1) + rt[:, 8] + rt[:, 9]
+        alive = ~o_term
+        close(total[alive], o_rew[alive], f"step {step} reward terms", rtol=1e-4)
+        st = compare_state(mdp, orc, f"step {step}")
+        # reset rows
+        n_reset = int(out.n_reset.item())
+        assert n_reset == len(o_ids), f"step {step}: n_reset {n_reset} vs {len(o_ids)}"
+        ids = out.reset_ids[:n_reset].long().sort().values
+        exact(ids, o_ids, f"step {step} reset ids")
+        if n_reset:
+            w = orc.reset_writes
+            root = torch.cat((w["root_pose"], w["root_velocity"]), dim=-1)
+            close(out.reset_root_state[ids], root, f"step {step} reset root_state")
+            close(out.reset_joint_pos[ids], w["joint_pos"], f"step {step} reset joint_pos")
+            close(out.reset_joint_vel[ids], w["joint_vel"], f"step {step} reset joint_vel")
+        if intended_regen and n_reset and len(orc.regenerated_ids):
+            close(st["steps_pos"], orc.steps_pos, f"step {step} regenerated steps_pos")
+            close(st["steps_dphi"], orc.steps_dphi, f"step {step} regenerated steps_dphi")
+            mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
+            totals["regen"] += len(orc.regenerated_ids)
+        stats = mdp.read_stats()
+        assert stats["n_reset"] == len(o_ids)
+        assert stats["n_terminated"] == int(o_term.sum())
+        assert stats["n_time_out"] == int(o_to.sum())
+        assert stats["sum_target_index"] == int(orc.pass1["curr_target_index"].sum())
+        totals["resets"] += n_reset
+        totals["advanced"] += stats["n_advanced"]
+        totals["promoted"] += int((orc.curriculum != level_before).any())
+        totals["fixups"] += int(n_reset == 0)
+    return totals, worst_obs, worst_rew
+
+
+@pytest.mark.parametrize("num_envs,steps", [(64, 40), (4096, 12)])
+def test_fused_step_matches_oracle(num_envs, steps):
+    totals, wo, wr = run_replay(num_envs, steps, seed=11)
+    assert totals["resets"] > 0 and totals["advanced"] > 0
+    print(f"N={num_envs}: {totals}, worst obs rel err {wo:.2e}, reward {wr:.2e}")
+
+
+def test_ragged_tile_and_isaac_strided_views():
+    # 1001 envs: last CTA has 105 valid rows (not a multiple of 4) -> cooperative path; (N,13) strided root views,
+    # full 17-body tensor with 13-float rows -> strided gathers
+    totals, _, _ = run_replay(1001, 10, seed=5, full_bodies=True, layout="isaac")
+    assert totals["resets"] > 0
+
+
+def test_full_body_tensor_contiguous():
+    totals, _, _ = run_replay(640, 8, seed=6, full_bodies=True)
+    assert totals["resets"] > 0
+
+
+def test_no_reset_steps_skip_pass2():
+    # nothing falls and episodes are young in most steps at N=64 => the reference runs a single pass (DRL:360);
+    # the CUDA path must take its fix-up route and still match bit for bit
+    totals, _, _ = run_replay(64, 30, seed=3, fall_fraction=0.0)
+    assert totals["fixups"] > 0
+
+
+def test_curriculum_promotion_rule():
+    totals, _, _ = run_replay(512, 14, seed=8, high_index=True)
+    assert totals["promoted"] > 0
+
+
+def test_per_env_levels_and_env_id_offset():
+    totals, _, _ = run_replay(384, 8, seed=21, per_env_levels=True, env_id_offset=1 << 20)
+    assert totals["resets"] > 0
+
+
+def test_intended_regeneration_extension():
+    totals, _, _ = run_replay(768, 10, seed=9, high_index=True, intended_regen=True, per_env_levels=True)
+    assert totals["regen"] > 0
+
+
+def test_explicit_stone_uniforms():
+    from oracle import allsteps_oracle as ao
+
+    sc = Scenario(300, seed=2)
+    levels = torch.randint(0, 10, (300,), generator=sc.gen)
+    u = torch.rand(5, 300, 20, generator=sc.gen)
+    pos, dphi = ao.generate_stones(sc.cfg, levels, u)
+    pos = pos + sc.env_origins[:, None, :]
+    mdp = make_cuda(300, 2)
+    mdp.import_state({"curriculum": levels})
+    mdp.generate_stones(sc.env_origins.cuda(), uniforms=u.cuda())
+    st = mdp.export_state()
+    close(st["steps_pos"], pos, "steps_pos")
+    close(st["steps_dphi"], dphi, "steps_dphi")
+    # a subset regenerated with other draws leaves the rest untouched
+    ids = torch.tensor([3, 17, 299])
+    u2 = torch.rand(5, 300, 20, generator=sc.gen)
+    pos2, _ = ao.generate_stones(sc.cfg, levels, u2)
+    pos2 = pos2 + sc.env_origins[:, None, :]
+    mdp.generate_stones(sc.env_origins.cuda(), env_ids=ids.cuda(), uniforms=u2.cuda())
+    st2 = mdp.export_state()
+    expect = pos.clone()
+    expect[ids] = pos2[ids]
+    close(st2["steps_pos"], expect, "steps_pos after partial regeneration")
+
+
+def test_three_call_path_matches_oracle():
+    """pass1 / reset / pass2 with the caller doing the 'PhysX writes' in between (the DirectRLEnv hook order)."""
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+    from oracle import allsteps_oracle as ao
+
+    N, seed = 1536, 13
+    sc = Scenario(N, seed=seed)
+    st0 = sc.initial_mdp_state()
+    orc = ao.AllstepsOracle(sc.cfg, N, sc.env_origins, sc.joint_limits, sc.body_indices, sc.stone_uniforms(0))
+    mdp = make_cuda(N, seed)
+    origins = sc.env_origins.cuda()
+    mdp.generate_stones(origins)
+    install_mdp_state(orc, st0)
+    mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                          "episode_length_buf", "potentials")})
+    mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
+    out = StepBuffers(N, "cuda:0")
+    ep_len = st0["episode_length_buf"].cuda()
+    for step in range(8):
+        phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+        # pass1 advances the step counter, so the reset that follows draws at step + 1
+        mirror_u, noise_u = sc.reset_uniforms(step + 1)
+        o_obs, o_rew, o_term, o_to, o_ids = orc.step(phys, phys["actions"], mirror_u, noise_u, None)
+        views, keep = to_views(phys, origins, sc.body_indices)
+        ep_len += 1  # DRL:351
+        mdp.pass1(views, keep["actions"], out, episode_length=ep_len)
+        exact(out.terminated, o_term, f"step {step} terminated")
+        exact(out.time_out, o_to, f"step {step} time_out")
+        close(out.reward, o_rew, f"step {step} reward")
+        ids = (out.terminated | out.time_out).nonzero().squeeze(-1)  # DRL:359
+        exact(ids, o_ids, f"step {step} ids")
+        if len(ids):
+            mdp.reset(origins, ids, out, episode_length=ep_len)
+            k = len(ids)
+            w = orc.reset_writes
+            close(out.reset_root_state[:k], torch.cat((w["root_pose"], w["root_velocity"]), -1), "root rows")
+            close(out.reset_joint_pos[:k], w["joint_pos"], "joint_pos rows")
+            # the PhysX writes (ART:316-489): data views change for the reset rows; contacts are zeroed
+            keep["root_pos_w"][ids] = out.reset_root_state[:k, 0:3]
+            keep["root_quat_w"][ids] = out.reset_root_state[:k, 3:7]
+            keep["root_lin_vel_w"][ids] = out.reset_root_state[:k, 7:10]
+            keep["joint_pos"][ids] = out.reset_joint_pos[:k]
+            keep["joint_vel"][ids] = out.reset_joint_vel[:k]
+            keep["force_matrix_right"][ids] = 0.0
+            keep["force_matrix_left"][ids] = 0.0
+            mdp.pass2(views, out)
+        torch.cuda.synchronize()
+        close_obs(out.obs, o_obs, f"step {step} obs")
+        exact(ep_len, orc.episode_length_buf, f"step {step} episode_length")
+        st = mdp.export_state()
+        exact(st["curr_target_index"], orc.curr_target_index, f"step {step} idx")
+        exact(st["swing_leg"], orc.swing_leg, f"step {step} leg")
+        exact(st["target_reach_count"], orc.target_reach_count, f"step {step} count")
+        exact(st["curriculum"], orc.curriculum, f"step {step} curriculum")
+        close(st["potentials"], orc.potentials, f"step {step} potentials")
+
+
+def test_action_path_and_mirror_rows():
+    from oracle import allsteps_oracle as ao
+
+    N = 777
+    sc = Scenario(N, seed=4)
+    orc = ao.AllstepsOracle(sc.cfg, N, sc.env_origins, sc.joint_limits, sc.body_indices, None)
+    levels = torch.randint(0, 10, (N,), generator=sc.gen)
+    orc.curriculum[:] = levels
+    actions = -1.5 + 3.0 * torch.rand(N, 21, generator=sc.gen)
+    orc.clamp_actions(actions)
+    mdp = make_cuda(N, 4)
+    mdp.import_state({"curriculum": levels})
+    eff = mdp.apply_action(actions.cuda())
+    close(eff, orc.joint_efforts(), "joint efforts")
+    # mirror augmentation, ENV:611-660 restated with index tables
+    cfg = sc.cfg
+    right = torch.tensor(cfg.right_joint_indices)
+    left = torch.tensor(cfg.left_joint_indices)
+    neg = torch.tensor(cfg.negation_joint_indices)
+    obs = torch.randn(N, 59, generator=sc.gen)
+    steps_neg = torch.tensor([3 * i + 1 for i in range(3)])
+    right_obs = torch.cat((right + 6, right + 6 + 21, torch.tensor([6 + 42])))
+    left_obs = torch.cat((left + 6, left + 6 + 21, torch.tensor([6 + 42 + 1])))
+    neg_obs = torch.cat((torch.tensor([1, 4]), 6 + neg, 6 + 21 + neg, 6 + 42 + 2 + steps_neg))
+    m = obs.clone()
+    m[:, right_obs] = obs[:, left_obs]
+    m[:, left_obs] = obs[:, right_obs]
+    m[:, neg_obs] = -obs[:, neg_obs]
+    exact(mdp.mirror_rows(obs.cuda(), "obs"), torch.vstack((obs, m)), "mirrored observations")
+    ma = actions.clone()
+    ma[:, right] = actions[:, left]
+    ma[:, left] = actions[:, right]
+    ma[:, neg] = -actions[:, neg]
+    exact(mdp.mirror_rows(actions.cuda(), "actions"), torch.vstack((actions, ma)), "mirrored actions")

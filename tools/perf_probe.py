@@ -1,0 +1,47 @@
+"""Quick device-time probe of the fused step at several env counts (development tool, not the bench)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from allsteps_isaaclab_b200.config import AllstepsCfg
+from allsteps_isaaclab_b200 import synthetic as syn
+from allsteps_isaaclab_b200.mdp import AllstepsMDP, PhysicsViews, StepBuffers
+
+B_ALG = 652
+
+
+def probe(N, steps=50, sets=4, warmup=10):
+    cfg = AllstepsCfg()
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    origins = syn.env_origins_grid(N, cfg.env_spacing).to(dev)
+    mdp = AllstepsMDP(N, device=dev, seed=1)
+    mdp.generate_stones(origins)
+    st0 = syn.random_mdp_state(cfg, N, torch.Generator().manual_seed(1))
+    mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                          "episode_length_buf", "potentials")})
+    st = mdp.export_state()
+    pool = []
+    for s in range(sets):
+        d = syn.random_physics_state(cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen)
+        pool.append((PhysicsViews.from_dict(d, origins), d))
+    out = StepBuffers(N, dev, reset_rows=("--rows" in sys.argv))
+    for i in range(warmup):
+        v, d = pool[i % sets]
+        mdp.step(v, d["actions"], out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        v, d = pool[i % sets]
+        mdp.step(v, d["actions"], out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    stats = mdp.read_stats()
+    print(f"N={N:>8}  {ms*1e3:9.1f} us/step  {N/ms/1e6:9.3f} G env-steps/s  {N*B_ALG/ms/1e6:8.1f} GB/s alg  "
+          f"resets/step={stats['n_reset']}  launches/step={mdp.launch_count/(steps+warmup):.1f}", flush=True)
+
+
+if __name__ == "__main__":
+    for n in (4096, 65536, 262144, 1048576):
+        probe(n)
