@@ -1,5 +1,6 @@
 // C ABI of the B200-native Allsteps-v0 MDP step (include/allsteps_b200.h): argument checking, launch geometry,
 // and nothing else.  All arithmetic lives in the kernels (as_step_kernel.cuh, as_aux_kernels.cuh).
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -18,6 +19,7 @@ struct AsHandle {
   Workspace ws;
   int64_t launches;
   MirrorTable mirror_obs, mirror_act;
+  JointConsts jc;
   bool pass1_done;
   bool pending_valid;   // a fused step was launched and still needs as_finish_step
   StepArgs pending;     // its arguments: the conditional fix-up re-reads the same inputs
@@ -102,11 +104,45 @@ void build_mirror_tables(AsHandle* h) {
   o.sign[51] = o.sign[54] = o.sign[57] = -1.0f;
 }
 
+// Correctly rounded fp32 reciprocal of d (needed by the two-FMA quotient in scale_joint).
+float rn_reciprocal(float d) {
+  float best = static_cast<float>(1.0 / static_cast<double>(d));
+  double best_err = std::fabs(1.0 - static_cast<double>(best) * static_cast<double>(d));  // product is exact
+  const float cands[2] = {std::nextafterf(best, 0.0f), std::nextafterf(best, 2.0f * best)};
+  for (float c : cands) {
+    const double err = std::fabs(1.0 - static_cast<double>(c) * static_cast<double>(d));
+    if (err < best_err) {
+      best = c;
+      best_err = err;
+    }
+  }
+  return best;
+}
+
+void build_joint_consts(AsHandle* h) {
+  const AsParams& P = h->params;
+  JointConsts& c = h->jc;
+  c.exact_div = 0;
+  for (int j = 0; j < kJ; ++j) {
+    // same fp32 roundings as MATH:36-40: offset = (lower + upper) * 0.5 ; denominator = upper - lower
+    volatile float sum = P.joint_lower[j] + P.joint_upper[j];
+    volatile float range = P.joint_upper[j] - P.joint_lower[j];
+    c.offset[j] = sum * 0.5f;
+    c.range[j] = range;
+    c.inv_range[j] = rn_reciprocal(range);
+    uint32_t bits;
+    const float r = range;
+    std::memcpy(&bits, &r, sizeof(bits));
+    if ((bits & 0x7FFFFFu) == 0x7FFFFFu) c.exact_div = 1;  // Markstein's excluded case
+  }
+}
+
 StepArgs make_step_args(AsHandle* h, const AsStateIn* in, const float* actions, int64_t actions_stride,
                         const AsStepOut* out) {
   StepArgs a;
   std::memset(&a, 0, sizeof(a));
   a.P = h->params;
+  a.jc = h->jc;
   if (in) a.in = *in;
   a.actions = actions;
   a.actions_stride = actions_stride;
@@ -192,6 +228,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->ws.reset_ids = reinterpret_cast<int32_t*>(base + l.reset_ids_off);
   h->ws.regen_ids = reinterpret_cast<int32_t*>(base + l.regen_ids_off);
   build_mirror_tables(h);
+  build_joint_consts(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(l.total), s);
   if (e != cudaSuccess) {
@@ -285,9 +322,12 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
   StepArgs a = make_step_args(h, in, actions, actions_stride, out);
   a.ext_episode_length = episode_length;
-  k_step<kModePass1><<<a.num_tiles, kTile, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  k_step<kModePass1><<<a.num_tiles, kTile, kSmemBytes, s>>>(a);
+  if (int rc = check_launch(h, "k_step<pass1>")) return rc;
+  k_fold_pass1<<<1, 128, 0, s>>>(h->ws.ctrl, h->num_envs);
   h->pass1_done = true;
-  return check_launch(h, "k_step<pass1>");
+  return check_launch(h, "k_fold_pass1");
 }
 
 int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids, int64_t* episode_length,

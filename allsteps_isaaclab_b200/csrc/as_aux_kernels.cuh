@@ -90,8 +90,16 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
   const int64_t n_reset = a.fused ? static_cast<int64_t>(ctrl->n_reset_list) : a.n_ids;
   // promotion decided in THIS step is already in force when stones are regenerated (ENV:471 precedes ENV:500)
   // (3-call path: as_reset ran k_decide_promotion first and left the decision in promote_cur)
-  const AsStats* g = a.global_stats ? a.global_stats : &ctrl->stats;
-  const int promote_now = a.fused ? static_cast<int>(promotion_decision(P, *g)) : static_cast<int>(ctrl->promote_cur);
+  int promote_now;
+  if (!a.fused) {
+    promote_now = static_cast<int>(ctrl->promote_cur);
+  } else if (a.global_stats) {
+    promote_now = static_cast<int>(promotion_decision(P, *a.global_stats));
+  } else {  // the step kernel's counters are still in the replicated slots (folded by the finish kernel)
+    const unsigned nr = slot_sum(ctrl, kCntReset);
+    const unsigned si = slot_sum(ctrl, kCntSumIndex);
+    promote_now = static_cast<int>(promotion_rule(P, nr, si, a.num_envs));
+  }
   const uint32_t parity = ctrl->parity;
   uint2* st_cur = a.fused ? a.ws.state[parity ^ 1u] : a.ws.state[parity];  // fused: the step wrote the other buffer
 

@@ -25,7 +25,16 @@ enum Counter {
   kCntAdvanced2,  // index advances in pass 2 (void when the fix-up discards pass 2)
   kCntSumIndex,   // sum of curr_target_index after pass 1 (numerator of ENV:471)
   kCntRegen,
+  kCntLevelMax,   // max curriculum level seen (combined with max, not add)
   kNumCounters = 12
+};
+
+// Per-joint constants of MATH:22-40 scale_transform, precomputed by as_create.
+struct JointConsts {
+  float offset[AS_NUM_JOINTS];     // (lower + upper) * 0.5
+  float range[AS_NUM_JOINTS];      // upper - lower
+  float inv_range[AS_NUM_JOINTS];  // RN(1 / range)
+  int32_t exact_div;               // 1: use a true division (a range with an all-ones significand)
 };
 
 // Packed per-env MDP state word (state.x); state.y holds the bits of `potentials`.
@@ -97,6 +106,7 @@ enum StepMode { kModeFused = 0, kModeFixup = 1, kModePass1 = 2, kModePass2 = 3 }
 
 struct StepArgs {
   AsParams P;
+  JointConsts jc;
   AsStateIn in;
   const float* actions;
   int64_t actions_stride;

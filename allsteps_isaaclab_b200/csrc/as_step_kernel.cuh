@@ -34,7 +34,7 @@ constexpr int kOffRq = kOffRp + kTile * 3 * 4;
 constexpr int kOffRv = kOffRq + kTile * 4 * 4;
 constexpr int kOffBody = kOffRv + kTile * 3 * 4;
 constexpr int kOffMisc = kOffBody + kTile * 9 * 4;
-constexpr int kSmemBytes = kOffMisc + 256;
+constexpr int kSmemBytes = kOffMisc + 384;
 static_assert(kTile * kObs * 4 <= kOffRp, "observation tile must fit over the joint/action tiles it aliases");
 static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffRq % 16 == 0 &&
                   kOffRv % 16 == 0 && kOffBody % 16 == 0 && kOffMisc % 16 == 0,
@@ -42,12 +42,12 @@ static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffR
 
 struct Misc {  // lives at kOffMisc, never aliased
   unsigned long long mbar;
-  unsigned int cnt[kNumCounters];
-  float reward_sum;
+  unsigned int wcnt[kTile / 32][kNumCounters];  // per-warp step counters
+  float wreward[kTile / 32];
   unsigned int is_last;
   unsigned int fold[kNumCounters];
 };
-static_assert(sizeof(Misc) <= 256, "misc block");
+static_assert(sizeof(Misc) <= 384, "misc block");
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -106,6 +106,10 @@ struct Mdp {
   int idx, leg, count;
   float pot;
 };
+struct FootGeom {  // ENV:421-431 relative to the CURRENT stone
+  bool press_r, press_l;
+  float d_r, d_l;
+};
 struct PassOut {
   float contact_r, contact_l;  // foot_contact (right, left) as 0/1 floats, ENV:426
   float d_swing;               // foot_to_target_dist_xy[n, swing_leg] with the POST-update leg, ENV:371
@@ -115,34 +119,39 @@ struct PassOut {
   Vec3 tb0, tb1, tb2;          // targets_b rows (prev, curr, next), ENV:302-316
 };
 
-// ENV:418-467 + ENV:302-316 + ENV:407-416.  `force_r/l` are the contact-force norms of the CURRENT stone,
-// (s_prev, s_curr, s_next) the stones at clamp(idx-1), idx, clamp(idx+1); `stone(i)` gathers stone i.
-template <class StoneFn>
-__device__ __forceinline__ void mdp_pass(const AsParams& P, const Vec3& p, const Quat& q, const Vec3& rf,
-                                         const Vec3& lf, float force_r, float force_l, float4& s_prev,
-                                         float4& s_curr, float4& s_next, StoneFn&& stone, Mdp& m, PassOut& o) {
-  const bool press_r = force_r > P.contact_epsilon;
-  const bool press_l = force_l > P.contact_epsilon;
-  o.contact_r = press_r ? 1.0f : 0.0f;
-  o.contact_l = press_l ? 1.0f : 0.0f;
-  const float d_r = norm2(rf.x - s_curr.x, rf.y - s_curr.y);
-  const float d_l = norm2(lf.x - s_curr.x, lf.y - s_curr.y);
-  o.reached = m.leg ? (press_l && d_l < P.step_radius) : (press_r && d_r < P.step_radius);
+__device__ __forceinline__ FootGeom foot_geometry(const AsParams& P, const Vec3& rf, const Vec3& lf, float force_r,
+                                                  float force_l, const float4& s_curr) {
+  FootGeom g;
+  g.press_r = force_r > P.contact_epsilon;  // ENV:425
+  g.press_l = force_l > P.contact_epsilon;
+  g.d_r = norm2(rf.x - s_curr.x, rf.y - s_curr.y);  // ENV:431
+  g.d_l = norm2(lf.x - s_curr.x, lf.y - s_curr.y);
+  return g;
+}
+
+// ENV:433-457: reach counter, leg flip, index advance.  Returns true when the index changed (window must shift).
+__device__ __forceinline__ bool foot_update(const AsParams& P, const FootGeom& g, Mdp& m, PassOut& o) {
+  o.contact_r = g.press_r ? 1.0f : 0.0f;
+  o.contact_l = g.press_l ? 1.0f : 0.0f;
+  o.reached = m.leg ? (g.press_l && g.d_l < P.step_radius) : (g.press_r && g.d_r < P.step_radius);
   m.count += o.reached ? 1 : 0;
   o.advanced = m.count >= P.stop_frames;
+  bool moved = false;
   if (o.advanced) {
     m.leg ^= 1;
     const int nidx = min(m.idx + 1, kS - 1);
-    if (nidx != m.idx) {
-      s_prev = s_curr;
-      s_curr = s_next;
-      s_next = stone(min(nidx + 1, kS - 1));
-    }
+    moved = nidx != m.idx;
     m.idx = nidx;
     m.count = 0;
   }
-  o.d_swing = m.leg ? d_l : d_r;
-  const Quat inv = quat_inverse(q);
+  o.d_swing = m.leg ? g.d_l : g.d_r;
+  return moved;
+}
+
+// ENV:459-467 + ENV:302-316 + ENV:407-416 for a general root orientation (`inv` = quat_inv(root_quat)).
+__device__ __forceinline__ void targets_and_potential(const AsParams& P, const Vec3& p, const Quat& inv,
+                                                      const float4& s_prev, const float4& s_curr,
+                                                      const float4& s_next, Mdp& m, PassOut& o) {
   o.tb0 = point_in_frame(p, inv, Vec3{s_prev.x, s_prev.y, s_prev.z});
   o.tb1 = point_in_frame(p, inv, Vec3{s_curr.x, s_curr.y, s_curr.z});
   o.tb2 = point_in_frame(p, inv, Vec3{s_next.x, s_next.y, s_next.z});
@@ -171,6 +180,18 @@ __device__ __forceinline__ void first_three_stones(const AsParams& P, const Vec3
                    static_cast<float>(z) + origin.z, 0.0f);
 }
 
+// MATH:22-40 with the per-joint constants precomputed on the host (JointConsts): the quotient
+// (2*(x - offset)) / range is produced by the two-FMA correction q = fma(fma(-q0, range, n), inv, q0), which is the
+// correctly rounded quotient when inv = RN(1/range) (Markstein); as_create falls back to a true division for a
+// joint whose range has an all-ones significand (the theorem's excluded case).
+__device__ __forceinline__ float scale_joint(const JointConsts& C, int j, float x) {
+  const float n = 2.0f * (x - C.offset[j]);
+  if (C.exact_div) return n / C.range[j];
+  const float q0 = n * C.inv_range[j];
+  const float e = fmaf(-q0, C.range[j], n);
+  return fmaf(e, C.inv_range[j], q0);
+}
+
 // Start-pose joint value of a reset env (ENV:505-560): running-start pose, optional mirror, uniform noise, clip.
 __device__ __forceinline__ float reset_joint_value(const AsParams& P, int j, bool mirror, float u) {
   const int src = mirror ? P.mirror_src[j] : j;
@@ -182,16 +203,23 @@ __device__ __forceinline__ float reset_joint_value(const AsParams& P, int j, boo
 }
 
 // ------------------------------------------------------------------------------------------------ statistics
-__device__ __forceinline__ void fold_stats(Ctrl* ctrl, Misc* misc, const StepArgs& a) {
+// Sum of one per-step counter over the replicated slots (any warp may call; all 32 lanes participate).
+__device__ __forceinline__ unsigned slot_sum(const Ctrl* ctrl, int which) {
+  const unsigned v = __ldcg(&ctrl->slots[threadIdx.x & 31][which]);
+  return __reduce_add_sync(0xffffffffu, v);
+}
+
+// Folds the slots into ctrl->stats and clears them.  Called by one CTA (>= 64 threads) after the step kernel.
+__device__ __forceinline__ void fold_stats(Ctrl* ctrl, unsigned int* fold, int64_t num_envs) {
   const int t = threadIdx.x;
   if (t < kNumCounters) {
     unsigned int acc = 0;
-    if (t == 10) {
+    if (t == kCntLevelMax) {
       for (int s = 0; s < kSlots; ++s) acc = max(acc, atomicExch(&ctrl->slots[s][t], 0u));
     } else {
       for (int s = 0; s < kSlots; ++s) acc += atomicExch(&ctrl->slots[s][t], 0u);
     }
-    misc->fold[t] = acc;
+    fold[t] = acc;
   }
   float rsum = 0.0f;
   if (t == 32) {
@@ -200,30 +228,43 @@ __device__ __forceinline__ void fold_stats(Ctrl* ctrl, Misc* misc, const StepArg
   __syncthreads();
   if (t == 0) {
     AsStats& st = ctrl->stats;
-    st.n_envs = a.num_envs;
-    st.n_reset = misc->fold[kCntReset];
-    st.n_terminated = misc->fold[kCntTerminated];
-    st.n_time_out = misc->fold[kCntTimeOut];
-    st.n_fell = misc->fold[kCntFell];
-    st.n_so_fast = misc->fold[kCntSoFast];
-    st.n_died = misc->fold[kCntDied];
-    st.n_advanced = static_cast<int64_t>(misc->fold[kCntAdvanced1]) + misc->fold[kCntAdvanced2];
-    st.sum_target_index = misc->fold[kCntSumIndex];
-    st.n_regenerated = misc->fold[kCntRegen];
-    st.level = misc->fold[10];
+    st.n_envs = num_envs;
+    st.n_reset = fold[kCntReset];
+    st.n_terminated = fold[kCntTerminated];
+    st.n_time_out = fold[kCntTimeOut];
+    st.n_fell = fold[kCntFell];
+    st.n_so_fast = fold[kCntSoFast];
+    st.n_died = fold[kCntDied];
+    st.n_advanced = static_cast<int64_t>(fold[kCntAdvanced1]) + fold[kCntAdvanced2];
+    st.sum_target_index = fold[kCntSumIndex];
+    st.n_regenerated = fold[kCntRegen];
+    st.level = fold[kCntLevelMax];
     st.step_counter = static_cast<int64_t>(ctrl->step_counter);
-    ctrl->last_adv2 = misc->fold[kCntAdvanced2];
-    ctrl->blocks_done = 0;
+    ctrl->last_adv2 = fold[kCntAdvanced2];
   }
   if (t == 32) ctrl->stats.sum_reward = static_cast<double>(rsum);
+  __syncthreads();
+}
+
+// ENV:471-472 promotion rule on step statistics (this shard's, or summed over ranks).
+__device__ __forceinline__ uint32_t promotion_rule(const AsParams& P, int64_t n_reset, int64_t sum_index,
+                                                   int64_t n_envs) {
+  if (n_reset <= 0 || n_envs <= 0) return 0u;  // `_reset_idx` is only entered when an env resets, DRL:360
+  const float mean = static_cast<float>(sum_index) / static_cast<float>(n_envs);
+  return mean > P.progress_threshold ? 1u : 0u;
+}
+__device__ __forceinline__ uint32_t promotion_decision(const AsParams& P, const AsStats& s) {
+  return promotion_rule(P, s.n_reset, s.sum_target_index, s.n_envs);
 }
 
 // ------------------------------------------------------------------------------------------------ the tile
 template <int MODE>
 __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32_t& phase, unsigned char* smem) {
   const AsParams& P = a.P;
+  const JointConsts& JC = a.jc;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int warp = tid >> 5;
   const int64_t env0 = static_cast<int64_t>(tile) * kTile;
   const int64_t rem = a.num_envs - env0;
   const int n_valid = rem < kTile ? static_cast<int>(rem) : kTile;
@@ -244,6 +285,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 
   constexpr bool kNeedActions = MODE != kModePass2;
   constexpr bool kPingPong = MODE == kModeFused || MODE == kModeFixup;
+  constexpr bool kStats = MODE == kModeFused || MODE == kModePass1;
 
   // ---------------------------------------------------------------- HBM -> SMEM (TMA bulk where the view allows)
   const bool body_compact = a.in.body_row_stride == 3 && a.in.body_env_stride == 9 && a.in.right_foot_row == 0 &&
@@ -261,13 +303,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     const uint32_t tx = (b_jp ? nv * kJ * 4 : 0) + (b_jv ? nv * kJ * 4 : 0) + (b_act ? nv * kJ * 4 : 0) +
                         (b_rp ? nv * 12 : 0) + (b_rq ? nv * 16 : 0) + (b_rv ? nv * 12 : 0) + (b_body ? nv * 36 : 0);
     mbar_arrive_expect_tx(bar, tx);
-    if (b_jp) bulk_g2s(smem_u32(s_jp), a.in.joint_pos + env0 * kJ, nv * kJ * 4, bar);
-    if (b_jv) bulk_g2s(smem_u32(s_jv), a.in.joint_vel + env0 * kJ, nv * kJ * 4, bar);
-    if (b_act) bulk_g2s(smem_u32(s_act), a.actions + env0 * kJ, nv * kJ * 4, bar);
     if (b_rp) bulk_g2s(smem_u32(s_rp), a.in.root_pos + env0 * 3, nv * 12, bar);
     if (b_rq) bulk_g2s(smem_u32(s_rq), a.in.root_quat + env0 * 4, nv * 16, bar);
     if (b_rv) bulk_g2s(smem_u32(s_rv), a.in.root_lin_vel + env0 * 3, nv * 12, bar);
     if (b_body) bulk_g2s(smem_u32(s_body), a.in.body_pos + env0 * 9, nv * 36, bar);
+    if (b_jp) bulk_g2s(smem_u32(s_jp), a.in.joint_pos + env0 * kJ, nv * kJ * 4, bar);
+    if (b_jv) bulk_g2s(smem_u32(s_jv), a.in.joint_vel + env0 * kJ, nv * kJ * 4, bar);
+    if (b_act) bulk_g2s(smem_u32(s_act), a.actions + env0 * kJ, nv * kJ * 4, bar);
   }
 
   // ---------------------------------------------------------------- per-env state word + dependent gathers
@@ -355,57 +397,58 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   bool fell = false, so_fast = false, died = false, adv1 = false, adv2 = false;
   float r_progress = 0.0f, r_roll = 0.0f, r_pitch = 0.0f, r_speed = 0.0f, r_step = 0.0f, r_bonus = 0.0f;
   int idx_after_pass1 = 0;
-  uint4 rblk = make_uint4(0, 0, 0, 0);
   const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
   const unsigned long long step_now = ctrl->step_counter;
+  FootGeom geom{};
+  Quat inv{1, 0, 0, 0};
 
+  const int idx_before = m.idx;
   if (active) {
-    h = torso_z - fminf(lf.z, rf.z);  // ENV:281-283
+    h = torso_z - fminf(lf.z, rf.z);   // ENV:281-283
     euler_roll_pitch(q, roll, pitch);  // ENV:285
     vb = rotate_by_inverse(q, v);      // ENV:293
-    mdp_pass(P, p, q, rf, lf, f_r, f_l, s_prev, s_curr, s_next, stone_at, m, po);
+    inv = quat_inverse(q);
+    geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
+    const bool moved = foot_update(P, geom, m, po);
+    if (moved) {
+      s_prev = s_curr;
+      s_curr = s_next;
+      s_next = stone_at(min(m.idx + 1, kS - 1));
+    }
+    targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
     adv1 = po.advanced;
     idx_after_pass1 = m.idx;
+    if (MODE != kModePass2) {
+      // ---- dones, ENV:396-405
+      time_out = ep >= P.max_episode_length - 1;
+      fell = h < P.termination_height[level];
+      const float speed = norm3(v.x, v.y, v.z);
+      so_fast = speed > P.max_root_speed;
+      died = p.z < P.termination_height_absolute;
+      terminated = fell || so_fast || died;
+      is_reset = terminated || time_out;
+      // ---- reward terms that do not need the joint loop, ENV:350-375
+      r_progress = m.pot - po.old_pot;
+      r_roll = (roll > 0.4f || roll < -0.4f) ? fabsf(roll) : 0.0f;
+      r_pitch = (pitch > 0.4f || pitch < -0.2f) ? fabsf(pitch) : 0.0f;
+      r_speed = speed > 1.6f ? speed - 1.6f : 0.0f;
+      const bool pays_step = po.reached && m.count == 1 && m.idx < kS - 1;
+      r_step = pays_step ? 50.0f * expf((-po.d_swing) / 0.25f) : 0.0f;
+      r_bonus = (m.idx == kS - 1 && po.body_dist < 0.15f) ? 10.0f : 0.0f;
+    }
   }
 
-  if (MODE != kModePass2 && active) {
-    // ---- dones, ENV:396-405
-    time_out = ep >= P.max_episode_length - 1;
-    fell = h < P.termination_height[level];
-    const float speed = norm3(v.x, v.y, v.z);
-    so_fast = speed > P.max_root_speed;
-    died = p.z < P.termination_height_absolute;
-    terminated = fell || so_fast || died;
-    is_reset = terminated || time_out;
-    // ---- reward terms that do not need the joint loop, ENV:350-375
-    r_progress = m.pot - po.old_pot;
-    r_roll = (roll > 0.4f || roll < -0.4f) ? fabsf(roll) : 0.0f;
-    r_pitch = (pitch > 0.4f || pitch < -0.2f) ? fabsf(pitch) : 0.0f;
-    r_speed = speed > 1.6f ? speed - 1.6f : 0.0f;
-    const bool pays_step = po.reached && m.count == 1 && m.idx < kS - 1;
-    r_step = pays_step ? 50.0f * expf((-po.d_swing) / 0.25f) : 0.0f;
-    r_bonus = (m.idx == kS - 1 && po.body_dist < 0.15f) ? 10.0f : 0.0f;
-  }
-
-  if (MODE == kModeFused) {
-    // ---- masked reset, ENV:487-538 (rows for PhysX are produced by the reset kernel from the same draws)
-    if (active && is_reset) {
+  if (MODE == kModeFused && active) {
+    if (is_reset) {
+      // ---- masked reset, ENV:487-538 (rows for PhysX are produced by the reset kernel from the same draws).
+      // Pass 2 on the post-reset state: identity orientation (vector part +-0), zero velocity, zero contacts
+      // (contact_sensor.py:155), stale body positions; so roll = pitch = v_b = 0 and targets_b = stone - root.
       regen = (P.flags & AS_FLAG_INTENDED_REGEN) && m.idx > kS / 2;
-      rblk = philox_block(P.seed, step_now, kStreamReset, gid, 0);
+      const uint4 rblk = philox_block(P.seed, step_now, kStreamReset, gid, 0);
       mirror = u32_to_unit(rblk.x) > 0.5f;  // ENV:518
       const float ox = __ldg(a.in.env_origins + e * 3), oy = __ldg(a.in.env_origins + e * 3 + 1),
                   oz = __ldg(a.in.env_origins + e * 3 + 2);
       p = Vec3{P.default_root_pos[0] + ox, P.default_root_pos[1] + oy, P.default_root_pos[2] + oz};
-      const float z = mirror ? -0.0f : 0.0f;  // ENV:535 flips the sign of the (zero) vector part
-      q = Quat{1.0f, z, z, z};
-      v = Vec3{0, 0, 0};
-      m.pot = 0.0f;
-      m.count = 0;
-      m.leg = mirror ? 1 : 0;  // ENV:491,538
-      m.idx = 1;
-      ep = 0;  // DRL:584
-      f_r = 0.0f;  // scene.reset zeroes the contact rows, contact_sensor.py:155
-      f_l = 0.0f;
       if (regen) {
         first_three_stones(P, Vec3{ox, oy, oz}, s_prev, s_curr, s_next);
       } else {
@@ -413,27 +456,39 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         s_curr = stone_at(1);
         s_next = stone_at(2);
       }
-      // root-frame quantities are recomputed on the post-reset state; body positions are stale (unchanged)
-      euler_roll_pitch(q, roll, pitch);
-      vb = rotate_by_inverse(q, v);
-    }
-    // ---- pass 2 over ALL envs, ENV:567; assumed to happen, the fix-up kernel undoes the assumption
-    const bool run_pass2 = active && (is_reset || !(P.flags & AS_FLAG_SKIP_PASS2));
-    if (run_pass2) {
-      if (!is_reset && adv1) {  // the current stone changed in pass 1: its contact column is a new gather
+      m.count = 0;
+      m.leg = mirror ? 1 : 0;  // ENV:491,538
+      m.idx = 1;
+      ep = 0;  // DRL:584
+      roll = 0.0f;
+      pitch = 0.0f;
+      vb = Vec3{0, 0, 0};
+      po.contact_r = 0.0f;
+      po.contact_l = 0.0f;
+      po.tb0 = Vec3{s_prev.x - p.x, s_prev.y - p.y, s_prev.z - p.z};
+      po.tb1 = Vec3{s_curr.x - p.x, s_curr.y - p.y, s_curr.z - p.z};
+      po.tb2 = Vec3{s_next.x - p.x, s_next.y - p.y, s_next.z - p.z};
+      po.body_dist = norm2(s_next.x - p.x, s_next.y - p.y);
+      m.pot = (-po.body_dist) / P.step_dt;  // ENV:487-488 zero both potentials, ENV:415-416 in pass 2
+    } else if (!(P.flags & AS_FLAG_SKIP_PASS2)) {
+      // ---- pass 2 over ALL envs, ENV:567, on unchanged physics: only the foot state machine can
+      // change anything.  Assumed to happen; the fix-up kernel undoes the assumption when no env reset.
+      if (idx_after_pass1 != idx_before) {  // the current stone changed in pass 1: new contact column
         const float* fr = cr_row + m.idx * 3;
         const float* fl = cl_row + m.idx * 3;
         f_r = norm3(__ldg(fr), __ldg(fr + 1), __ldg(fr + 2));
         f_l = norm3(__ldg(fl), __ldg(fl + 1), __ldg(fl + 2));
+        geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
       }
-      auto stone_after = [&](int i) -> float4 {
-        if (regen) {  // stone 3 of a regenerated sequence is not known here; unreachable (count restarts at 0)
-          return s_next;
-        }
-        return stone_at(i);
-      };
-      mdp_pass(P, p, q, rf, lf, f_r, f_l, s_prev, s_curr, s_next, stone_after, m, po);
+      const bool moved = foot_update(P, geom, m, po);
       adv2 = po.advanced;
+      if (moved) {
+        s_prev = s_curr;
+        s_curr = s_next;
+        s_next = stone_at(min(m.idx + 1, kS - 1));
+        targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
+      }
+      // (unmoved: targets, body distance and potential are recomputed to the same values; old_potentials is dead)
     }
   }
 
@@ -447,22 +502,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     const float* my_act = s_act + tid * kJ;
 #pragma unroll
     for (int j = 0; j < kJ; ++j) {
-      const float jp = my_jp[j];
-      float jv = my_jv[j];
-      float sc = scale_to_unit(jp, P.joint_lower[j], P.joint_upper[j]);  // ENV:287-291
+      const float jv = my_jv[j];
+      const float sc = scale_joint(JC, j, my_jp[j]);  // ENV:287-291
       if (kNeedActions) {
         const float act = fminf(fmaxf(my_act[j], -1.0f), 1.0f);  // ENV:268
         at_limit += fabsf(sc) > 0.99f ? 1 : 0;                   // ENV:367
         energy += fabsf(jv * act);                               // ENV:365
         act_sq = fmaf(act, act, act_sq);                         // ENV:364
-      }
-      if (MODE == kModeFused) {
-        if (((1 + j) & 3) == 0 && is_reset) rblk = philox_block(P.seed, step_now, kStreamReset, gid, (1 + j) >> 2);
-        if (is_reset) {
-          const float u = u32_to_unit(lane_of(rblk, (1 + j) & 3));
-          sc = scale_to_unit(reset_joint_value(P, j, mirror, u), P.joint_lower[j], P.joint_upper[j]);
-          jv = mirror ? 0.0f * P.mirror_sign[j] : 0.0f;  // default_joint_vel is all zeros, ENV:513,528-532
-        }
       }
       o_jp[j] = sc;
       o_jv[j] = fminf(fmaxf(jv * P.dof_vel_scale, -5.0f), 5.0f);  // ENV:337
@@ -502,8 +548,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   }
 
   // ---------------------------------------------------------------- reset / regeneration lists (warp ballots)
+  const unsigned rmask = (MODE == kModeFused) ? __ballot_sync(0xffffffffu, is_reset) : 0u;
   if (MODE == kModeFused) {
-    const unsigned rmask = __ballot_sync(0xffffffffu, is_reset);
     if (rmask && a.want_reset_list) {
       const int leader = __ffs(rmask) - 1;
       unsigned base = 0;
@@ -521,30 +567,34 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
   }
 
-  // ---------------------------------------------------------------- statistics (warp -> CTA)
-  if (MODE == kModeFused || MODE == kModePass1) {
-    auto count_into = [&](int which, bool flag) {
-      const unsigned bm = __ballot_sync(0xffffffffu, flag);
-      if (lane == 0 && bm) atomicAdd(&misc->cnt[which], __popc(bm));
-    };
-    count_into(kCntReset, is_reset);
-    count_into(kCntTerminated, terminated);
-    count_into(kCntTimeOut, time_out);
-    count_into(kCntFell, fell);
-    count_into(kCntSoFast, so_fast);
-    count_into(kCntDied, died);
-    count_into(kCntAdvanced1, adv1);
-    count_into(kCntAdvanced2, adv2);
-    count_into(kCntRegen, regen);
-    const unsigned sidx = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(active ? idx_after_pass1 : 0));
+  // ---------------------------------------------------------------- statistics: packed warp reductions
+  if (kStats) {
+    const unsigned w0 = (is_reset ? 1u : 0u) | (terminated ? 1u << 8 : 0u) | (time_out ? 1u << 16 : 0u) |
+                        (fell ? 1u << 24 : 0u);
+    const unsigned w1 = (so_fast ? 1u : 0u) | (died ? 1u << 8 : 0u) | (adv1 ? 1u << 16 : 0u) |
+                        (adv2 ? 1u << 24 : 0u);
+    const unsigned w2 = (regen ? 1u : 0u) | (static_cast<unsigned>(active ? idx_after_pass1 : 0) << 8);
+    const unsigned s0 = __reduce_add_sync(0xffffffffu, w0);
+    const unsigned s1 = __reduce_add_sync(0xffffffffu, w1);
+    const unsigned s2 = __reduce_add_sync(0xffffffffu, w2);
     const unsigned lmax = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(active ? level : 0));
     float rs = active ? reward : 0.0f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
     if (lane == 0) {
-      atomicAdd(&misc->cnt[kCntSumIndex], sidx);
-      atomicMax(&misc->cnt[10], lmax);
-      atomicAdd(&misc->reward_sum, rs);
+      unsigned* wc = misc->wcnt[warp];
+      wc[kCntReset] = s0 & 255u;
+      wc[kCntTerminated] = (s0 >> 8) & 255u;
+      wc[kCntTimeOut] = (s0 >> 16) & 255u;
+      wc[kCntFell] = s0 >> 24;
+      wc[kCntSoFast] = s1 & 255u;
+      wc[kCntDied] = (s1 >> 8) & 255u;
+      wc[kCntAdvanced1] = (s1 >> 16) & 255u;
+      wc[kCntAdvanced2] = s1 >> 24;
+      wc[kCntRegen] = s2 & 255u;
+      wc[kCntSumIndex] = s2 >> 8;
+      wc[kCntLevelMax] = lmax;
+      misc->wreward[warp] = rs;
     }
   }
 
@@ -569,6 +619,27 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     row[53] = po.tb1.x; row[54] = po.tb1.y; row[55] = po.tb1.z;
     row[56] = po.tb2.x; row[57] = po.tb2.y; row[58] = po.tb2.z;
   }
+  if (MODE == kModeFused && rmask) {
+    // Joint part of the observation rows of the envs that reset, written by the whole warp: lane j produces
+    // joint j of the start pose (ENV:505-560, same Philox draws as the reset kernel) -- keeps the per-env joint
+    // loop above free of the divergent reset path.
+    __syncwarp();
+    unsigned todo = rmask;
+    while (todo) {
+      const int r = __ffs(todo) - 1;
+      todo &= todo - 1u;
+      const uint32_t gid_r = __shfl_sync(0xffffffffu, gid, r);
+      const bool mirror_r = __shfl_sync(0xffffffffu, mirror ? 1 : 0, r) != 0;
+      if (lane < kJ) {
+        const float u = philox_uniform(P.seed, step_now, kStreamReset, gid_r, 1 + lane);
+        const float val = reset_joint_value(P, lane, mirror_r, u);
+        float* row = s_obs + (warp * 32 + r) * kObs;
+        row[6 + lane] = scale_to_unit(val, P.joint_lower[lane], P.joint_upper[lane]);
+        const float jv0 = mirror_r ? 0.0f * P.mirror_sign[lane] : 0.0f;  // default_joint_vel is zero, ENV:513
+        row[6 + kJ + lane] = fminf(fmaxf(jv0 * P.dof_vel_scale, -5.0f), 5.0f);
+      }
+    }
+  }
   float* obs_dst = a.out.obs + env0 * kObs;
   const bool b_obs = ((reinterpret_cast<uintptr_t>(obs_dst) & 15u) == 0) && (((n_valid * kObs) & 3) == 0);
   if (b_obs) {
@@ -582,68 +653,62 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     __syncthreads();
     for (int i = tid; i < n_valid * kObs; i += kTile) obs_dst[i] = s_obs[i];
   }
+  if (kStats && tid <= kCntLevelMax) {  // CTA totals -> one replicated global slot (fire and forget)
+    const unsigned tot = tid == kCntLevelMax
+                             ? max(max(misc->wcnt[0][tid], misc->wcnt[1][tid]), max(misc->wcnt[2][tid], misc->wcnt[3][tid]))
+                             : misc->wcnt[0][tid] + misc->wcnt[1][tid] + misc->wcnt[2][tid] + misc->wcnt[3][tid];
+    const int slot = blockIdx.x & (kSlots - 1);
+    if (tot) {
+      if (tid == kCntLevelMax) atomicMax(&ctrl->slots[slot][tid], tot);
+      else atomicAdd(&ctrl->slots[slot][tid], tot);
+    }
+  }
+  if (kStats && tid == 32) {
+    const float rs = (misc->wreward[0] + misc->wreward[1]) + (misc->wreward[2] + misc->wreward[3]);
+    atomicAdd(&ctrl->slot_reward[blockIdx.x & (kSlots - 1)], rs);
+  }
   if (tid == 0 && b_obs) bulk_wait_read_all();  // shared memory must stay intact until the engine has read it
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
 template <int MODE>
-__global__ void __launch_bounds__(kTile, 4) k_step(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kTile, 5) k_step(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
-  const int tid = threadIdx.x;
-  if (tid == 0) mbar_init(smem_u32(&misc->mbar), 1);
-  if (tid < kNumCounters) misc->cnt[tid] = 0;
-  if (tid == 0) misc->reward_sum = 0.0f;
+  if (threadIdx.x == 0) mbar_init(smem_u32(&misc->mbar), 1);
   __syncthreads();
   uint32_t phase = 0;
   process_tile<MODE>(a, blockIdx.x, phase, smem);
-
-  if (MODE == kModeFused || MODE == kModePass1) {
-    Ctrl* ctrl = a.ws.ctrl;
-    __syncthreads();
-    const int slot = blockIdx.x & (kSlots - 1);
-    if (tid < kNumCounters && misc->cnt[tid]) {
-      if (tid == 10) atomicMax(&ctrl->slots[slot][tid], misc->cnt[tid]);
-      else atomicAdd(&ctrl->slots[slot][tid], misc->cnt[tid]);
-    }
-    if (tid == 32) atomicAdd(&ctrl->slot_reward[slot], misc->reward_sum);
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned t = atomicAdd(&ctrl->blocks_done, 1u);
-      misc->is_last = (t == gridDim.x - 1) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (misc->is_last) {
-      __threadfence();
-      fold_stats(ctrl, misc, a);
-      if (MODE == kModePass1 && tid == 0) {
-        ctrl->promote_cur = 0;       // applied by every CTA above; consumed
-        ctrl->step_counter += 1ull;  // 3-call path: a reset that follows draws at the advanced counter
-      }
-    }
-  }
 }
 
-// ENV:471-472 promotion rule on folded statistics (this shard's, or summed over ranks).
-__device__ __forceinline__ uint32_t promotion_decision(const AsParams& P, const AsStats& s) {
-  if (s.n_reset <= 0 || s.n_envs <= 0) return 0u;  // `_reset_idx` is only entered when an env resets, DRL:360
-  const float mean = static_cast<float>(s.sum_target_index) / static_cast<float>(s.n_envs);
-  return mean > P.progress_threshold ? 1u : 0u;
+// 3-call path: folds the statistics of pass 1, consumes the promotion every CTA applied, advances the counter.
+__global__ void __launch_bounds__(128) k_fold_pass1(Ctrl* ctrl, int64_t num_envs) {
+  __shared__ unsigned int fold[kNumCounters];
+  fold_stats(ctrl, fold, num_envs);
+  if (threadIdx.x == 0) {
+    ctrl->promote_cur = 0;
+    ctrl->step_counter += 1ull;  // a reset that follows draws at the advanced counter
+  }
 }
 
 // Fix-up + finish.  If NO env of this shard reset, the reference never runs pass 2 (DRL:360): redo every tile
 // without it from the untouched pre-step state buffer (rare: needs zero resets among all envs).  The last CTA
-// then publishes next step's promotion, flips the state parity and advances the Philox step counter.
+// then folds the statistics, publishes next step's promotion, flips the state parity and advances the Philox
+// step counter.
 __global__ void __launch_bounds__(kTile, 4) k_fixup_finish(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
   Ctrl* ctrl = a.ws.ctrl;
   const int tid = threadIdx.x;
-  const bool need_fixup = ctrl->stats.n_reset == 0 && !(a.P.flags & AS_FLAG_SKIP_PASS2);
+  if (tid < 32) {
+    const unsigned n = slot_sum(ctrl, kCntReset);
+    if (tid == 0) misc->is_last = n;  // reused as "number of resets this step"
+  }
+  if (tid == 0) mbar_init(smem_u32(&misc->mbar), 1);
+  __syncthreads();
+  const bool need_fixup = misc->is_last == 0 && !(a.P.flags & AS_FLAG_SKIP_PASS2);
+  __syncthreads();
   if (need_fixup) {
-    if (tid == 0) mbar_init(smem_u32(&misc->mbar), 1);
-    __syncthreads();
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       process_tile<kModeFixup>(a, tile, phase, smem);
@@ -654,8 +719,13 @@ __global__ void __launch_bounds__(kTile, 4) k_fixup_finish(const __grid_constant
   __syncthreads();
   if (tid == 0) {
     const unsigned t = atomicAdd(&ctrl->blocks_done2, 1u);
-    if (t == gridDim.x - 1) {
-      __threadfence();
+    misc->is_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (misc->is_last) {
+    __threadfence();
+    fold_stats(ctrl, misc->fold, a.num_envs);
+    if (tid == 0) {
       const AsStats* g = a.global_stats ? a.global_stats : &ctrl->stats;
       ctrl->promote_cur = promotion_decision(a.P, *g);
       ctrl->parity ^= 1u;

@@ -324,3 +324,34 @@ def test_action_path_and_mirror_rows():
     ma[:, left] = actions[:, right]
     ma[:, neg] = -actions[:, neg]
     exact(mdp.mirror_rows(actions.cuda(), "actions"), torch.vstack((actions, ma)), "mirrored actions")
+
+
+def test_joint_scaling_is_bit_exact():
+    """The kernel divides with precomputed reciprocals + a two-FMA correction (csrc scale_joint); the quotient must
+    be the correctly rounded one, i.e. bit-identical to torch's `2*(x-offset)/(hi-lo)` (feeds the at-limit count)."""
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+    from oracle import allsteps_oracle as ao
+
+    N = 1 << 18
+    sc = Scenario(N, seed=77)
+    mdp = make_cuda(N, 77, skip_pass2=True)
+    origins = sc.env_origins.cuda()
+    mdp.generate_stones(origins)
+    st = mdp.export_state()
+    out = StepBuffers(N, "cuda:0", reset_rows=False)
+    lim = sc.joint_limits
+    for rep in range(3):
+        phys = sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+        span = lim[:, 1] - lim[:, 0]
+        if rep == 1:  # hug the limits, where |scaled| ~ 0.99 .. 1.01 decides the at-limit count
+            side = torch.randint(0, 2, (N, 21), generator=sc.gen).float()
+            phys["joint_pos"] = lim[:, 0] + side * span + (torch.rand(N, 21, generator=sc.gen) - 0.5) * 0.02 * span
+        if rep == 2:  # wide dynamic range incl. tiny values
+            phys["joint_pos"] = torch.randn(N, 21, generator=sc.gen) * torch.logspace(-6, 1, 21)
+        views, keep = to_views(phys, origins, sc.body_indices)
+        mdp.step(views, keep["actions"], out)
+        torch.cuda.synchronize()
+        expect = ao.scale_to_unit(phys["joint_pos"], lim[:, 0], lim[:, 1])
+        keep_rows = ~(out.terminated | out.time_out).cpu()  # reset rows show the start pose instead
+        got = out.obs[:, 6:27].cpu()
+        assert torch.equal(got[keep_rows], expect[keep_rows]), "joint_pos_scaled is not bit-identical to torch"

@@ -43,5 +43,7 @@ def probe(N, steps=50, sets=4, warmup=10):
 
 
 if __name__ == "__main__":
-    for n in (4096, 65536, 262144, 1048576):
-        probe(n)
+    ns = [int(a) for a in sys.argv[1:] if a.isdigit()] or [4096, 65536, 262144, 1048576]
+    steps = 12 if "--short" in sys.argv else 50
+    for n in ns:
+        probe(n, steps=steps, warmup=4 if "--short" in sys.argv else 10)
