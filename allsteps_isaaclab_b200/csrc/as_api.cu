@@ -285,14 +285,14 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   const bool want_rows = reset_out && (reset_out->root_state || reset_out->joint_pos || reset_out->joint_vel ||
                                        reset_out->reset_ids || reset_out->n_reset);
   const bool regen_enabled = (h->params.flags & AS_FLAG_INTENDED_REGEN) != 0;
-  a.want_reset_list = want_rows ? 1 : 0;
+  a.want_reset_list = (reset_out && reset_out->reset_ids) ? 1 : 0;
+  if (want_rows) a.rows = *reset_out;  // start-pose rows are written by the step kernel itself
   k_step<kModeFused><<<a.num_tiles, kTile, kSmemBytes, s>>>(a);
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
-  if (want_rows || regen_enabled) {
+  if (regen_enabled) {  // kernel (b): warp-per-env stone regeneration over the compacted list
     ResetArgs r = make_reset_args(h, in->env_origins);
-    if (reset_out) r.out = *reset_out;
     r.fused = 1;
-    const int grid = grid_for(h->num_envs, 64, h->sm_count, 4);
+    const int grid = grid_for(h->num_envs, 64, h->sm_count, 8);
     k_reset_rows<<<grid, 256, 0, s>>>(r);
     if (int rc = check_launch(h, "k_reset_rows")) return rc;
   }
@@ -307,7 +307,7 @@ int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   StepArgs a = h->pending;  // the fix-up re-reads the inputs of the step it closes
   a.global_stats = global_stats;
-  const int grid = grid_for(a.num_tiles, 1, h->sm_count, 4);
+  const int grid = grid_for(a.num_tiles, 1, h->sm_count, 1);
   k_fixup_finish<<<grid, kTile, kSmemBytes, s>>>(a);
   h->pending_valid = false;
   return check_launch(h, "k_fixup_finish");

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const unsigned long long step = ctrl->step_counter;
-  const int64_t n_reset = a.fused ? static_cast<int64_t>(ctrl->n_reset_list) : a.n_ids;
+  const int64_t n_reset = a.fused ? 0 : a.n_ids;  // fused: the step kernel already wrote the start-pose rows
   // promotion decided in THIS step is already in force when stones are regenerated (ENV:471 precedes ENV:500)
   // (3-call path: as_reset ran k_decide_promotion first and left the decision in promote_cur)
   int promote_now;
@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
   }
   const uint32_t parity = ctrl->parity;
   uint2* st_cur = a.fused ? a.ws.state[parity ^ 1u] : a.ws.state[parity];  // fused: the step wrote the other buffer
+  float t_lo, t_hi, t_pose, t_pose_m, t_vel_m;  // this lane's joint constants, fetched once
+  load_reset_tables(P, lane, t_lo, t_hi, t_pose, t_pose_m, t_vel_m);
 
   for (int64_t w = warp; w < n_reset; w += n_warps) {
     const int64_t e = a.fused ? a.ws.reset_ids[w] : a.env_ids[w];
@@ -112,8 +114,9 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
     const float ox = a.env_origins[e * 3], oy = a.env_origins[e * 3 + 1], oz = a.env_origins[e * 3 + 2];
     if (lane < kJ) {
       const float u = philox_uniform(P.seed, step, kStreamReset, gid, 1 + lane);
-      if (a.out.joint_pos) a.out.joint_pos[row * kJ + lane] = reset_joint_value(P, lane, mirror, u);
-      if (a.out.joint_vel) a.out.joint_vel[row * kJ + lane] = mirror ? 0.0f * P.mirror_sign[lane] : 0.0f;
+      if (a.out.joint_pos)
+        a.out.joint_pos[row * kJ + lane] = reset_joint_value(P, mirror ? t_pose_m : t_pose, t_lo, t_hi, u);
+      if (a.out.joint_vel) a.out.joint_vel[row * kJ + lane] = mirror ? t_vel_m : 0.0f;
     }
     if (a.out.root_state && lane < AS_ROOT_STATE_DIM) {
       const float z = mirror ? -0.0f : 0.0f;

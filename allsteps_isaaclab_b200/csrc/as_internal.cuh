@@ -117,7 +117,8 @@ struct StepArgs {
   int64_t num_envs;
   int64_t env_id_offset;
   int32_t num_tiles;
-  int32_t want_reset_list;            // fused: append reset env ids to ws.reset_ids
+  int32_t want_reset_list;            // fused: compact the ids of the envs that reset
+  AsResetOut rows;                    // fused: start-pose rows for PhysX, written at the env's own row (optional)
 };
 
 struct ResetArgs {

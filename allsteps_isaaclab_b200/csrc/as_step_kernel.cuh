@@ -34,11 +34,17 @@ constexpr int kOffRq = kOffRp + kTile * 3 * 4;
 constexpr int kOffRv = kOffRq + kTile * 4 * 4;
 constexpr int kOffBody = kOffRv + kTile * 3 * 4;
 constexpr int kOffMisc = kOffBody + kTile * 9 * 4;
-constexpr int kSmemBytes = kOffMisc + 384;
+constexpr int kSmemBytes = kOffMisc + 1024;
 static_assert(kTile * kObs * 4 <= kOffRp, "observation tile must fit over the joint/action tiles it aliases");
 static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffRq % 16 == 0 &&
                   kOffRv % 16 == 0 && kOffBody % 16 == 0 && kOffMisc % 16 == 0,
               "bulk copies need 16-byte aligned shared addresses");
+
+// Per-joint tables of the reset pose, one entry per lane.  Lane-indexed reads of kernel parameters would go
+// through the constant bank, which serialises divergent addresses; shared memory / registers do not.
+struct ResetTables {
+  float lower[32], upper[32], pose[32], pose_mirrored[32], vel_mirrored[32];
+};
 
 struct Misc {  // lives at kOffMisc, never aliased
   unsigned long long mbar;
@@ -46,8 +52,9 @@ struct Misc {  // lives at kOffMisc, never aliased
   float wreward[kTile / 32];
   unsigned int is_last;
   unsigned int fold[kNumCounters];
+  ResetTables rt;
 };
-static_assert(sizeof(Misc) <= 384, "misc block");
+static_assert(sizeof(Misc) <= 1024, "misc block");
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -192,14 +199,24 @@ __device__ __forceinline__ float scale_joint(const JointConsts& C, int j, float 
   return fmaf(e, C.inv_range[j], q0);
 }
 
-// Start-pose joint value of a reset env (ENV:505-560): running-start pose, optional mirror, uniform noise, clip.
-__device__ __forceinline__ float reset_joint_value(const AsParams& P, int j, bool mirror, float u) {
-  const int src = mirror ? P.mirror_src[j] : j;
-  const float base = mirror ? P.reset_pose[src] * P.mirror_sign[j] : P.reset_pose[src];
+// Start-pose joint value of a reset env (ENV:505-560): running-start pose (already mirrored or not), uniform
+// noise, clip in the unit range.  `base`, `lo`, `hi` are this joint's table entries.
+__device__ __forceinline__ float reset_joint_value(const AsParams& P, float base, float lo, float hi, float u) {
   const float noisy = base + (u * P.noise_span + P.noise_lower);
-  float unit = scale_to_unit(noisy, P.joint_lower[j], P.joint_upper[j]);
+  float unit = scale_to_unit(noisy, lo, hi);
   unit = fminf(fmaxf(unit, P.clip_lower), P.clip_upper);
-  return unscale_from_unit(unit, P.joint_lower[j], P.joint_upper[j]);
+  return unscale_from_unit(unit, lo, hi);
+}
+
+// Fills one lane's entries of the reset tables (called once per CTA by the first warp, or kept in registers).
+__device__ __forceinline__ void load_reset_tables(const AsParams& P, int lane, float& lo, float& hi, float& pose,
+                                                  float& pose_m, float& vel_m) {
+  const int j = lane < kJ ? lane : 0;
+  lo = P.joint_lower[j];
+  hi = P.joint_upper[j];
+  pose = P.reset_pose[j];
+  pose_m = P.reset_pose[P.mirror_src[j]] * P.mirror_sign[j];  // ENV:522-526
+  vel_m = 0.0f * P.mirror_sign[j];                             // default_joint_vel is zero, ENV:513,528-532
 }
 
 // ------------------------------------------------------------------------------------------------ statistics
@@ -212,18 +229,18 @@ __device__ __forceinline__ unsigned slot_sum(const Ctrl* ctrl, int which) {
 // Folds the slots into ctrl->stats and clears them.  Called by one CTA (>= 64 threads) after the step kernel.
 __device__ __forceinline__ void fold_stats(Ctrl* ctrl, unsigned int* fold, int64_t num_envs) {
   const int t = threadIdx.x;
-  if (t < kNumCounters) {
-    unsigned int acc = 0;
-    if (t == kCntLevelMax) {
-      for (int s = 0; s < kSlots; ++s) acc = max(acc, atomicExch(&ctrl->slots[s][t], 0u));
-    } else {
-      for (int s = 0; s < kSlots; ++s) acc += atomicExch(&ctrl->slots[s][t], 0u);
-    }
-    fold[t] = acc;
+  const int lane = t & 31;
+  // one warp per counter, one lane per slot: a single atomic round trip per counter instead of 32 in sequence
+  for (int c = t >> 5; c < kNumCounters; c += blockDim.x >> 5) {
+    const unsigned v = atomicExch(&ctrl->slots[lane][c], 0u);
+    const unsigned r = c == kCntLevelMax ? __reduce_max_sync(0xffffffffu, v) : __reduce_add_sync(0xffffffffu, v);
+    if (lane == 0) fold[c] = r;
   }
   float rsum = 0.0f;
-  if (t == 32) {
-    for (int s = 0; s < kSlots; ++s) rsum += atomicExch(&ctrl->slot_reward[s], 0.0f);
+  if (t >= 32 && t < 64) {
+    rsum = atomicExch(&ctrl->slot_reward[lane], 0.0f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
   }
   __syncthreads();
   if (t == 0) {
@@ -555,7 +572,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       unsigned base = 0;
       if (lane == leader) base = atomicAdd(&ctrl->n_reset_list, __popc(rmask));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (is_reset) a.ws.reset_ids[base + __popc(rmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
+      int32_t* ids_dst = a.rows.reset_ids ? a.rows.reset_ids : a.ws.reset_ids;
+      if (is_reset) ids_dst[base + __popc(rmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
     }
     const unsigned gmask = __ballot_sync(0xffffffffu, regen);
     if (gmask) {
@@ -620,9 +638,9 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     row[56] = po.tb2.x; row[57] = po.tb2.y; row[58] = po.tb2.z;
   }
   if (MODE == kModeFused && rmask) {
-    // Joint part of the observation rows of the envs that reset, written by the whole warp: lane j produces
-    // joint j of the start pose (ENV:505-560, same Philox draws as the reset kernel) -- keeps the per-env joint
-    // loop above free of the divergent reset path.
+    // Envs that reset are finished by the whole warp: lane j produces joint j of the start pose (ENV:505-560) and
+    // stores it both into the observation row (as joint_pos_scaled, what pass 2 sees) and, coalesced, into the
+    // start-pose rows handed to PhysX (ENV:563-565) -- keeps the per-env joint loop free of the divergent path.
     __syncwarp();
     unsigned todo = rmask;
     while (todo) {
@@ -631,12 +649,31 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       const uint32_t gid_r = __shfl_sync(0xffffffffu, gid, r);
       const bool mirror_r = __shfl_sync(0xffffffffu, mirror ? 1 : 0, r) != 0;
       if (lane < kJ) {
+        const ResetTables& T = misc->rt;
         const float u = philox_uniform(P.seed, step_now, kStreamReset, gid_r, 1 + lane);
-        const float val = reset_joint_value(P, lane, mirror_r, u);
+        const float val = reset_joint_value(P, mirror_r ? T.pose_mirrored[lane] : T.pose[lane], T.lower[lane],
+                                            T.upper[lane], u);
         float* row = s_obs + (warp * 32 + r) * kObs;
-        row[6 + lane] = scale_to_unit(val, P.joint_lower[lane], P.joint_upper[lane]);
-        const float jv0 = mirror_r ? 0.0f * P.mirror_sign[lane] : 0.0f;  // default_joint_vel is zero, ENV:513
+        row[6 + lane] = scale_to_unit(val, T.lower[lane], T.upper[lane]);
+        const float jv0 = mirror_r ? T.vel_mirrored[lane] : 0.0f;
         row[6 + kJ + lane] = fminf(fmaxf(jv0 * P.dof_vel_scale, -5.0f), 5.0f);
+        const int64_t e_r = env0 + warp * 32 + r;
+        if (a.rows.joint_pos) a.rows.joint_pos[e_r * kJ + lane] = val;
+        if (a.rows.joint_vel) a.rows.joint_vel[e_r * kJ + lane] = jv0;
+      }
+      if (a.rows.root_state && lane < AS_ROOT_STATE_DIM) {
+        const int64_t e_r = env0 + warp * 32 + r;
+        const float z = mirror_r ? -0.0f : 0.0f;  // ENV:535 flips the sign of the (zero) vector part
+        float val = 0.0f;
+        if (lane < 3) {
+          const float d = lane == 0 ? P.default_root_pos[0] : (lane == 1 ? P.default_root_pos[1] : P.default_root_pos[2]);
+          val = d + __ldg(a.in.env_origins + e_r * 3 + lane);  // ENV:515
+        } else if (lane == 3) {
+          val = 1.0f;
+        } else if (lane <= 6) {
+          val = z;
+        }
+        a.rows.root_state[e_r * AS_ROOT_STATE_DIM + lane] = val;
       }
     }
   }
@@ -676,6 +713,11 @@ __global__ void __launch_bounds__(kTile, 5) k_step(const __grid_constant__ StepA
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
   if (threadIdx.x == 0) mbar_init(smem_u32(&misc->mbar), 1);
+  if (MODE == kModeFused && threadIdx.x < 32) {
+    ResetTables& T = misc->rt;
+    const int l = threadIdx.x;
+    load_reset_tables(a.P, l, T.lower[l], T.upper[l], T.pose[l], T.pose_mirrored[l], T.vel_mirrored[l]);
+  }
   __syncthreads();
   uint32_t phase = 0;
   process_tile<MODE>(a, blockIdx.x, phase, smem);
@@ -728,6 +770,7 @@ __global__ void __launch_bounds__(kTile, 4) k_fixup_finish(const __grid_constant
     if (tid == 0) {
       const AsStats* g = a.global_stats ? a.global_stats : &ctrl->stats;
       ctrl->promote_cur = promotion_decision(a.P, *g);
+      if (a.rows.n_reset) *a.rows.n_reset = static_cast<int32_t>(a.want_reset_list ? ctrl->n_reset_list : ctrl->stats.n_reset);
       ctrl->parity ^= 1u;
       ctrl->step_counter += 1ull;
       ctrl->n_reset_list = 0;

@@ -42,7 +42,20 @@ def probe(N, steps=50, sets=4, warmup=10):
           f"resets/step={stats['n_reset']}  launches/step={mdp.launch_count/(steps+warmup):.1f}", flush=True)
 
 
+def set_l2_fetch_granularity(nbytes):
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    torch.cuda.init(); torch.zeros(1, device="cuda")
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(nbytes))  # cudaLimitMaxL2FetchGranularity
+    val = ctypes.c_size_t(0)
+    rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+    print("cudaLimitMaxL2FetchGranularity ->", val.value, "rc", rc, flush=True)
+
+
 if __name__ == "__main__":
+    for a in sys.argv[1:]:
+        if a.startswith("--l2gran="):
+            set_l2_fetch_granularity(int(a.split("=")[1]))
     ns = [int(a) for a in sys.argv[1:] if a.isdigit()] or [4096, 65536, 262144, 1048576]
     steps = 12 if "--short" in sys.argv else 50
     for n in ns:
