@@ -1,0 +1,70 @@
+"""CPU, build container only: the oracle port against the UNMODIFIED reference executed live (skipped where
+/root/reference is not mounted, e.g. on the GPU box -- the golden fixtures cover that case)."""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.reference_available(), reason="reference checkout not mounted")
+
+
+@pytest.mark.parametrize("num_envs,steps,high", [(64, 25, False), (1024, 10, True)])
+def test_port_is_bit_identical_to_live_reference(num_envs, steps, high):
+    from allsteps_isaaclab_b200.config import BODY_NAMES, JOINT_NAMES
+    from oracle import allsteps_oracle as ao
+    from oracle import ref_fake_env as rf
+    from scenario import Scenario, install_mdp_state
+
+    sc = Scenario(num_envs, seed=31 + num_envs, full_bodies=True)
+    su = sc.stone_uniforms(0)
+    st0 = sc.initial_mdp_state()
+    if high:
+        st0["curr_target_index"] = torch.randint(12, 20, (num_envs,), generator=sc.gen)
+    orc = ao.AllstepsOracle(sc.cfg, num_envs, sc.env_origins, sc.joint_limits, sc.body_indices, su)
+    phys = sc.physics(orc.steps_pos, st0["curr_target_index"], st0["swing_leg"])
+    world = dict(phys)
+    world["env_origins"] = sc.env_origins
+    world["joint_pos_limits"] = sc.joint_limits.unsqueeze(0).repeat(num_envs, 1, 1)
+    ref = rf.make_reference_env(world, sc.cfg, BODY_NAMES, JOINT_NAMES, su)
+    assert torch.equal(ref.steps_pos, orc.steps_pos) and torch.equal(ref.steps_dphi, orc.steps_dphi)
+    install_mdp_state(ref, st0)
+    install_mdp_state(orc, st0)
+    for step in range(steps):
+        phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+        m, n = sc.reset_uniforms(step)
+        rf.load_physics(ref, phys)
+        r = rf.step_mdp(ref, phys["actions"], rf.UniformTables(m, n, sc.stone_uniforms(step)))
+        o = orc.step(phys, phys["actions"], m, n, sc.stone_uniforms(step))
+        for a, b, what in zip(r, o, ("obs", "reward", "terminated", "time_out", "reset ids")):
+            assert torch.equal(a, b), f"step {step}: {what}"
+        for k in ("curr_target_index", "prev_target_index", "next_target_index", "swing_leg", "target_reach_count",
+                  "episode_length_buf", "curriculum", "potentials", "old_potentials", "targets_w", "targets_b",
+                  "foot_contact"):
+            assert torch.equal(getattr(ref, k), getattr(orc, k)), f"step {step}: {k}"
+        if len(r[4]):
+            c = ref.robot.rec.calls
+            assert torch.equal(c["root_pose"][0], orc.reset_writes["root_pose"])
+            assert torch.equal(c["joint_state"][0], orc.reset_writes["joint_pos"])
+        assert torch.equal(ref.applied_gain_curriculum[ref.curriculum].unsqueeze(-1) * ref.joint_gears.unsqueeze(0)
+                           * ref.actions, orc.joint_efforts())
+
+
+def test_reference_cfg_constants_match_product_config():
+    """The product's constants (allsteps_isaaclab_b200/config.py) against the reference's own cfg class / env."""
+    from allsteps_isaaclab_b200.config import AllstepsCfg
+
+    ref = ref_loader.load_reference()
+    R, C = ref.AllstepsEnvCfg, AllstepsCfg()
+    assert R.num_steps == C.num_steps and R.step_radius == C.step_radius
+    assert list(R.joint_gears) == list(C.joint_gears)
+    assert tuple(R.right_body_names) == C.right_body_names and tuple(R.left_body_names) == C.left_body_names
+    assert tuple(R.negation_body_names) == C.negation_body_names
+    for k in ("energy_cost_scale", "actions_cost_scale", "alive_reward_scale", "dof_vel_scale",
+              "joint_at_limit_cost_scale", "death_cost", "termination_height_absolute", "episode_length_s",
+              "decimation"):
+        assert getattr(R, k) == getattr(C, k), k
+    assert tuple(R.initial_joint_angle_range) == C.initial_joint_angle_range
+    assert tuple(R.initial_joint_angle_clip_range) == C.initial_joint_angle_clip_range
+    assert ref.env_module.EPSILON == C.contact_epsilon
