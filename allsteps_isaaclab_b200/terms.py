@@ -1,0 +1,180 @@
+"""B2 face: Isaac Lab manager terms `func(env, **params) -> torch.Tensor` for the Allsteps task.
+
+The reference task is a `DirectRLEnv`; `BASELINE.json:north_star` also asks for the manager-term surface
+(ObservationManager / RewardManager / TerminationManager / EventManager reset / CurriculumManager).  These functions
+satisfy the call conventions of the reference's managers:
+
+    observation  f(env, **params) -> (N, d)      observation_manager.py:308   (cat order = cfg order => 59 columns)
+    reward       f(env, **params) -> (N,)        reward_manager.py:148        (manager multiplies by weight * dt)
+    termination  f(env, **params) -> (N,) bool   termination_manager.py:165
+    event reset  f(env, env_ids, **params)       event_manager.py:240
+    curriculum   f(env, env_ids, **params)       curriculum_manager.py:138
+
+All terms of one env step are slices of ONE kernel launch: the first term that needs results runs pass 1 (cached on
+`env.common_step_counter`), `reset_allsteps` runs the masked reset + pass 2, observation terms slice the observation
+buffer.  `env` needs: `num_envs`, `device`, `common_step_counter`, `episode_length_buf`, `scene` holding
+`env_origins` and the entities named by the params (`scene["robot"]`, `scene["foot_contacts_left/right"]`), and
+`action_manager.action` (or `env.actions`).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .config import AllstepsCfg
+from .mdp import AllstepsMDP, PhysicsViews, StepBuffers
+
+_KEY = "_allsteps_b200"
+
+# observation columns, ENV:330-343
+OBS_SLICES = {"torso_to_feet_height": (0, 1), "root_roll_pitch": (1, 3), "root_lin_vel_b": (3, 6),
+              "joint_pos_scaled": (6, 27), "joint_vel_scaled_clipped": (27, 48), "foot_contact": (48, 50),
+              "stone_targets_b": (50, 59)}
+# AsStepOut.reward_terms columns (costs are positive numbers)
+REWARD_COLUMNS = {"alive": 0, "progress": 1, "roll_cost": 2, "pitch_cost": 3, "speed_cost": 4, "energy_cost": 5,
+                  "action_cost": 6, "joint_at_limit_cost": 7, "step_reward": 8, "target_bonus": 9}
+
+
+class _Binding:
+    """Per-env glue shared by all terms: the MDP object, the output buffers and the per-step cache."""
+
+    def __init__(self, env, robot="robot", left="foot_contacts_left", right="foot_contacts_right", seed=0,
+                 task_cfg: Optional[AllstepsCfg] = None):
+        self.cfg = task_cfg or AllstepsCfg()
+        self.names = (robot, left, right)
+        dev = torch.device(env.device)
+        self.mdp = AllstepsMDP(env.num_envs, device=dev, cfg=self.cfg, seed=seed)
+        self.buf = StepBuffers(env.num_envs, dev, reward_terms=True)
+        rob = env.scene[robot]
+        bn = list(rob.data.body_names)
+        self.body_rows = (bn.index(self.cfg.foot_names[0]), bn.index(self.cfg.foot_names[1]),
+                          bn.index(self.cfg.torso_name))
+        self.mdp.generate_stones(env.scene.env_origins)
+        self.epoch = None
+        self.fell = self.so_fast = self.died = None
+
+    def views(self, env) -> PhysicsViews:
+        robot, left, right = (env.scene[n] for n in self.names)
+        d = robot.data
+        return PhysicsViews(root_pos_w=d.root_pos_w, root_quat_w=d.root_quat_w, root_lin_vel_w=d.root_lin_vel_w,
+                            body_pos_w=d.body_pos_w, joint_pos=d.joint_pos, joint_vel=d.joint_vel,
+                            force_matrix_right=right.data.force_matrix_w, force_matrix_left=left.data.force_matrix_w,
+                            env_origins=env.scene.env_origins, body_rows=self.body_rows)
+
+    def ensure_pass1(self, env):
+        if self.epoch == env.common_step_counter:
+            return
+        am = getattr(env, "action_manager", None)
+        actions = am.action if am is not None else env.actions
+        self.mdp.pass1(self.views(env), actions, self.buf, episode_length=env.episode_length_buf)
+        self.epoch = env.common_step_counter
+
+
+def binding(env, **kw) -> _Binding:
+    b = getattr(env, _KEY, None)
+    if b is None:
+        b = _Binding(env, **kw)
+        setattr(env, _KEY, b)
+    return b
+
+
+# ---------------------------------------------------------------------------------------------- observations
+def _obs(env, name: str) -> torch.Tensor:
+    b = binding(env)
+    b.ensure_pass1(env)  # no-op when termination/reward terms already ran this step (the usual order)
+    lo, hi = OBS_SLICES[name]
+    return b.buf.obs[:, lo:hi]
+
+
+def torso_to_feet_height(env) -> torch.Tensor:  # ENV:332
+    return _obs(env, "torso_to_feet_height")
+
+
+def root_roll_pitch(env) -> torch.Tensor:  # ENV:333-334
+    return _obs(env, "root_roll_pitch")
+
+
+def root_lin_vel_b(env) -> torch.Tensor:  # ENV:335
+    return _obs(env, "root_lin_vel_b")
+
+
+def joint_pos_scaled(env) -> torch.Tensor:  # ENV:336
+    return _obs(env, "joint_pos_scaled")
+
+
+def joint_vel_scaled_clipped(env) -> torch.Tensor:  # ENV:337
+    return _obs(env, "joint_vel_scaled_clipped")
+
+
+def foot_contact(env) -> torch.Tensor:  # ENV:338
+    return _obs(env, "foot_contact")
+
+
+def stone_targets_b(env) -> torch.Tensor:  # ENV:339
+    return _obs(env, "stone_targets_b")
+
+
+OBSERVATION_TERMS = (torso_to_feet_height, root_roll_pitch, root_lin_vel_b, joint_pos_scaled,
+                     joint_vel_scaled_clipped, foot_contact, stone_targets_b)
+
+
+# ---------------------------------------------------------------------------------------------- rewards
+def allsteps_total_reward(env) -> torch.Tensor:
+    """ENV:377-394 in one term.  RewardManager multiplies by `weight * dt` (reward_manager.py:148): use
+    weight = 1 / env.step_dt to reproduce the DirectRLEnv reward."""
+    b = binding(env)
+    b.ensure_pass1(env)
+    return b.buf.reward
+
+
+def reward_term(env, name: str) -> torch.Tensor:
+    """One of the ten terms of ENV:350-375 (see REWARD_COLUMNS; costs are returned positive, give them a negative
+    weight).  Their signed sum equals `allsteps_total_reward` for envs that did not terminate."""
+    b = binding(env)
+    b.ensure_pass1(env)
+    return b.buf.reward_terms[:, REWARD_COLUMNS[name]]
+
+
+# ---------------------------------------------------------------------------------------------- terminations
+def allsteps_terminated(env) -> torch.Tensor:  # ENV:401-405 fell | so_fast | died
+    b = binding(env)
+    b.ensure_pass1(env)
+    return b.buf.terminated
+
+
+def allsteps_time_out(env) -> torch.Tensor:
+    """ENV:399: `episode_length_buf >= max_episode_length - 1` (the stock mdp.time_out uses `>= max`)."""
+    b = binding(env)
+    b.ensure_pass1(env)
+    return b.buf.time_out
+
+
+# ---------------------------------------------------------------------------------------------- reset event
+def reset_allsteps(env, env_ids: torch.Tensor, write_to_sim: bool = True):
+    """EventManager `mode="reset"` term, ENV:469-567: MDP reset + start pose + PhysX writes + pass 2."""
+    b = binding(env)
+    b.ensure_pass1(env)
+    if env_ids is None:
+        env_ids = torch.arange(env.num_envs, device=env.device)
+    if len(env_ids) == 0:
+        return
+    b.mdp.reset(env.scene.env_origins, env_ids, b.buf, episode_length=env.episode_length_buf)
+    k = len(env_ids)
+    if write_to_sim:
+        robot = env.scene[b.names[0]]
+        root = b.buf.reset_root_state[:k]
+        robot.write_root_pose_to_sim(root[:, :7], env_ids)
+        robot.write_root_velocity_to_sim(root[:, 7:], env_ids)
+        robot.write_joint_state_to_sim(b.buf.reset_joint_pos[:k], b.buf.reset_joint_vel[:k], None, env_ids)
+    b.mdp.pass2(b.views(env), b.buf)
+
+
+# ---------------------------------------------------------------------------------------------- curriculum
+def allsteps_level(env, env_ids: torch.Tensor) -> Dict[str, float]:
+    """CurriculumManager term (logged under Curriculum/<name>, curriculum_manager.py:103-117): the current level
+    and the statistic the promotion rule of ENV:471 looks at.  The promotion itself happens inside `reset`."""
+    b = binding(env)
+    s = b.mdp.read_stats()
+    n = max(int(s["n_envs"]), 1)
+    return {"level": float(s["level"]), "mean_target_index": float(s["sum_target_index"]) / n}
