@@ -23,7 +23,7 @@ FLAG_SKIP_PASS2 = 1 << 1
 FLAG_GRID_CURRICULUM = 1 << 2
 
 LIB_NAME = "liballsteps_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+LIB_PATH = os.environ.get("ALLSTEPS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 _f = C.c_float
 _i32 = C.c_int32

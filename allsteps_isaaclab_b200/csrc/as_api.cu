@@ -225,6 +225,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->ws.state[0] = reinterpret_cast<uint2*>(base + l.state0_off);
   h->ws.state[1] = reinterpret_cast<uint2*>(base + l.state1_off);
   h->ws.stones = reinterpret_cast<float4*>(base + l.stones_off);
+  h->ws.window = reinterpret_cast<float4*>(base + l.window_off);
   h->ws.reset_ids = reinterpret_cast<int32_t*>(base + l.reset_ids_off);
   h->ws.regen_ids = reinterpret_cast<int32_t*>(base + l.regen_ids_off);
   build_mirror_tables(h);

@@ -59,6 +59,16 @@ __device__ __forceinline__ void generate_stones_warp(const AsParams& P, int lane
   if (lane < kS) out_row[lane] = make_float4(x + origin.x, y + origin.y, z + origin.z, phi);  // ENV:111
 }
 
+// Rebuilds one env's stone window from its stone row (lanes 0..3); call after the row was (re)written.
+__device__ __forceinline__ void rebuild_window_warp(const float4* stone_row, float4* window_row, int idx, int lane) {
+  __syncwarp();
+  if (lane < 4) {
+    float4 v = stone_row[window_slot_stone(idx, lane)];
+    if (lane == 0) v.w = __int_as_float(idx);
+    window_row[lane] = v;
+  }
+}
+
 __device__ __forceinline__ void stone_draws(const ResetArgs& a, unsigned long long step, int64_t e, uint32_t gid,
                                             int lane, float& u_dr, float& u_dphi, float& u_dth) {
   u_dr = u_dphi = u_dth = 0.0f;
@@ -147,6 +157,7 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
         generate_stones_warp(P, lane, level, Vec3{ox, oy, oz}, u0, u1, u2, a.ws.stones + e * kS);
         if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->stats.n_regenerated), 1ull);
       }
+      rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, 1, lane);
     }
   }
   if (a.fused) {
@@ -159,6 +170,7 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
       float u0, u1, u2;
       stone_draws(a, step, e, gid, lane, u0, u1, u2);
       generate_stones_warp(P, lane, level, origin, u0, u1, u2, a.ws.stones + e * kS);
+      rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, 1, lane);  // a reset env restarts at index 1
     }
   }
   if (a.out.n_reset && blockIdx.x == 0 && threadIdx.x == 0) *a.out.n_reset = static_cast<int32_t>(n_reset);
@@ -182,6 +194,7 @@ __global__ void __launch_bounds__(256) k_generate_stones(const __grid_constant__
     float u0, u1, u2;
     stone_draws(a, step, e, gid, lane, u0, u1, u2);
     generate_stones_warp(a.P, lane, level, origin, u0, u1, u2, a.ws.stones + e * kS);
+    rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, state_idx(st[e].x), lane);
   }
 }
 
@@ -288,6 +301,11 @@ __global__ void __launch_bounds__(256) k_import(const __grid_constant__ AsParams
         if (src.steps_dphi) v.w = src.steps_dphi[e * kS + s];
         ws.stones[e * kS + s] = v;
       }
+    }
+    for (int k = 0; k < 4; ++k) {  // index and/or stones may have changed: rebuild the window
+      float4 v = ws.stones[e * kS + window_slot_stone(idx, k)];
+      if (k == 0) v.w = __int_as_float(idx);
+      ws.window[e * 4 + k] = v;
     }
   }
 }

@@ -53,6 +53,12 @@ __host__ __device__ inline int state_level(uint32_t w) { return static_cast<int>
 __host__ __device__ inline int state_ep(uint32_t w) { return static_cast<int>(w >> 12); }
 constexpr int kMaxEpisodeLength = (1 << 20) - 2;
 
+// The stone window: a validated cache of the four stones around `curr_target_index` so that the step reads one
+// coalesced 64-byte record per env instead of three scattered 16-byte gathers out of the 320-byte stone row.
+// It is valid iff the tag equals the env's current index; every writer of the index or of the stones rewrites it,
+// and a reader that finds a stale tag falls back to gathering from `stones` (which is always authoritative).
+__device__ __forceinline__ int window_slot_stone(int idx, int slot) { return min(max(idx - 1 + slot, 0), kS - 1); }
+
 // Device control block at the head of the workspace.
 struct Ctrl {
   uint32_t parity;        // state buffer holding the CURRENT MDP state (fused path ping-pongs)
@@ -73,12 +79,13 @@ struct Workspace {
   Ctrl* ctrl;
   uint2* state[2];    // (N) packed state / potentials, ping-pong
   float4* stones;     // (N,S) x,y,z (world frame), cumulative yaw
+  float4* window;     // (N,4) cache of stones idx-1, idx, idx+1, idx+2 (clamped); entry 0's .w holds idx as a tag
   int32_t* reset_ids; // (N)
   int32_t* regen_ids; // (N)
 };
 
 struct WorkspaceLayout {
-  int64_t ctrl_off, state0_off, state1_off, stones_off, reset_ids_off, regen_ids_off, total;
+  int64_t ctrl_off, state0_off, state1_off, stones_off, window_off, reset_ids_off, regen_ids_off, total;
 };
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -94,6 +101,8 @@ inline WorkspaceLayout workspace_layout(int64_t n) {
   off = align_up(off + n * 8, 256);
   l.stones_off = off;
   off = align_up(off + n * kS * 16, 256);
+  l.window_off = off;
+  off = align_up(off + n * 4 * 16, 256);
   l.reset_ids_off = off;
   off = align_up(off + n * 4, 256);
   l.regen_ids_off = off;

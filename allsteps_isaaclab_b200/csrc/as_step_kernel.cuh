@@ -108,6 +108,35 @@ __device__ __forceinline__ void coop_load(float* dst, const float* base, int64_t
   }
 }
 
+// Norm of the 12-byte contact-force vector of stone `idx` inside one env's (S,3) row.  When the row is 16-byte
+// aligned the vector is fetched with one or two aligned 128-bit loads instead of three scalar ones: the same
+// sectors, half the requests through the L1 miss path.
+__device__ __forceinline__ float contact_norm(const float* row, int idx, bool aligned16) {
+  float x, y, z;
+  if (aligned16) {
+    const int o = idx * 3;
+    const int k = o & 3;
+    const float4* c = reinterpret_cast<const float4*>(row) + (o >> 2);
+    const float4 c0 = __ldg(c);
+    if (k == 0) {
+      x = c0.x; y = c0.y; z = c0.z;
+    } else if (k == 1) {
+      x = c0.y; y = c0.z; z = c0.w;
+    } else {
+      const float4 c1 = __ldg(c + 1);
+      if (k == 2) {
+        x = c0.z; y = c0.w; z = c1.x;
+      } else {
+        x = c0.w; y = c1.x; z = c1.y;
+      }
+    }
+  } else {
+    const float* f = row + idx * 3;
+    x = __ldg(f); y = __ldg(f + 1); z = __ldg(f + 2);
+  }
+  return norm3(x, y, z);  // ENV:421-424
+}
+
 // ------------------------------------------------------------------------------------------------ one pass
 struct Mdp {
   int idx, leg, count;
@@ -335,14 +364,21 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   uint2* st_out = kPingPong ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
   const float4* stones = a.ws.stones + e * kS;
   auto stone_at = [&](int i) -> float4 { return __ldg(stones + i); };
+  float4* wrow = a.ws.window + e * 4;
+  const bool contact_aligned = ((reinterpret_cast<uintptr_t>(a.in.contact_right) | reinterpret_cast<uintptr_t>(
+                                    a.in.contact_left)) & 15u) == 0 &&
+                               ((a.in.contact_right_stride | a.in.contact_left_stride) & 3) == 0;
 
   Mdp m{1, 0, 0, 0.0f};
   int level = 0, ep = 0;
-  float4 s_prev = make_float4(0, 0, 0, 0), s_curr = s_prev, s_next = s_prev;
+  float4 s_prev = make_float4(0, 0, 0, 0), s_curr = s_prev, s_next = s_prev, s_next2 = s_prev;
+  bool win_valid = false, win_dirty = false, have_next2 = false;
   float f_r = 0.0f, f_l = 0.0f;
   const float* cr_row = nullptr;
   const float* cl_row = nullptr;
   if (active) {
+    // the stone window does not depend on the state word: its four coalesced loads go out first
+    const float4 w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3];
     const uint2 sw = st_in[e];
     m.idx = state_idx(sw.x);
     m.leg = state_leg(sw.x);
@@ -358,16 +394,31 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
     cr_row = a.in.contact_right + e * a.in.contact_right_stride;
     cl_row = a.in.contact_left + e * a.in.contact_left_stride;
-    const float* fr = cr_row + m.idx * 3;
-    const float* fl = cl_row + m.idx * 3;
-    const float frx = __ldg(fr), fry = __ldg(fr + 1), frz = __ldg(fr + 2);
-    const float flx = __ldg(fl), fly = __ldg(fl + 1), flz = __ldg(fl + 2);
-    s_prev = stone_at(max(m.idx - 1, 0));
-    s_curr = stone_at(m.idx);
-    s_next = stone_at(min(m.idx + 1, kS - 1));
-    f_r = norm3(frx, fry, frz);  // ENV:421-424
-    f_l = norm3(flx, fly, flz);
+    f_r = contact_norm(cr_row, m.idx, contact_aligned);
+    f_l = contact_norm(cl_row, m.idx, contact_aligned);
+    win_valid = __float_as_int(w0.w) == m.idx;
+    if (win_valid) {
+      s_prev = w0; s_curr = w1; s_next = w2; s_next2 = w3;
+    } else {  // stale cache (first use, or the fix-up re-reading an env the step already advanced): gather
+      s_prev = stone_at(window_slot_stone(m.idx, 0));
+      s_curr = stone_at(window_slot_stone(m.idx, 1));
+      s_next = stone_at(window_slot_stone(m.idx, 2));
+      s_next2 = stone_at(window_slot_stone(m.idx, 3));
+    }
+    have_next2 = true;
   }
+  // the index advanced by one: slide the window (the stone entering at the far end is fetched when written back)
+  auto slide_window = [&]() {
+    s_prev = s_curr;
+    s_curr = s_next;
+    if (have_next2) {
+      s_next = s_next2;
+      have_next2 = false;
+    } else {
+      s_next = stone_at(min(m.idx + 1, kS - 1));
+    }
+    win_dirty = true;
+  };
 
   // views the bulk path cannot take (strided (N,13) root_state_w slices, full (N,B,3/13) body tensor, ragged tail)
   if (!b_jp) coop_load<kJ>(s_jp, a.in.joint_pos, a.in.joint_pos_stride, env0, n_valid);
@@ -427,11 +478,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     inv = quat_inverse(q);
     geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
     const bool moved = foot_update(P, geom, m, po);
-    if (moved) {
-      s_prev = s_curr;
-      s_curr = s_next;
-      s_next = stone_at(min(m.idx + 1, kS - 1));
-    }
+    if (moved) slide_window();
     targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
     adv1 = po.advanced;
     idx_after_pass1 = m.idx;
@@ -473,6 +520,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         s_curr = stone_at(1);
         s_next = stone_at(2);
       }
+      have_next2 = false;
+      win_dirty = true;
       m.count = 0;
       m.leg = mirror ? 1 : 0;  // ENV:491,538
       m.idx = 1;
@@ -491,18 +540,14 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       // ---- pass 2 over ALL envs, ENV:567, on unchanged physics: only the foot state machine can
       // change anything.  Assumed to happen; the fix-up kernel undoes the assumption when no env reset.
       if (idx_after_pass1 != idx_before) {  // the current stone changed in pass 1: new contact column
-        const float* fr = cr_row + m.idx * 3;
-        const float* fl = cl_row + m.idx * 3;
-        f_r = norm3(__ldg(fr), __ldg(fr + 1), __ldg(fr + 2));
-        f_l = norm3(__ldg(fl), __ldg(fl + 1), __ldg(fl + 2));
+        f_r = contact_norm(cr_row, m.idx, contact_aligned);
+        f_l = contact_norm(cl_row, m.idx, contact_aligned);
         geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
       }
       const bool moved = foot_update(P, geom, m, po);
       adv2 = po.advanced;
       if (moved) {
-        s_prev = s_curr;
-        s_curr = s_next;
-        s_next = stone_at(min(m.idx + 1, kS - 1));
+        slide_window();
         targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
       }
       // (unmoved: targets, body distance and potential are recomputed to the same values; old_potentials is dead)
@@ -562,6 +607,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     sw.x = pack_state(m.idx, m.leg, m.count, level, ep);
     sw.y = __float_as_uint(m.pot);
     st_out[e] = sw;
+    if ((win_dirty || !win_valid) && !regen) {  // (a regenerated env's window is written by the regeneration kernel)
+      if (!have_next2) s_next2 = stone_at(window_slot_stone(m.idx, 3));
+      s_prev.w = __int_as_float(m.idx);  // tag
+      wrow[0] = s_prev; wrow[1] = s_curr; wrow[2] = s_next; wrow[3] = s_next2;
+    }
   }
 
   // ---------------------------------------------------------------- reset / regeneration lists (warp ballots)
@@ -708,8 +758,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
+#ifndef AS_STEP_MIN_CTAS
+#define AS_STEP_MIN_CTAS 5
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kTile, 5) k_step(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kTile, AS_STEP_MIN_CTAS) k_step(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
   if (threadIdx.x == 0) mbar_init(smem_u32(&misc->mbar), 1);

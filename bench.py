@@ -398,7 +398,7 @@ def main_b200(args):
                              "launches_per_step": l2 / max(args.steps, 200), "bound": "launch latency (L2 resident)"}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N=1 only (rank 0 host cores)
         r = run_cpu_port(CPU_SAMPLE_ENVS, 24, 3)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"{CPU_SAMPLE_ENVS} envs x 24 steps of the same synthetic workload "
