@@ -2,6 +2,7 @@
 // and nothing else.  All arithmetic lives in the kernels (as_step_kernel.cuh, as_aux_kernels.cuh).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -151,6 +152,25 @@ StepArgs make_step_args(AsHandle* h, const AsStateIn* in, const float* actions, 
   a.num_envs = h->num_envs;
   a.env_id_offset = h->env_id_offset;
   a.num_tiles = num_tiles(h->num_envs);
+  // which views the TMA engine can take: dense rows and a 16-byte aligned base (tiles start every 128 rows)
+  auto dense = [](const void* p, int64_t stride, int64_t width) {
+    return p != nullptr && stride == width && (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+  };
+  uint32_t bits = 0;
+  if (in) {
+    if (dense(in->joint_pos, in->joint_pos_stride, kJ)) bits |= kDenseJp;
+    if (dense(in->joint_vel, in->joint_vel_stride, kJ)) bits |= kDenseJv;
+    if (dense(in->root_pos, in->root_pos_stride, 3)) bits |= kDenseRp;
+    if (dense(in->root_quat, in->root_quat_stride, 4)) bits |= kDenseRq;
+    if (dense(in->root_lin_vel, in->root_lin_vel_stride, 3)) bits |= kDenseRv;
+    if (in->body_row_stride == 3 && in->right_foot_row == 0 && in->left_foot_row == 1 && in->torso_row == 2 &&
+        dense(in->body_pos, in->body_env_stride, 9))
+      bits |= kDenseBody;
+    if (dense(in->env_origins, 3, 3)) bits |= kDenseOrg;
+  }
+  if (dense(actions, actions_stride, kJ)) bits |= kDenseAct;
+  if (out && dense(out->obs, kObs, kObs)) bits |= kDenseObs;
+  a.dense16 = bits;
   return a;
 }
 
@@ -288,7 +308,7 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   const bool regen_enabled = (h->params.flags & AS_FLAG_INTENDED_REGEN) != 0;
   a.want_reset_list = (reset_out && reset_out->reset_ids) ? 1 : 0;
   if (want_rows) a.rows = *reset_out;  // start-pose rows are written by the step kernel itself
-  k_step<kModeFused><<<a.num_tiles, kTile, kSmemBytes, s>>>(a);
+  k_step<kModeFused><<<a.num_tiles, kThreads, kSmemBytes, s>>>(a);
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
   if (regen_enabled) {  // kernel (b): warp-per-env stone regeneration over the compacted list
     ResetArgs r = make_reset_args(h, in->env_origins);
@@ -309,7 +329,7 @@ int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream) {
   StepArgs a = h->pending;  // the fix-up re-reads the inputs of the step it closes
   a.global_stats = global_stats;
   const int grid = grid_for(a.num_tiles, 1, h->sm_count, 1);
-  k_fixup_finish<<<grid, kTile, kSmemBytes, s>>>(a);
+  k_fixup_finish<<<grid, kThreads, kSmemBytes, s>>>(a);
   h->pending_valid = false;
   return check_launch(h, "k_fixup_finish");
 }
@@ -324,7 +344,7 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   StepArgs a = make_step_args(h, in, actions, actions_stride, out);
   a.ext_episode_length = episode_length;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  k_step<kModePass1><<<a.num_tiles, kTile, kSmemBytes, s>>>(a);
+  k_step<kModePass1><<<a.num_tiles, kThreads, kSmemBytes, s>>>(a);
   if (int rc = check_launch(h, "k_step<pass1>")) return rc;
   k_fold_pass1<<<1, 128, 0, s>>>(h->ws.ctrl, h->num_envs);
   h->pass1_done = true;
@@ -358,7 +378,7 @@ int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
   std::memset(&out, 0, sizeof(out));
   out.obs = obs;
   StepArgs a = make_step_args(h, in, nullptr, 0, &out);
-  k_step<kModePass2><<<a.num_tiles, kTile, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
+  k_step<kModePass2><<<a.num_tiles, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
   return check_launch(h, "k_step<pass2>");
 }
 

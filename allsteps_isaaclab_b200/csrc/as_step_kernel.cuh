@@ -33,11 +33,12 @@ constexpr int kOffRp = kOffAct + kTile * kJ * 4;
 constexpr int kOffRq = kOffRp + kTile * 3 * 4;
 constexpr int kOffRv = kOffRq + kTile * 4 * 4;
 constexpr int kOffBody = kOffRv + kTile * 3 * 4;
-constexpr int kOffMisc = kOffBody + kTile * 9 * 4;
-constexpr int kSmemBytes = kOffMisc + 1024;
+constexpr int kOffOrg = kOffBody + kTile * 9 * 4;   // env origins of the tile (needed by the envs that reset)
+constexpr int kOffMisc = kOffOrg + kTile * 3 * 4;
+constexpr int kSmemBytes = kOffMisc + 3072;
 static_assert(kTile * kObs * 4 <= kOffRp, "observation tile must fit over the joint/action tiles it aliases");
 static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffRq % 16 == 0 &&
-                  kOffRv % 16 == 0 && kOffBody % 16 == 0 && kOffMisc % 16 == 0,
+                  kOffRv % 16 == 0 && kOffBody % 16 == 0 && kOffOrg % 16 == 0 && kOffMisc % 16 == 0,
               "bulk copies need 16-byte aligned shared addresses");
 
 // Per-joint tables of the reset pose, one entry per lane.  Lane-indexed reads of kernel parameters would go
@@ -46,15 +47,23 @@ struct ResetTables {
   float lower[32], upper[32], pose[32], pose_mirrored[32], vel_mirrored[32];
 };
 
+constexpr int kThreads = 2 * kTile;  // two threads per env: one MDP-role and one joint-role warp per 32 envs
+
 struct Misc {  // lives at kOffMisc, never aliased
-  unsigned long long mbar;
+  unsigned long long mbar_root;   // completion of the root / body tiles
+  unsigned long long mbar_joint;  // completion of the joint_pos / joint_vel / actions tiles
   unsigned int wcnt[kTile / 32][kNumCounters];  // per-warp step counters
   float wreward[kTile / 32];
   unsigned int is_last;
   unsigned int fold[kNumCounters];
   ResetTables rt;
+  // exchanged between the two roles at the CTA barrier
+  float red_energy[kTile];   // sum_j |joint_vel * action|, ENV:365
+  float red_actsq[kTile];    // sum_j action^2, ENV:364
+  int red_limit[kTile];      // count_j |joint_pos_scaled| > 0.99, ENV:367
+  unsigned int flags[kTile]; // bit 0: env resets this step, bit 1: its start pose is mirrored
 };
-static_assert(sizeof(Misc) <= 1024, "misc block");
+static_assert(sizeof(Misc) <= 3072, "misc block");
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -93,15 +102,22 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ------------------------------------------------------------------------------------------------ staging
+// A tile of an (N,W) view can be moved by the bulk-copy engine when the view is dense (stride == W), the tile starts
+// on a 16-byte boundary and its byte count is a multiple of 16.  The first two are properties of the view: the
+// host evaluates them once per launch (StepArgs::dense16, one bit per array; every tile starts on a multiple of
+// 128 rows, and 128 * W * 4 is a multiple of 16 for every W); only the ragged last tile needs the third.
+enum DenseBit { kDenseJp = 1, kDenseJv = 2, kDenseAct = 4, kDenseRp = 8, kDenseRq = 16, kDenseRv = 32, kDenseBody = 64,
+                kDenseOrg = 128, kDenseObs = 256 };
 template <int W>
-__device__ __forceinline__ bool bulk_ok(const float* base, int64_t stride, int64_t env0, int n_valid) {
-  return stride == W && ((reinterpret_cast<uintptr_t>(base + env0 * W) & 15u) == 0) && (((n_valid * W) & 3) == 0);
+__device__ __forceinline__ bool bulk_ok(uint32_t dense16, uint32_t bit, int n_valid) {
+  return (dense16 & bit) && (((n_valid * W) & 3) == 0);
 }
 template <int W>
 __device__ __forceinline__ void coop_load(float* dst, const float* base, int64_t stride, int64_t env0, int n_valid) {
-  for (int i = threadIdx.x; i < n_valid * W; i += kTile) {
+  for (int i = threadIdx.x; i < n_valid * W; i += 2 * kTile) {
     const int r = i / W;
     const int c = i - r * W;
     dst[i] = __ldg(base + (env0 + r) * stride + c);
@@ -304,18 +320,31 @@ __device__ __forceinline__ uint32_t promotion_decision(const AsParams& P, const 
 }
 
 // ------------------------------------------------------------------------------------------------ the tile
+// A CTA is 8 warps on one 128-env tile, two threads per env:
+//   warps 0-3  "MDP role"    thread t owns env t: state word, stone window, contact gathers, pass 1, dones, reward,
+//                            masked reset, pass 2, head/tail of the observation row
+//   warps 4-7  "joint role"  thread t owns env t's three 21-float rows: scaled joint positions, clipped joint
+//                            velocities, the reward's energy / action / at-limit sums, and (as a warp) the start
+//                            pose of the envs that reset
+// The two roles wait on separate mbarriers (root/body tiles vs joint/action tiles), run concurrently, meet at one
+// CTA barrier (inputs consumed; sums and reset flags exchanged through shared memory) and then fill disjoint
+// columns of the observation tile.  Twice the resident warps of a one-thread-per-env CTA for the same shared
+// memory, and half the serial instruction stream per env.
 template <int MODE>
-__device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32_t& phase, unsigned char* smem) {
+__device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32_t& phase_root,
+                                             uint32_t& phase_joint, unsigned char* smem) {
   const AsParams& P = a.P;
   const JointConsts& JC = a.jc;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  const bool joint_role = warp >= kTile / 32;
+  const int t = tid & (kTile - 1);  // env row inside the tile (both roles)
   const int64_t env0 = static_cast<int64_t>(tile) * kTile;
   const int64_t rem = a.num_envs - env0;
   const int n_valid = rem < kTile ? static_cast<int>(rem) : kTile;
-  const bool active = tid < n_valid;
-  const int64_t e = env0 + tid;
+  const bool active = t < n_valid;
+  const int64_t e = env0 + t;
 
   float* s_jp = reinterpret_cast<float*>(smem + kOffJp);
   float* s_jv = reinterpret_cast<float*>(smem + kOffJv);
@@ -324,9 +353,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   float* s_rq = reinterpret_cast<float*>(smem + kOffRq);
   float* s_rv = reinterpret_cast<float*>(smem + kOffRv);
   float* s_body = reinterpret_cast<float*>(smem + kOffBody);
+  float* s_org = reinterpret_cast<float*>(smem + kOffOrg);
   float* s_obs = reinterpret_cast<float*>(smem);
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
-  const uint32_t bar = smem_u32(&misc->mbar);
+  const uint32_t bar_root = smem_u32(&misc->mbar_root);
+  const uint32_t bar_joint = smem_u32(&misc->mbar_joint);
   Ctrl* ctrl = a.ws.ctrl;
 
   constexpr bool kNeedActions = MODE != kModePass2;
@@ -334,31 +365,39 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   constexpr bool kStats = MODE == kModeFused || MODE == kModePass1;
 
   // ---------------------------------------------------------------- HBM -> SMEM (TMA bulk where the view allows)
-  const bool body_compact = a.in.body_row_stride == 3 && a.in.body_env_stride == 9 && a.in.right_foot_row == 0 &&
-                            a.in.left_foot_row == 1 && a.in.torso_row == 2;
-  const bool b_jp = bulk_ok<kJ>(a.in.joint_pos, a.in.joint_pos_stride, env0, n_valid);
-  const bool b_jv = bulk_ok<kJ>(a.in.joint_vel, a.in.joint_vel_stride, env0, n_valid);
-  const bool b_act = kNeedActions && bulk_ok<kJ>(a.actions, a.actions_stride, env0, n_valid);
-  const bool b_rp = bulk_ok<3>(a.in.root_pos, a.in.root_pos_stride, env0, n_valid);
-  const bool b_rq = bulk_ok<4>(a.in.root_quat, a.in.root_quat_stride, env0, n_valid);
-  const bool b_rv = bulk_ok<3>(a.in.root_lin_vel, a.in.root_lin_vel_stride, env0, n_valid);
-  const bool b_body = body_compact && bulk_ok<9>(a.in.body_pos, 9, env0, n_valid);
-  const bool any_bulk = b_jp || b_jv || b_act || b_rp || b_rq || b_rv || b_body;
-  if (tid == 0 && any_bulk) {
+  const uint32_t dense = a.dense16;
+  const bool b_jp = bulk_ok<kJ>(dense, kDenseJp, n_valid);
+  const bool b_jv = bulk_ok<kJ>(dense, kDenseJv, n_valid);
+  const bool b_act = kNeedActions && bulk_ok<kJ>(dense, kDenseAct, n_valid);
+  const bool b_rp = bulk_ok<3>(dense, kDenseRp, n_valid);
+  const bool b_rq = bulk_ok<4>(dense, kDenseRq, n_valid);
+  const bool b_rv = bulk_ok<3>(dense, kDenseRv, n_valid);
+  const bool b_body = bulk_ok<9>(dense, kDenseBody, n_valid);
+  const bool b_org = MODE == kModeFused && bulk_ok<3>(dense, kDenseOrg, n_valid);
+  const bool bulk_root = b_rp || b_rq || b_rv || b_body || b_org;
+  const bool bulk_joint = b_jp || b_jv || b_act;
+  const bool any_coop = !b_jp || !b_jv || (kNeedActions && !b_act) || !b_rp || !b_rq || !b_rv || !b_body ||
+                        (MODE == kModeFused && !b_org);
+  if (tid == 0) {
     const uint32_t nv = static_cast<uint32_t>(n_valid);
-    const uint32_t tx = (b_jp ? nv * kJ * 4 : 0) + (b_jv ? nv * kJ * 4 : 0) + (b_act ? nv * kJ * 4 : 0) +
-                        (b_rp ? nv * 12 : 0) + (b_rq ? nv * 16 : 0) + (b_rv ? nv * 12 : 0) + (b_body ? nv * 36 : 0);
-    mbar_arrive_expect_tx(bar, tx);
-    if (b_rp) bulk_g2s(smem_u32(s_rp), a.in.root_pos + env0 * 3, nv * 12, bar);
-    if (b_rq) bulk_g2s(smem_u32(s_rq), a.in.root_quat + env0 * 4, nv * 16, bar);
-    if (b_rv) bulk_g2s(smem_u32(s_rv), a.in.root_lin_vel + env0 * 3, nv * 12, bar);
-    if (b_body) bulk_g2s(smem_u32(s_body), a.in.body_pos + env0 * 9, nv * 36, bar);
-    if (b_jp) bulk_g2s(smem_u32(s_jp), a.in.joint_pos + env0 * kJ, nv * kJ * 4, bar);
-    if (b_jv) bulk_g2s(smem_u32(s_jv), a.in.joint_vel + env0 * kJ, nv * kJ * 4, bar);
-    if (b_act) bulk_g2s(smem_u32(s_act), a.actions + env0 * kJ, nv * kJ * 4, bar);
+    if (bulk_root) {
+      mbar_arrive_expect_tx(bar_root, (b_rp ? nv * 12 : 0) + (b_rq ? nv * 16 : 0) + (b_rv ? nv * 12 : 0) +
+                                          (b_body ? nv * 36 : 0) + (b_org ? nv * 12 : 0));
+      if (b_org) bulk_g2s(smem_u32(s_org), a.in.env_origins + env0 * 3, nv * 12, bar_root);
+      if (b_rp) bulk_g2s(smem_u32(s_rp), a.in.root_pos + env0 * 3, nv * 12, bar_root);
+      if (b_rq) bulk_g2s(smem_u32(s_rq), a.in.root_quat + env0 * 4, nv * 16, bar_root);
+      if (b_rv) bulk_g2s(smem_u32(s_rv), a.in.root_lin_vel + env0 * 3, nv * 12, bar_root);
+      if (b_body) bulk_g2s(smem_u32(s_body), a.in.body_pos + env0 * 9, nv * 36, bar_root);
+    }
+    if (bulk_joint) {
+      mbar_arrive_expect_tx(bar_joint, (b_jp ? nv * kJ * 4 : 0) + (b_jv ? nv * kJ * 4 : 0) + (b_act ? nv * kJ * 4 : 0));
+      if (b_jp) bulk_g2s(smem_u32(s_jp), a.in.joint_pos + env0 * kJ, nv * kJ * 4, bar_joint);
+      if (b_jv) bulk_g2s(smem_u32(s_jv), a.in.joint_vel + env0 * kJ, nv * kJ * 4, bar_joint);
+      if (b_act) bulk_g2s(smem_u32(s_act), a.actions + env0 * kJ, nv * kJ * 4, bar_joint);
+    }
   }
 
-  // ---------------------------------------------------------------- per-env state word + dependent gathers
+  // ---------------------------------------------------------------- MDP role: state word + dependent gathers
   const uint32_t parity = ctrl->parity;
   const uint2* st_in = a.ws.state[parity];
   uint2* st_out = kPingPong ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
@@ -376,7 +415,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   float f_r = 0.0f, f_l = 0.0f;
   const float* cr_row = nullptr;
   const float* cl_row = nullptr;
-  if (active) {
+  if (!joint_role && active) {
     // the stone window does not depend on the state word: its four coalesced loads go out first
     const float4 w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3];
     const uint2 sw = st_in[e];
@@ -421,43 +460,28 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   };
 
   // views the bulk path cannot take (strided (N,13) root_state_w slices, full (N,B,3/13) body tensor, ragged tail)
-  if (!b_jp) coop_load<kJ>(s_jp, a.in.joint_pos, a.in.joint_pos_stride, env0, n_valid);
-  if (!b_jv) coop_load<kJ>(s_jv, a.in.joint_vel, a.in.joint_vel_stride, env0, n_valid);
-  if (kNeedActions && !b_act) coop_load<kJ>(s_act, a.actions, a.actions_stride, env0, n_valid);
-  if (!b_rp) coop_load<3>(s_rp, a.in.root_pos, a.in.root_pos_stride, env0, n_valid);
-  if (!b_rq) coop_load<4>(s_rq, a.in.root_quat, a.in.root_quat_stride, env0, n_valid);
-  if (!b_rv) coop_load<3>(s_rv, a.in.root_lin_vel, a.in.root_lin_vel_stride, env0, n_valid);
-  if (!b_body) {
-    for (int i = tid; i < n_valid * 9; i += kTile) {
-      const int r = i / 9;
-      const int c = i - r * 9;
-      const int b = c / 3;
-      const int k = c - b * 3;
-      const int row = b == 0 ? a.in.right_foot_row : (b == 1 ? a.in.left_foot_row : a.in.torso_row);
-      s_body[i] = __ldg(a.in.body_pos + (env0 + r) * a.in.body_env_stride + row * a.in.body_row_stride + k);
+  if (any_coop) {
+    if (!b_jp) coop_load<kJ>(s_jp, a.in.joint_pos, a.in.joint_pos_stride, env0, n_valid);
+    if (!b_jv) coop_load<kJ>(s_jv, a.in.joint_vel, a.in.joint_vel_stride, env0, n_valid);
+    if (kNeedActions && !b_act) coop_load<kJ>(s_act, a.actions, a.actions_stride, env0, n_valid);
+    if (!b_rp) coop_load<3>(s_rp, a.in.root_pos, a.in.root_pos_stride, env0, n_valid);
+    if (!b_rq) coop_load<4>(s_rq, a.in.root_quat, a.in.root_quat_stride, env0, n_valid);
+    if (!b_rv) coop_load<3>(s_rv, a.in.root_lin_vel, a.in.root_lin_vel_stride, env0, n_valid);
+    if (MODE == kModeFused && !b_org) coop_load<3>(s_org, a.in.env_origins, 3, env0, n_valid);
+    if (!b_body) {
+      for (int i = tid; i < n_valid * 9; i += kThreads) {
+        const int r = i / 9;
+        const int c = i - r * 9;
+        const int b = c / 3;
+        const int k = c - b * 3;
+        const int row = b == 0 ? a.in.right_foot_row : (b == 1 ? a.in.left_foot_row : a.in.torso_row);
+        s_body[i] = __ldg(a.in.body_pos + (env0 + r) * a.in.body_env_stride + row * a.in.body_row_stride + k);
+      }
     }
-  }
-  __syncthreads();
-  if (any_bulk) {
-    mbar_wait(bar, phase);
-    phase ^= 1u;
+    __syncthreads();
   }
 
-  // ---------------------------------------------------------------- compute (registers)
-  Vec3 p{0, 0, 0}, v{0, 0, 0}, rf{0, 0, 0}, lf{0, 0, 0};
-  Quat q{1, 0, 0, 0};
-  float torso_z = 0.0f;
-  if (active) {
-    p = Vec3{s_rp[tid * 3], s_rp[tid * 3 + 1], s_rp[tid * 3 + 2]};
-    const float4 q4 = *reinterpret_cast<const float4*>(s_rq + tid * 4);
-    q = Quat{q4.x, q4.y, q4.z, q4.w};
-    v = Vec3{s_rv[tid * 3], s_rv[tid * 3 + 1], s_rv[tid * 3 + 2]};
-    rf = Vec3{s_body[tid * 9 + 0], s_body[tid * 9 + 1], s_body[tid * 9 + 2]};
-    lf = Vec3{s_body[tid * 9 + 3], s_body[tid * 9 + 4], s_body[tid * 9 + 5]};
-    torso_z = s_body[tid * 9 + 8];
-  }
-
-  // head of the observation row; refreshed by whichever pass ran last
+  // values that cross the CTA barrier in registers
   float h = 0.0f, roll = 0.0f, pitch = 0.0f;
   Vec3 vb{0, 0, 0};
   PassOut po{};
@@ -465,270 +489,310 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   bool fell = false, so_fast = false, died = false, adv1 = false, adv2 = false;
   float r_progress = 0.0f, r_roll = 0.0f, r_pitch = 0.0f, r_speed = 0.0f, r_step = 0.0f, r_bonus = 0.0f;
   int idx_after_pass1 = 0;
-  const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
   const unsigned long long step_now = ctrl->step_counter;
-  FootGeom geom{};
-  Quat inv{1, 0, 0, 0};
+  float o_jp[kJ], o_jv[kJ];
 
-  const int idx_before = m.idx;
-  if (active) {
-    h = torso_z - fminf(lf.z, rf.z);   // ENV:281-283
-    euler_roll_pitch(q, roll, pitch);  // ENV:285
-    vb = rotate_by_inverse(q, v);      // ENV:293
-    inv = quat_inverse(q);
-    geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
-    const bool moved = foot_update(P, geom, m, po);
-    if (moved) slide_window();
-    targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
-    adv1 = po.advanced;
-    idx_after_pass1 = m.idx;
-    if (MODE != kModePass2) {
-      // ---- dones, ENV:396-405
+  if (!joint_role) {
+    // ================================================================ MDP role, before the barrier
+    if (bulk_root) mbar_wait(bar_root, phase_root);
+    Vec3 p{0, 0, 0}, v{0, 0, 0}, rf{0, 0, 0}, lf{0, 0, 0};
+    Quat q{1, 0, 0, 0};
+    float torso_z = 0.0f;
+    if (active) {
+      p = Vec3{s_rp[t * 3], s_rp[t * 3 + 1], s_rp[t * 3 + 2]};
+      const float4 q4 = *reinterpret_cast<const float4*>(s_rq + t * 4);
+      q = Quat{q4.x, q4.y, q4.z, q4.w};
+      v = Vec3{s_rv[t * 3], s_rv[t * 3 + 1], s_rv[t * 3 + 2]};
+      rf = Vec3{s_body[t * 9 + 0], s_body[t * 9 + 1], s_body[t * 9 + 2]};
+      lf = Vec3{s_body[t * 9 + 3], s_body[t * 9 + 4], s_body[t * 9 + 5]};
+      torso_z = s_body[t * 9 + 8];
+    }
+    const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
+    FootGeom geom{};
+    Quat inv{1, 0, 0, 0};
+    const int idx_before = m.idx;
+    float speed = 0.0f;
+    if (active && MODE != kModePass2) {
+      // ---- dones first, ENV:396-405: they need only the staged root / body rows, and knowing early which envs
+      // reset lets their extra loads fly while pass 1 is being computed
+      h = torso_z - fminf(lf.z, rf.z);  // ENV:281-283
       time_out = ep >= P.max_episode_length - 1;
       fell = h < P.termination_height[level];
-      const float speed = norm3(v.x, v.y, v.z);
+      speed = norm3(v.x, v.y, v.z);
       so_fast = speed > P.max_root_speed;
       died = p.z < P.termination_height_absolute;
       terminated = fell || so_fast || died;
       is_reset = terminated || time_out;
-      // ---- reward terms that do not need the joint loop, ENV:350-375
-      r_progress = m.pot - po.old_pot;
-      r_roll = (roll > 0.4f || roll < -0.4f) ? fabsf(roll) : 0.0f;
-      r_pitch = (pitch > 0.4f || pitch < -0.2f) ? fabsf(pitch) : 0.0f;
-      r_speed = speed > 1.6f ? speed - 1.6f : 0.0f;
-      const bool pays_step = po.reached && m.count == 1 && m.idx < kS - 1;
-      r_step = pays_step ? 50.0f * expf((-po.d_swing) / 0.25f) : 0.0f;
-      r_bonus = (m.idx == kS - 1 && po.body_dist < 0.15f) ? 10.0f : 0.0f;
+      // an env that resets restarts on stones 0..3 (one 64-byte record at the head of its stone row): start
+      // pulling it in now, it is read after pass 1
+      if (MODE == kModeFused && is_reset) prefetch_l1(stones);
     }
-  }
-
-  if (MODE == kModeFused && active) {
-    if (is_reset) {
-      // ---- masked reset, ENV:487-538 (rows for PhysX are produced by the reset kernel from the same draws).
-      // Pass 2 on the post-reset state: identity orientation (vector part +-0), zero velocity, zero contacts
-      // (contact_sensor.py:155), stale body positions; so roll = pitch = v_b = 0 and targets_b = stone - root.
-      regen = (P.flags & AS_FLAG_INTENDED_REGEN) && m.idx > kS / 2;
-      const uint4 rblk = philox_block(P.seed, step_now, kStreamReset, gid, 0);
-      mirror = u32_to_unit(rblk.x) > 0.5f;  // ENV:518
-      const float ox = __ldg(a.in.env_origins + e * 3), oy = __ldg(a.in.env_origins + e * 3 + 1),
-                  oz = __ldg(a.in.env_origins + e * 3 + 2);
-      p = Vec3{P.default_root_pos[0] + ox, P.default_root_pos[1] + oy, P.default_root_pos[2] + oz};
-      if (regen) {
-        first_three_stones(P, Vec3{ox, oy, oz}, s_prev, s_curr, s_next);
-      } else {
-        s_prev = stone_at(0);
-        s_curr = stone_at(1);
-        s_next = stone_at(2);
-      }
-      have_next2 = false;
-      win_dirty = true;
-      m.count = 0;
-      m.leg = mirror ? 1 : 0;  // ENV:491,538
-      m.idx = 1;
-      ep = 0;  // DRL:584
-      roll = 0.0f;
-      pitch = 0.0f;
-      vb = Vec3{0, 0, 0};
-      po.contact_r = 0.0f;
-      po.contact_l = 0.0f;
-      po.tb0 = Vec3{s_prev.x - p.x, s_prev.y - p.y, s_prev.z - p.z};
-      po.tb1 = Vec3{s_curr.x - p.x, s_curr.y - p.y, s_curr.z - p.z};
-      po.tb2 = Vec3{s_next.x - p.x, s_next.y - p.y, s_next.z - p.z};
-      po.body_dist = norm2(s_next.x - p.x, s_next.y - p.y);
-      m.pot = (-po.body_dist) / P.step_dt;  // ENV:487-488 zero both potentials, ENV:415-416 in pass 2
-    } else if (!(P.flags & AS_FLAG_SKIP_PASS2)) {
-      // ---- pass 2 over ALL envs, ENV:567, on unchanged physics: only the foot state machine can
-      // change anything.  Assumed to happen; the fix-up kernel undoes the assumption when no env reset.
-      if (idx_after_pass1 != idx_before) {  // the current stone changed in pass 1: new contact column
-        f_r = contact_norm(cr_row, m.idx, contact_aligned);
-        f_l = contact_norm(cl_row, m.idx, contact_aligned);
-        geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
-      }
+    if (active) {
+      h = torso_z - fminf(lf.z, rf.z);   // ENV:281-283
+      euler_roll_pitch(q, roll, pitch);  // ENV:285
+      vb = rotate_by_inverse(q, v);      // ENV:293
+      inv = quat_inverse(q);
+      geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
       const bool moved = foot_update(P, geom, m, po);
-      adv2 = po.advanced;
-      if (moved) {
-        slide_window();
-        targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
+      if (moved) slide_window();
+      targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
+      adv1 = po.advanced;
+      idx_after_pass1 = m.idx;
+      if (MODE != kModePass2) {
+        // ---- reward terms that do not need the joint sums, ENV:350-375
+        r_progress = m.pot - po.old_pot;
+        r_roll = (roll > 0.4f || roll < -0.4f) ? fabsf(roll) : 0.0f;
+        r_pitch = (pitch > 0.4f || pitch < -0.2f) ? fabsf(pitch) : 0.0f;
+        r_speed = speed > 1.6f ? speed - 1.6f : 0.0f;
+        const bool pays_step = po.reached && m.count == 1 && m.idx < kS - 1;
+        r_step = pays_step ? 50.0f * expf((-po.d_swing) / 0.25f) : 0.0f;
+        r_bonus = (m.idx == kS - 1 && po.body_dist < 0.15f) ? 10.0f : 0.0f;
       }
-      // (unmoved: targets, body distance and potential are recomputed to the same values; old_potentials is dead)
     }
-  }
 
-  // ---------------------------------------------------------------- joint loop: reward sums + observation body
-  float o_jp[kJ], o_jv[kJ];
-  float energy = 0.0f, act_sq = 0.0f;
-  int at_limit = 0;
-  if (active) {
-    const float* my_jp = s_jp + tid * kJ;
-    const float* my_jv = s_jv + tid * kJ;
-    const float* my_act = s_act + tid * kJ;
+    if (MODE == kModeFused && active) {
+      if (is_reset) {
+        // ---- masked reset, ENV:487-538.  Pass 2 on the post-reset state: identity orientation (vector part +-0),
+        // zero velocity, zero contacts (contact_sensor.py:155), stale body positions; so roll = pitch = v_b = 0 and
+        // targets_b = stone - root.  The start-pose joints are produced by the joint-role warps.
+        regen = (P.flags & AS_FLAG_INTENDED_REGEN) && m.idx > kS / 2;
+        const uint4 rblk = philox_block(P.seed, step_now, kStreamReset, gid, 0);
+        mirror = u32_to_unit(rblk.x) > 0.5f;  // ENV:518
+        const Vec3 org{s_org[t * 3], s_org[t * 3 + 1], s_org[t * 3 + 2]};
+        p = Vec3{P.default_root_pos[0] + org.x, P.default_root_pos[1] + org.y, P.default_root_pos[2] + org.z};
+        if (regen) {
+          first_three_stones(P, org, s_prev, s_curr, s_next);
+          have_next2 = false;
+        } else {
+          s_prev = stone_at(0);
+          s_curr = stone_at(1);
+          s_next = stone_at(2);
+          s_next2 = stone_at(3);
+          have_next2 = true;
+        }
+        win_dirty = true;
+        m.count = 0;
+        m.leg = mirror ? 1 : 0;  // ENV:491,538
+        m.idx = 1;
+        ep = 0;  // DRL:584
+        roll = 0.0f;
+        pitch = 0.0f;
+        vb = Vec3{0, 0, 0};
+        po.contact_r = 0.0f;
+        po.contact_l = 0.0f;
+        po.tb0 = Vec3{s_prev.x - p.x, s_prev.y - p.y, s_prev.z - p.z};
+        po.tb1 = Vec3{s_curr.x - p.x, s_curr.y - p.y, s_curr.z - p.z};
+        po.tb2 = Vec3{s_next.x - p.x, s_next.y - p.y, s_next.z - p.z};
+        po.body_dist = norm2(s_next.x - p.x, s_next.y - p.y);
+        m.pot = (-po.body_dist) / P.step_dt;  // ENV:487-488 zero both potentials, ENV:415-416 in pass 2
+      } else if (!(P.flags & AS_FLAG_SKIP_PASS2)) {
+        // ---- pass 2 over ALL envs, ENV:567, on unchanged physics: only the foot state machine can
+        // change anything.  Assumed to happen; the fix-up kernel undoes the assumption when no env reset.
+        if (idx_after_pass1 != idx_before) {  // the current stone changed in pass 1: new contact column
+          f_r = contact_norm(cr_row, m.idx, contact_aligned);
+          f_l = contact_norm(cl_row, m.idx, contact_aligned);
+          geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
+        }
+        const bool moved = foot_update(P, geom, m, po);
+        adv2 = po.advanced;
+        if (moved) {
+          slide_window();
+          targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
+        }
+        // (unmoved: targets, body distance and potential are recomputed to the same values; old_potentials is dead)
+      }
+    }
+    if (active) {
+      uint2 sw;
+      sw.x = pack_state(m.idx, m.leg, m.count, level, ep);
+      sw.y = __float_as_uint(m.pot);
+      st_out[e] = sw;
+      if ((win_dirty || !win_valid) && !regen) {  // (a regenerated env's window is written by the regeneration kernel)
+        if (!have_next2) s_next2 = stone_at(window_slot_stone(m.idx, 3));
+        s_prev.w = __int_as_float(m.idx);  // tag
+        wrow[0] = s_prev; wrow[1] = s_curr; wrow[2] = s_next; wrow[3] = s_next2;
+      }
+    }
+    if (MODE == kModeFused) {
+      misc->flags[t] = (is_reset ? 1u : 0u) | (mirror ? 2u : 0u);
+      // ---- reset / regeneration id lists (warp ballots)
+      const unsigned rmask = __ballot_sync(0xffffffffu, is_reset);
+      if (rmask && a.want_reset_list) {
+        const int leader = __ffs(rmask) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&ctrl->n_reset_list, __popc(rmask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        int32_t* ids_dst = a.rows.reset_ids ? a.rows.reset_ids : a.ws.reset_ids;
+        if (is_reset) ids_dst[base + __popc(rmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
+      }
+      const unsigned gmask = __ballot_sync(0xffffffffu, regen);
+      if (gmask) {
+        const int leader = __ffs(gmask) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&ctrl->n_regen_list, __popc(gmask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (regen) a.ws.regen_ids[base + __popc(gmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
+      }
+    }
+  } else {
+    // ================================================================ joint role, before the barrier
+    if (bulk_joint) mbar_wait(bar_joint, phase_joint);
+    float energy = 0.0f, act_sq = 0.0f;
+    int at_limit = 0;
+    if (active) {
+      const float* my_jp = s_jp + t * kJ;
+      const float* my_jv = s_jv + t * kJ;
+      const float* my_act = s_act + t * kJ;
 #pragma unroll
-    for (int j = 0; j < kJ; ++j) {
-      const float jv = my_jv[j];
-      const float sc = scale_joint(JC, j, my_jp[j]);  // ENV:287-291
-      if (kNeedActions) {
-        const float act = fminf(fmaxf(my_act[j], -1.0f), 1.0f);  // ENV:268
-        at_limit += fabsf(sc) > 0.99f ? 1 : 0;                   // ENV:367
-        energy += fabsf(jv * act);                               // ENV:365
-        act_sq = fmaf(act, act, act_sq);                         // ENV:364
+      for (int j = 0; j < kJ; ++j) {
+        const float jv = my_jv[j];
+        const float sc = scale_joint(JC, j, my_jp[j]);  // ENV:287-291
+        if (kNeedActions) {
+          const float act = fminf(fmaxf(my_act[j], -1.0f), 1.0f);  // ENV:268
+          at_limit += fabsf(sc) > 0.99f ? 1 : 0;                   // ENV:367
+          energy += fabsf(jv * act);                               // ENV:365
+          act_sq = fmaf(act, act, act_sq);                         // ENV:364
+        }
+        o_jp[j] = sc;
+        o_jv[j] = fminf(fmaxf(jv * P.dof_vel_scale, -5.0f), 5.0f);  // ENV:337
       }
-      o_jp[j] = sc;
-      o_jv[j] = fminf(fmaxf(jv * P.dof_vel_scale, -5.0f), 5.0f);  // ENV:337
+    }
+    if (kNeedActions) {
+      misc->red_energy[t] = energy;
+      misc->red_actsq[t] = act_sq;
+      misc->red_limit[t] = at_limit;
     }
   }
+  if (bulk_root) phase_root ^= 1u;
+  if (bulk_joint) phase_joint ^= 1u;
 
-  // ---------------------------------------------------------------- reward, ENV:377-394
+  __syncthreads();  // every input row is consumed (the observation tile may overwrite them); sums and flags are visible
+
   float reward = 0.0f;
-  if (MODE != kModePass2 && active) {
-    const float r_energy = P.energy_cost_scale * energy;
-    const float r_action = P.actions_cost_scale * sqrtf(act_sq);
-    const float r_limit = static_cast<float>(at_limit) * P.joint_at_limit_cost_scale;
-    float total = P.alive_reward_scale + r_progress;
-    total = total - r_roll;
-    total = total - r_pitch;
-    total = total - r_speed;
-    total = total - r_energy;
-    total = total - r_action;
-    total = total - r_limit;
-    total = total + r_step;
-    total = total + r_bonus;
-    reward = terminated ? P.death_cost : total;
-    a.out.reward[e] = reward;
-    a.out.terminated[e] = terminated ? 1 : 0;
-    a.out.time_out[e] = time_out ? 1 : 0;
-    if (a.out.reward_terms) {
-      float* rt = a.out.reward_terms + e * AS_NUM_REWARD_TERMS;
-      rt[0] = P.alive_reward_scale; rt[1] = r_progress; rt[2] = r_roll; rt[3] = r_pitch; rt[4] = r_speed;
-      rt[5] = r_energy; rt[6] = r_action; rt[7] = r_limit; rt[8] = r_step; rt[9] = r_bonus;
+  if (!joint_role) {
+    // ================================================================ MDP role, after the barrier
+    if (MODE != kModePass2 && active) {  // reward, ENV:377-394
+      const float r_energy = P.energy_cost_scale * misc->red_energy[t];
+      const float r_action = P.actions_cost_scale * sqrtf(misc->red_actsq[t]);
+      const float r_limit = static_cast<float>(misc->red_limit[t]) * P.joint_at_limit_cost_scale;
+      float total = P.alive_reward_scale + r_progress;
+      total = total - r_roll;
+      total = total - r_pitch;
+      total = total - r_speed;
+      total = total - r_energy;
+      total = total - r_action;
+      total = total - r_limit;
+      total = total + r_step;
+      total = total + r_bonus;
+      reward = terminated ? P.death_cost : total;
+      a.out.reward[e] = reward;
+      a.out.terminated[e] = terminated ? 1 : 0;
+      a.out.time_out[e] = time_out ? 1 : 0;
+      if (a.out.reward_terms) {
+        float* rt = a.out.reward_terms + e * AS_NUM_REWARD_TERMS;
+        rt[0] = P.alive_reward_scale; rt[1] = r_progress; rt[2] = r_roll; rt[3] = r_pitch; rt[4] = r_speed;
+        rt[5] = r_energy; rt[6] = r_action; rt[7] = r_limit; rt[8] = r_step; rt[9] = r_bonus;
+      }
     }
-  }
-  if (active) {
-    uint2 sw;
-    sw.x = pack_state(m.idx, m.leg, m.count, level, ep);
-    sw.y = __float_as_uint(m.pot);
-    st_out[e] = sw;
-    if ((win_dirty || !win_valid) && !regen) {  // (a regenerated env's window is written by the regeneration kernel)
-      if (!have_next2) s_next2 = stone_at(window_slot_stone(m.idx, 3));
-      s_prev.w = __int_as_float(m.idx);  // tag
-      wrow[0] = s_prev; wrow[1] = s_curr; wrow[2] = s_next; wrow[3] = s_next2;
+    if (active) {  // head and tail of the observation row, ENV:330-343
+      float* row = s_obs + t * kObs;
+      row[0] = h;
+      row[1] = roll;
+      row[2] = pitch;
+      row[3] = vb.x;
+      row[4] = vb.y;
+      row[5] = vb.z;
+      row[48] = po.contact_r;
+      row[49] = po.contact_l;
+      row[50] = po.tb0.x; row[51] = po.tb0.y; row[52] = po.tb0.z;
+      row[53] = po.tb1.x; row[54] = po.tb1.y; row[55] = po.tb1.z;
+      row[56] = po.tb2.x; row[57] = po.tb2.y; row[58] = po.tb2.z;
     }
-  }
-
-  // ---------------------------------------------------------------- reset / regeneration lists (warp ballots)
-  const unsigned rmask = (MODE == kModeFused) ? __ballot_sync(0xffffffffu, is_reset) : 0u;
-  if (MODE == kModeFused) {
-    if (rmask && a.want_reset_list) {
-      const int leader = __ffs(rmask) - 1;
-      unsigned base = 0;
-      if (lane == leader) base = atomicAdd(&ctrl->n_reset_list, __popc(rmask));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      int32_t* ids_dst = a.rows.reset_ids ? a.rows.reset_ids : a.ws.reset_ids;
-      if (is_reset) ids_dst[base + __popc(rmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
-    }
-    const unsigned gmask = __ballot_sync(0xffffffffu, regen);
-    if (gmask) {
-      const int leader = __ffs(gmask) - 1;
-      unsigned base = 0;
-      if (lane == leader) base = atomicAdd(&ctrl->n_regen_list, __popc(gmask));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (regen) a.ws.regen_ids[base + __popc(gmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
-    }
-  }
-
-  // ---------------------------------------------------------------- statistics: packed warp reductions
-  if (kStats) {
-    const unsigned w0 = (is_reset ? 1u : 0u) | (terminated ? 1u << 8 : 0u) | (time_out ? 1u << 16 : 0u) |
-                        (fell ? 1u << 24 : 0u);
-    const unsigned w1 = (so_fast ? 1u : 0u) | (died ? 1u << 8 : 0u) | (adv1 ? 1u << 16 : 0u) |
-                        (adv2 ? 1u << 24 : 0u);
-    const unsigned w2 = (regen ? 1u : 0u) | (static_cast<unsigned>(active ? idx_after_pass1 : 0) << 8);
-    const unsigned s0 = __reduce_add_sync(0xffffffffu, w0);
-    const unsigned s1 = __reduce_add_sync(0xffffffffu, w1);
-    const unsigned s2 = __reduce_add_sync(0xffffffffu, w2);
-    const unsigned lmax = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(active ? level : 0));
-    float rs = active ? reward : 0.0f;
+    if (kStats) {  // packed warp reductions of the step counters
+      const unsigned w0 = (is_reset ? 1u : 0u) | (terminated ? 1u << 8 : 0u) | (time_out ? 1u << 16 : 0u) |
+                          (fell ? 1u << 24 : 0u);
+      const unsigned w1 = (so_fast ? 1u : 0u) | (died ? 1u << 8 : 0u) | (adv1 ? 1u << 16 : 0u) |
+                          (adv2 ? 1u << 24 : 0u);
+      const unsigned w2 = (regen ? 1u : 0u) | (static_cast<unsigned>(active ? idx_after_pass1 : 0) << 8);
+      const unsigned s0 = __reduce_add_sync(0xffffffffu, w0);
+      const unsigned s1 = __reduce_add_sync(0xffffffffu, w1);
+      const unsigned s2 = __reduce_add_sync(0xffffffffu, w2);
+      const unsigned lmax = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(active ? level : 0));
+      float rs = active ? reward : 0.0f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-    if (lane == 0) {
-      unsigned* wc = misc->wcnt[warp];
-      wc[kCntReset] = s0 & 255u;
-      wc[kCntTerminated] = (s0 >> 8) & 255u;
-      wc[kCntTimeOut] = (s0 >> 16) & 255u;
-      wc[kCntFell] = s0 >> 24;
-      wc[kCntSoFast] = s1 & 255u;
-      wc[kCntDied] = (s1 >> 8) & 255u;
-      wc[kCntAdvanced1] = (s1 >> 16) & 255u;
-      wc[kCntAdvanced2] = s1 >> 24;
-      wc[kCntRegen] = s2 & 255u;
-      wc[kCntSumIndex] = s2 >> 8;
-      wc[kCntLevelMax] = lmax;
-      misc->wreward[warp] = rs;
+      for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+      if (lane == 0) {
+        unsigned* wc = misc->wcnt[warp];
+        wc[kCntReset] = s0 & 255u;
+        wc[kCntTerminated] = (s0 >> 8) & 255u;
+        wc[kCntTimeOut] = (s0 >> 16) & 255u;
+        wc[kCntFell] = s0 >> 24;
+        wc[kCntSoFast] = s1 & 255u;
+        wc[kCntDied] = (s1 >> 8) & 255u;
+        wc[kCntAdvanced1] = (s1 >> 16) & 255u;
+        wc[kCntAdvanced2] = s1 >> 24;
+        wc[kCntRegen] = s2 & 255u;
+        wc[kCntSumIndex] = s2 >> 8;
+        wc[kCntLevelMax] = lmax;
+        misc->wreward[warp] = rs;
+      }
+    }
+  } else {
+    // ================================================================ joint role, after the barrier
+    if (active) {
+      float* row = s_obs + t * kObs;
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        row[6 + j] = o_jp[j];
+        row[6 + kJ + j] = o_jv[j];
+      }
+    }
+    if (MODE == kModeFused) {
+      // Envs that reset are finished by the whole warp: lane j produces joint j of the start pose (ENV:505-560) and
+      // stores it both into the observation row (as joint_pos_scaled, what pass 2 sees) and, coalesced, into the
+      // start-pose rows handed to PhysX (ENV:563-565).
+      const unsigned fl = misc->flags[t];
+      unsigned todo = __ballot_sync(0xffffffffu, (fl & 1u) != 0);
+      __syncwarp();
+      const int row0 = (warp - kTile / 32) * 32;
+      while (todo) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const bool mirror_r = (__shfl_sync(0xffffffffu, fl, r) & 2u) != 0;
+        const int64_t e_r = env0 + row0 + r;
+        const uint32_t gid_r = static_cast<uint32_t>(e_r + a.env_id_offset);
+        if (lane < kJ) {
+          const ResetTables& T = misc->rt;
+          const float u = philox_uniform(P.seed, step_now, kStreamReset, gid_r, 1 + lane);
+          const float val = reset_joint_value(P, mirror_r ? T.pose_mirrored[lane] : T.pose[lane], T.lower[lane],
+                                              T.upper[lane], u);
+          float* row = s_obs + (row0 + r) * kObs;
+          row[6 + lane] = scale_to_unit(val, T.lower[lane], T.upper[lane]);
+          const float jv0 = mirror_r ? T.vel_mirrored[lane] : 0.0f;
+          row[6 + kJ + lane] = fminf(fmaxf(jv0 * P.dof_vel_scale, -5.0f), 5.0f);
+          if (a.rows.joint_pos) a.rows.joint_pos[e_r * kJ + lane] = val;
+          if (a.rows.joint_vel) a.rows.joint_vel[e_r * kJ + lane] = jv0;
+        }
+        if (a.rows.root_state && lane < AS_ROOT_STATE_DIM) {
+          const float z = mirror_r ? -0.0f : 0.0f;  // ENV:535 flips the sign of the (zero) vector part
+          float val = 0.0f;
+          if (lane < 3) {
+            const float d = lane == 0 ? P.default_root_pos[0] : (lane == 1 ? P.default_root_pos[1] : P.default_root_pos[2]);
+            val = d + s_org[(row0 + r) * 3 + lane];  // ENV:515
+          } else if (lane == 3) {
+            val = 1.0f;
+          } else if (lane <= 6) {
+            val = z;
+          }
+          a.rows.root_state[e_r * AS_ROOT_STATE_DIM + lane] = val;
+        }
+      }
     }
   }
 
   // ---------------------------------------------------------------- observation tile -> HBM, ENV:326-345
-  __syncthreads();  // every thread has consumed its input rows: the tile may be overwritten
-  if (active) {
-    float* row = s_obs + tid * kObs;
-    row[0] = h;
-    row[1] = roll;
-    row[2] = pitch;
-    row[3] = vb.x;
-    row[4] = vb.y;
-    row[5] = vb.z;
-#pragma unroll
-    for (int j = 0; j < kJ; ++j) {
-      row[6 + j] = o_jp[j];
-      row[6 + kJ + j] = o_jv[j];
-    }
-    row[48] = po.contact_r;
-    row[49] = po.contact_l;
-    row[50] = po.tb0.x; row[51] = po.tb0.y; row[52] = po.tb0.z;
-    row[53] = po.tb1.x; row[54] = po.tb1.y; row[55] = po.tb1.z;
-    row[56] = po.tb2.x; row[57] = po.tb2.y; row[58] = po.tb2.z;
-  }
-  if (MODE == kModeFused && rmask) {
-    // Envs that reset are finished by the whole warp: lane j produces joint j of the start pose (ENV:505-560) and
-    // stores it both into the observation row (as joint_pos_scaled, what pass 2 sees) and, coalesced, into the
-    // start-pose rows handed to PhysX (ENV:563-565) -- keeps the per-env joint loop free of the divergent path.
-    __syncwarp();
-    unsigned todo = rmask;
-    while (todo) {
-      const int r = __ffs(todo) - 1;
-      todo &= todo - 1u;
-      const uint32_t gid_r = __shfl_sync(0xffffffffu, gid, r);
-      const bool mirror_r = __shfl_sync(0xffffffffu, mirror ? 1 : 0, r) != 0;
-      if (lane < kJ) {
-        const ResetTables& T = misc->rt;
-        const float u = philox_uniform(P.seed, step_now, kStreamReset, gid_r, 1 + lane);
-        const float val = reset_joint_value(P, mirror_r ? T.pose_mirrored[lane] : T.pose[lane], T.lower[lane],
-                                            T.upper[lane], u);
-        float* row = s_obs + (warp * 32 + r) * kObs;
-        row[6 + lane] = scale_to_unit(val, T.lower[lane], T.upper[lane]);
-        const float jv0 = mirror_r ? T.vel_mirrored[lane] : 0.0f;
-        row[6 + kJ + lane] = fminf(fmaxf(jv0 * P.dof_vel_scale, -5.0f), 5.0f);
-        const int64_t e_r = env0 + warp * 32 + r;
-        if (a.rows.joint_pos) a.rows.joint_pos[e_r * kJ + lane] = val;
-        if (a.rows.joint_vel) a.rows.joint_vel[e_r * kJ + lane] = jv0;
-      }
-      if (a.rows.root_state && lane < AS_ROOT_STATE_DIM) {
-        const int64_t e_r = env0 + warp * 32 + r;
-        const float z = mirror_r ? -0.0f : 0.0f;  // ENV:535 flips the sign of the (zero) vector part
-        float val = 0.0f;
-        if (lane < 3) {
-          const float d = lane == 0 ? P.default_root_pos[0] : (lane == 1 ? P.default_root_pos[1] : P.default_root_pos[2]);
-          val = d + __ldg(a.in.env_origins + e_r * 3 + lane);  // ENV:515
-        } else if (lane == 3) {
-          val = 1.0f;
-        } else if (lane <= 6) {
-          val = z;
-        }
-        a.rows.root_state[e_r * AS_ROOT_STATE_DIM + lane] = val;
-      }
-    }
-  }
   float* obs_dst = a.out.obs + env0 * kObs;
-  const bool b_obs = ((reinterpret_cast<uintptr_t>(obs_dst) & 15u) == 0) && (((n_valid * kObs) & 3) == 0);
+  const bool b_obs = bulk_ok<kObs>(dense, kDenseObs, n_valid);
   if (b_obs) {
     fence_proxy_async_smem();  // make the generic-proxy writes visible to the TMA engine
     __syncthreads();
@@ -738,7 +802,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
   } else {
     __syncthreads();
-    for (int i = tid; i < n_valid * kObs; i += kTile) obs_dst[i] = s_obs[i];
+    for (int i = tid; i < n_valid * kObs; i += kThreads) obs_dst[i] = s_obs[i];
   }
   if (kStats && tid <= kCntLevelMax) {  // CTA totals -> one replicated global slot (fire and forget)
     const unsigned tot = tid == kCntLevelMax
@@ -759,21 +823,24 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 
 // ------------------------------------------------------------------------------------------------ kernels
 #ifndef AS_STEP_MIN_CTAS
-#define AS_STEP_MIN_CTAS 5
+#define AS_STEP_MIN_CTAS 4
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(kTile, AS_STEP_MIN_CTAS) k_step(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
-  if (threadIdx.x == 0) mbar_init(smem_u32(&misc->mbar), 1);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&misc->mbar_root), 1);
+    mbar_init(smem_u32(&misc->mbar_joint), 1);
+  }
   if (MODE == kModeFused && threadIdx.x < 32) {
     ResetTables& T = misc->rt;
     const int l = threadIdx.x;
     load_reset_tables(a.P, l, T.lower[l], T.upper[l], T.pose[l], T.pose_mirrored[l], T.vel_mirrored[l]);
   }
   __syncthreads();
-  uint32_t phase = 0;
-  process_tile<MODE>(a, blockIdx.x, phase, smem);
+  uint32_t phase_root = 0, phase_joint = 0;
+  process_tile<MODE>(a, blockIdx.x, phase_root, phase_joint, smem);
 }
 
 // 3-call path: folds the statistics of pass 1, consumes the promotion every CTA applied, advances the counter.
@@ -790,7 +857,7 @@ __global__ void __launch_bounds__(128) k_fold_pass1(Ctrl* ctrl, int64_t num_envs
 // without it from the untouched pre-step state buffer (rare: needs zero resets among all envs).  The last CTA
 // then folds the statistics, publishes next step's promotion, flips the state parity and advances the Philox
 // step counter.
-__global__ void __launch_bounds__(kTile, 4) k_fixup_finish(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
   Ctrl* ctrl = a.ws.ctrl;
@@ -799,14 +866,17 @@ __global__ void __launch_bounds__(kTile, 4) k_fixup_finish(const __grid_constant
     const unsigned n = slot_sum(ctrl, kCntReset);
     if (tid == 0) misc->is_last = n;  // reused as "number of resets this step"
   }
-  if (tid == 0) mbar_init(smem_u32(&misc->mbar), 1);
+  if (tid == 0) {
+    mbar_init(smem_u32(&misc->mbar_root), 1);
+    mbar_init(smem_u32(&misc->mbar_joint), 1);
+  }
   __syncthreads();
   const bool need_fixup = misc->is_last == 0 && !(a.P.flags & AS_FLAG_SKIP_PASS2);
   __syncthreads();
   if (need_fixup) {
-    uint32_t phase = 0;
+    uint32_t phase_root = 0, phase_joint = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      process_tile<kModeFixup>(a, tile, phase, smem);
+      process_tile<kModeFixup>(a, tile, phase_root, phase_joint, smem);
       __syncthreads();
     }
   }

@@ -14,7 +14,7 @@ def probe(N, steps=50, sets=4, warmup=10):
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev).manual_seed(1234)
     origins = syn.env_origins_grid(N, cfg.env_spacing).to(dev)
-    mdp = AllstepsMDP(N, device=dev, seed=1)
+    mdp = AllstepsMDP(N, device=dev, seed=1, skip_pass2=("--skip-pass2" in sys.argv))
     mdp.generate_stones(origins)
     st0 = syn.random_mdp_state(cfg, N, torch.Generator().manual_seed(1))
     mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
