@@ -275,15 +275,18 @@ __device__ __forceinline__ unsigned slot_sum(const Ctrl* ctrl, int which) {
 __device__ __forceinline__ void fold_stats(Ctrl* ctrl, unsigned int* fold, int64_t num_envs) {
   const int t = threadIdx.x;
   const int lane = t & 31;
-  // one warp per counter, one lane per slot: a single atomic round trip per counter instead of 32 in sequence
+  // one warp per counter, one lane per slot.  No kernel is adding to the slots any more (stream order), so plain
+  // L2 loads followed by independent zeroing stores do: one memory round trip for the whole fold.
   for (int c = t >> 5; c < kNumCounters; c += blockDim.x >> 5) {
-    const unsigned v = atomicExch(&ctrl->slots[lane][c], 0u);
+    const unsigned v = __ldcg(&ctrl->slots[lane][c]);
+    __stcg(&ctrl->slots[lane][c], 0u);
     const unsigned r = c == kCntLevelMax ? __reduce_max_sync(0xffffffffu, v) : __reduce_add_sync(0xffffffffu, v);
     if (lane == 0) fold[c] = r;
   }
   float rsum = 0.0f;
   if (t >= 32 && t < 64) {
-    rsum = atomicExch(&ctrl->slot_reward[lane], 0.0f);
+    rsum = __ldcg(&ctrl->slot_reward[lane]);
+    __stcg(&ctrl->slot_reward[lane], 0.0f);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
   }
@@ -873,22 +876,24 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
   __syncthreads();
   const bool need_fixup = misc->is_last == 0 && !(a.P.flags & AS_FLAG_SKIP_PASS2);
   __syncthreads();
+  bool finisher = blockIdx.x == 0;  // common case (some env reset): nothing to wait for, CTA 0 finishes alone
   if (need_fixup) {
     uint32_t phase_root = 0, phase_joint = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       process_tile<kModeFixup>(a, tile, phase_root, phase_joint, smem);
       __syncthreads();
     }
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned t = atomicAdd(&ctrl->blocks_done2, 1u);
-    misc->is_last = (t == gridDim.x - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (misc->is_last) {
     __threadfence();
+    __syncthreads();
+    if (tid == 0) {  // the last CTA to get here finishes
+      const unsigned t = atomicAdd(&ctrl->blocks_done2, 1u);
+      misc->is_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    finisher = misc->is_last != 0;
+    if (finisher) __threadfence();
+  }
+  if (finisher) {
     fold_stats(ctrl, misc->fold, a.num_envs);
     if (tid == 0) {
       const AsStats* g = a.global_stats ? a.global_stats : &ctrl->stats;

@@ -115,6 +115,24 @@ class StepBuffers:
                                           _ptr(self.reset_joint_vel), _ptr(self.reset_ids), _ptr(self.n_reset))
 
 
+class CapturedStep:
+    """A fused step captured as a CUDA graph (see AllstepsMDP.capture_step)."""
+
+    def __init__(self, mdp: "AllstepsMDP", views: PhysicsViews, actions: torch.Tensor, out: StepBuffers,
+                 global_stats: Optional[torch.Tensor] = None):
+        self.mdp = mdp
+        self.keep = (views, actions, out, global_stats)
+        self.graph = torch.cuda.CUDAGraph()
+        before = mdp.launch_count
+        with torch.cuda.device(mdp.device):
+            with torch.cuda.graph(self.graph):  # stream capture: the kernels are recorded, not executed
+                mdp.step(views, actions, out, global_stats)
+        self.kernels_per_replay = mdp.launch_count - before
+
+    def replay(self):
+        self.graph.replay()
+
+
 class AllstepsMDP:
     def __init__(self, num_envs: int, device="cuda:0", cfg: Optional[AllstepsCfg] = None, seed: int = 0,
                  env_id_offset: int = 0, intended_regen: bool = False, skip_pass2: bool = False):
@@ -190,6 +208,13 @@ class AllstepsMDP:
         self._keepalive = (views, actions, out)
         if finish:
             self.finish_step(global_stats)
+
+    def capture_step(self, views: PhysicsViews, actions: torch.Tensor, out: StepBuffers,
+                     global_stats: Optional[torch.Tensor] = None) -> "CapturedStep":
+        """Record one fused step (all its launches) into a CUDA graph bound to these buffers.  Replaying costs one
+        graph launch instead of several library calls -- what matters at 4 K..64 K envs, where the step is
+        launch-latency bound.  The producer of the physics tensors must write into the same storage every step."""
+        return CapturedStep(self, views, actions, out, global_stats)
 
     def finish_step(self, global_stats: Optional[torch.Tensor] = None):
         """Close the fused step: conditional no-reset fix-up, promotion rule (ENV:471-479), counters."""

@@ -355,3 +355,39 @@ def test_joint_scaling_is_bit_exact():
         keep_rows = ~(out.terminated | out.time_out).cpu()  # reset rows show the start pose instead
         got = out.obs[:, 6:27].cpu()
         assert torch.equal(got[keep_rows], expect[keep_rows]), "joint_pos_scaled is not bit-identical to torch"
+
+
+def test_cuda_graph_replay_is_identical_to_eager_steps():
+    """The launch-bound small-N regime runs the step as one captured CUDA graph; results must not change."""
+    from allsteps_isaaclab_b200.mdp import PhysicsViews, StepBuffers
+
+    N, seed = 4096, 41
+    sc = Scenario(N, seed=seed)
+    st0 = sc.initial_mdp_state()
+    origins = sc.env_origins.cuda()
+    mdps = [make_cuda(N, seed) for _ in range(2)]
+    for m in mdps:
+        m.generate_stones(origins)
+        m.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                            "episode_length_buf", "potentials")})
+    stones = mdps[0].export_state()["steps_pos"].cpu()
+    phys = sc.physics(stones, st0["curr_target_index"], st0["swing_leg"])
+    static = {k: v.cuda() for k, v in phys.items()}          # the graph is bound to these tensors
+    views = PhysicsViews.from_dict(static, origins, sc.body_indices)
+    out_g, out_e = StepBuffers(N, "cuda:0"), StepBuffers(N, "cuda:0")
+    step = mdps[0].capture_step(views, static["actions"], out_g)
+    assert step.kernels_per_replay >= 2
+    for i in range(6):
+        st = mdps[1].export_state()
+        phys = sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+        for k, v in phys.items():
+            static[k].copy_(v)                                # "physics" writes in place
+        step.replay()
+        mdps[1].step(views, static["actions"], out_e)
+        torch.cuda.synchronize()
+        for name in ("obs", "reward", "terminated", "time_out", "reset_root_state", "reset_joint_pos"):
+            assert torch.equal(getattr(out_g, name), getattr(out_e, name)), f"step {i}: {name}"
+        a, b = mdps[0].export_state(), mdps[1].export_state()
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"step {i}: state {k}"
+        assert mdps[0].read_stats()["step_counter"] == mdps[1].read_stats()["step_counter"]
