@@ -216,6 +216,8 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   AS_REQUIRE(params->max_episode_length > 1 && params->max_episode_length < kMaxEpisodeLength,
              "max_episode_length out of range");
   AS_REQUIRE(params->step_dt > 0.0f, "step_dt must be positive");
+  if (params->flags & AS_FLAG_GRID_CURRICULUM)
+    AS_REQUIRE(params->grid_bins >= 2 && params->grid_bins <= 16, "grid_bins must be in 2..16");
   for (int j = 0; j < kJ; ++j) {
     AS_REQUIRE(params->joint_upper[j] > params->joint_lower[j], "joint limits must satisfy lower < upper");
     AS_REQUIRE(params->mirror_src[j] >= 0 && params->mirror_src[j] < kJ, "mirror_src out of range");
@@ -248,6 +250,8 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->ws.window = reinterpret_cast<float4*>(base + l.window_off);
   h->ws.reset_ids = reinterpret_cast<int32_t*>(base + l.reset_ids_off);
   h->ws.regen_ids = reinterpret_cast<int32_t*>(base + l.regen_ids_off);
+  h->ws.regen_info = reinterpret_cast<uint8_t*>(base + l.regen_info_off);
+  h->ws.bin = reinterpret_cast<uint8_t*>(base + l.bin_off);
   build_mirror_tables(h);
   build_joint_consts(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -305,11 +309,19 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   StepArgs a = make_step_args(h, in, actions, actions_stride, out);
   const bool want_rows = reset_out && (reset_out->root_state || reset_out->joint_pos || reset_out->joint_vel ||
                                        reset_out->reset_ids || reset_out->n_reset);
-  const bool regen_enabled = (h->params.flags & AS_FLAG_INTENDED_REGEN) != 0;
+  const bool grid = (h->params.flags & AS_FLAG_GRID_CURRICULUM) != 0;
+  const bool regen_enabled = grid || (h->params.flags & AS_FLAG_INTENDED_REGEN) != 0;
   a.want_reset_list = (reset_out && reset_out->reset_ids) ? 1 : 0;
   if (want_rows) a.rows = *reset_out;  // start-pose rows are written by the step kernel itself
   k_step<kModeFused><<<a.num_tiles, kThreads, kSmemBytes, s>>>(a);
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
+  if (grid) {  // kernel (c): outcomes into the difficulty histogram, then new bins by inverse-CDF sampling
+    const int g = grid_for(h->num_envs, 256 * 8, h->sm_count, 1);
+    k_grid_hist<<<g, 256, 0, s>>>(h->params, h->ws);
+    if (int rc = check_launch(h, "k_grid_hist")) return rc;
+    k_grid_sample<<<g, 256, 0, s>>>(h->params, h->ws, h->env_id_offset);
+    if (int rc = check_launch(h, "k_grid_sample")) return rc;
+  }
   if (regen_enabled) {  // kernel (b): warp-per-env stone regeneration over the compacted list
     ResetArgs r = make_reset_args(h, in->env_origins);
     r.fused = 1;
@@ -419,6 +431,16 @@ int as_import_state(AsHandle* h, const AsMdpState* src, void* stream) {
   if (int rc = check_launch(h, "k_import")) return rc;
   k_clear_promotion<<<1, 32, 0, s>>>(h->ws.ctrl);
   return check_launch(h, "k_clear_promotion");
+}
+
+int as_grid_state(AsHandle* h, uint8_t* bins_dst, const uint8_t* bins_src, uint32_t* hist_dst, const uint32_t* hist_src,
+                  void* stream) {
+  AS_REQUIRE(h, "handle is null");
+  if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
+  const int grid = grid_for(h->num_envs > kMaxGridBins ? h->num_envs : kMaxGridBins, 256, h->sm_count, 8);
+  k_grid_state<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->ws, bins_dst, bins_src, hist_dst, hist_src,
+                                                                     h->num_envs);
+  return check_launch(h, "k_grid_state");
 }
 
 int64_t as_launch_count(const AsHandle* h) { return h ? h->launches : 0; }

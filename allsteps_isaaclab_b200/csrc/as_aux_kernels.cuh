@@ -29,17 +29,38 @@ __device__ __forceinline__ float warp_cumsum_sequential(float x, int lane) {
   return mine;
 }
 
-// ENV:125-174 for one env, one stone per lane (lanes >= kS idle).  `u_dr/u_dphi/u_dtheta` are this lane's draws.
-__device__ __forceinline__ void generate_stones_warp(const AsParams& P, int lane, int level, const Vec3& origin,
-                                                     float u_dr, float u_dphi, float u_dtheta, float4* out_row) {
-  const float deg2rad = 0.017453292519943295f;  // torch.deg2rad multiplies by float32(pi/180)
-  const float half_pi = 1.5707963705062866f;
+// How hard an env's stone sequence is: the reference has one scalar ratio = level / max_level for yaw and pitch and
+// a per-level upper bound of the stone distance (ENV:126-133); the grid-curriculum extension has one ratio per axis.
+struct Difficulty {
+  float ratio_yaw, ratio_pitch, dist_upper;
+};
+__device__ __forceinline__ Difficulty difficulty_of_level(const AsParams& P, int level) {
   level = min(level, P.max_level);                                                   // ENV:126
   const float ratio = static_cast<float>(level) / static_cast<float>(P.max_level);   // ENV:127
-  const float yaw_lo = (P.yaw_range_deg[0] * ratio) * deg2rad, yaw_hi = (P.yaw_range_deg[1] * ratio) * deg2rad;
-  const float pit_lo = (P.pitch_range_deg[0] * ratio) * deg2rad + half_pi;           // ENV:132
-  const float pit_hi = (P.pitch_range_deg[1] * ratio) * deg2rad + half_pi;
-  float dr = torch_lerp(P.dist_lower, P.dist_upper[level], u_dr);                    // ENV:137
+  return Difficulty{ratio, ratio, P.dist_upper[level]};
+}
+// bin = i * B + j (i: pitch bin, j: yaw bin); see oracle/grid_curriculum.py for the definition
+__device__ __forceinline__ Difficulty difficulty_of_bin(const AsParams& P, int bin) {
+  const int B = static_cast<int>(P.grid_bins);
+  const int i = bin / B, j = bin - i * B;
+  const float denom = static_cast<float>(B - 1);
+  const int k = (max(i, j) * P.max_level) / (B - 1);
+  return Difficulty{static_cast<float>(j) / denom, static_cast<float>(i) / denom, P.dist_upper[k]};
+}
+__device__ __forceinline__ Difficulty difficulty_of_env(const AsParams& P, const Workspace& ws, int64_t e, int level) {
+  return (P.flags & AS_FLAG_GRID_CURRICULUM) ? difficulty_of_bin(P, ws.bin[e]) : difficulty_of_level(P, level);
+}
+
+// ENV:125-174 for one env, one stone per lane (lanes >= kS idle).  `u_dr/u_dphi/u_dtheta` are this lane's draws.
+__device__ __forceinline__ void generate_stones_warp(const AsParams& P, int lane, const Difficulty& D,
+                                                     const Vec3& origin, float u_dr, float u_dphi, float u_dtheta,
+                                                     float4* out_row) {
+  const float deg2rad = 0.017453292519943295f;  // torch.deg2rad multiplies by float32(pi/180)
+  const float half_pi = 1.5707963705062866f;
+  const float yaw_lo = (P.yaw_range_deg[0] * D.ratio_yaw) * deg2rad, yaw_hi = (P.yaw_range_deg[1] * D.ratio_yaw) * deg2rad;
+  const float pit_lo = (P.pitch_range_deg[0] * D.ratio_pitch) * deg2rad + half_pi;   // ENV:132
+  const float pit_hi = (P.pitch_range_deg[1] * D.ratio_pitch) * deg2rad + half_pi;
+  float dr = torch_lerp(P.dist_lower, D.dist_upper, u_dr);                           // ENV:137
   float dphi = torch_lerp(yaw_lo, yaw_hi, u_dphi);                                   // ENV:138
   float dth = torch_lerp(pit_lo, pit_hi, u_dtheta);                                  // ENV:139
   if (lane == 0) {                                                                   // ENV:144-146
@@ -154,7 +175,8 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
       if (regen) {
         float u0, u1, u2;
         stone_draws(a, step, e, gid, lane, u0, u1, u2);
-        generate_stones_warp(P, lane, level, Vec3{ox, oy, oz}, u0, u1, u2, a.ws.stones + e * kS);
+        generate_stones_warp(P, lane, difficulty_of_env(P, a.ws, e, level), Vec3{ox, oy, oz}, u0, u1, u2,
+                             a.ws.stones + e * kS);
         if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->stats.n_regenerated), 1ull);
       }
       rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, 1, lane);
@@ -169,7 +191,7 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
       const Vec3 origin{a.env_origins[e * 3], a.env_origins[e * 3 + 1], a.env_origins[e * 3 + 2]};
       float u0, u1, u2;
       stone_draws(a, step, e, gid, lane, u0, u1, u2);
-      generate_stones_warp(P, lane, level, origin, u0, u1, u2, a.ws.stones + e * kS);
+      generate_stones_warp(P, lane, difficulty_of_env(P, a.ws, e, level), origin, u0, u1, u2, a.ws.stones + e * kS);
       rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, 1, lane);  // a reset env restarts at index 1
     }
   }
@@ -193,7 +215,7 @@ __global__ void __launch_bounds__(256) k_generate_stones(const __grid_constant__
     const Vec3 origin{a.env_origins[e * 3], a.env_origins[e * 3 + 1], a.env_origins[e * 3 + 2]};
     float u0, u1, u2;
     stone_draws(a, step, e, gid, lane, u0, u1, u2);
-    generate_stones_warp(a.P, lane, level, origin, u0, u1, u2, a.ws.stones + e * kS);
+    generate_stones_warp(a.P, lane, difficulty_of_env(a.P, a.ws, e, level), origin, u0, u1, u2, a.ws.stones + e * kS);
     rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, state_idx(st[e].x), lane);
   }
 }
@@ -306,6 +328,98 @@ __global__ void __launch_bounds__(256) k_import(const __grid_constant__ AsParams
       float4 v = ws.stones[e * kS + window_slot_stone(idx, k)];
       if (k == 0) v.w = __int_as_float(idx);
       ws.window[e * 4 + k] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel (c)
+// Grid-curriculum extension (no reference counterpart; specification = oracle/grid_curriculum.py).
+// k_grid_hist:   shared-memory histogram of this step's episode outcomes over the difficulty grid, flushed with one
+//                atomic per touched bin and CTA.
+// k_grid_sample: every CTA rebuilds the integer CDF of the bin weights with a warp-scan (shuffle) prefix sum, then
+//                draws a new bin for each env that reset by inverse-CDF search with its Philox uniform.
+// Both walk the id list the step kernel compacted (ws.regen_ids / ws.regen_info).
+constexpr uint32_t kStreamGrid = 2;
+
+__global__ void __launch_bounds__(256) k_grid_hist(const __grid_constant__ AsParams P, Workspace ws) {
+  __shared__ unsigned int s_att[kMaxGridBins], s_succ[kMaxGridBins];
+  Ctrl* ctrl = ws.ctrl;
+  for (int i = threadIdx.x; i < kMaxGridBins; i += blockDim.x) s_att[i] = s_succ[i] = 0;
+  __syncthreads();
+  const int64_t n = ctrl->n_regen_list;
+  for (int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; w < n;
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = ws.bin[ws.regen_ids[w]];
+    atomicAdd(&s_att[b], 1u);
+    if (ws.regen_info[w] > kS / 2) atomicAdd(&s_succ[b], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMaxGridBins; i += blockDim.x) {
+    if (s_att[i]) atomicAdd(&ctrl->grid_attempts[i], s_att[i]);
+    if (s_succ[i]) atomicAdd(&ctrl->grid_successes[i], s_succ[i]);
+  }
+}
+
+__device__ __forceinline__ unsigned int grid_weight(unsigned int a, unsigned int s) {
+  if (a == 0) return 256u;  // unvisited bins are tried
+  const unsigned long long A = a, S = s;
+  return 1u + static_cast<unsigned int>((1024ull * S * (A - S)) / (A * A + 1ull));  // peaks at a 50 % success rate
+}
+
+__global__ void __launch_bounds__(256) k_grid_sample(const __grid_constant__ AsParams P, Workspace ws,
+                                                     int64_t env_id_offset) {
+  __shared__ unsigned int s_cdf[kMaxGridBins];
+  __shared__ unsigned int s_warp_tot[8];
+  Ctrl* ctrl = ws.ctrl;
+  const int nb = static_cast<int>(P.grid_bins * P.grid_bins);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  // inclusive prefix sum of the weights: shuffle scan inside each warp, then the warp totals
+  unsigned int v = t < nb ? grid_weight(__ldcg(&ctrl->grid_attempts[t]), __ldcg(&ctrl->grid_successes[t])) : 0u;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int up = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += up;
+  }
+  if (lane == 31) s_warp_tot[warp] = v;
+  __syncthreads();
+  unsigned int base = 0;
+  for (int w = 0; w < warp; ++w) base += s_warp_tot[w];
+  s_cdf[t] = v + base;
+  __syncthreads();
+  const unsigned long long total = s_cdf[nb - 1];
+  const unsigned long long step = ctrl->step_counter;
+  const int64_t n = ctrl->n_regen_list;
+  for (int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + t; w < n;
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e = ws.regen_ids[w];
+    const uint4 blk = philox_block(P.seed, step, kStreamGrid, static_cast<uint32_t>(e + env_id_offset), 0);
+    const unsigned long long target = (static_cast<unsigned long long>(blk.x >> 8) * total) >> 24;
+    int lo = 0, hi = nb - 1;  // first bin with cdf > target
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_cdf[mid] > target) hi = mid; else lo = mid + 1;
+    }
+    ws.bin[e] = static_cast<uint8_t>(lo);
+  }
+}
+
+// bins / histograms in and out (tests, checkpoints)
+__global__ void __launch_bounds__(256) k_grid_state(Workspace ws, uint8_t* bins_dst, const uint8_t* bins_src,
+                                                    unsigned int* hist_dst, const unsigned int* hist_src,
+                                                    int64_t num_envs) {
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (int64_t e = i0; e < num_envs; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (bins_src) ws.bin[e] = bins_src[e];
+    if (bins_dst) bins_dst[e] = ws.bin[e];
+  }
+  if (i0 < kMaxGridBins) {
+    if (hist_src) {
+      ws.ctrl->grid_attempts[i0] = hist_src[i0];
+      ws.ctrl->grid_successes[i0] = hist_src[kMaxGridBins + i0];
+    }
+    if (hist_dst) {
+      hist_dst[i0] = ws.ctrl->grid_attempts[i0];
+      hist_dst[kMaxGridBins + i0] = ws.ctrl->grid_successes[i0];
     }
   }
 }

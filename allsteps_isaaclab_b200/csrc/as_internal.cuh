@@ -11,6 +11,7 @@ constexpr int kJ = AS_NUM_JOINTS;
 constexpr int kS = AS_NUM_STONES;
 constexpr int kObs = AS_OBS_DIM;
 constexpr int kTile = AS_TILE_ENVS;  // envs per CTA == threads per CTA
+constexpr int kMaxGridBins = 256;    // grid curriculum: up to 16 x 16 bins
 constexpr int kSlots = 32;           // replicated statistic accumulators (spreads same-address atomics)
 
 // Per-step counters accumulated by the step kernels (index into Ctrl::slots[slot][]).
@@ -73,6 +74,8 @@ struct Ctrl {
   AsStats stats;          // folded statistics of the last step (this shard)
   unsigned int slots[kSlots][kNumCounters];
   float slot_reward[kSlots];
+  unsigned int grid_attempts[kMaxGridBins];   // grid curriculum extension: episodes ended per difficulty bin
+  unsigned int grid_successes[kMaxGridBins];  // ... of which the env had passed half of the stones
 };
 
 struct Workspace {
@@ -82,10 +85,13 @@ struct Workspace {
   float4* window;     // (N,4) cache of stones idx-1, idx, idx+1, idx+2 (clamped); entry 0's .w holds idx as a tag
   int32_t* reset_ids; // (N)
   int32_t* regen_ids; // (N)
+  uint8_t* regen_info;// (N) curr_target_index at the end of the episode, parallel to regen_ids (grid curriculum)
+  uint8_t* bin;       // (N) difficulty-grid bin of each env (grid curriculum extension)
 };
 
 struct WorkspaceLayout {
-  int64_t ctrl_off, state0_off, state1_off, stones_off, window_off, reset_ids_off, regen_ids_off, total;
+  int64_t ctrl_off, state0_off, state1_off, stones_off, window_off, reset_ids_off, regen_ids_off, regen_info_off,
+      bin_off, total;
 };
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -107,6 +113,10 @@ inline WorkspaceLayout workspace_layout(int64_t n) {
   off = align_up(off + n * 4, 256);
   l.regen_ids_off = off;
   off = align_up(off + n * 4, 256);
+  l.regen_info_off = off;
+  off = align_up(off + n, 256);
+  l.bin_off = off;
+  off = align_up(off + n, 256);
   l.total = off;
   return l;
 }

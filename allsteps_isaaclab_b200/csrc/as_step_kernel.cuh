@@ -558,7 +558,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         // ---- masked reset, ENV:487-538.  Pass 2 on the post-reset state: identity orientation (vector part +-0),
         // zero velocity, zero contacts (contact_sensor.py:155), stale body positions; so roll = pitch = v_b = 0 and
         // targets_b = stone - root.  The start-pose joints are produced by the joint-role warps.
-        regen = (P.flags & AS_FLAG_INTENDED_REGEN) && m.idx > kS / 2;
+        regen = ((P.flags & AS_FLAG_INTENDED_REGEN) && m.idx > kS / 2) || (P.flags & AS_FLAG_GRID_CURRICULUM);
         const uint4 rblk = philox_block(P.seed, step_now, kStreamReset, gid, 0);
         mirror = u32_to_unit(rblk.x) > 0.5f;  // ENV:518
         const Vec3 org{s_org[t * 3], s_org[t * 3 + 1], s_org[t * 3 + 2]};
@@ -634,7 +634,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         unsigned base = 0;
         if (lane == leader) base = atomicAdd(&ctrl->n_regen_list, __popc(gmask));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (regen) a.ws.regen_ids[base + __popc(gmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
+        if (regen) {
+          const unsigned pos = base + __popc(gmask & ((1u << lane) - 1u));
+          a.ws.regen_ids[pos] = static_cast<int32_t>(e);
+          a.ws.regen_info[pos] = static_cast<uint8_t>(idx_after_pass1);  // where the episode ended
+        }
       }
     }
   } else {

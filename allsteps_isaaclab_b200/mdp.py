@@ -135,7 +135,8 @@ class CapturedStep:
 
 class AllstepsMDP:
     def __init__(self, num_envs: int, device="cuda:0", cfg: Optional[AllstepsCfg] = None, seed: int = 0,
-                 env_id_offset: int = 0, intended_regen: bool = False, skip_pass2: bool = False):
+                 env_id_offset: int = 0, intended_regen: bool = False, skip_pass2: bool = False,
+                 grid_bins: int = 0):
         self.lib = _cabi.load()  # raises if the CUDA library was not built: there is no fallback
         self.cfg = cfg or AllstepsCfg()
         self.device = torch.device(device)
@@ -144,7 +145,9 @@ class AllstepsMDP:
         self.num_envs = int(num_envs)
         self.env_id_offset = int(env_id_offset)
         flags = (_cabi.FLAG_INTENDED_REGEN if intended_regen else 0) | (_cabi.FLAG_SKIP_PASS2 if skip_pass2 else 0)
-        self.params = make_params(self.cfg, seed=seed, flags=flags)
+        flags |= _cabi.FLAG_GRID_CURRICULUM if grid_bins else 0
+        self.grid_bins = int(grid_bins)
+        self.params = make_params(self.cfg, seed=seed, flags=flags, grid_bins=self.grid_bins)
         nbytes = self.lib.as_workspace_bytes(self.num_envs)
         with torch.cuda.device(self.device):
             self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -304,6 +307,28 @@ class AllstepsMDP:
             get("steps_pos", torch.float32, (N, NUM_STONES, 3)), get("steps_dphi", torch.float32, (N, NUM_STONES)))
         _cabi.check(self.lib.as_import_state(self.handle, C.byref(st), self._stream()), "as_import_state")
         self._keepalive = keep
+
+    # ------------------------------------------------------------------ grid curriculum extension
+    def grid_state(self):
+        """(bins (N,) uint8, attempts (B*B,) int64, successes (B*B,) int64) of the difficulty-grid curriculum."""
+        bins = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        hist = torch.empty(512, dtype=torch.int32, device=self.device)
+        _cabi.check(self.lib.as_grid_state(self.handle, bins.data_ptr(), None, hist.data_ptr(), None,
+                                           self._stream()), "as_grid_state")
+        nb = self.grid_bins * self.grid_bins
+        return bins, hist[:nb].long(), hist[256:256 + nb].long()
+
+    def set_grid_state(self, bins: Optional[torch.Tensor] = None, attempts=None, successes=None):
+        b = None if bins is None else bins.to(device=self.device, dtype=torch.uint8).contiguous()
+        hist = None
+        if attempts is not None:
+            hist = torch.zeros(512, dtype=torch.int32, device=self.device)
+            nb = self.grid_bins * self.grid_bins
+            hist[:nb] = attempts.to(self.device).int()
+            hist[256:256 + nb] = successes.to(self.device).int()
+        _cabi.check(self.lib.as_grid_state(self.handle, None, _ptr(b), None, _ptr(hist), self._stream()),
+                    "as_grid_state")
+        self._keepalive = (b, hist)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Checkpoint: MDP buffers + the Philox position (seed is in the params, step counter in the stats)."""

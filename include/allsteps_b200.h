@@ -216,6 +216,15 @@ typedef struct AsMdpState {
 int as_export_state(AsHandle* h, const AsMdpState* dst, void* stream);
 int as_import_state(AsHandle* h, const AsMdpState* src, void* stream);
 
+/* ---- grid curriculum (EXTENSION: AS_FLAG_GRID_CURRICULUM; no reference counterpart, specification in
+ * oracle/grid_curriculum.py) --------------------------------------------------------------------------------------
+ * With the flag set, every env that resets in as_step_fused has its episode outcome added to a (grid_bins x
+ * grid_bins) pitch x yaw difficulty histogram, is assigned a new bin by inverse-CDF sampling, and gets a stone
+ * sequence regenerated at that bin's difficulty.  as_grid_state copies the per-env bins (N bytes) and the two
+ * histograms (attempts[256] then successes[256], uint32) out of / into the device state; NULL = skip. */
+int as_grid_state(AsHandle* h, uint8_t* bins_dst, const uint8_t* bins_src, uint32_t* hist_dst, const uint32_t* hist_src,
+                  void* stream);
+
 /* Host-side introspection used by the tests: number of kernel launches issued by this handle so far, and
  * sizeof() of the public structs (0 AsParams, 1 AsStateIn, 2 AsStepOut, 3 AsResetOut, 4 AsStats, 5 AsMdpState)
  * so that a foreign-language binding can verify its struct layout. */

@@ -120,7 +120,7 @@ class AllstepsOracle:
 
     def __init__(self, cfg, num_envs: int, env_origins: torch.Tensor, joint_limits: torch.Tensor,
                  body_indices=(0, 1, 2), stone_uniforms: Optional[torch.Tensor] = None,
-                 intended_regen: bool = False):
+                 intended_regen: bool = False, grid=None, seed: int = 0):
         self.cfg = cfg
         self.N = N = num_envs
         self.S = S = cfg.num_steps
@@ -132,6 +132,9 @@ class AllstepsOracle:
         self.step_dt = cfg.sim_dt * cfg.decimation
         self.max_episode_length = cfg.max_episode_length
         self.intended_regen = intended_regen  # extension: regen mask taken BEFORE the index reset
+        self.grid = grid  # extension: oracle.grid_curriculum.GridCurriculum (every reset env is re-binned + regenerated)
+        self.seed = seed
+        self.step_index = 0
         # ENV:45-48
         self.termination_curriculum = torch.linspace(*cfg.termination_height_range, cfg.max_curriculum + 1)
         self.applied_gain_curriculum = torch.linspace(*cfg.applied_gain_range, cfg.max_curriculum + 1)
@@ -275,6 +278,7 @@ class AllstepsOracle:
         if self.curr_target_index.float().mean() > c.curriculum_progress_threshold:
             self.curriculum = torch.clamp(self.curriculum + 1, 0, c.max_curriculum)
         regen_mask_before = self.curr_target_index > S // 2
+        index_at_end = self.curr_target_index[env_ids].clone()
         # scene.reset + base class, DRL:563-584, contact_sensor.py:155
         p["force_matrix_left"][env_ids] = 0.0
         p["force_matrix_right"][env_ids] = 0.0
@@ -290,9 +294,20 @@ class AllstepsOracle:
         # ENV:497-500: evaluated after the index reset => never true in the reference
         regen_mask = regen_mask_before if self.intended_regen else (self.curr_target_index > S // 2)
         replace_ids = env_ids[torch.isin(env_ids, regen_mask.nonzero(as_tuple=False).flatten())]
-        self.regenerated_ids = replace_ids
-        if len(replace_ids) > 0:
+        if self.grid is not None:
+            # grid-curriculum extension: outcome -> histogram, new bin by inverse CDF, stones at the bin's difficulty
+            from . import grid_curriculum as gc
+
+            replace_ids = env_ids
+            self.grid.episode_end(env_ids.numpy(), index_at_end.numpy(), S, self.seed, self.step_index)
+            pos, dphi = gc.generate_stones_for_bins(c, torch.from_numpy(self.grid.bins.copy()), self.grid.B,
+                                                    stone_uniforms)
+            pos = pos + self.env_origins.unsqueeze(1)
+            self.steps_pos[env_ids] = pos[env_ids]
+            self.steps_dphi[env_ids] = dphi[env_ids]
+        elif len(replace_ids) > 0:
             self.regenerate_stones(replace_ids, stone_uniforms)
+        self.regenerated_ids = replace_ids
         # running-start pose, ENV:505-515
         k = env_ids.shape[0]
         joint_pos = self.reset_pose.unsqueeze(0).repeat(k, 1)
@@ -369,4 +384,5 @@ class AllstepsOracle:
         if len(ids) > 0:
             self.reset_rows(ids, mirror_u[ids], noise_u[ids], stone_uniforms)
         obs = self.observations()
+        self.step_index += 1
         return obs, reward, self.reset_terminated.clone(), self.reset_time_outs.clone(), ids

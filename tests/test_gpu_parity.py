@@ -391,3 +391,47 @@ def test_cuda_graph_replay_is_identical_to_eager_steps():
         for k in a:
             assert torch.equal(a[k], b[k]), f"step {i}: state {k}"
         assert mdps[0].read_stats()["step_counter"] == mdps[1].read_stats()["step_counter"]
+
+
+def test_grid_curriculum_extension():
+    """Kernel (c): difficulty histogram + inverse-CDF bin sampling + regeneration at the bin's difficulty.  No
+    reference counterpart: checked bit for bit against its specification, oracle/grid_curriculum.py."""
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+    from oracle import allsteps_oracle as ao
+    from oracle import grid_curriculum as gc
+
+    N, seed, B = 3000, 19, 11
+    sc = Scenario(N, seed=seed, fall_fraction=0.05)
+    st0 = sc.initial_mdp_state()
+    grid = gc.GridCurriculum(N, B)
+    orc = ao.AllstepsOracle(sc.cfg, N, sc.env_origins, sc.joint_limits, sc.body_indices, sc.stone_uniforms(0),
+                            grid=grid, seed=seed)
+    mdp = make_cuda(N, seed, grid_bins=B)
+    origins = sc.env_origins.cuda()
+    mdp.generate_stones(origins)
+    install_mdp_state(orc, st0)
+    mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                          "episode_length_buf", "potentials")})
+    mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
+    out = StepBuffers(N, "cuda:0")
+    total_reset = 0
+    for step in range(10):
+        phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+        m, n = sc.reset_uniforms(step)
+        o_obs, o_rew, o_term, o_to, o_ids = orc.step(phys, phys["actions"], m, n, sc.stone_uniforms(step))
+        views, keep = to_views(phys, origins, sc.body_indices)
+        mdp.step(views, keep["actions"], out)
+        torch.cuda.synchronize()
+        exact(out.terminated, o_term, f"step {step} terminated")
+        close(out.reward, o_rew, f"step {step} reward")
+        close_obs(out.obs, o_obs, f"step {step} obs")
+        bins, att, succ = mdp.grid_state()
+        exact(bins, torch.from_numpy(grid.bins.copy()), f"step {step} bins")
+        exact(att, torch.from_numpy(grid.attempts.astype(np.int64)), f"step {step} attempts histogram")
+        exact(succ, torch.from_numpy(grid.successes.astype(np.int64)), f"step {step} successes histogram")
+        st = compare_state(mdp, orc, f"step {step}")
+        close(st["steps_pos"], orc.steps_pos, f"step {step} regenerated stones")
+        mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
+        total_reset += len(o_ids)
+    assert total_reset > 500 and int(att.sum()) == total_reset
+    assert len(np.unique(grid.bins)) > 30  # the sampler spreads over the grid
