@@ -365,9 +365,10 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
 
 int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids, int64_t* episode_length,
              const AsResetOut* compact_out, void* stream) {
-  AS_REQUIRE(h && env_origins && env_ids, "handle/env_origins/env_ids is null");
+  AS_REQUIRE(h, "handle is null");
   AS_REQUIRE(n_ids >= 0 && n_ids <= h->num_envs, "id count out of range");
-  if (n_ids == 0) return AS_OK;  // DRL:360: `_reset_idx` is not entered
+  if (n_ids == 0) return AS_OK;  // DRL:360: `_reset_idx` is not entered (an empty id tensor has a null pointer)
+  AS_REQUIRE(env_origins && env_ids, "env_origins/env_ids is null");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   k_decide_promotion<<<1, 32, 0, s>>>(h->params, h->ws.ctrl, nullptr, 1);
   if (int rc = check_launch(h, "k_decide_promotion")) return rc;

@@ -435,3 +435,134 @@ def test_grid_curriculum_extension():
         total_reset += len(o_ids)
     assert total_reset > 500 and int(att.sum()) == total_reset
     assert len(np.unique(grid.bins)) > 30  # the sampler spreads over the grid
+
+
+@pytest.mark.parametrize("num_envs", [1, 3, 5, 127, 129])
+def test_tiny_and_ragged_env_counts(num_envs):
+    # fewer envs than a tile, not a multiple of 4 (no TMA for the ragged tile), one more than a tile
+    run_replay(num_envs, 6, seed=100 + num_envs, fall_fraction=0.2)
+
+
+def test_reset_with_empty_id_list_is_a_no_op():
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+
+    mdp = make_cuda(64, 1)
+    origins = torch.zeros(64, 3, device="cuda")
+    mdp.generate_stones(origins)
+    before = mdp.export_state()
+    n0 = mdp.launch_count
+    mdp.reset(origins, torch.zeros(0, dtype=torch.long, device="cuda"), StepBuffers(64, "cuda:0"))
+    assert mdp.launch_count == n0  # DRL:360: `_reset_idx` is not entered for an empty id list
+    after = mdp.export_state()
+    for k in before:
+        assert torch.equal(before[k], after[k])
+
+
+def test_api_misuse_is_reported():
+    from allsteps_isaaclab_b200 import _cabi
+    from allsteps_isaaclab_b200.mdp import PhysicsViews, StepBuffers
+
+    N = 256
+    sc = Scenario(N, seed=1)
+    mdp = make_cuda(N, 1)
+    origins = sc.env_origins.cuda()
+    mdp.generate_stones(origins)
+    st = mdp.export_state()
+    phys = {k: v.cuda() for k, v in sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(),
+                                               st["swing_leg"].cpu()).items()}
+    views = PhysicsViews.from_dict(phys, origins)
+    out = StepBuffers(N, "cuda:0")
+    with pytest.raises(_cabi.AllstepsLibraryError, match="pass1"):
+        mdp.pass2(views, out)  # pass 2 without pass 1
+    mdp.step(views, phys["actions"], out, finish=False)
+    with pytest.raises(_cabi.AllstepsLibraryError, match="as_finish_step"):
+        mdp.step(views, phys["actions"], out)  # a fused step is still open
+    with pytest.raises(_cabi.AllstepsLibraryError):
+        mdp.export_state()
+    mdp.finish_step()
+    with pytest.raises(_cabi.AllstepsLibraryError):
+        mdp.finish_step()  # nothing to close
+    with pytest.raises(ValueError):
+        mdp.step(PhysicsViews.from_dict({k: v[:128] for k, v in phys.items()}, origins[:128]), phys["actions"], out)
+    with pytest.raises(TypeError):
+        mdp.step(views, phys["actions"].double(), out)
+
+
+def test_one_million_envs_against_the_oracle_and_invariants():
+    """BASELINE.json's full size.  Two steps against the CPU oracle, plus size-independent properties: results do not
+    depend on how the envs are sharded (env-id offset + Philox keyed by global id), and a rigid translation of the
+    whole world leaves the root-frame observation unchanged."""
+    from allsteps_isaaclab_b200.mdp import AllstepsMDP, StepBuffers
+    from oracle import allsteps_oracle as ao
+
+    N, seed = 1 << 20, 5
+    sc = Scenario(N, seed=seed)
+    st0 = sc.initial_mdp_state()
+    orc = ao.AllstepsOracle(sc.cfg, N, sc.env_origins, sc.joint_limits, sc.body_indices, sc.stone_uniforms(0))
+    install_mdp_state(orc, st0)
+    mdp = make_cuda(N, seed)
+    origins = sc.env_origins.cuda()
+    mdp.generate_stones(origins)
+    keys = ("curr_target_index", "swing_leg", "target_reach_count", "episode_length_buf", "potentials")
+    mdp.import_state({k: st0[k] for k in keys})
+    mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
+    # the same envs as two shards of 512K with their own handles
+    half = N // 2
+    shards = [AllstepsMDP(half, device="cuda:0", seed=seed, env_id_offset=r * half) for r in range(2)]
+    for r, sh in enumerate(shards):
+        sl = slice(r * half, (r + 1) * half)
+        sh.import_state({k: st0[k][sl] for k in keys})
+        sh.import_state({"steps_pos": orc.steps_pos[sl], "steps_dphi": orc.steps_dphi[sl]})
+    out = StepBuffers(N, "cuda:0")
+    outs = [StepBuffers(half, "cuda:0") for _ in range(2)]
+    for step in range(2):
+        phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+        m, n = sc.reset_uniforms(step)
+        o_obs, o_rew, o_term, o_to, o_ids = orc.step(phys, phys["actions"], m, n, None)
+        views, keep = to_views(phys, origins, sc.body_indices)
+        mdp.step(views, keep["actions"], out)
+        torch.cuda.synchronize()
+        exact(out.terminated, o_term, f"step {step} terminated")
+        exact(out.time_out, o_to, f"step {step} time_out")
+        close(out.reward, o_rew, f"step {step} reward")
+        close_obs(out.obs, o_obs, f"step {step} obs")
+        compare_state(mdp, orc, f"step {step}")
+        assert int(out.n_reset.item()) == len(o_ids)
+        for r, sh in enumerate(shards):
+            sl = slice(r * half, (r + 1) * half)
+            v, k = to_views({kk: vv[sl] for kk, vv in phys.items()}, origins[sl].contiguous(), sc.body_indices)
+            sh.step(v, k["actions"], outs[r])
+            torch.cuda.synchronize()
+            for name in ("obs", "reward", "terminated", "time_out", "reset_joint_pos", "reset_root_state"):
+                assert torch.equal(getattr(outs[r], name), getattr(out, name)[sl]), f"shard {r} step {step}: {name}"
+    # translation invariance of the root-frame part of the observation (columns 50..58) and of everything else
+    shift = torch.tensor([8.0, -16.0, 2.0])
+    phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+    a = make_cuda(4096, seed, skip_pass2=True)
+    b = make_cuda(4096, seed, skip_pass2=True)
+    sub = slice(0, 4096)
+    st = {k: getattr(orc, k)[sub] for k in ("curr_target_index", "swing_leg", "target_reach_count", "potentials")}
+    st["episode_length_buf"] = orc.episode_length_buf[sub]
+    a.import_state({**st, "steps_pos": orc.steps_pos[sub], "steps_dphi": orc.steps_dphi[sub]})
+    b.import_state({**st, "steps_pos": orc.steps_pos[sub] + shift, "steps_dphi": orc.steps_dphi[sub]})
+    pa = {k: v[sub].clone() for k, v in phys.items()}
+    pb = {k: v[sub].clone() for k, v in phys.items()}
+    pb["root_pos_w"] = pb["root_pos_w"] + shift
+    pb["body_pos_w"] = pb["body_pos_w"] + shift
+    pb["root_pos_w"][:, 2] -= shift[2]  # keep the absolute-height termination (root z < 0.4) the same ...
+    pb["body_pos_w"][:, :, 2] -= shift[2]  # ... by translating in the horizontal plane only
+    stones_b = orc.steps_pos[sub].clone()
+    stones_b[..., :2] += shift[:2]
+    b.import_state({"steps_pos": stones_b})
+    oa, ob = StepBuffers(4096, "cuda:0"), StepBuffers(4096, "cuda:0")
+    va, ka = to_views(pa, origins[sub].contiguous(), sc.body_indices)
+    vb, kb = to_views(pb, (sc.env_origins[sub] + torch.tensor([shift[0], shift[1], 0.0])).cuda().contiguous(),
+                      sc.body_indices)
+    a.step(va, ka["actions"], oa)
+    b.step(vb, kb["actions"], ob)
+    torch.cuda.synchronize()
+    exact(oa.terminated, ob.terminated, "translated world: terminated")
+    keep_rows = ~(oa.terminated | oa.time_out).cpu()
+    assert torch.allclose(oa.obs.cpu()[keep_rows], ob.obs.cpu()[keep_rows], atol=2e-4, rtol=0)
+    # the progress term is 60 x a difference of distances of world coordinates ~1e3 m (fp32 ulp 1e-4)
+    assert torch.allclose(oa.reward.cpu()[keep_rows], ob.reward.cpu()[keep_rows], atol=5e-2, rtol=0)
