@@ -21,6 +21,7 @@ struct AsHandle {
   int64_t launches;
   MirrorTable mirror_obs, mirror_act;
   JointConsts jc;
+  cudaEvent_t ev_start, ev_stop;  // optional timing hook around k_step<fused>
   bool pass1_done;
   bool pending_valid;   // a fused step was launched and still needs as_finish_step
   StepArgs pending;     // its arguments: the conditional fix-up re-reads the same inputs
@@ -56,6 +57,12 @@ int check_launch(AsHandle* h, const char* what) {
 }
 
 int num_tiles(int64_t n) { return static_cast<int>((n + kTile - 1) / kTile); }
+
+int launch_contact_gather(AsHandle* h, const AsStateIn* in, cudaStream_t s) {
+  const unsigned blocks = static_cast<unsigned>((h->num_envs + 255) / 256);
+  k_contact_gather<<<blocks, 256, 0, s>>>(*in, h->ws, h->num_envs);
+  return check_launch(h, "k_contact_gather");
+}
 
 int validate_state_in(const AsStateIn* in, bool need_origins) {
   AS_REQUIRE(in != nullptr, "AsStateIn is null");
@@ -242,6 +249,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->launches = 0;
   h->pass1_done = false;
   h->pending_valid = false;
+  h->ev_start = h->ev_stop = nullptr;
   unsigned char* base = static_cast<unsigned char*>(workspace);
   h->ws.ctrl = reinterpret_cast<Ctrl*>(base + l.ctrl_off);
   h->ws.state[0] = reinterpret_cast<uint2*>(base + l.state0_off);
@@ -252,6 +260,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->ws.regen_ids = reinterpret_cast<int32_t*>(base + l.regen_ids_off);
   h->ws.regen_info = reinterpret_cast<uint8_t*>(base + l.regen_info_off);
   h->ws.bin = reinterpret_cast<uint8_t*>(base + l.bin_off);
+  h->ws.contact_pre = reinterpret_cast<float2*>(base + l.contact_pre_off);
   build_mirror_tables(h);
   build_joint_consts(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -313,8 +322,11 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   const bool regen_enabled = grid || (h->params.flags & AS_FLAG_INTENDED_REGEN) != 0;
   a.want_reset_list = (reset_out && reset_out->reset_ids) ? 1 : 0;
   if (want_rows) a.rows = *reset_out;  // start-pose rows are written by the step kernel itself
+  if (int rc = launch_contact_gather(h, in, s)) return rc;
+  if (h->ev_start) AS_CUDA(cudaEventRecord(h->ev_start, s));
   k_step<kModeFused><<<a.num_tiles, kThreads, kSmemBytes, s>>>(a);
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
+  if (h->ev_stop) AS_CUDA(cudaEventRecord(h->ev_stop, s));
   if (grid) {  // kernel (c): outcomes into the difficulty histogram, then new bins by inverse-CDF sampling
     const int g = grid_for(h->num_envs, 256 * 8, h->sm_count, 1);
     k_grid_hist<<<g, 256, 0, s>>>(h->params, h->ws);
@@ -356,6 +368,7 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   StepArgs a = make_step_args(h, in, actions, actions_stride, out);
   a.ext_episode_length = episode_length;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = launch_contact_gather(h, in, s)) return rc;
   k_step<kModePass1><<<a.num_tiles, kThreads, kSmemBytes, s>>>(a);
   if (int rc = check_launch(h, "k_step<pass1>")) return rc;
   k_fold_pass1<<<1, 128, 0, s>>>(h->ws.ctrl, h->num_envs);
@@ -391,6 +404,7 @@ int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
   std::memset(&out, 0, sizeof(out));
   out.obs = obs;
   StepArgs a = make_step_args(h, in, nullptr, 0, &out);
+  if (int rc = launch_contact_gather(h, in, static_cast<cudaStream_t>(stream))) return rc;
   k_step<kModePass2><<<a.num_tiles, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
   return check_launch(h, "k_step<pass2>");
 }
@@ -442,6 +456,14 @@ int as_grid_state(AsHandle* h, uint8_t* bins_dst, const uint8_t* bins_src, uint3
   k_grid_state<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->ws, bins_dst, bins_src, hist_dst, hist_src,
                                                                      h->num_envs);
   return check_launch(h, "k_grid_state");
+}
+
+int as_set_timing_events(AsHandle* h, void* start_event, void* stop_event) {
+  AS_REQUIRE(h, "handle is null");
+  AS_REQUIRE((start_event == nullptr) == (stop_event == nullptr), "give both events or none");
+  h->ev_start = static_cast<cudaEvent_t>(start_event);
+  h->ev_stop = static_cast<cudaEvent_t>(stop_event);
+  return AS_OK;
 }
 
 int64_t as_launch_count(const AsHandle* h) { return h ? h->launches : 0; }

@@ -10,7 +10,10 @@ namespace as {
 constexpr int kJ = AS_NUM_JOINTS;
 constexpr int kS = AS_NUM_STONES;
 constexpr int kObs = AS_OBS_DIM;
-constexpr int kTile = AS_TILE_ENVS;  // envs per CTA == threads per CTA
+#ifndef AS_KTILE
+#define AS_KTILE AS_TILE_ENVS
+#endif
+constexpr int kTile = AS_KTILE;  // envs per CTA (two threads per env)
 constexpr int kMaxGridBins = 256;    // grid curriculum: up to 16 x 16 bins
 constexpr int kSlots = 32;           // replicated statistic accumulators (spreads same-address atomics)
 
@@ -87,11 +90,12 @@ struct Workspace {
   int32_t* regen_ids; // (N)
   uint8_t* regen_info;// (N) curr_target_index at the end of the episode, parallel to regen_ids (grid curriculum)
   uint8_t* bin;       // (N) difficulty-grid bin of each env (grid curriculum extension)
+  float2* contact_pre;// (N) |F_right|, |F_left| of each env's current stone, gathered by k_contact_gather
 };
 
 struct WorkspaceLayout {
   int64_t ctrl_off, state0_off, state1_off, stones_off, window_off, reset_ids_off, regen_ids_off, regen_info_off,
-      bin_off, total;
+      bin_off, contact_pre_off, total;
 };
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -117,6 +121,8 @@ inline WorkspaceLayout workspace_layout(int64_t n) {
   off = align_up(off + n, 256);
   l.bin_off = off;
   off = align_up(off + n, 256);
+  l.contact_pre_off = off;
+  off = align_up(off + n * 8, 256);
   l.total = off;
   return l;
 }

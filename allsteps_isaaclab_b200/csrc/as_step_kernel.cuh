@@ -436,8 +436,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
     cr_row = a.in.contact_right + e * a.in.contact_right_stride;
     cl_row = a.in.contact_left + e * a.in.contact_left_stride;
-    f_r = contact_norm(cr_row, m.idx, contact_aligned);
-    f_l = contact_norm(cl_row, m.idx, contact_aligned);
+    {  // |F| of the current stone under each foot, gathered by k_contact_gather just before this kernel
+      const float2 pre = a.ws.contact_pre[e];
+      f_r = pre.x;
+      f_l = pre.y;
+    }
     win_valid = __float_as_int(w0.w) == m.idx;
     if (win_valid) {
       s_prev = w0; s_curr = w1; s_next = w2; s_next2 = w3;
@@ -812,9 +815,9 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     for (int i = tid; i < n_valid * kObs; i += kThreads) obs_dst[i] = s_obs[i];
   }
   if (kStats && tid <= kCntLevelMax) {  // CTA totals -> one replicated global slot (fire and forget)
-    const unsigned tot = tid == kCntLevelMax
-                             ? max(max(misc->wcnt[0][tid], misc->wcnt[1][tid]), max(misc->wcnt[2][tid], misc->wcnt[3][tid]))
-                             : misc->wcnt[0][tid] + misc->wcnt[1][tid] + misc->wcnt[2][tid] + misc->wcnt[3][tid];
+    unsigned tot = 0;
+#pragma unroll
+    for (int w = 0; w < kTile / 32; ++w) tot = tid == kCntLevelMax ? max(tot, misc->wcnt[w][tid]) : tot + misc->wcnt[w][tid];
     const int slot = blockIdx.x & (kSlots - 1);
     if (tot) {
       if (tid == kCntLevelMax) atomicMax(&ctrl->slots[slot][tid], tot);
@@ -822,15 +825,33 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
   }
   if (kStats && tid == 32) {
-    const float rs = (misc->wreward[0] + misc->wreward[1]) + (misc->wreward[2] + misc->wreward[3]);
+    float rs = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kTile / 32; ++w) rs += misc->wreward[w];
     atomicAdd(&ctrl->slot_reward[blockIdx.x & (kSlots - 1)], rs);
   }
   if (tid == 0 && b_obs) bulk_wait_read_all();  // shared memory must stay intact until the engine has read it
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
+// The data-dependent part of the step's input: for every env the 12-byte contact-force vectors of its CURRENT stone
+// out of the two (N,1,S,3) PhysX matrices (ENV:421-425).  These random DRAM reads are what floors the step
+// (profiles/r01_membound_probe.txt); as a kernel of their own they run at full occupancy with nothing else on the
+// critical path -- state word (coalesced) -> two gathers -> one coalesced 8-byte store -- instead of stalling a
+// 46-KB CTA of the step kernel, which then reads the two norms as a coalesced record.
+__global__ void __launch_bounds__(256) k_contact_gather(const AsStateIn in, Workspace ws, int64_t num_envs) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= num_envs) return;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in.contact_right) | reinterpret_cast<uintptr_t>(in.contact_left)) &
+                        15u) == 0 && ((in.contact_right_stride | in.contact_left_stride) & 3) == 0;
+  const int idx = state_idx(ws.state[ws.ctrl->parity][e].x);
+  const float f_r = contact_norm(in.contact_right + e * in.contact_right_stride, idx, aligned);
+  const float f_l = contact_norm(in.contact_left + e * in.contact_left_stride, idx, aligned);
+  ws.contact_pre[e] = make_float2(f_r, f_l);
+}
+
 #ifndef AS_STEP_MIN_CTAS
-#define AS_STEP_MIN_CTAS 4
+#define AS_STEP_MIN_CTAS (512 / AS_KTILE)
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __grid_constant__ StepArgs a) {

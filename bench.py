@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 24)")
     ap.add_argument("--stats-interval", type=int, default=16, help="all-reduce step statistics every k steps")
     ap.add_argument("--small-sizes", default="4096,65536", help="extra env counts timed for latency (N=1 only)")
+    # other BASELINE.json configs (the default flags are the headline workload)
+    ap.add_argument("--fall-fraction", type=float, default=0.02, help="fraction of envs dying per step (0.3 = config 5)")
+    ap.add_argument("--intended-regen", action="store_true", help="regenerate stones of reset envs past S/2 (extension)")
+    ap.add_argument("--grid-bins", type=int, default=0, help="pitch x yaw grid curriculum with B x B bins (config 3)")
     return ap.parse_args()
 
 
@@ -177,7 +181,7 @@ def main_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- CUDA arm
-def build_pool(torch, syn, cfg, mdp, origins, sets, device, seed):
+def build_pool(torch, syn, cfg, mdp, origins, sets, device, seed, fall_fraction=0.02):
     """`sets` distinct synthetic post-physics states, generated on the device (throughput only)."""
     from allsteps_isaaclab_b200.mdp import PhysicsViews
 
@@ -185,7 +189,8 @@ def build_pool(torch, syn, cfg, mdp, origins, sets, device, seed):
     st = mdp.export_state()
     pool = []
     for _ in range(sets):
-        d = syn.random_physics_state(cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen)
+        d = syn.random_physics_state(cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen,
+                                     fall_fraction=fall_fraction)
         d.pop("root_ang_vel_w", None)
         pool.append((PhysicsViews.from_dict(d, origins), d))
     return pool
@@ -237,22 +242,26 @@ def time_steps_graph(torch, mdp, pool, out, steps, warmup):
 
 
 def time_kernel_only(torch, mdp, pool, out, steps):
-    """Average duration of the fused step kernel alone: events around each as_step_fused issued without PhysX-row
-    outputs (exactly one launch, k_step<fused>), on the launching stream."""
-    import ctypes as C
+    """Average duration of the dominant kernel alone, k_step<fused>: the library records a pair of CUDA events on the
+    launching stream immediately around that launch (as_set_timing_events).  Also returns the duration of the whole
+    device-side step (contact-gather kernel + step kernel + finish kernel) from events around the two API calls."""
     from allsteps_isaaclab_b200 import _cabi
 
     dev = mdp.device
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    pairs = []
+    for _ in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); b.record()  # creates the underlying cudaEvent_t
+        pairs.append((a, b))
+    torch.cuda.synchronize(dev)
     for i in range(steps):
         v, d = pool[i % len(pool)]
-        evs[i][0].record()
-        _cabi.check(mdp.lib.as_step_fused(mdp.handle, C.byref(v.struct), d["actions"].data_ptr(), 21,
-                                          C.byref(out.step_out), None, mdp._stream()), "as_step_fused")
-        evs[i][1].record()
-        mdp.finish_step()
+        a, b = pairs[i]
+        _cabi.check(mdp.lib.as_set_timing_events(mdp.handle, a.cuda_event, b.cuda_event), "as_set_timing_events")
+        mdp.step(v, d["actions"], out)
+    _cabi.check(mdp.lib.as_set_timing_events(mdp.handle, None, None), "as_set_timing_events")
     torch.cuda.synchronize(dev)
-    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    ms = sorted(a.elapsed_time(b) for a, b in pairs)
     return sum(ms) / len(ms), ms[len(ms) // 2]
 
 
@@ -363,12 +372,13 @@ def main_b200(args):
 
     def make(num_envs, seed=1234):
         origins = syn.env_origins_grid(num_envs, cfg.env_spacing).to(dev)
-        mdp = AllstepsMDP(num_envs, device=dev, seed=seed, env_id_offset=rank * num_envs)
+        mdp = AllstepsMDP(num_envs, device=dev, seed=seed, env_id_offset=rank * num_envs,
+                          intended_regen=args.intended_regen, grid_bins=args.grid_bins)
         mdp.generate_stones(origins)
         st0 = syn.random_mdp_state(cfg, num_envs, torch.Generator().manual_seed(seed + rank))
         mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
                                               "episode_length_buf", "potentials")})
-        pool = build_pool(torch, syn, cfg, mdp, origins, args.input_sets, dev, seed + rank)
+        pool = build_pool(torch, syn, cfg, mdp, origins, args.input_sets, dev, seed + rank, args.fall_fraction)
         return mdp, origins, pool, StepBuffers(num_envs, dev)
 
     mdp, origins, pool, out = make(N)
@@ -389,7 +399,10 @@ def main_b200(args):
     stats = mdp.read_stats()
 
     peak, peak_src = measured_peaks()
-    achieved = N * B_ALG / (k_avg * 1e-3) / 1e9
+    # k_step<fused> moves everything except the 24 B/env of contact vectors, which k_contact_gather fetches for it
+    b_kernel = B_ALG - 24
+    achieved = N * b_kernel / (k_avg * 1e-3) / 1e9
+    achieved_step = N * B_ALG / (ms_step * 1e-3) / 1e9
     traffic = profiled_traffic()
 
     e2e = None
@@ -428,7 +441,10 @@ def main_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"Allsteps-v0 fused MDP step, {N} envs per GPU, ~4% of envs resetting per step",
+            "config": {"workload": f"Allsteps-v0 fused MDP step, {N} envs per GPU, "
+                                   f"{100.0 * stats['n_reset'] / N:.0f}% of envs resetting per step"
+                                   + (", stone regeneration on reset" if args.intended_regen else "")
+                                   + (f", {args.grid_bins}x{args.grid_bins} grid curriculum" if args.grid_bins else ""),
                        "envs_per_gpu": N, "global_envs": N * world, "parallelism": f"env-id shards x{world}",
                        "l2_policy": f"{args.input_sets} rotating input sets of {N * 808 / 1e6:.0f} MB each "
                                     "(larger than the 126 MB L2)",
@@ -439,8 +455,11 @@ def main_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
                          "kernel": "as::k_step<fused>", "kernel_ms_avg": k_avg, "kernel_ms_median": k_med,
-                         "algorithmic_bytes_per_env_step": B_ALG, "peak_source": peak_src,
-                         "frac_of_nominal_8TBs": achieved / 8000.0},
+                         "algorithmic_bytes_per_env_step": b_kernel, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "whole_step": {"achieved": achieved_step, "frac": achieved_step / peak,
+                                        "algorithmic_bytes_per_env_step": B_ALG,
+                                        "kernels": "k_contact_gather + k_step<fused> + k_fixup_finish"}},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
             "step_stats": {k: stats[k] for k in ("n_reset", "n_terminated", "n_time_out", "n_advanced", "level")},

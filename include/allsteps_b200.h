@@ -225,6 +225,10 @@ int as_import_state(AsHandle* h, const AsMdpState* src, void* stream);
 int as_grid_state(AsHandle* h, uint8_t* bins_dst, const uint8_t* bins_src, uint32_t* hist_dst, const uint32_t* hist_src,
                   void* stream);
 
+/* Measurement hook: two `cudaEvent_t` (as void*) that as_step_fused records on its stream immediately before and
+ * after the launch of the fused step kernel alone (bench.py times the dominant kernel with them); NULL = off. */
+int as_set_timing_events(AsHandle* h, void* start_event, void* stop_event);
+
 /* Host-side introspection used by the tests: number of kernel launches issued by this handle so far, and
  * sizeof() of the public structs (0 AsParams, 1 AsStateIn, 2 AsStepOut, 3 AsResetOut, 4 AsStats, 5 AsMdpState)
  * so that a foreign-language binding can verify its struct layout. */

@@ -59,4 +59,5 @@ if __name__ == "__main__":
     ns = [int(a) for a in sys.argv[1:] if a.isdigit()] or [4096, 65536, 262144, 1048576]
     steps = 12 if "--short" in sys.argv else 50
     for n in ns:
-        probe(n, steps=steps, warmup=4 if "--short" in sys.argv else 10)
+        sets = [int(a.split('=')[1]) for a in sys.argv if a.startswith('--sets=')]
+        probe(n, steps=steps, warmup=4 if "--short" in sys.argv else 10, sets=sets[0] if sets else 4)
