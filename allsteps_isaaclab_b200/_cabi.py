@@ -113,6 +113,7 @@ SIGNATURES = {
     "as_import_state": (C.c_int, [_ptr, C.POINTER(AsMdpState), _ptr]),
     "as_grid_state": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "as_set_timing_events": (C.c_int, [_ptr, _ptr, _ptr]),
+    "as_debug_timing": (C.c_int, [_ptr, _ptr, C.c_int, _ptr]),
     "as_launch_count": (_i64, [_ptr]),
     "as_sizeof": (_i64, [_i32]),
 }

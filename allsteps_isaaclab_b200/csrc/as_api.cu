@@ -239,6 +239,11 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
     return fail(AS_ERR_CUDA, "this library contains sm_100a code only; device is sm_" + std::to_string(prop.major) +
                                  std::to_string(prop.minor));
   }
+  // the step kernels stage more than the default 48 KB of dynamic shared memory
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_fixup_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AsHandle* h = new (std::nothrow) AsHandle();
   AS_REQUIRE(h != nullptr, "out of host memory");
   h->params = *params;
@@ -463,6 +468,15 @@ int as_set_timing_events(AsHandle* h, void* start_event, void* stop_event) {
   AS_REQUIRE((start_event == nullptr) == (stop_event == nullptr), "give both events or none");
   h->ev_start = static_cast<cudaEvent_t>(start_event);
   h->ev_stop = static_cast<cudaEvent_t>(stop_event);
+  return AS_OK;
+}
+
+int as_debug_timing(AsHandle* h, uint64_t* host16, int reset, void* stream) {
+  AS_REQUIRE(h && host16, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  AS_CUDA(cudaMemcpyAsync(host16, h->ws.ctrl->dbg_t, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  if (reset) AS_CUDA(cudaMemsetAsync(h->ws.ctrl->dbg_t, 0, 16 * sizeof(uint64_t), s));
+  AS_CUDA(cudaStreamSynchronize(s));
   return AS_OK;
 }
 

@@ -79,6 +79,7 @@ struct Ctrl {
   float slot_reward[kSlots];
   unsigned int grid_attempts[kMaxGridBins];   // grid curriculum extension: episodes ended per difficulty bin
   unsigned int grid_successes[kMaxGridBins];  // ... of which the env had passed half of the stones
+  unsigned long long dbg_t[16];               // -DAS_TIMING builds only: summed clock64() phase durations per CTA
 };
 
 struct Workspace {

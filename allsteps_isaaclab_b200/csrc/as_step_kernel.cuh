@@ -35,7 +35,7 @@ constexpr int kOffRv = kOffRq + kTile * 4 * 4;
 constexpr int kOffBody = kOffRv + kTile * 3 * 4;
 constexpr int kOffOrg = kOffBody + kTile * 9 * 4;   // env origins of the tile (needed by the envs that reset)
 constexpr int kOffMisc = kOffOrg + kTile * 3 * 4;
-constexpr int kSmemBytes = kOffMisc + 3072;
+constexpr int kSmemBytes = kOffMisc + 6144;
 static_assert(kTile * kObs * 4 <= kOffRp, "observation tile must fit over the joint/action tiles it aliases");
 static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffRq % 16 == 0 &&
                   kOffRv % 16 == 0 && kOffBody % 16 == 0 && kOffOrg % 16 == 0 && kOffMisc % 16 == 0,
@@ -62,8 +62,11 @@ struct Misc {  // lives at kOffMisc, never aliased
   float red_actsq[kTile];    // sum_j action^2, ENV:364
   int red_limit[kTile];      // count_j |joint_pos_scaled| > 0.99, ENV:367
   unsigned int flags[kTile]; // bit 0: env resets this step, bit 1: its start pose is mirrored
+  // orientation results computed by the joint role from the root tile while its own tiles are in flight
+  float x_roll[kTile], x_pitch[kTile];
+  float x_inv[4][kTile];     // quat_inv(root_quat), MATH:238-248
 };
-static_assert(sizeof(Misc) <= 3072, "misc block");
+static_assert(sizeof(Misc) <= 6144, "misc block");
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -102,6 +105,10 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Named barrier 1: the joint role arrives when the orientation results are in shared memory, the MDP role waits for
+// them just before it needs them (barrier 0 is __syncthreads).
+__device__ __forceinline__ void orient_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(2 * kTile) : "memory"); }
+__device__ __forceinline__ void orient_wait() { asm volatile("bar.sync 1, %0;" ::"n"(2 * kTile) : "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ------------------------------------------------------------------------------------------------ staging
@@ -333,6 +340,14 @@ __device__ __forceinline__ uint32_t promotion_decision(const AsParams& P, const 
 // CTA barrier (inputs consumed; sums and reset flags exchanged through shared memory) and then fill disjoint
 // columns of the observation tile.  Twice the resident warps of a one-thread-per-env CTA for the same shared
 // memory, and half the serial instruction stream per env.
+#ifdef AS_TIMING
+#define AS_T(var) const long long var = clock64()
+#define AS_TACC(slot, from, to) atomicAdd(&ctrl->dbg_t[slot], static_cast<unsigned long long>((to) - (from)))
+#else
+#define AS_T(var)
+#define AS_TACC(slot, from, to)
+#endif
+
 template <int MODE>
 __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32_t& phase_root,
                                              uint32_t& phase_joint, unsigned char* smem) {
@@ -363,6 +378,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   const uint32_t bar_joint = smem_u32(&misc->mbar_joint);
   Ctrl* ctrl = a.ws.ctrl;
 
+  AS_T(t_start);
   constexpr bool kNeedActions = MODE != kModePass2;
   constexpr bool kPingPong = MODE == kModeFused || MODE == kModeFixup;
   constexpr bool kStats = MODE == kModeFused || MODE == kModePass1;
@@ -500,14 +516,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 
   if (!joint_role) {
     // ================================================================ MDP role, before the barrier
+    AS_T(t_m0);  // state word + window + contact norms are in registers (their consumers ran above)
     if (bulk_root) mbar_wait(bar_root, phase_root);
+    AS_T(t_m1);
     Vec3 p{0, 0, 0}, v{0, 0, 0}, rf{0, 0, 0}, lf{0, 0, 0};
-    Quat q{1, 0, 0, 0};
     float torso_z = 0.0f;
     if (active) {
       p = Vec3{s_rp[t * 3], s_rp[t * 3 + 1], s_rp[t * 3 + 2]};
-      const float4 q4 = *reinterpret_cast<const float4*>(s_rq + t * 4);
-      q = Quat{q4.x, q4.y, q4.z, q4.w};
       v = Vec3{s_rv[t * 3], s_rv[t * 3 + 1], s_rv[t * 3 + 2]};
       rf = Vec3{s_body[t * 9 + 0], s_body[t * 9 + 1], s_body[t * 9 + 2]};
       lf = Vec3{s_body[t * 9 + 3], s_body[t * 9 + 4], s_body[t * 9 + 5]};
@@ -533,14 +548,18 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       // pulling it in now, it is read after pass 1
       if (MODE == kModeFused && is_reset) prefetch_l1(stones);
     }
+    bool moved1 = false;
     if (active) {
       h = torso_z - fminf(lf.z, rf.z);   // ENV:281-283
-      euler_roll_pitch(q, roll, pitch);  // ENV:285
-      vb = rotate_by_inverse(q, v);      // ENV:293
-      inv = quat_inverse(q);
       geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
-      const bool moved = foot_update(P, geom, m, po);
-      if (moved) slide_window();
+      moved1 = foot_update(P, geom, m, po);
+      if (moved1) slide_window();
+    }
+    orient_wait();  // roll / pitch / quat_inv of this env were computed by the joint role (ENV:285, MATH:238-248)
+    if (active) {
+      roll = misc->x_roll[t];
+      pitch = misc->x_pitch[t];
+      inv = Quat{misc->x_inv[0][t], misc->x_inv[1][t], misc->x_inv[2][t], misc->x_inv[3][t]};
       targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
       adv1 = po.advanced;
       idx_after_pass1 = m.idx;
@@ -581,9 +600,6 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         m.leg = mirror ? 1 : 0;  // ENV:491,538
         m.idx = 1;
         ep = 0;  // DRL:584
-        roll = 0.0f;
-        pitch = 0.0f;
-        vb = Vec3{0, 0, 0};
         po.contact_r = 0.0f;
         po.contact_l = 0.0f;
         po.tb0 = Vec3{s_prev.x - p.x, s_prev.y - p.y, s_prev.z - p.z};
@@ -619,6 +635,9 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         wrow[0] = s_prev; wrow[1] = s_curr; wrow[2] = s_next; wrow[3] = s_next2;
       }
     }
+#ifdef AS_TIMING
+    if (tid == 0) { AS_T(t_m2); AS_TACC(0, t_start, t_m0); AS_TACC(1, t_m0, t_m1); AS_TACC(2, t_m1, t_m2); }
+#endif
     if (MODE == kModeFused) {
       misc->flags[t] = (is_reset ? 1u : 0u) | (mirror ? 2u : 0u);
       // ---- reset / regeneration id lists (warp ballots)
@@ -646,7 +665,23 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
   } else {
     // ================================================================ joint role, before the barrier
+    // The root tile is small and lands first: do the orientation math of this env (ENV:285,293; MATH:238-248) while
+    // the three joint tiles are still in flight, and hand roll / pitch / quat_inv to the MDP role.
+    if (bulk_root) mbar_wait(bar_root, phase_root);
+    if (active) {
+      const float4 q4 = *reinterpret_cast<const float4*>(s_rq + t * 4);
+      const Quat q{q4.x, q4.y, q4.z, q4.w};
+      const Vec3 v{s_rv[t * 3], s_rv[t * 3 + 1], s_rv[t * 3 + 2]};
+      euler_roll_pitch(q, roll, pitch);
+      vb = rotate_by_inverse(q, v);
+      const Quat inv = quat_inverse(q);
+      misc->x_roll[t] = roll;
+      misc->x_pitch[t] = pitch;
+      misc->x_inv[0][t] = inv.w; misc->x_inv[1][t] = inv.x; misc->x_inv[2][t] = inv.y; misc->x_inv[3][t] = inv.z;
+    }
+    orient_arrive();
     if (bulk_joint) mbar_wait(bar_joint, phase_joint);
+    AS_T(t_j0);
     float energy = 0.0f, act_sq = 0.0f;
     int at_limit = 0;
     if (active) {
@@ -667,6 +702,9 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         o_jv[j] = fminf(fmaxf(jv * P.dof_vel_scale, -5.0f), 5.0f);  // ENV:337
       }
     }
+#ifdef AS_TIMING
+    if (tid == kTile) { AS_T(t_j1); AS_TACC(8, t_start, t_j0); AS_TACC(9, t_j0, t_j1); }
+#endif
     if (kNeedActions) {
       misc->red_energy[t] = energy;
       misc->red_actsq[t] = act_sq;
@@ -675,8 +713,10 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   }
   if (bulk_root) phase_root ^= 1u;
   if (bulk_joint) phase_joint ^= 1u;
+  AS_T(t_b1a);
 
   __syncthreads();  // every input row is consumed (the observation tile may overwrite them); sums and flags are visible
+  AS_T(t_b1b);
 
   float reward = 0.0f;
   if (!joint_role) {
@@ -707,11 +747,6 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     if (active) {  // head and tail of the observation row, ENV:330-343
       float* row = s_obs + t * kObs;
       row[0] = h;
-      row[1] = roll;
-      row[2] = pitch;
-      row[3] = vb.x;
-      row[4] = vb.y;
-      row[5] = vb.z;
       row[48] = po.contact_r;
       row[49] = po.contact_l;
       row[50] = po.tb0.x; row[51] = po.tb0.y; row[52] = po.tb0.z;
@@ -751,6 +786,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     // ================================================================ joint role, after the barrier
     if (active) {
       float* row = s_obs + t * kObs;
+      // an env that reset is observed in its start pose: identity orientation, zero velocity (pass 2, ENV:567)
+      const bool was_reset = MODE == kModeFused && (misc->flags[t] & 1u);
+      row[1] = was_reset ? 0.0f : roll;
+      row[2] = was_reset ? 0.0f : pitch;
+      row[3] = was_reset ? 0.0f : vb.x;
+      row[4] = was_reset ? 0.0f : vb.y;
+      row[5] = was_reset ? 0.0f : vb.z;
 #pragma unroll
       for (int j = 0; j < kJ; ++j) {
         row[6 + j] = o_jp[j];
@@ -801,6 +843,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   }
 
   // ---------------------------------------------------------------- observation tile -> HBM, ENV:326-345
+  AS_T(t_post);
   float* obs_dst = a.out.obs + env0 * kObs;
   const bool b_obs = bulk_ok<kObs>(dense, kDenseObs, n_valid);
   if (b_obs) {
@@ -810,6 +853,9 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       bulk_s2g(obs_dst, smem_u32(s_obs), static_cast<uint32_t>(n_valid) * kObs * 4);
       bulk_commit();
     }
+#ifdef AS_TIMING
+    if (tid == 0 || tid == kTile) { AS_T(t_b2); AS_TACC(tid == 0 ? 3 : 10, t_b1a, t_b1b); AS_TACC(tid == 0 ? 4 : 11, t_b1b, t_post); AS_TACC(tid == 0 ? 5 : 12, t_post, t_b2); }
+#endif
   } else {
     __syncthreads();
     for (int i = tid; i < n_valid * kObs; i += kThreads) obs_dst[i] = s_obs[i];
@@ -830,7 +876,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     for (int w = 0; w < kTile / 32; ++w) rs += misc->wreward[w];
     atomicAdd(&ctrl->slot_reward[blockIdx.x & (kSlots - 1)], rs);
   }
+#ifdef AS_TIMING
+  AS_T(t_w0);
+#endif
   if (tid == 0 && b_obs) bulk_wait_read_all();  // shared memory must stay intact until the engine has read it
+#ifdef AS_TIMING
+  if (tid == 0) { AS_T(t_w1); AS_TACC(6, t_w0, t_w1); AS_TACC(7, t_start, t_w1); atomicAdd(&ctrl->dbg_t[15], 1ull); }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ kernels

@@ -229,6 +229,10 @@ int as_grid_state(AsHandle* h, uint8_t* bins_dst, const uint8_t* bins_src, uint3
  * after the launch of the fused step kernel alone (bench.py times the dominant kernel with them); NULL = off. */
 int as_set_timing_events(AsHandle* h, void* start_event, void* stop_event);
 
+/* Development aid: per-phase clock64() sums of the step kernel (all zero unless the library was built with
+ * -DAS_TIMING); copies 16 counters to the host and optionally clears them.  Synchronises `stream`. */
+int as_debug_timing(AsHandle* h, uint64_t* host16, int reset, void* stream);
+
 /* Host-side introspection used by the tests: number of kernel launches issued by this handle so far, and
  * sizeof() of the public structs (0 AsParams, 1 AsStateIn, 2 AsStepOut, 3 AsResetOut, 4 AsStats, 5 AsMdpState)
  * so that a foreign-language binding can verify its struct layout. */

@@ -37,6 +37,20 @@ def probe(N, steps=50, sets=4, warmup=10):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    if "--timing" in sys.argv:
+        import ctypes
+        buf = (ctypes.c_uint64 * 16)()
+        mdp.lib.as_debug_timing(mdp.handle, buf, 1, mdp._stream())
+        for i in range(warmup):
+            v, d = pool[i % sets]; mdp.step(v, d["actions"], out)
+        mdp.lib.as_debug_timing(mdp.handle, buf, 0, mdp._stream())
+        n = max(buf[15], 1)
+        names = ["M: start->state/window regs", "M: wait root tiles", "M: pass1+reset+pass2+stores", "M: wait at CTA barrier",
+                 "M: post-barrier work", "M: fence+barrier+store issue", "M: wait bulk store read", "M: whole CTA",
+                 "J: start->joint tiles", "J: joint loop", "J: wait at CTA barrier", "J: post-barrier (obs cols, reset rows)",
+                 "J: fence+barrier"]
+        for i, nm in enumerate(names):
+            print(f"   {nm:42s} {buf[i] / n / 1965.0:7.2f} us")
     stats = mdp.read_stats()
     print(f"N={N:>8}  {ms*1e3:9.1f} us/step  {N/ms/1e6:9.3f} G env-steps/s  {N*B_ALG/ms/1e6:8.1f} GB/s alg  "
           f"resets/step={stats['n_reset']}  launches/step={mdp.launch_count/(steps+warmup):.1f}", flush=True)
