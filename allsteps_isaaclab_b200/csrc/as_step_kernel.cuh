@@ -109,6 +109,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // them just before it needs them (barrier 0 is __syncthreads).
 __device__ __forceinline__ void orient_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(2 * kTile) : "memory"); }
 __device__ __forceinline__ void orient_wait() { asm volatile("bar.sync 1, %0;" ::"n"(2 * kTile) : "memory"); }
+// TMA prefetch of a contiguous global range into L2 (no shared memory involved).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ------------------------------------------------------------------------------------------------ staging
@@ -413,6 +417,29 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       if (b_jp) bulk_g2s(smem_u32(s_jp), a.in.joint_pos + env0 * kJ, nv * kJ * 4, bar_joint);
       if (b_jv) bulk_g2s(smem_u32(s_jv), a.in.joint_vel + env0 * kJ, nv * kJ * 4, bar_joint);
       if (b_act) bulk_g2s(smem_u32(s_act), a.actions + env0 * kJ, nv * kJ * 4, bar_joint);
+    }
+  }
+
+  // ---------------------------------------------------------------- L2 prefetch for a LATER tile
+  // A CTA's shared memory is held for its whole lifetime, a third of which was spent waiting for its first loads
+  // to come back from DRAM (profiles/r01_cta_phase_timeline.txt).  L2 is 126 MB and idle: one thread asks the copy
+  // engine to pull the inputs of the tile that will be processed about one wave of CTAs later into L2, so that
+  // the CTA owning that tile finds them at L2 latency.  (Tiles, state words, stone windows and contact norms are all
+  // contiguous per tile.)
+  if (tid == 0 && a.prefetch_tiles > 0) {
+    const int64_t ptile = static_cast<int64_t>(tile) + a.prefetch_tiles;
+    const int64_t penv0 = ptile * kTile;
+    if (penv0 + kTile <= a.num_envs) {  // full tiles only
+      if (dense & kDenseRp) bulk_prefetch_l2(a.in.root_pos + penv0 * 3, kTile * 12);
+      if (dense & kDenseRv) bulk_prefetch_l2(a.in.root_lin_vel + penv0 * 3, kTile * 12);
+      if (dense & kDenseBody) bulk_prefetch_l2(a.in.body_pos + penv0 * 9, kTile * 36);
+      if (dense & kDenseRq) bulk_prefetch_l2(a.in.root_quat + penv0 * 4, kTile * 16);
+      if (dense & kDenseJp) bulk_prefetch_l2(a.in.joint_pos + penv0 * kJ, kTile * kJ * 4);
+      if (dense & kDenseJv) bulk_prefetch_l2(a.in.joint_vel + penv0 * kJ, kTile * kJ * 4);
+      if (kNeedActions && (dense & kDenseAct)) bulk_prefetch_l2(a.actions + penv0 * kJ, kTile * kJ * 4);
+      bulk_prefetch_l2(a.ws.state[ctrl->parity] + penv0, kTile * 8);
+      bulk_prefetch_l2(a.ws.window + penv0 * 4, kTile * 64);
+      bulk_prefetch_l2(a.ws.contact_pre + penv0, kTile * 8);
     }
   }
 
