@@ -566,3 +566,33 @@ def test_one_million_envs_against_the_oracle_and_invariants():
     assert torch.allclose(oa.obs.cpu()[keep_rows], ob.obs.cpu()[keep_rows], atol=2e-4, rtol=0)
     # the progress term is 60 x a difference of distances of world coordinates ~1e3 m (fp32 ulp 1e-4)
     assert torch.allclose(oa.reward.cpu()[keep_rows], ob.reward.cpu()[keep_rows], atol=5e-2, rtol=0)
+
+
+def test_pinned_host_contact_matrices_are_read_in_place():
+    """Zero-copy ingest: the (N,1,20,3) contact matrices stay in pinned host memory; results are unchanged."""
+    from allsteps_isaaclab_b200.mdp import PhysicsViews, StepBuffers
+
+    N, seed = 5000, 77
+    sc = Scenario(N, seed=seed)
+    st0 = sc.initial_mdp_state()
+    origins = sc.env_origins.cuda()
+    mdps = [make_cuda(N, seed) for _ in range(2)]
+    for m in mdps:
+        m.generate_stones(origins)
+        m.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                            "episode_length_buf", "potentials")})
+    outs = [StepBuffers(N, "cuda:0"), StepBuffers(N, "cuda:0")]
+    for step in range(4):
+        st = mdps[0].export_state()
+        phys = sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+        dev = {k: v.cuda() for k, v in phys.items()}
+        mixed = dict(dev)
+        mixed["force_matrix_right"] = phys["force_matrix_right"].pin_memory()
+        mixed["force_matrix_left"] = phys["force_matrix_left"].pin_memory()
+        mdps[0].step(PhysicsViews.from_dict(dev, origins), dev["actions"], outs[0])
+        mdps[1].step(PhysicsViews.from_dict(mixed, origins), dev["actions"], outs[1])
+        torch.cuda.synchronize()
+        for name in ("obs", "reward", "terminated", "time_out"):
+            assert torch.equal(getattr(outs[0], name), getattr(outs[1], name)), f"step {step}: {name}"
+    with pytest.raises(ValueError, match="pinned"):
+        PhysicsViews.from_dict({**dev, "force_matrix_left": phys["force_matrix_left"]}, origins)
