@@ -59,7 +59,12 @@ int check_launch(AsHandle* h, const char* what) {
 
 int num_tiles(int64_t n) { return static_cast<int>((n + kTile - 1) / kTile); }
 
+// Below this batch size the step is launch-latency bound (working set in L2, a handful of CTAs per SM): one launch
+// fewer beats the better latency hiding of the separate gather kernel.
+constexpr int64_t kSeparateGatherMinEnvs = 1 << 17;
+
 int launch_contact_gather(AsHandle* h, const AsStateIn* in, cudaStream_t s) {
+  if (h->num_envs < kSeparateGatherMinEnvs) return AS_OK;
   const unsigned blocks = static_cast<unsigned>((h->num_envs + 255) / 256);
   k_contact_gather<<<blocks, 256, 0, s>>>(*in, h->ws, h->num_envs);
   return check_launch(h, "k_contact_gather");
@@ -179,6 +184,7 @@ StepArgs make_step_args(AsHandle* h, const AsStateIn* in, const float* actions, 
   if (dense(actions, actions_stride, kJ)) bits |= kDenseAct;
   if (out && dense(out->obs, kObs, kObs)) bits |= kDenseObs;
   a.dense16 = bits;
+  a.use_pre = h->num_envs >= kSeparateGatherMinEnvs ? 1 : 0;
   a.prefetch_tiles = h->prefetch_tiles;
   return a;
 }

@@ -439,7 +439,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       if (kNeedActions && (dense & kDenseAct)) bulk_prefetch_l2(a.actions + penv0 * kJ, kTile * kJ * 4);
       bulk_prefetch_l2(a.ws.state[ctrl->parity] + penv0, kTile * 8);
       bulk_prefetch_l2(a.ws.window + penv0 * 4, kTile * 64);
-      bulk_prefetch_l2(a.ws.contact_pre + penv0, kTile * 8);
+      if (a.use_pre) bulk_prefetch_l2(a.ws.contact_pre + penv0, kTile * 8);
     }
   }
 
@@ -479,10 +479,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
     cr_row = a.in.contact_right + e * a.in.contact_right_stride;
     cl_row = a.in.contact_left + e * a.in.contact_left_stride;
-    {  // |F| of the current stone under each foot, gathered by k_contact_gather just before this kernel
+    if (a.use_pre) {  // |F| of the current stone under each foot, gathered by k_contact_gather just before
       const float2 pre = a.ws.contact_pre[e];
       f_r = pre.x;
       f_l = pre.y;
+    } else {  // small batches are launch-bound: the gathers stay in this kernel and a launch is saved
+      f_r = contact_norm(cr_row, m.idx, contact_aligned);
+      f_l = contact_norm(cl_row, m.idx, contact_aligned);
     }
     win_valid = __float_as_int(w0.w) == m.idx;
     if (win_valid) {
