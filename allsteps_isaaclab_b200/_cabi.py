@@ -53,7 +53,7 @@ class AsStateIn(C.Structure):
         ("root_quat", _ptr), ("root_quat_stride", _i64),
         ("root_lin_vel", _ptr), ("root_lin_vel_stride", _i64),
         ("body_pos", _ptr), ("body_env_stride", _i64), ("body_row_stride", _i64),
-        ("right_foot_row", _i32), ("left_foot_row", _i32), ("torso_row", _i32), ("_pad0", _i32),
+        ("right_foot_row", _i32), ("left_foot_row", _i32), ("torso_row", _i32), ("quat_xyzw", _i32),
         ("joint_pos", _ptr), ("joint_pos_stride", _i64),
         ("joint_vel", _ptr), ("joint_vel_stride", _i64),
         ("contact_right", _ptr), ("contact_right_stride", _i64),
@@ -63,7 +63,8 @@ class AsStateIn(C.Structure):
 
 
 class AsStepOut(C.Structure):
-    _fields_ = [("obs", _ptr), ("reward", _ptr), ("terminated", _ptr), ("time_out", _ptr), ("reward_terms", _ptr)]
+    _fields_ = [("obs", _ptr), ("reward", _ptr), ("terminated", _ptr), ("time_out", _ptr), ("reward_terms", _ptr),
+                ("dones", _ptr)]
 
 
 class AsResetOut(C.Structure):
@@ -105,6 +106,7 @@ SIGNATURES = {
     "as_reset": (C.c_int, [_ptr, _ptr, _ptr, _i64, _ptr, C.POINTER(AsResetOut), _ptr]),
     "as_step_pass2": (C.c_int, [_ptr, C.POINTER(AsStateIn), _ptr, _ptr]),
     "as_stats_device_ptr": (C.c_int, [_ptr, C.POINTER(_ptr)]),
+    "as_fold_stats": (C.c_int, [_ptr, _ptr]),
     "as_finish_step": (C.c_int, [_ptr, _ptr, _ptr]),
     "as_read_stats": (C.c_int, [_ptr, C.POINTER(AsStats), _ptr]),
     "as_apply_action": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr]),

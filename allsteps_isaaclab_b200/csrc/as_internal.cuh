@@ -73,6 +73,8 @@ struct Ctrl {
   uint32_t n_regen_list;  // entries of regen_ids written this step
   uint32_t fixup_ran;     // diagnostics: how many steps needed the no-reset fix-up
   uint32_t last_adv2;     // pass-2 index advances of the last step (discarded again if the fix-up runs)
+  uint32_t stats_folded;  // as_fold_stats already folded this step's counters (the finish kernel must not redo it)
+  uint32_t _pad1;
   unsigned long long step_counter;
   AsStats stats;          // folded statistics of the last step (this shard)
   unsigned int slots[kSlots][kNumCounters];

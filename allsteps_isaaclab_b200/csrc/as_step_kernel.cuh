@@ -700,7 +700,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     if (bulk_root) mbar_wait(bar_root, phase_root);
     if (active) {
       const float4 q4 = *reinterpret_cast<const float4*>(s_rq + t * 4);
-      const Quat q{q4.x, q4.y, q4.z, q4.w};
+      const Quat q = a.in.quat_xyzw ? Quat{q4.w, q4.x, q4.y, q4.z} : Quat{q4.x, q4.y, q4.z, q4.w};
       const Vec3 v{s_rv[t * 3], s_rv[t * 3 + 1], s_rv[t * 3 + 2]};
       euler_roll_pitch(q, roll, pitch);
       vb = rotate_by_inverse(q, v);
@@ -768,6 +768,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       a.out.reward[e] = reward;
       a.out.terminated[e] = terminated ? 1 : 0;
       a.out.time_out[e] = time_out ? 1 : 0;
+      if (a.out.dones) a.out.dones[e] = is_reset ? 1 : 0;
       if (a.out.reward_terms) {
         float* rt = a.out.reward_terms + e * AS_NUM_REWARD_TERMS;
         rt[0] = P.alive_reward_scale; rt[1] = r_progress; rt[2] = r_roll; rt[3] = r_pitch; rt[4] = r_speed;
@@ -953,6 +954,13 @@ __global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __gri
   process_tile<MODE>(a, blockIdx.x, phase_root, phase_joint, smem);
 }
 
+// as_fold_stats: fold early so that the caller can all-reduce the statistics before as_finish_step.
+__global__ void __launch_bounds__(128) k_fold_early(Ctrl* ctrl, int64_t num_envs) {
+  __shared__ unsigned int fold[kNumCounters];
+  fold_stats(ctrl, fold, num_envs);
+  if (threadIdx.x == 0) ctrl->stats_folded = 1;
+}
+
 // 3-call path: folds the statistics of pass 1, consumes the promotion every CTA applied, advances the counter.
 __global__ void __launch_bounds__(128) k_fold_pass1(Ctrl* ctrl, int64_t num_envs) {
   __shared__ unsigned int fold[kNumCounters];
@@ -972,8 +980,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
   Ctrl* ctrl = a.ws.ctrl;
   const int tid = threadIdx.x;
+  const bool prefolded = ctrl->stats_folded != 0;  // as_fold_stats ran: the slots are empty, the totals are in stats
   if (tid < 32) {
-    const unsigned n = slot_sum(ctrl, kCntReset);
+    const unsigned n = prefolded ? static_cast<unsigned>(ctrl->stats.n_reset) : slot_sum(ctrl, kCntReset);
     if (tid == 0) misc->is_last = n;  // reused as "number of resets this step"
   }
   if (tid == 0) {
@@ -1001,8 +1010,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
     if (finisher) __threadfence();
   }
   if (finisher) {
-    fold_stats(ctrl, misc->fold, a.num_envs);
+    if (!prefolded) fold_stats(ctrl, misc->fold, a.num_envs);
     if (tid == 0) {
+      ctrl->stats_folded = 0;
       const AsStats* g = a.global_stats ? a.global_stats : &ctrl->stats;
       ctrl->promote_cur = promotion_decision(a.P, *g);
       if (a.rows.n_reset) *a.rows.n_reset = static_cast<int32_t>(a.want_reset_list ? ctrl->n_reset_list : ctrl->stats.n_reset);

@@ -41,7 +41,7 @@ class PhysicsViews:
     """
 
     def __init__(self, *, root_pos_w, root_quat_w, root_lin_vel_w, body_pos_w, joint_pos, joint_vel,
-                 force_matrix_right, force_matrix_left, env_origins, body_rows=(0, 1, 2)):
+                 force_matrix_right, force_matrix_left, env_origins, body_rows=(0, 1, 2), quat_xyzw=False):
         self.tensors = dict(root_pos_w=root_pos_w, root_quat_w=root_quat_w, root_lin_vel_w=root_lin_vel_w,
                             body_pos_w=body_pos_w, joint_pos=joint_pos, joint_vel=joint_vel,
                             force_matrix_right=force_matrix_right, force_matrix_left=force_matrix_left,
@@ -68,6 +68,7 @@ class PhysicsViews:
         s.body_env_stride = body_pos_w.stride(0) if N > 1 else B * 3
         s.body_row_stride = body_pos_w.stride(1) if B > 1 else 3
         s.right_foot_row, s.left_foot_row, s.torso_row = (int(b) for b in body_rows)
+        s.quat_xyzw = 1 if quat_xyzw else 0  # PhysX' own order; Isaac Lab's root_quat_w is w,x,y,z
         if max(body_rows) >= B:
             raise ValueError("body row index out of range")
         for name, t in (("force_matrix_right", force_matrix_right), ("force_matrix_left", force_matrix_left)):
@@ -75,7 +76,7 @@ class PhysicsViews:
                 raise ValueError(f"{name} must be float32 (N,1,{NUM_STONES},3)")
             if not t[0].is_contiguous():
                 raise ValueError(f"{name}: the per-env (1,S,3) block must be contiguous")
-            if t.device.type == "cpu" and not t.is_pinned():
+            if t.device.type == "cpu" and root_pos_w.device.type == "cuda" and not t.is_pinned():
                 raise ValueError(f"{name}: a host tensor must be pinned (page-locked) to be read by the device")
         s.contact_right = force_matrix_right.data_ptr()
         s.contact_right_stride = force_matrix_right.stride(0) if N > 1 else NUM_STONES * 3
@@ -90,11 +91,11 @@ class PhysicsViews:
         self.device = root_pos_w.device
 
     @classmethod
-    def from_dict(cls, d: Dict[str, torch.Tensor], env_origins, body_rows=(0, 1, 2)) -> "PhysicsViews":
+    def from_dict(cls, d: Dict[str, torch.Tensor], env_origins, body_rows=(0, 1, 2), quat_xyzw=False) -> "PhysicsViews":
         return cls(root_pos_w=d["root_pos_w"], root_quat_w=d["root_quat_w"], root_lin_vel_w=d["root_lin_vel_w"],
                    body_pos_w=d["body_pos_w"], joint_pos=d["joint_pos"], joint_vel=d["joint_vel"],
                    force_matrix_right=d["force_matrix_right"], force_matrix_left=d["force_matrix_left"],
-                   env_origins=env_origins, body_rows=body_rows)
+                   env_origins=env_origins, body_rows=body_rows, quat_xyzw=quat_xyzw)
 
 
 class StepBuffers:
@@ -106,6 +107,7 @@ class StepBuffers:
         self.reward = torch.empty(num_envs, dtype=torch.float32, **kw)
         self.terminated = torch.zeros(num_envs, dtype=torch.bool, **kw)
         self.time_out = torch.zeros(num_envs, dtype=torch.bool, **kw)
+        self.dones = torch.zeros(num_envs, dtype=torch.bool, **kw)  # terminated | time_out (reset_buf)
         self.reward_terms = (torch.empty(num_envs, _cabi.NUM_REWARD_TERMS, dtype=torch.float32, **kw)
                              if reward_terms else None)
         self.reset_root_state = self.reset_joint_pos = self.reset_joint_vel = None
@@ -117,7 +119,7 @@ class StepBuffers:
             self.reset_ids = torch.zeros(num_envs, dtype=torch.int32, **kw)
             self.n_reset = torch.zeros(1, dtype=torch.int32, **kw)
         self.step_out = _cabi.AsStepOut(_ptr(self.obs), _ptr(self.reward), _ptr(self.terminated),
-                                        _ptr(self.time_out), _ptr(self.reward_terms))
+                                        _ptr(self.time_out), _ptr(self.reward_terms), _ptr(self.dones))
         self.reset_out = _cabi.AsResetOut(_ptr(self.reset_root_state), _ptr(self.reset_joint_pos),
                                           _ptr(self.reset_joint_vel), _ptr(self.reset_ids), _ptr(self.n_reset))
 
@@ -225,6 +227,11 @@ class AllstepsMDP:
         graph launch instead of several library calls -- what matters at 4 K..64 K envs, where the step is
         launch-latency bound.  The producer of the physics tensors must write into the same storage every step."""
         return CapturedStep(self, views, actions, out, global_stats)
+
+    def fold_stats(self):
+        """Between `step(..., finish=False)` and `finish_step(global)`: make this step's counters available in
+        `stats_tensor` so they can be all-reduced over the shards first (promotion on the global mean)."""
+        _cabi.check(self.lib.as_fold_stats(self.handle, self._stream()), "as_fold_stats")
 
     def finish_step(self, global_stats: Optional[torch.Tensor] = None):
         """Close the fused step: conditional no-reset fix-up, promotion rule (ENV:471-479), counters."""

@@ -98,7 +98,8 @@ typedef struct AsStateIn {
   const float* body_pos;      int64_t body_env_stride;     /* robot.data.body_pos_w      (N,B,3)            */
   int64_t body_row_stride;                                  /* floats between bodies of one env (3 or 13)    */
   int32_t right_foot_row, left_foot_row, torso_row;         /* ENV:87-88                                     */
-  int32_t _pad0;
+  int32_t quat_xyzw;  /* 1: root_quat is x,y,z,w as PhysX' own root transforms are (skips Isaac Lab's convert_quat,
+                         articulation_data.py:372-379); 0: w,x,y,z as robot.data.root_quat_w                        */
   const float* joint_pos;     int64_t joint_pos_stride;    /* robot.data.joint_pos       (N,21)             */
   const float* joint_vel;     int64_t joint_vel_stride;    /* robot.data.joint_vel       (N,21)             */
   const float* contact_right; int64_t contact_right_stride;/* sensor_right.data.force_matrix_w (N,1,S,3)    */
@@ -114,6 +115,8 @@ typedef struct AsStepOut {
   uint8_t* time_out;     /* (N)     ENV:399                                                                */
   float* reward_terms;   /* optional (N,10): alive, progress, roll, pitch, speed, energy, action, limit,
                             step, bonus (costs positive) -- for per-term manager logging; NULL to skip     */
+  uint8_t* dones;        /* optional (N): terminated | time_out, what RlGamesVecEnvWrapper.step hands to
+                            rl_games (isaaclab_rl/rl_games.py:256) and DirectRLEnv keeps as reset_buf      */
 } AsStepOut;
 
 /* What `_reset_idx` hands to PhysX (ENV:563-565).  Rows are written AT THE ENV'S OWN ROW (full-size buffers),
@@ -187,6 +190,10 @@ int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream);
  * the accumulators.  When envs are sharded, pass `global_stats` = device AsStats summed over ranks (NCCL) to
  * promote on the global mean; NULL = promote on this shard's own envs (what `--distributed` replicas do). */
 int as_stats_device_ptr(AsHandle* h, AsStats** device_stats);
+/* Optional, between as_step_fused and as_finish_step: fold this step's counters into the device AsStats now, so
+ * that the caller can all-reduce them and pass the sum to as_finish_step(global_stats) for a promotion decision on
+ * the global mean in the same step. */
+int as_fold_stats(AsHandle* h, void* stream);
 /* Closes the step opened by as_step_fused (required once per fused step, on the same stream; the buffers given
  * to as_step_fused must stay alive until then because the conditional no-reset fix-up re-reads them). */
 int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream);

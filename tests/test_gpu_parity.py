@@ -596,3 +596,55 @@ def test_pinned_host_contact_matrices_are_read_in_place():
             assert torch.equal(getattr(outs[0], name), getattr(outs[1], name)), f"step {step}: {name}"
     with pytest.raises(ValueError, match="pinned"):
         PhysicsViews.from_dict({**dev, "force_matrix_left": phys["force_matrix_left"]}, origins)
+
+
+def test_global_promotion_over_shards_and_wrapper_outputs():
+    """Sharded promotion on the GLOBAL mean (as_fold_stats -> sum over shards -> as_finish_step(global)) equals one
+    handle owning all envs; `dones` is terminated | time_out; PhysX-ordered (x,y,z,w) quaternions are accepted."""
+    from allsteps_isaaclab_b200.mdp import AllstepsMDP, PhysicsViews, StepBuffers
+
+    N, seed, half = 2048, 3, 1024
+    sc = Scenario(N, seed=seed)
+    st0 = sc.initial_mdp_state()
+    # shard 0 far along, shard 1 at the start: only the global mean crosses the threshold of 12
+    st0["curr_target_index"][:half] = 19
+    st0["curr_target_index"][half:] = 7
+    whole = make_cuda(N, seed)
+    shards = [AllstepsMDP(half, device="cuda:0", seed=seed, env_id_offset=r * half) for r in range(2)]
+    origins = sc.env_origins.cuda()
+    whole.generate_stones(origins)
+    keys = ("curr_target_index", "swing_leg", "target_reach_count", "episode_length_buf", "potentials")
+    whole.import_state({k: st0[k] for k in keys})
+    stw = whole.export_state()
+    for r, sh in enumerate(shards):
+        sl = slice(r * half, (r + 1) * half)
+        sh.import_state({**{k: st0[k][sl] for k in keys}, "steps_pos": stw["steps_pos"][sl],
+                         "steps_dphi": stw["steps_dphi"][sl]})
+    out = StepBuffers(N, "cuda:0")
+    outs = [StepBuffers(half, "cuda:0") for _ in range(2)]
+    for step in range(3):
+        st = whole.export_state()
+        phys = sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+        dev = {k: v.cuda() for k, v in phys.items()}
+        # PhysX order for the shards: x,y,z,w
+        dev_xyzw = dict(dev)
+        dev_xyzw["root_quat_w"] = dev["root_quat_w"][:, [1, 2, 3, 0]].contiguous()
+        whole.step(PhysicsViews.from_dict(dev, origins, sc.body_indices), dev["actions"], out)
+        for r, sh in enumerate(shards):
+            sl = slice(r * half, (r + 1) * half)
+            v = PhysicsViews.from_dict({k: t[sl] for k, t in dev_xyzw.items()}, origins[sl].contiguous(),
+                                       sc.body_indices, quat_xyzw=True)
+            sh.step(v, dev["actions"][sl], outs[r], finish=False)
+            sh.fold_stats()
+        g = shards[0].stats_tensor.clone()
+        g[:10] = shards[0].stats_tensor[:10] + shards[1].stats_tensor[:10]  # what the NCCL all-reduce produces
+        for sh in shards:
+            sh.finish_step(g)
+        torch.cuda.synchronize()
+        for r in range(2):
+            sl = slice(r * half, (r + 1) * half)
+            for name in ("obs", "reward", "terminated", "time_out", "dones"):
+                assert torch.equal(getattr(outs[r], name), getattr(out, name)[sl]), f"step {step} shard {r}: {name}"
+            assert torch.equal(shards[r].export_state()["curriculum"], whole.export_state()["curriculum"][sl])
+        exact(out.dones, (out.terminated | out.time_out), "dones")
+    assert int(whole.export_state()["curriculum"].max()) >= 1, "the global mean (13) must have promoted"
