@@ -109,6 +109,15 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // them just before it needs them (barrier 0 is __syncthreads).
 __device__ __forceinline__ void orient_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(2 * kTile) : "memory"); }
 __device__ __forceinline__ void orient_wait() { asm volatile("bar.sync 1, %0;" ::"n"(2 * kTile) : "memory"); }
+// Named barrier 2: reset flags, MDP role (producer, early) -> joint role (consumer).
+__device__ __forceinline__ void flags_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(2 * kTile) : "memory"); }
+__device__ __forceinline__ void flags_wait() { asm volatile("bar.sync 2, %0;" ::"n"(2 * kTile) : "memory"); }
+// Named barrier 3: the joint-role warps among themselves -- every joint/action row has been consumed, the observation
+// tile may overwrite them.
+__device__ __forceinline__ void joint_rows_consumed() { asm volatile("bar.sync 3, %0;" ::"n"(kTile) : "memory"); }
+// Named barrier 4: "rows consumed + reward sums written", joint role (producer) -> MDP role (consumer).
+__device__ __forceinline__ void sums_arrive() { asm volatile("bar.arrive 4, %0;" ::"n"(2 * kTile) : "memory"); }
+__device__ __forceinline__ void sums_wait() { asm volatile("bar.sync 4, %0;" ::"n"(2 * kTile) : "memory"); }
 // TMA prefetch of a contiguous global range into L2 (no shared memory involved).
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
@@ -543,6 +552,9 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   int idx_after_pass1 = 0;
   const unsigned long long step_now = ctrl->step_counter;
   float o_jp[kJ], o_jv[kJ];
+#ifdef AS_TIMING
+  long long t_b1a = 0, t_b1b = 0;
+#endif
 
   if (!joint_role) {
     // ================================================================ MDP role, before the barrier
@@ -576,7 +588,15 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       is_reset = terminated || time_out;
       // an env that resets restarts on stones 0..3 (one 64-byte record at the head of its stone row): start
       // pulling it in now, it is read after pass 1
-      if (MODE == kModeFused && is_reset) prefetch_l1(stones);
+      if (MODE == kModeFused && is_reset) {
+        prefetch_l1(stones);
+        const uint4 rblk = philox_block(P.seed, step_now, kStreamReset, gid, 0);
+        mirror = u32_to_unit(rblk.x) > 0.5f;  // ENV:518
+      }
+    }
+    if (MODE == kModeFused) {  // the joint role finishes the envs that reset: tell it early which ones they are
+      misc->flags[t] = (is_reset ? 1u : 0u) | (mirror ? 2u : 0u);
+      flags_arrive();
     }
     bool moved1 = false;
     if (active) {
@@ -611,8 +631,6 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         // zero velocity, zero contacts (contact_sensor.py:155), stale body positions; so roll = pitch = v_b = 0 and
         // targets_b = stone - root.  The start-pose joints are produced by the joint-role warps.
         regen = ((P.flags & AS_FLAG_INTENDED_REGEN) && m.idx > kS / 2) || (P.flags & AS_FLAG_GRID_CURRICULUM);
-        const uint4 rblk = philox_block(P.seed, step_now, kStreamReset, gid, 0);
-        mirror = u32_to_unit(rblk.x) > 0.5f;  // ENV:518
         const Vec3 org{s_org[t * 3], s_org[t * 3 + 1], s_org[t * 3 + 2]};
         p = Vec3{P.default_root_pos[0] + org.x, P.default_root_pos[1] + org.y, P.default_root_pos[2] + org.z};
         if (regen) {
@@ -669,7 +687,6 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     if (tid == 0) { AS_T(t_m2); AS_TACC(0, t_start, t_m0); AS_TACC(1, t_m0, t_m1); AS_TACC(2, t_m1, t_m2); }
 #endif
     if (MODE == kModeFused) {
-      misc->flags[t] = (is_reset ? 1u : 0u) | (mirror ? 2u : 0u);
       // ---- reset / regeneration id lists (warp ballots)
       const unsigned rmask = __ballot_sync(0xffffffffu, is_reset);
       if (rmask && a.want_reset_list) {
@@ -740,17 +757,88 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       misc->red_actsq[t] = act_sq;
       misc->red_limit[t] = at_limit;
     }
+    // The joint role does not wait for the MDP role: once all FOUR joint warps have consumed their rows the
+    // observation tile may be written; the MDP role is told the same (and that the sums are ready), and it told us
+    // earlier which envs reset.
+#ifdef AS_TIMING
+    t_b1a = clock64();
+#endif
+    joint_rows_consumed();
+    sums_arrive();
+    if (MODE == kModeFused) flags_wait();
+#ifdef AS_TIMING
+    t_b1b = clock64();
+#endif
+    if (active) {
+      float* row = s_obs + t * kObs;
+      // an env that reset is observed in its start pose: identity orientation, zero velocity (pass 2, ENV:567)
+      const bool was_reset = MODE == kModeFused && (misc->flags[t] & 1u);
+      row[1] = was_reset ? 0.0f : roll;
+      row[2] = was_reset ? 0.0f : pitch;
+      row[3] = was_reset ? 0.0f : vb.x;
+      row[4] = was_reset ? 0.0f : vb.y;
+      row[5] = was_reset ? 0.0f : vb.z;
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        row[6 + j] = o_jp[j];
+        row[6 + kJ + j] = o_jv[j];
+      }
+    }
+    if (MODE == kModeFused) {
+      // Envs that reset are finished by the whole warp: lane j produces joint j of the start pose (ENV:505-560) and
+      // stores it both into the observation row (as joint_pos_scaled, what pass 2 sees) and, coalesced, into the
+      // start-pose rows handed to PhysX (ENV:563-565).
+      const unsigned fl = misc->flags[t];
+      unsigned todo = __ballot_sync(0xffffffffu, (fl & 1u) != 0);
+      __syncwarp();
+      const int row0 = (warp - kTile / 32) * 32;
+      while (todo) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const bool mirror_r = (__shfl_sync(0xffffffffu, fl, r) & 2u) != 0;
+        const int64_t e_r = env0 + row0 + r;
+        const uint32_t gid_r = static_cast<uint32_t>(e_r + a.env_id_offset);
+        if (lane < kJ) {
+          const ResetTables& T = misc->rt;
+          const float u = philox_uniform(P.seed, step_now, kStreamReset, gid_r, 1 + lane);
+          const float val = reset_joint_value(P, mirror_r ? T.pose_mirrored[lane] : T.pose[lane], T.lower[lane],
+                                              T.upper[lane], u);
+          float* row = s_obs + (row0 + r) * kObs;
+          row[6 + lane] = scale_to_unit(val, T.lower[lane], T.upper[lane]);
+          const float jv0 = mirror_r ? T.vel_mirrored[lane] : 0.0f;
+          row[6 + kJ + lane] = fminf(fmaxf(jv0 * P.dof_vel_scale, -5.0f), 5.0f);
+          if (a.rows.joint_pos) a.rows.joint_pos[e_r * kJ + lane] = val;
+          if (a.rows.joint_vel) a.rows.joint_vel[e_r * kJ + lane] = jv0;
+        }
+        if (a.rows.root_state && lane < AS_ROOT_STATE_DIM) {
+          const float z = mirror_r ? -0.0f : 0.0f;  // ENV:535 flips the sign of the (zero) vector part
+          float val = 0.0f;
+          if (lane < 3) {
+            const float d = lane == 0 ? P.default_root_pos[0] : (lane == 1 ? P.default_root_pos[1] : P.default_root_pos[2]);
+            val = d + s_org[(row0 + r) * 3 + lane];  // ENV:515
+          } else if (lane == 3) {
+            val = 1.0f;
+          } else if (lane <= 6) {
+            val = z;
+          }
+          a.rows.root_state[e_r * AS_ROOT_STATE_DIM + lane] = val;
+        }
+      }
+    }
   }
   if (bulk_root) phase_root ^= 1u;
   if (bulk_joint) phase_joint ^= 1u;
-  AS_T(t_b1a);
-
-  __syncthreads();  // every input row is consumed (the observation tile may overwrite them); sums and flags are visible
-  AS_T(t_b1b);
 
   float reward = 0.0f;
   if (!joint_role) {
-    // ================================================================ MDP role, after the barrier
+    // ================================================================ MDP role, once the joint rows are consumed
+#ifdef AS_TIMING
+    t_b1a = clock64();
+#endif
+    sums_wait();
+#ifdef AS_TIMING
+    t_b1b = clock64();
+#endif
     if (MODE != kModePass2 && active) {  // reward, ENV:377-394
       const float r_energy = P.energy_cost_scale * misc->red_energy[t];
       const float r_action = P.actions_cost_scale * sqrtf(misc->red_actsq[t]);
@@ -811,64 +899,6 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         wc[kCntSumIndex] = s2 >> 8;
         wc[kCntLevelMax] = lmax;
         misc->wreward[warp] = rs;
-      }
-    }
-  } else {
-    // ================================================================ joint role, after the barrier
-    if (active) {
-      float* row = s_obs + t * kObs;
-      // an env that reset is observed in its start pose: identity orientation, zero velocity (pass 2, ENV:567)
-      const bool was_reset = MODE == kModeFused && (misc->flags[t] & 1u);
-      row[1] = was_reset ? 0.0f : roll;
-      row[2] = was_reset ? 0.0f : pitch;
-      row[3] = was_reset ? 0.0f : vb.x;
-      row[4] = was_reset ? 0.0f : vb.y;
-      row[5] = was_reset ? 0.0f : vb.z;
-#pragma unroll
-      for (int j = 0; j < kJ; ++j) {
-        row[6 + j] = o_jp[j];
-        row[6 + kJ + j] = o_jv[j];
-      }
-    }
-    if (MODE == kModeFused) {
-      // Envs that reset are finished by the whole warp: lane j produces joint j of the start pose (ENV:505-560) and
-      // stores it both into the observation row (as joint_pos_scaled, what pass 2 sees) and, coalesced, into the
-      // start-pose rows handed to PhysX (ENV:563-565).
-      const unsigned fl = misc->flags[t];
-      unsigned todo = __ballot_sync(0xffffffffu, (fl & 1u) != 0);
-      __syncwarp();
-      const int row0 = (warp - kTile / 32) * 32;
-      while (todo) {
-        const int r = __ffs(todo) - 1;
-        todo &= todo - 1u;
-        const bool mirror_r = (__shfl_sync(0xffffffffu, fl, r) & 2u) != 0;
-        const int64_t e_r = env0 + row0 + r;
-        const uint32_t gid_r = static_cast<uint32_t>(e_r + a.env_id_offset);
-        if (lane < kJ) {
-          const ResetTables& T = misc->rt;
-          const float u = philox_uniform(P.seed, step_now, kStreamReset, gid_r, 1 + lane);
-          const float val = reset_joint_value(P, mirror_r ? T.pose_mirrored[lane] : T.pose[lane], T.lower[lane],
-                                              T.upper[lane], u);
-          float* row = s_obs + (row0 + r) * kObs;
-          row[6 + lane] = scale_to_unit(val, T.lower[lane], T.upper[lane]);
-          const float jv0 = mirror_r ? T.vel_mirrored[lane] : 0.0f;
-          row[6 + kJ + lane] = fminf(fmaxf(jv0 * P.dof_vel_scale, -5.0f), 5.0f);
-          if (a.rows.joint_pos) a.rows.joint_pos[e_r * kJ + lane] = val;
-          if (a.rows.joint_vel) a.rows.joint_vel[e_r * kJ + lane] = jv0;
-        }
-        if (a.rows.root_state && lane < AS_ROOT_STATE_DIM) {
-          const float z = mirror_r ? -0.0f : 0.0f;  // ENV:535 flips the sign of the (zero) vector part
-          float val = 0.0f;
-          if (lane < 3) {
-            const float d = lane == 0 ? P.default_root_pos[0] : (lane == 1 ? P.default_root_pos[1] : P.default_root_pos[2]);
-            val = d + s_org[(row0 + r) * 3 + lane];  // ENV:515
-          } else if (lane == 3) {
-            val = 1.0f;
-          } else if (lane <= 6) {
-            val = z;
-          }
-          a.rows.root_state[e_r * AS_ROOT_STATE_DIM + lane] = val;
-        }
       }
     }
   }
