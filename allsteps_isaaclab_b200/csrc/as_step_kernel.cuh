@@ -135,6 +135,13 @@ template <int W>
 __device__ __forceinline__ bool bulk_ok(uint32_t dense16, uint32_t bit, int n_valid) {
   return (dense16 & bit) && (((n_valid * W) & 3) == 0);
 }
+// All arrays at once: a full tile keeps every dense bit; a ragged tile keeps those whose byte count is a multiple of 16.
+__device__ __forceinline__ uint32_t bulk_mask(uint32_t dense16, int n_valid) {
+  if (n_valid == kTile) return dense16;
+  uint32_t m = dense16 & (kDenseRq);  // 16-byte rows always qualify
+  if ((n_valid & 3) == 0) m = dense16;  // every other row width (84, 12, 36, 236 bytes) needs a multiple of 4 rows
+  return m;
+}
 template <int W>
 __device__ __forceinline__ void coop_load(float* dst, const float* base, int64_t stride, int64_t env0, int n_valid) {
   for (int i = threadIdx.x; i < n_valid * W; i += 2 * kTile) {
@@ -398,14 +405,15 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 
   // ---------------------------------------------------------------- HBM -> SMEM (TMA bulk where the view allows)
   const uint32_t dense = a.dense16;
-  const bool b_jp = bulk_ok<kJ>(dense, kDenseJp, n_valid);
-  const bool b_jv = bulk_ok<kJ>(dense, kDenseJv, n_valid);
-  const bool b_act = kNeedActions && bulk_ok<kJ>(dense, kDenseAct, n_valid);
-  const bool b_rp = bulk_ok<3>(dense, kDenseRp, n_valid);
-  const bool b_rq = bulk_ok<4>(dense, kDenseRq, n_valid);
-  const bool b_rv = bulk_ok<3>(dense, kDenseRv, n_valid);
-  const bool b_body = bulk_ok<9>(dense, kDenseBody, n_valid);
-  const bool b_org = MODE == kModeFused && bulk_ok<3>(dense, kDenseOrg, n_valid);
+  const uint32_t bm = bulk_mask(dense, n_valid);
+  const bool b_jp = bm & kDenseJp;
+  const bool b_jv = bm & kDenseJv;
+  const bool b_act = kNeedActions && (bm & kDenseAct);
+  const bool b_rp = bm & kDenseRp;
+  const bool b_rq = bm & kDenseRq;
+  const bool b_rv = bm & kDenseRv;
+  const bool b_body = bm & kDenseBody;
+  const bool b_org = MODE == kModeFused && (bm & kDenseOrg);
   const bool bulk_root = b_rp || b_rq || b_rv || b_body || b_org;
   const bool bulk_joint = b_jp || b_jv || b_act;
   const bool any_coop = !b_jp || !b_jv || (kNeedActions && !b_act) || !b_rp || !b_rq || !b_rv || !b_body ||
@@ -906,7 +914,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   // ---------------------------------------------------------------- observation tile -> HBM, ENV:326-345
   AS_T(t_post);
   float* obs_dst = a.out.obs + env0 * kObs;
-  const bool b_obs = bulk_ok<kObs>(dense, kDenseObs, n_valid);
+  const bool b_obs = bm & kDenseObs;
   if (b_obs) {
     fence_proxy_async_smem();  // make the generic-proxy writes visible to the TMA engine
     __syncthreads();
