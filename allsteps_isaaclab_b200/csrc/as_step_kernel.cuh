@@ -473,14 +473,15 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 
   Mdp m{1, 0, 0, 0.0f};
   int level = 0, ep = 0;
-  float4 s_prev = make_float4(0, 0, 0, 0), s_curr = s_prev, s_next = s_prev, s_next2 = s_prev;
-  bool win_valid = false, win_dirty = false, have_next2 = false;
+  float4 s_prev = make_float4(0, 0, 0, 0), s_curr = s_prev, s_next = s_prev;
+  bool win_valid = false, win_dirty = false;
   float f_r = 0.0f, f_l = 0.0f;
   const float* cr_row = nullptr;
   const float* cl_row = nullptr;
   if (!joint_role && active) {
     // the stone window does not depend on the state word: its four coalesced loads go out first
-    const float4 w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3];
+    // (entry 3, the stone that enters when the window slides, is fetched only by the few envs that do slide)
+    const float4 w0 = wrow[0], w1 = wrow[1], w2 = wrow[2];
     const uint2 sw = st_in[e];
     m.idx = state_idx(sw.x);
     m.leg = state_leg(sw.x);
@@ -506,25 +507,18 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
     win_valid = __float_as_int(w0.w) == m.idx;
     if (win_valid) {
-      s_prev = w0; s_curr = w1; s_next = w2; s_next2 = w3;
+      s_prev = w0; s_curr = w1; s_next = w2;
     } else {  // stale cache (first use, or the fix-up re-reading an env the step already advanced): gather
       s_prev = stone_at(window_slot_stone(m.idx, 0));
       s_curr = stone_at(window_slot_stone(m.idx, 1));
       s_next = stone_at(window_slot_stone(m.idx, 2));
-      s_next2 = stone_at(window_slot_stone(m.idx, 3));
     }
-    have_next2 = true;
   }
   // the index advanced by one: slide the window (the stone entering at the far end is fetched when written back)
   auto slide_window = [&]() {
     s_prev = s_curr;
     s_curr = s_next;
-    if (have_next2) {
-      s_next = s_next2;
-      have_next2 = false;
-    } else {
-      s_next = stone_at(min(m.idx + 1, kS - 1));
-    }
+    s_next = stone_at(min(m.idx + 1, kS - 1));  // == window entry 3 when the cache is valid; a 16-byte gather
     win_dirty = true;
   };
 
@@ -556,7 +550,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   PassOut po{};
   bool terminated = false, time_out = false, is_reset = false, mirror = false, regen = false;
   bool fell = false, so_fast = false, died = false, adv1 = false, adv2 = false;
-  float r_progress = 0.0f, r_roll = 0.0f, r_pitch = 0.0f, r_speed = 0.0f, r_step = 0.0f, r_bonus = 0.0f;
+  float r_partial = 0.0f, r_step = 0.0f, r_bonus = 0.0f;  // alive + progress - roll - pitch - speed costs, ENV:378-383
   int idx_after_pass1 = 0;
   const unsigned long long step_now = ctrl->step_counter;
   float o_jp[kJ], o_jv[kJ];
@@ -623,10 +617,19 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       idx_after_pass1 = m.idx;
       if (MODE != kModePass2) {
         // ---- reward terms that do not need the joint sums, ENV:350-375
-        r_progress = m.pot - po.old_pot;
-        r_roll = (roll > 0.4f || roll < -0.4f) ? fabsf(roll) : 0.0f;
-        r_pitch = (pitch > 0.4f || pitch < -0.2f) ? fabsf(pitch) : 0.0f;
-        r_speed = speed > 1.6f ? speed - 1.6f : 0.0f;
+        const float r_progress = m.pot - po.old_pot;
+        const float r_roll = (roll > 0.4f || roll < -0.4f) ? fabsf(roll) : 0.0f;
+        const float r_pitch = (pitch > 0.4f || pitch < -0.2f) ? fabsf(pitch) : 0.0f;
+        const float r_speed = speed > 1.6f ? speed - 1.6f : 0.0f;
+        // the head of the reference's left-to-right sum (ENV:378-383) is final here: keep one register, not four
+        r_partial = P.alive_reward_scale + r_progress;
+        r_partial = r_partial - r_roll;
+        r_partial = r_partial - r_pitch;
+        r_partial = r_partial - r_speed;
+        if (a.out.reward_terms) {
+          float* rt = a.out.reward_terms + e * AS_NUM_REWARD_TERMS;
+          rt[0] = P.alive_reward_scale; rt[1] = r_progress; rt[2] = r_roll; rt[3] = r_pitch; rt[4] = r_speed;
+        }
         const bool pays_step = po.reached && m.count == 1 && m.idx < kS - 1;
         r_step = pays_step ? 50.0f * expf((-po.d_swing) / 0.25f) : 0.0f;
         r_bonus = (m.idx == kS - 1 && po.body_dist < 0.15f) ? 10.0f : 0.0f;
@@ -643,13 +646,10 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         p = Vec3{P.default_root_pos[0] + org.x, P.default_root_pos[1] + org.y, P.default_root_pos[2] + org.z};
         if (regen) {
           first_three_stones(P, org, s_prev, s_curr, s_next);
-          have_next2 = false;
         } else {
           s_prev = stone_at(0);
           s_curr = stone_at(1);
           s_next = stone_at(2);
-          s_next2 = stone_at(3);
-          have_next2 = true;
         }
         win_dirty = true;
         m.count = 0;
@@ -686,9 +686,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       sw.y = __float_as_uint(m.pot);
       st_out[e] = sw;
       if ((win_dirty || !win_valid) && !regen) {  // (a regenerated env's window is written by the regeneration kernel)
-        if (!have_next2) s_next2 = stone_at(window_slot_stone(m.idx, 3));
         s_prev.w = __int_as_float(m.idx);  // tag
-        wrow[0] = s_prev; wrow[1] = s_curr; wrow[2] = s_next; wrow[3] = s_next2;
+        wrow[0] = s_prev; wrow[1] = s_curr; wrow[2] = s_next; wrow[3] = stone_at(window_slot_stone(m.idx, 3));
       }
     }
 #ifdef AS_TIMING
@@ -851,11 +850,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       const float r_energy = P.energy_cost_scale * misc->red_energy[t];
       const float r_action = P.actions_cost_scale * sqrtf(misc->red_actsq[t]);
       const float r_limit = static_cast<float>(misc->red_limit[t]) * P.joint_at_limit_cost_scale;
-      float total = P.alive_reward_scale + r_progress;
-      total = total - r_roll;
-      total = total - r_pitch;
-      total = total - r_speed;
-      total = total - r_energy;
+      float total = r_partial - r_energy;
       total = total - r_action;
       total = total - r_limit;
       total = total + r_step;
@@ -867,7 +862,6 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       if (a.out.dones) a.out.dones[e] = is_reset ? 1 : 0;
       if (a.out.reward_terms) {
         float* rt = a.out.reward_terms + e * AS_NUM_REWARD_TERMS;
-        rt[0] = P.alive_reward_scale; rt[1] = r_progress; rt[2] = r_roll; rt[3] = r_pitch; rt[4] = r_speed;
         rt[5] = r_energy; rt[6] = r_action; rt[7] = r_limit; rt[8] = r_step; rt[9] = r_bonus;
       }
     }
