@@ -550,7 +550,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   PassOut po{};
   bool terminated = false, time_out = false, is_reset = false, mirror = false, regen = false;
   bool fell = false, so_fast = false, died = false, adv1 = false, adv2 = false;
-  float r_partial = 0.0f, r_step = 0.0f, r_bonus = 0.0f;  // alive + progress - roll - pitch - speed costs, ENV:378-383
+  float r_partial = 0.0f, r_speed = 0.0f, r_step = 0.0f, r_bonus = 0.0f;
   int idx_after_pass1 = 0;
   const unsigned long long step_now = ctrl->step_counter;
   float o_jp[kJ], o_jv[kJ];
@@ -609,8 +609,6 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
     orient_wait();  // roll / pitch / quat_inv of this env were computed by the joint role (ENV:285, MATH:238-248)
     if (active) {
-      roll = misc->x_roll[t];
-      pitch = misc->x_pitch[t];
       inv = Quat{misc->x_inv[0][t], misc->x_inv[1][t], misc->x_inv[2][t], misc->x_inv[3][t]};
       targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
       adv1 = po.advanced;
@@ -618,17 +616,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       if (MODE != kModePass2) {
         // ---- reward terms that do not need the joint sums, ENV:350-375
         const float r_progress = m.pot - po.old_pot;
-        const float r_roll = (roll > 0.4f || roll < -0.4f) ? fabsf(roll) : 0.0f;
-        const float r_pitch = (pitch > 0.4f || pitch < -0.2f) ? fabsf(pitch) : 0.0f;
-        const float r_speed = speed > 1.6f ? speed - 1.6f : 0.0f;
-        // the head of the reference's left-to-right sum (ENV:378-383) is final here: keep one register, not four
-        r_partial = P.alive_reward_scale + r_progress;
-        r_partial = r_partial - r_roll;
-        r_partial = r_partial - r_pitch;
-        r_partial = r_partial - r_speed;
+        r_speed = speed > 1.6f ? speed - 1.6f : 0.0f;
+        r_partial = P.alive_reward_scale + r_progress;  // head of the reference's left-to-right sum, ENV:378-380
         if (a.out.reward_terms) {
           float* rt = a.out.reward_terms + e * AS_NUM_REWARD_TERMS;
-          rt[0] = P.alive_reward_scale; rt[1] = r_progress; rt[2] = r_roll; rt[3] = r_pitch; rt[4] = r_speed;
+          rt[0] = P.alive_reward_scale; rt[1] = r_progress; rt[4] = r_speed;
         }
         const bool pays_step = po.reached && m.count == 1 && m.idx < kS - 1;
         r_step = pays_step ? 50.0f * expf((-po.d_swing) / 0.25f) : 0.0f;
@@ -722,18 +714,21 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     // The root tile is small and lands first: do the orientation math of this env (ENV:285,293; MATH:238-248) while
     // the three joint tiles are still in flight, and hand roll / pitch / quat_inv to the MDP role.
     if (bulk_root) mbar_wait(bar_root, phase_root);
+    Quat q{1, 0, 0, 0};
     if (active) {
       const float4 q4 = *reinterpret_cast<const float4*>(s_rq + t * 4);
-      const Quat q = a.in.quat_xyzw ? Quat{q4.w, q4.x, q4.y, q4.z} : Quat{q4.x, q4.y, q4.z, q4.w};
-      const Vec3 v{s_rv[t * 3], s_rv[t * 3 + 1], s_rv[t * 3 + 2]};
-      euler_roll_pitch(q, roll, pitch);
-      vb = rotate_by_inverse(q, v);
-      const Quat inv = quat_inverse(q);
-      misc->x_roll[t] = roll;
-      misc->x_pitch[t] = pitch;
+      q = a.in.quat_xyzw ? Quat{q4.w, q4.x, q4.y, q4.z} : Quat{q4.x, q4.y, q4.z, q4.w};
+      const Quat inv = quat_inverse(q);  // first: the MDP role is waiting for it to transform the targets
       misc->x_inv[0][t] = inv.w; misc->x_inv[1][t] = inv.x; misc->x_inv[2][t] = inv.y; misc->x_inv[3][t] = inv.z;
     }
-    orient_arrive();
+    orient_arrive();  // (warp-convergent: outside the `active` branch)
+    if (active) {
+      const Vec3 v{s_rv[t * 3], s_rv[t * 3 + 1], s_rv[t * 3 + 2]};
+      euler_roll_pitch(q, roll, pitch);  // read by the MDP role only after the sums hand-off further down
+      vb = rotate_by_inverse(q, v);
+      misc->x_roll[t] = roll;
+      misc->x_pitch[t] = pitch;
+    }
     if (bulk_joint) mbar_wait(bar_joint, phase_joint);
     AS_T(t_j0);
     float energy = 0.0f, act_sq = 0.0f;
@@ -850,7 +845,14 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       const float r_energy = P.energy_cost_scale * misc->red_energy[t];
       const float r_action = P.actions_cost_scale * sqrtf(misc->red_actsq[t]);
       const float r_limit = static_cast<float>(misc->red_limit[t]) * P.joint_at_limit_cost_scale;
-      float total = r_partial - r_energy;
+      // roll / pitch were written by the joint role before it signalled the sums (ENV:356-359)
+      const float roll_j = misc->x_roll[t], pitch_j = misc->x_pitch[t];
+      const float r_roll = (roll_j > 0.4f || roll_j < -0.4f) ? fabsf(roll_j) : 0.0f;
+      const float r_pitch = (pitch_j > 0.4f || pitch_j < -0.2f) ? fabsf(pitch_j) : 0.0f;
+      float total = r_partial - r_roll;
+      total = total - r_pitch;
+      total = total - r_speed;
+      total = total - r_energy;
       total = total - r_action;
       total = total - r_limit;
       total = total + r_step;
@@ -862,6 +864,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       if (a.out.dones) a.out.dones[e] = is_reset ? 1 : 0;
       if (a.out.reward_terms) {
         float* rt = a.out.reward_terms + e * AS_NUM_REWARD_TERMS;
+        rt[2] = r_roll; rt[3] = r_pitch;
         rt[5] = r_energy; rt[6] = r_action; rt[7] = r_limit; rt[8] = r_step; rt[9] = r_bonus;
       }
     }
