@@ -648,3 +648,49 @@ def test_global_promotion_over_shards_and_wrapper_outputs():
             assert torch.equal(shards[r].export_state()["curriculum"], whole.export_state()["curriculum"][sl])
         exact(out.dones, (out.terminated | out.time_out), "dones")
     assert int(whole.export_state()["curriculum"].max()) >= 1, "the global mean (13) must have promoted"
+
+
+def test_long_replay_100_steps():
+    """SURVEY section 7's minimum slice asks for a 100-step replay; run it with everything on (resets, promotion as
+    the mean index climbs, per-env levels)."""
+    totals, wo, wr = run_replay(2048, 100, seed=123, fall_fraction=0.01, per_env_levels=True)
+    assert totals["resets"] > 1000 and totals["advanced"] > 10000
+    print(f"100-step replay: {totals}, worst obs rel err {wo:.2e}, reward {wr:.2e}")
+
+
+def test_config3_size_with_grid_curriculum():
+    """BASELINE.json config 3: 65,536 envs with the pitch x yaw grid curriculum (extension), a few steps."""
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+    from oracle import allsteps_oracle as ao
+    from oracle import grid_curriculum as gc
+
+    N, seed, B = 65536, 29, 11
+    sc = Scenario(N, seed=seed)
+    st0 = sc.initial_mdp_state()
+    grid = gc.GridCurriculum(N, B)
+    orc = ao.AllstepsOracle(sc.cfg, N, sc.env_origins, sc.joint_limits, sc.body_indices, sc.stone_uniforms(0),
+                            grid=grid, seed=seed)
+    mdp = make_cuda(N, seed, grid_bins=B)
+    origins = sc.env_origins.cuda()
+    mdp.generate_stones(origins)
+    install_mdp_state(orc, st0)
+    mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                          "episode_length_buf", "potentials")})
+    mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
+    out = StepBuffers(N, "cuda:0")
+    for step in range(3):
+        phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+        m, n = sc.reset_uniforms(step)
+        o_obs, o_rew, o_term, o_to, o_ids = orc.step(phys, phys["actions"], m, n, sc.stone_uniforms(step))
+        views, keep = to_views(phys, origins, sc.body_indices)
+        mdp.step(views, keep["actions"], out)
+        torch.cuda.synchronize()
+        exact(out.terminated, o_term, f"step {step} terminated")
+        exact(out.time_out, o_to, f"step {step} time_out")
+        close(out.reward, o_rew, f"step {step} reward")
+        close_obs(out.obs, o_obs, f"step {step} obs")
+        bins, att, succ = mdp.grid_state()
+        exact(bins, torch.from_numpy(grid.bins.copy()), f"step {step} bins")
+        exact(att, torch.from_numpy(grid.attempts.astype(np.int64)), f"step {step} attempts")
+        compare_state(mdp, orc, f"step {step}")
+        mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
