@@ -65,6 +65,13 @@ constexpr int64_t kSeparateGatherMinEnvs = 1 << 17;
 
 int launch_contact_gather(AsHandle* h, const AsStateIn* in, cudaStream_t s) {
   if (h->num_envs < kSeparateGatherMinEnvs) return AS_OK;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in->contact_right) | reinterpret_cast<uintptr_t>(in->contact_left)) &
+                        15u) == 0 && ((in->contact_right_stride | in->contact_left_stride) & 3) == 0;
+  if (aligned) {  // two lanes per env: one memory request per force vector
+    const unsigned blocks = static_cast<unsigned>((2 * h->num_envs + 255) / 256);
+    k_contact_gather_paired<<<blocks, 256, 0, s>>>(*in, h->ws, h->num_envs);
+    return check_launch(h, "k_contact_gather_paired");
+  }
   const unsigned blocks = static_cast<unsigned>((h->num_envs + 255) / 256);
   k_contact_gather<<<blocks, 256, 0, s>>>(*in, h->ws, h->num_envs);
   return check_launch(h, "k_contact_gather");

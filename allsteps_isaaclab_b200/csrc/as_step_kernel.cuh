@@ -968,6 +968,41 @@ __global__ void __launch_bounds__(256) k_contact_gather(const AsStateIn in, Work
   ws.contact_pre[e] = make_float2(f_r, f_l);
 }
 
+// Same gather with TWO lanes per env: the even lane fetches the 16-byte chunk the vector starts in, the odd lane the
+// following chunk when the vector runs into it, in ONE load instruction.  The two chunks then travel as one request
+// whenever they share a 128-byte line, which is what counts when the matrices live in pinned host memory: PCIe reads
+// are bound by the number of requests in flight, not by their size (tools/e2e_probe.py).  Needs 16-byte aligned rows.
+__global__ void __launch_bounds__(256) k_contact_gather_paired(const AsStateIn in, Workspace ws, int64_t num_envs) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t e = t >> 1;
+  const bool live = e < num_envs;  // both lanes of a pair agree; no early exit, the shuffles below need the warp
+  const int half = static_cast<int>(t & 1);
+  const int idx = live ? state_idx(ws.state[ws.ctrl->parity][e].x) : 0;
+  const int o = idx * 3;
+  const int k = o & 3;
+  const bool fetch = live && (half == 0 || k >= 2);
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f), l = r;
+  if (fetch) {
+    r = __ldg(reinterpret_cast<const float4*>(in.contact_right + e * in.contact_right_stride) + (o >> 2) + half);
+    l = __ldg(reinterpret_cast<const float4*>(in.contact_left + e * in.contact_left_stride) + (o >> 2) + half);
+  }
+  // the odd lane's first two floats are all the even lane can need from the second chunk
+  const float r1x = __shfl_down_sync(0xffffffffu, r.x, 1), r1y = __shfl_down_sync(0xffffffffu, r.y, 1);
+  const float l1x = __shfl_down_sync(0xffffffffu, l.x, 1), l1y = __shfl_down_sync(0xffffffffu, l.y, 1);
+  if (!live || half) return;
+  float rx, ry, rz, lx, ly, lz;
+  if (k == 0) {
+    rx = r.x; ry = r.y; rz = r.z; lx = l.x; ly = l.y; lz = l.z;
+  } else if (k == 1) {
+    rx = r.y; ry = r.z; rz = r.w; lx = l.y; ly = l.z; lz = l.w;
+  } else if (k == 2) {
+    rx = r.z; ry = r.w; rz = r1x; lx = l.z; ly = l.w; lz = l1x;
+  } else {
+    rx = r.w; ry = r1x; rz = r1y; lx = l.w; ly = l1x; lz = l1y;
+  }
+  ws.contact_pre[e] = make_float2(norm3(rx, ry, rz), norm3(lx, ly, lz));  // ENV:421-424
+}
+
 #ifndef AS_STEP_MIN_CTAS
 #define AS_STEP_MIN_CTAS (512 / AS_KTILE)
 #endif
@@ -1007,9 +1042,11 @@ __global__ void __launch_bounds__(128) k_fold_pass1(Ctrl* ctrl, int64_t num_envs
 }
 
 // Fix-up + finish.  If NO env of this shard reset, the reference never runs pass 2 (DRL:360): redo every tile
-// without it from the untouched pre-step state buffer (rare: needs zero resets among all envs).  The last CTA
-// then folds the statistics, publishes next step's promotion, flips the state parity and advances the Philox
-// step counter.
+// without it from the untouched pre-step state buffer (rare: needs zero resets among all envs).  The LAST CTA to
+// have taken that decision (and done its share of the fix-up, if any) then folds the statistics, publishes next
+// step's promotion, flips the state parity and advances the Philox step counter.  It has to be the last one: the
+// finisher rewrites exactly the words the decision is read from (the counter slots, stats_folded), so nobody may
+// still be about to read them.
 __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
@@ -1027,7 +1064,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
   __syncthreads();
   const bool need_fixup = misc->is_last == 0 && !(a.P.flags & AS_FLAG_SKIP_PASS2);
   __syncthreads();
-  bool finisher = blockIdx.x == 0;  // common case (some env reset): nothing to wait for, CTA 0 finishes alone
   if (need_fixup) {
     uint32_t phase_root = 0, phase_joint = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -1036,30 +1072,28 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) {  // the last CTA to get here finishes
-      const unsigned t = atomicAdd(&ctrl->blocks_done2, 1u);
-      misc->is_last = (t == gridDim.x - 1) ? 1u : 0u;
-    }
-    __syncthreads();
-    finisher = misc->is_last != 0;
-    if (finisher) __threadfence();
   }
-  if (finisher) {
-    if (!prefolded) fold_stats(ctrl, misc->fold, a.num_envs);
-    if (tid == 0) {
-      ctrl->stats_folded = 0;
-      const AsStats* g = a.global_stats ? a.global_stats : &ctrl->stats;
-      ctrl->promote_cur = promotion_decision(a.P, *g);
-      if (a.rows.n_reset) *a.rows.n_reset = static_cast<int32_t>(a.want_reset_list ? ctrl->n_reset_list : ctrl->stats.n_reset);
-      ctrl->parity ^= 1u;
-      ctrl->step_counter += 1ull;
-      ctrl->n_reset_list = 0;
-      ctrl->n_regen_list = 0;
-      ctrl->blocks_done2 = 0;
-      if (need_fixup) {
-        ctrl->fixup_ran += 1;
-        ctrl->stats.n_advanced -= ctrl->last_adv2;  // pass-2 advances were discarded with pass 2
-      }
+  if (tid == 0) {
+    const unsigned t = atomicAdd(&ctrl->blocks_done2, 1u);
+    misc->is_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (misc->is_last == 0) return;
+  __threadfence();
+  if (!prefolded) fold_stats(ctrl, misc->fold, a.num_envs);
+  if (tid == 0) {
+    ctrl->stats_folded = 0;
+    const AsStats* g = a.global_stats ? a.global_stats : &ctrl->stats;
+    ctrl->promote_cur = promotion_decision(a.P, *g);
+    if (a.rows.n_reset) *a.rows.n_reset = static_cast<int32_t>(a.want_reset_list ? ctrl->n_reset_list : ctrl->stats.n_reset);
+    ctrl->parity ^= 1u;
+    ctrl->step_counter += 1ull;
+    ctrl->n_reset_list = 0;
+    ctrl->n_regen_list = 0;
+    ctrl->blocks_done2 = 0;
+    if (need_fixup) {
+      ctrl->fixup_ran += 1;
+      ctrl->stats.n_advanced -= ctrl->last_adv2;  // pass-2 advances were discarded with pass 2
     }
   }
 }

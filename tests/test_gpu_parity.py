@@ -72,6 +72,18 @@ def to_views(phys, env_origins_cuda, body_rows, layout="contiguous"):
         d["root_pos_w"], d["root_quat_w"], d["root_lin_vel_w"] = root_state[:, 0:3], root_state[:, 3:7], root_state[:, 7:10]
         d["body_pos_w"] = body_state[..., 0:3]
         d["_keep"] = (root_state, body_state)
+    elif layout == "unaligned_contact":
+        # contact matrices that start 4 bytes into their allocation: the 128-bit gather path must not be taken
+        keep = []
+        for k in ("force_matrix_right", "force_matrix_left"):
+            flat = torch.zeros(d[k].numel() + 1, device="cuda")
+            flat[1:] = d[k].reshape(-1)
+            d[k] = flat[1:].view(d[k].shape)
+            keep.append(flat)
+        d["_keep"] = tuple(keep)
+    elif layout == "pinned_contact":
+        for k in ("force_matrix_right", "force_matrix_left"):
+            d[k] = phys[k].pin_memory()
     return PhysicsViews.from_dict(d, env_origins_cuda, body_rows), d
 
 
@@ -164,6 +176,14 @@ def run_replay(num_envs, steps, seed, full_bodies=False, layout="contiguous", fa
         totals["promoted"] += int((orc.curriculum != level_before).any())
         totals["fixups"] += int(n_reset == 0)
     return totals, worst_obs, worst_rew
+
+
+@pytest.mark.parametrize("layout", ["contiguous", "unaligned_contact", "pinned_contact"])
+def test_separate_contact_gather_kernels(layout):
+    """From 2^17 envs on the current stone's contact vectors are gathered by a kernel of their own: two lanes per env
+    on 16-byte aligned rows (device or pinned host memory), one lane per env otherwise."""
+    totals, _, _ = run_replay((1 << 17) + 37, 2, seed=29, layout=layout, high_index=(layout == "contiguous"))
+    assert totals["advanced"] > 0
 
 
 @pytest.mark.parametrize("num_envs,steps", [(64, 40), (4096, 12)])
@@ -386,7 +406,12 @@ def test_cuda_graph_replay_is_identical_to_eager_steps():
         mdps[1].step(views, static["actions"], out_e)
         torch.cuda.synchronize()
         for name in ("obs", "reward", "terminated", "time_out", "reset_root_state", "reset_joint_pos"):
-            assert torch.equal(getattr(out_g, name), getattr(out_e, name)), f"step {i}: {name}"
+            g, e = getattr(out_g, name), getattr(out_e, name)
+            if not torch.equal(g, e):
+                bad = (g != e).nonzero()
+                vals = [(g[tuple(b)].item(), e[tuple(b)].item()) for b in bad[:8]]
+                raise AssertionError(f"step {i}: {name} differs at {len(bad)} places, first {bad[:8].tolist()}: {vals}; "
+                                     f"n_reset graph/eager = {int(out_g.n_reset)}/{int(out_e.n_reset)}")
         a, b = mdps[0].export_state(), mdps[1].export_state()
         for k in a:
             assert torch.equal(a[k], b[k]), f"step {i}: state {k}"
