@@ -435,7 +435,7 @@ def main_b200(args):
                "ms_per_step": variants[best]["ms_per_step"], "mode": best, "variants": variants,
                "note": "pinned host buffers; H2D of step t+1 and D2H of step t-1 overlap the kernel of step t; in "
                        "zero_copy_contact_matrices the (N,1,20,3) contact tensors stay in pinned host memory and "
-                       "k_contact_gather reads the current stone's vectors through PCIe"}
+                       "k_contact_gather_paired reads the current stone's vectors through PCIe"}
 
     small = {}
     if rank == 0 and world == 1 and args.small_sizes:
@@ -479,7 +479,7 @@ def main_b200(args):
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "whole_step": {"achieved": achieved_step, "frac": achieved_step / peak,
                                         "algorithmic_bytes_per_env_step": B_ALG,
-                                        "kernels": "k_contact_gather + k_step<fused> + k_fixup_finish"}},
+                                        "kernels": "k_contact_gather_paired + k_step<fused> + k_fixup_finish"}},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
             "step_stats": {k: stats[k] for k in ("n_reset", "n_terminated", "n_time_out", "n_advanced", "level")},
