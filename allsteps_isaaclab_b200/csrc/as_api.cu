@@ -21,6 +21,8 @@ struct AsHandle {
   int64_t launches;
   MirrorTable mirror_obs, mirror_act;
   JointConsts jc;
+  int pdl;             // programmatic dependent launch: >= 1 k_fixup_finish after the step kernel, >= 2 also the step
+                       // kernel after the gather kernel (ALLSTEPS_PDL, default 2; 0 = plain stream order)
   int prefetch_tiles;  // L2 prefetch distance of the step kernel, in 128-env tiles (about one wave of CTAs)
   cudaEvent_t ev_start, ev_stop;  // optional timing hook around k_step<fused>
   bool pass1_done;
@@ -275,6 +277,8 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
     // or more loses (the lines are evicted before use) -- DESIGN.md section 6
     const char* pf = std::getenv("ALLSTEPS_PREFETCH_TILES");
     h->prefetch_tiles = pf ? std::atoi(pf) : 0;
+    const char* pdl = std::getenv("ALLSTEPS_PDL");
+    h->pdl = pdl ? std::atoi(pdl) : 2;
   }
   unsigned char* base = static_cast<unsigned char*>(workspace);
   h->ws.ctrl = reinterpret_cast<Ctrl*>(base + l.ctrl_off);
@@ -350,7 +354,24 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   if (want_rows) a.rows = *reset_out;  // start-pose rows are written by the step kernel itself
   if (int rc = launch_contact_gather(h, in, s)) return rc;
   if (h->ev_start) AS_CUDA(cudaEventRecord(h->ev_start, s));
-  k_step<kModeFused><<<a.num_tiles, kThreads, kSmemBytes, s>>>(a);
+  if (h->pdl >= 2 && a.use_pre && !h->ev_start) {
+    // dependent of the gather kernel: tiles, state words and windows are loaded while the gather's last wave runs;
+    // the MDP role waits for the gather (griddepcontrol.wait) right before it reads the contact norms
+    a.pdl_wait = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(a.num_tiles));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AS_CUDA(cudaLaunchKernelEx(&cfg, k_step<kModeFused>, a));
+  } else {
+    k_step<kModeFused><<<a.num_tiles, kThreads, kSmemBytes, s>>>(a);
+  }
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
   if (h->ev_stop) AS_CUDA(cudaEventRecord(h->ev_stop, s));
   if (grid) {  // kernel (c): outcomes into the difficulty histogram, then new bins by inverse-CDF sampling
@@ -386,7 +407,24 @@ int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream) {
   StepArgs a = h->pending;  // the fix-up re-reads the inputs of the step it closes
   a.global_stats = global_stats;
   const int grid = grid_for(a.num_tiles, 1, h->sm_count, 1);
-  k_fixup_finish<<<grid, kThreads, kSmemBytes, s>>>(a);
+  if (h->pdl) {
+    // programmatic dependent launch: the step kernel releases its dependents as soon as its last wave of CTAs is
+    // resident, so this kernel's launch and prologue overlap that wave; it waits (griddepcontrol.wait) for the
+    // step kernel to complete and flush before it reads anything
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AS_CUDA(cudaLaunchKernelEx(&cfg, k_fixup_finish, a));
+  } else {
+    k_fixup_finish<<<grid, kThreads, kSmemBytes, s>>>(a);
+  }
   h->pending_valid = false;
   return check_launch(h, "k_fixup_finish");
 }

@@ -147,6 +147,7 @@ struct StepArgs {
   int32_t num_tiles;
   int32_t want_reset_list;            // fused: compact the ids of the envs that reset
   int32_t use_pre;                    // 1: contact norms come from k_contact_gather (large batches), 0: gather here
+  int32_t pdl_wait;                   // 1: launched as a programmatic dependent of k_contact_gather*
   int32_t prefetch_tiles;             // the step kernel pulls the inputs of tile + prefetch_tiles into L2 (0 = off)
   uint32_t dense16;                   // per-array "dense and 16-byte aligned" bits (DenseBit), evaluated by the host
   AsResetOut rows;                    // fused: start-pose rows for PhysX, written at the env's own row (optional)

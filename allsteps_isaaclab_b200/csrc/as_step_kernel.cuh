@@ -498,6 +498,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     cr_row = a.in.contact_right + e * a.in.contact_right_stride;
     cl_row = a.in.contact_left + e * a.in.contact_left_stride;
     if (a.use_pre) {  // |F| of the current stone under each foot, gathered by k_contact_gather just before
+      if (a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
       const float2 pre = a.ws.contact_pre[e];
       f_r = pre.x;
       f_l = pre.y;
@@ -958,6 +959,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 // critical path -- state word (coalesced) -> two gathers -> one coalesced 8-byte store -- instead of stalling a
 // 46-KB CTA of the step kernel, which then reads the two norms as a coalesced record.
 __global__ void __launch_bounds__(256) k_contact_gather(const AsStateIn in, Workspace ws, int64_t num_envs) {
+  asm volatile("griddepcontrol.launch_dependents;");
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= num_envs) return;
   const bool aligned = ((reinterpret_cast<uintptr_t>(in.contact_right) | reinterpret_cast<uintptr_t>(in.contact_left)) &
@@ -973,6 +975,7 @@ __global__ void __launch_bounds__(256) k_contact_gather(const AsStateIn in, Work
 // whenever they share a 128-byte line, which is what counts when the matrices live in pinned host memory: PCIe reads
 // are bound by the number of requests in flight, not by their size (tools/e2e_probe.py).  Needs 16-byte aligned rows.
 __global__ void __launch_bounds__(256) k_contact_gather_paired(const AsStateIn in, Workspace ws, int64_t num_envs) {
+  asm volatile("griddepcontrol.launch_dependents;");  // the step kernel may stage its tiles under our last wave
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t e = t >> 1;
   const bool live = e < num_envs;  // both lanes of a pair agree; no early exit, the shuffles below need the warp
@@ -1010,6 +1013,9 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
+  // lets a kernel launched as a programmatic dependent (k_fixup_finish) become resident once every CTA of this grid
+  // has started; it still waits for this grid to complete before touching memory.  No effect otherwise.
+  if (MODE == kModeFused) asm volatile("griddepcontrol.launch_dependents;");
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&misc->mbar_root), 1);
     mbar_init(smem_u32(&misc->mbar_joint), 1);
@@ -1052,6 +1058,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
   Ctrl* ctrl = a.ws.ctrl;
   const int tid = threadIdx.x;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // (returns at once unless launched as a programmatic dependent)
   const bool prefolded = ctrl->stats_folded != 0;  // as_fold_stats ran: the slots are empty, the totals are in stats
   if (tid < 32) {
     const unsigned n = prefolded ? static_cast<unsigned>(ctrl->stats.n_reset) : slot_sum(ctrl, kCntReset);
