@@ -151,6 +151,21 @@ __device__ __forceinline__ void coop_load(float* dst, const float* base, int64_t
   }
 }
 
+// Scattered reads (one 12/16-byte item out of a 240/320-byte row per env): by default a miss makes L2 pull the whole
+// 128-byte line out of DRAM; the L2::64B qualifier limits the fill to the 64-byte half that holds the item.  These
+// gathers are DRAM-byte bound, so that halves their cost (tools/gather_probe.cu: 259 -> 143 DRAM bytes per env,
+// 44 -> 27 us per 1M envs).  SASS: LDG.E.LTC64B...CONSTANT.
+__device__ __forceinline__ float4 ldg64_f4(const float4* p) {
+  float4 r;
+  asm("ld.global.nc.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg64_f(const float* p) {
+  float r;
+  asm("ld.global.nc.L2::64B.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
 // Norm of the 12-byte contact-force vector of stone `idx` inside one env's (S,3) row.  When the row is 16-byte
 // aligned the vector is fetched with one or two aligned 128-bit loads instead of three scalar ones: the same
 // sectors, half the requests through the L1 miss path.
@@ -160,13 +175,13 @@ __device__ __forceinline__ float contact_norm(const float* row, int idx, bool al
     const int o = idx * 3;
     const int k = o & 3;
     const float4* c = reinterpret_cast<const float4*>(row) + (o >> 2);
-    const float4 c0 = __ldg(c);
+    const float4 c0 = ldg64_f4(c);
     if (k == 0) {
       x = c0.x; y = c0.y; z = c0.z;
     } else if (k == 1) {
       x = c0.y; y = c0.z; z = c0.w;
     } else {
-      const float4 c1 = __ldg(c + 1);
+      const float4 c1 = ldg64_f4(c + 1);
       if (k == 2) {
         x = c0.z; y = c0.w; z = c1.x;
       } else {
@@ -175,7 +190,7 @@ __device__ __forceinline__ float contact_norm(const float* row, int idx, bool al
     }
   } else {
     const float* f = row + idx * 3;
-    x = __ldg(f); y = __ldg(f + 1); z = __ldg(f + 2);
+    x = ldg64_f(f); y = ldg64_f(f + 1); z = ldg64_f(f + 2);
   }
   return norm3(x, y, z);  // ENV:421-424
 }
@@ -465,7 +480,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   const uint2* st_in = a.ws.state[parity];
   uint2* st_out = kPingPong ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
   const float4* stones = a.ws.stones + e * kS;
-  auto stone_at = [&](int i) -> float4 { return __ldg(stones + i); };
+  auto stone_at = [&](int i) -> float4 { return ldg64_f4(stones + i); };
   float4* wrow = a.ws.window + e * 4;
   const bool contact_aligned = ((reinterpret_cast<uintptr_t>(a.in.contact_right) | reinterpret_cast<uintptr_t>(
                                     a.in.contact_left)) & 15u) == 0 &&
@@ -986,8 +1001,8 @@ __global__ void __launch_bounds__(256) k_contact_gather_paired(const AsStateIn i
   const bool fetch = live && (half == 0 || k >= 2);
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f), l = r;
   if (fetch) {
-    r = __ldg(reinterpret_cast<const float4*>(in.contact_right + e * in.contact_right_stride) + (o >> 2) + half);
-    l = __ldg(reinterpret_cast<const float4*>(in.contact_left + e * in.contact_left_stride) + (o >> 2) + half);
+    r = ldg64_f4(reinterpret_cast<const float4*>(in.contact_right + e * in.contact_right_stride) + (o >> 2) + half);
+    l = ldg64_f4(reinterpret_cast<const float4*>(in.contact_left + e * in.contact_left_stride) + (o >> 2) + half);
   }
   // the odd lane's first two floats are all the even lane can need from the second chunk
   const float r1x = __shfl_down_sync(0xffffffffu, r.x, 1), r1y = __shfl_down_sync(0xffffffffu, r.y, 1);
