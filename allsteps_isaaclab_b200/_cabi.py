@@ -64,7 +64,7 @@ class AsStateIn(C.Structure):
 
 class AsStepOut(C.Structure):
     _fields_ = [("obs", _ptr), ("reward", _ptr), ("terminated", _ptr), ("time_out", _ptr), ("reward_terms", _ptr),
-                ("dones", _ptr)]
+                ("dones", _ptr), ("obs_clip", _f), ("_reserved", C.c_uint32)]
 
 
 class AsResetOut(C.Structure):

@@ -21,6 +21,7 @@ struct AsHandle {
   int64_t launches;
   MirrorTable mirror_obs, mirror_act;
   JointConsts jc;
+  float obs_clip_pass1;  // AsStepOut.obs_clip of the last as_step_pass1 (applied by as_step_pass2 too)
   int pdl;             // programmatic dependent launch: >= 1 k_fixup_finish after the step kernel, >= 2 also the step
                        // kernel after the gather kernel (ALLSTEPS_PDL, default 2; 0 = plain stream order)
   int prefetch_tiles;  // L2 prefetch distance of the step kernel, in 128-env tiles (about one wave of CTAs)
@@ -270,6 +271,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->sm_count = prop.multiProcessorCount;
   h->launches = 0;
   h->pass1_done = false;
+  h->obs_clip_pass1 = 0.0f;
   h->pending_valid = false;
   h->ev_start = h->ev_stop = nullptr;
   {
@@ -343,6 +345,7 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   if (int rc = validate_state_in(in, true)) return rc;
   AS_REQUIRE(actions_stride >= kJ, "actions stride too small");
   AS_REQUIRE(out->obs && out->reward && out->terminated && out->time_out, "step outputs must be set");
+  AS_REQUIRE(out->obs_clip >= 0.0f, "obs_clip must be >= 0");
   if (h->pending_valid) return fail(AS_ERR_STATE, "previous fused step was not closed with as_finish_step");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   StepArgs a = make_step_args(h, in, actions, actions_stride, out);
@@ -436,8 +439,10 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   AS_REQUIRE(actions_stride >= kJ, "actions stride too small");
   AS_REQUIRE(out->obs && out->reward && out->terminated && out->time_out, "step outputs must be set");
   if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
+  AS_REQUIRE(out->obs_clip >= 0.0f, "obs_clip must be >= 0");
   StepArgs a = make_step_args(h, in, actions, actions_stride, out);
   a.ext_episode_length = episode_length;
+  h->obs_clip_pass1 = out->obs_clip;  // as_step_pass2 rewrites the same observation buffer: same epilogue
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (int rc = launch_contact_gather(h, in, s)) return rc;
   k_step<kModePass1><<<a.num_tiles, kThreads, kSmemBytes, s>>>(a);
@@ -474,6 +479,7 @@ int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
   AsStepOut out;
   std::memset(&out, 0, sizeof(out));
   out.obs = obs;
+  out.obs_clip = h->obs_clip_pass1;
   StepArgs a = make_step_args(h, in, nullptr, 0, &out);
   if (int rc = launch_contact_gather(h, in, static_cast<cudaStream_t>(stream))) return rc;
   k_step<kModePass2><<<a.num_tiles, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);

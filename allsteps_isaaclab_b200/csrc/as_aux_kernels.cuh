@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) k_apply_action(const __grid_constant__ As
     const int64_t e = i / kJ;
     const int j = static_cast<int>(i - e * kJ);
     const int level = min(state_level(st[e].x) + pending, P.max_level);
-    const float act = fminf(fmaxf(actions[e * stride + j], -1.0f), 1.0f);
+    const float act = clamp_nan(actions[e * stride + j], -1.0f, 1.0f);
     efforts[i] = (P.applied_gain[level] * P.joint_gears[j]) * act;
   }
 }

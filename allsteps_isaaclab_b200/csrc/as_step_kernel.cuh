@@ -291,7 +291,7 @@ __device__ __forceinline__ float scale_joint(const JointConsts& C, int j, float 
 __device__ __forceinline__ float reset_joint_value(const AsParams& P, float base, float lo, float hi, float u) {
   const float noisy = base + (u * P.noise_span + P.noise_lower);
   float unit = scale_to_unit(noisy, lo, hi);
-  unit = fminf(fmaxf(unit, P.clip_lower), P.clip_upper);
+  unit = clamp_nan(unit, P.clip_lower, P.clip_upper);
   return unscale_from_unit(unit, lo, hi);
 }
 
@@ -596,7 +596,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     if (active && MODE != kModePass2) {
       // ---- dones first, ENV:396-405: they need only the staged root / body rows, and knowing early which envs
       // reset lets their extra loads fly while pass 1 is being computed
-      h = torso_z - fminf(lf.z, rf.z);  // ENV:281-283
+      h = torso_z - min_nan(lf.z, rf.z);  // ENV:281-283
       time_out = ep >= P.max_episode_length - 1;
       fell = h < P.termination_height[level];
       speed = norm3(v.x, v.y, v.z);
@@ -618,7 +618,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
     bool moved1 = false;
     if (active) {
-      h = torso_z - fminf(lf.z, rf.z);   // ENV:281-283
+      h = torso_z - min_nan(lf.z, rf.z);   // ENV:281-283
       geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
       moved1 = foot_update(P, geom, m, po);
       if (moved1) slide_window();
@@ -758,13 +758,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         const float jv = my_jv[j];
         const float sc = scale_joint(JC, j, my_jp[j]);  // ENV:287-291
         if (kNeedActions) {
-          const float act = fminf(fmaxf(my_act[j], -1.0f), 1.0f);  // ENV:268
+          const float act = clamp_nan(my_act[j], -1.0f, 1.0f);  // ENV:268
           at_limit += fabsf(sc) > 0.99f ? 1 : 0;                   // ENV:367
           energy += fabsf(jv * act);                               // ENV:365
           act_sq = fmaf(act, act, act_sq);                         // ENV:364
         }
         o_jp[j] = sc;
-        o_jv[j] = fminf(fmaxf(jv * P.dof_vel_scale, -5.0f), 5.0f);  // ENV:337
+        o_jv[j] = clamp_nan(jv * P.dof_vel_scale, -5.0f, 5.0f);  // ENV:337
       }
     }
 #ifdef AS_TIMING
@@ -824,7 +824,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
           float* row = s_obs + (row0 + r) * kObs;
           row[6 + lane] = scale_to_unit(val, T.lower[lane], T.upper[lane]);
           const float jv0 = mirror_r ? T.vel_mirrored[lane] : 0.0f;
-          row[6 + kJ + lane] = fminf(fmaxf(jv0 * P.dof_vel_scale, -5.0f), 5.0f);
+          row[6 + kJ + lane] = clamp_nan(jv0 * P.dof_vel_scale, -5.0f, 5.0f);
           if (a.rows.joint_pos) a.rows.joint_pos[e_r * kJ + lane] = val;
           if (a.rows.joint_vel) a.rows.joint_vel[e_r * kJ + lane] = jv0;
         }
@@ -928,6 +928,16 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   AS_T(t_post);
   float* obs_dst = a.out.obs + env0 * kObs;
   const bool b_obs = bm & kDenseObs;
+  if (a.out.obs_clip > 0.0f) {
+    // RL-wrapper epilogue (isaaclab_rl/rl_games.py:293): clamp the finished tile in place.  Comparisons, not
+    // fminf/fmaxf: torch.clamp hands NaN through.
+    const float c = a.out.obs_clip;
+    __syncthreads();
+    for (int i = tid; i < n_valid * kObs; i += kThreads) {
+      const float v = s_obs[i];
+      s_obs[i] = v < -c ? -c : (v > c ? c : v);
+    }
+  }
   if (b_obs) {
     fence_proxy_async_smem();  // make the generic-proxy writes visible to the TMA engine
     __syncthreads();

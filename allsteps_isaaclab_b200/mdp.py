@@ -101,8 +101,12 @@ class PhysicsViews:
 class StepBuffers:
     """Output tensors of a step; allocated once, overwritten every step (the caller clones what it keeps)."""
 
-    def __init__(self, num_envs: int, device, reward_terms: bool = False, reset_rows: bool = True):
+    def __init__(self, num_envs: int, device, reward_terms: bool = False, reset_rows: bool = True,
+                 obs_clip: float = 0.0):
+        """obs_clip > 0: `obs` comes out clamped to +-obs_clip, the `clip_obs` of RlGamesVecEnvWrapper._process_obs
+        (isaaclab_rl/rl_games.py:293) folded into the kernel's observation write; 0 keeps the raw ENV:326-345 values."""
         kw = dict(device=device)
+        self.obs_clip = float(obs_clip)
         self.obs = torch.empty(num_envs, OBS_DIM, dtype=torch.float32, **kw)
         self.reward = torch.empty(num_envs, dtype=torch.float32, **kw)
         self.terminated = torch.zeros(num_envs, dtype=torch.bool, **kw)
@@ -119,7 +123,8 @@ class StepBuffers:
             self.reset_ids = torch.zeros(num_envs, dtype=torch.int32, **kw)
             self.n_reset = torch.zeros(1, dtype=torch.int32, **kw)
         self.step_out = _cabi.AsStepOut(_ptr(self.obs), _ptr(self.reward), _ptr(self.terminated),
-                                        _ptr(self.time_out), _ptr(self.reward_terms), _ptr(self.dones))
+                                        _ptr(self.time_out), _ptr(self.reward_terms), _ptr(self.dones),
+                                        self.obs_clip, 0)
         self.reset_out = _cabi.AsResetOut(_ptr(self.reset_root_state), _ptr(self.reset_joint_pos),
                                           _ptr(self.reset_joint_vel), _ptr(self.reset_ids), _ptr(self.n_reset))
 

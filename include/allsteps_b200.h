@@ -117,6 +117,11 @@ typedef struct AsStepOut {
                             step, bonus (costs positive) -- for per-term manager logging; NULL to skip     */
   uint8_t* dones;        /* optional (N): terminated | time_out, what RlGamesVecEnvWrapper.step hands to
                             rl_games (isaaclab_rl/rl_games.py:256) and DirectRLEnv keeps as reset_buf      */
+  float obs_clip;        /* > 0: obs is written as clamp(obs, -obs_clip, +obs_clip), the `clip_obs` step of
+                            RlGamesVecEnvWrapper._process_obs (isaaclab_rl/rl_games.py:293; NaN is kept, like
+                            torch.clamp), so the wrapper can hand the buffer on as it is.  0: raw (ENV:326-345).
+                            as_step_pass2 applies the value given to the as_step_pass1 before it.           */
+  uint32_t _reserved;
 } AsStepOut;
 
 /* What `_reset_idx` hands to PhysX (ENV:563-565).  Rows are written AT THE ENV'S OWN ROW (full-size buffers),

@@ -719,3 +719,119 @@ def test_config3_size_with_grid_curriculum():
         exact(att, torch.from_numpy(grid.attempts.astype(np.int64)), f"step {step} attempts")
         compare_state(mdp, orc, f"step {step}")
         mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
+
+
+def _twin_mdps(N, seed, sc):
+    st0 = sc.initial_mdp_state()
+    origins = sc.env_origins.cuda()
+    mdps = [make_cuda(N, seed) for _ in range(2)]
+    for m in mdps:
+        m.generate_stones(origins)
+        m.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                            "episode_length_buf", "potentials")})
+    return mdps, origins, st0
+
+
+@pytest.mark.parametrize("num_envs", [1001, 4096])
+def test_obs_clip_epilogue_equals_the_wrapper_clamp(num_envs):
+    """AsStepOut.obs_clip folds RlGamesVecEnvWrapper._process_obs' clamp (isaaclab_rl/rl_games.py:293) into the
+    observation write: the clipped buffer is bit-identical to torch.clamp of the raw one, on the fused path and on
+    the pass1 / reset / pass2 path; nothing else changes."""
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+
+    seed, clip = 23, 0.8
+    sc = Scenario(num_envs, seed=seed)
+    (raw_mdp, clip_mdp), origins, st0 = _twin_mdps(num_envs, seed, sc)
+    raw, clipped = StepBuffers(num_envs, "cuda:0"), StepBuffers(num_envs, "cuda:0", obs_clip=clip)
+    for step in range(4):
+        st = raw_mdp.export_state()
+        phys = sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+        views, keep = to_views(phys, origins, sc.body_indices)
+        raw_mdp.step(views, keep["actions"], raw)
+        clip_mdp.step(views, keep["actions"], clipped)
+        torch.cuda.synchronize()
+        assert (raw.obs.abs() > clip).any()
+        assert torch.equal(clipped.obs, torch.clamp(raw.obs, -clip, clip)), f"fused step {step}"
+        for name in ("reward", "terminated", "time_out", "dones", "reset_joint_pos"):
+            assert torch.equal(getattr(raw, name), getattr(clipped, name)), f"fused step {step}: {name}"
+    # 3-call path: the clip given to pass1 also applies to the observation rewrite of pass2
+    ep_raw = raw_mdp.export_state()["episode_length_buf"].cuda()
+    ep_clip = ep_raw.clone()
+    for step in range(3):
+        st = raw_mdp.export_state()
+        phys = sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+        for mdp, out, ep in ((raw_mdp, raw, ep_raw), (clip_mdp, clipped, ep_clip)):
+            views, keep = to_views(phys, origins, sc.body_indices)
+            ep += 1
+            mdp.pass1(views, keep["actions"], out, episode_length=ep)
+            ids = (out.terminated | out.time_out).nonzero().squeeze(-1)
+            if len(ids):
+                mdp.reset(origins, ids, out, episode_length=ep)
+                k = len(ids)
+                keep["root_pos_w"][ids] = out.reset_root_state[:k, 0:3]
+                keep["root_quat_w"][ids] = out.reset_root_state[:k, 3:7]
+                keep["root_lin_vel_w"][ids] = out.reset_root_state[:k, 7:10]
+                keep["joint_pos"][ids] = out.reset_joint_pos[:k]
+                keep["joint_vel"][ids] = out.reset_joint_vel[:k]
+                keep["force_matrix_right"][ids] = 0.0
+                keep["force_matrix_left"][ids] = 0.0
+                mdp.pass2(views, out)
+            torch.cuda.synchronize()
+        assert torch.equal(clipped.obs, torch.clamp(raw.obs, -clip, clip)), f"3-call step {step}"
+        assert torch.equal(raw.reward, clipped.reward)
+    with pytest.raises(Exception, match="obs_clip"):
+        bad = StepBuffers(num_envs, "cuda:0", obs_clip=-1.0)
+        raw_mdp.step(views, keep["actions"], bad)
+
+
+def test_nan_inputs_propagate_like_torch():
+    """A blown-up physics state (NaN in actions, joint velocities, a foot height, the root quaternion) must show in
+    the outputs exactly where it shows in the reference: torch.clamp / torch.minimum hand NaN through (ENV:268,281,337;
+    MATH:81-92), comparisons with NaN are false."""
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+    from oracle import allsteps_oracle as ao
+
+    N, seed = 512, 31
+    sc = Scenario(N, seed=seed, fall_fraction=0.0)
+    st0 = sc.initial_mdp_state()
+    orc = ao.AllstepsOracle(sc.cfg, N, sc.env_origins, sc.joint_limits, sc.body_indices, sc.stone_uniforms(0))
+    mdp = make_cuda(N, seed)
+    origins = sc.env_origins.cuda()
+    mdp.generate_stones(origins)
+    install_mdp_state(orc, st0)
+    mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                          "episode_length_buf", "potentials")})
+    mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
+    out = StepBuffers(N, "cuda:0")
+    nan = float("nan")
+    for step in range(3):
+        phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+        phys["actions"][3, 2] = nan
+        phys["actions"][200, 20] = nan
+        phys["joint_vel"][7, 5] = nan
+        phys["joint_pos"][9, 0] = nan
+        phys["body_pos_w"][11, sc.body_indices[0], 2] = nan   # right foot height
+        phys["body_pos_w"][12, sc.body_indices[1], 2] = nan   # left foot height
+        phys["root_quat_w"][13, 1] = nan
+        phys["root_lin_vel_w"][14, 0] = nan
+        mirror_u, noise_u = sc.reset_uniforms(step)
+        o_obs, o_rew, o_term, o_to, o_ids = orc.step(phys, phys["actions"], mirror_u, noise_u, sc.stone_uniforms(step))
+        views, keep = to_views(phys, origins, sc.body_indices)
+        mdp.step(views, keep["actions"], out)
+        torch.cuda.synchronize()
+        exact(out.terminated, o_term, f"step {step} terminated")
+        exact(out.time_out, o_to, f"step {step} time_out")
+        for name, got, want in (("obs", out.obs.cpu(), o_obs), ("reward", out.reward.cpu(), o_rew)):
+            gn, wn = torch.isnan(got), torch.isnan(want)
+            assert torch.equal(gn, wn), (f"step {step}: NaN pattern of {name} differs at "
+                                         f"{(gn != wn).nonzero()[:8].tolist()}")
+            assert wn.any(), f"step {step}: the reference shows no NaN in {name}; the test would prove nothing"
+            ok = ~wn
+            if name == "obs":
+                close_obs(torch.where(ok, got, torch.zeros_like(got)), torch.where(ok, want, torch.zeros_like(want)),
+                          f"step {step} obs")
+            else:
+                close(got[ok], want[ok], f"step {step} reward")
+        st = mdp.export_state()
+        exact(st["curr_target_index"], orc.curr_target_index, f"step {step} idx")
+        exact(st["target_reach_count"], orc.target_reach_count, f"step {step} count")
