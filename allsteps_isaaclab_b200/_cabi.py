@@ -112,6 +112,7 @@ SIGNATURES = {
     "as_apply_action": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr]),
     "as_mirror_rows": (C.c_int, [_ptr, _ptr, _ptr, _i64, _i32, _ptr]),
     "as_export_state": (C.c_int, [_ptr, C.POINTER(AsMdpState), _ptr]),
+    "as_export_stone_poses": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "as_import_state": (C.c_int, [_ptr, C.POINTER(AsMdpState), _ptr]),
     "as_grid_state": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "as_set_timing_events": (C.c_int, [_ptr, _ptr, _ptr]),

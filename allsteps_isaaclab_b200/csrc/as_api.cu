@@ -514,6 +514,20 @@ int as_export_state(AsHandle* h, const AsMdpState* dst, void* stream) {
   return check_launch(h, "k_export");
 }
 
+int as_export_stone_poses(AsHandle* h, const int32_t* env_ids, int64_t n_ids, float* view_poses, int32_t* view_ids,
+                          void* stream) {
+  AS_REQUIRE(h && view_poses, "null argument");
+  AS_REQUIRE(n_ids >= 0 && n_ids <= h->num_envs, "n_ids out of range");
+  AS_REQUIRE(h->num_envs * kS < (1ll << 31), "view indices must fit 32 bits");
+  if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
+  if (!env_ids) n_ids = h->num_envs;
+  if (n_ids == 0) return AS_OK;
+  const int grid = grid_for(n_ids * kS, 256, h->sm_count, 8);
+  k_export_stone_poses<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->ws, env_ids, n_ids, h->num_envs,
+                                                                             view_poses, view_ids);
+  return check_launch(h, "k_export_stone_poses");
+}
+
 int as_import_state(AsHandle* h, const AsMdpState* src, void* stream) {
   AS_REQUIRE(h && src, "null argument");
   if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");

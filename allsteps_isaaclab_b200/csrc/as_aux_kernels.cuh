@@ -403,6 +403,28 @@ __global__ void __launch_bounds__(256) k_grid_sample(const __grid_constant__ AsP
   }
 }
 
+// Stone poses of the listed envs in PhysX' object-major (S*N,7) x,y,z,w layout plus the matching view indices
+// (rigid_object_collection.py:295-301,650-659,675).  One thread per (stone, listed env): consecutive threads write
+// consecutive 28-byte rows when the ids are consecutive.
+__global__ void __launch_bounds__(256) k_export_stone_poses(Workspace ws, const int32_t* __restrict__ env_ids,
+                                                            int64_t n_ids, int64_t num_envs,
+                                                            float* __restrict__ view_poses,
+                                                            int32_t* __restrict__ view_ids) {
+  const int64_t total = n_ids * kS;
+  for (int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; w < total;
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t s = w / n_ids;
+    const int64_t i = w - s * n_ids;
+    const int64_t e = env_ids ? env_ids[i] : i;
+    const float4 v = ws.stones[e * kS + s];
+    const int64_t row = s * num_envs + e;
+    float* dst = view_poses + row * 7;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
+    dst[3] = 0.0f; dst[4] = 0.0f; dst[5] = 0.0f; dst[6] = 1.0f;  // identity, x,y,z,w
+    if (view_ids) view_ids[w] = static_cast<int32_t>(row);
+  }
+}
+
 // bins / histograms in and out (tests, checkpoints)
 __global__ void __launch_bounds__(256) k_grid_state(Workspace ws, uint8_t* bins_dst, const uint8_t* bins_src,
                                                     unsigned int* hist_dst, const unsigned int* hist_src,

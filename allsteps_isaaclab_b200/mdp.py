@@ -305,6 +305,28 @@ class AllstepsMDP:
         d["next_target_index"] = torch.clamp(d["curr_target_index"] + 1, 0, NUM_STONES - 1)  # ENV:77
         return d
 
+    def export_stone_poses(self, env_ids: Optional[torch.Tensor] = None, view_poses: Optional[torch.Tensor] = None):
+        """Stone poses of `env_ids` (None: all envs) the way PhysX takes them: rows of the object-major
+        (S*N,7) x,y,z,w tensor plus their view indices -- `steps.root_physx_view.set_transforms(view_poses,
+        indices=view_ids)` replaces ENV:119-120 + rigid_object_collection.py:295-301 (no whole-tensor clone, quaternion
+        conversion or transpose).  `view_poses` may be a persistent buffer; rows of other envs are left untouched."""
+        N, dev = self.num_envs, self.device
+        if view_poses is None:
+            view_poses = torch.zeros(NUM_STONES * N, 7, dtype=torch.float32, device=dev)
+        _require(view_poses, torch.float32, dev, "view_poses")
+        if tuple(view_poses.shape) != (NUM_STONES * N, 7) or not view_poses.is_contiguous():
+            raise ValueError("view_poses must be a contiguous (S*N,7) tensor")
+        ids_ptr, k = None, N
+        if env_ids is not None:
+            env_ids = env_ids.to(device=dev, dtype=torch.int32).contiguous()
+            ids_ptr, k = env_ids.data_ptr(), env_ids.numel()
+        view_ids = torch.empty(NUM_STONES * k, dtype=torch.int32, device=dev)
+        if k:
+            _cabi.check(self.lib.as_export_stone_poses(self.handle, ids_ptr, k, view_poses.data_ptr(),
+                                                       view_ids.data_ptr(), self._stream()), "as_export_stone_poses")
+        self._keepalive_poses = (env_ids, view_poses, view_ids)
+        return view_poses, view_ids
+
     def import_state(self, state: Dict[str, torch.Tensor]):
         keep = {}
 

@@ -228,6 +228,17 @@ typedef struct AsMdpState {
 int as_export_state(AsHandle* h, const AsMdpState* dst, void* stream);
 int as_import_state(AsHandle* h, const AsMdpState* src, void* stream);
 
+/* Stone poses in the layout PhysX takes them.  Replaces the egress of `_generate_foot_steps`,
+ * ENV:119-120 -> RigidObjectCollection.write_object_pose_to_sim, rigid_object_collection.py:295-301: instead of
+ * cat((steps_pos, [1,0,0,0])) -> scatter into object_state_w -> clone + convert_quat(to="xyzw") of the WHOLE (N,S,7)
+ * tensor -> einsum transpose (reshape_data_to_view, :650-659), the kernel writes, for the k listed envs only, the rows
+ * `view_poses[s*N + e] = (x, y, z, 0, 0, 0, 1)` of the object-major (S*N,7) x,y,z,w tensor and the index list
+ * `view_ids[s*k + i] = s*N + env_ids[i]` (_env_obj_ids_to_view_ids, :675) -- the two arguments of
+ * root_physx_view.set_transforms(view_poses, indices=view_ids).  env_ids == NULL: all envs (k = N, in order).
+ * view_ids may be NULL. */
+int as_export_stone_poses(AsHandle* h, const int32_t* env_ids, int64_t n_ids, float* view_poses, int32_t* view_ids,
+                          void* stream);
+
 /* ---- grid curriculum (EXTENSION: AS_FLAG_GRID_CURRICULUM; no reference counterpart, specification in
  * oracle/grid_curriculum.py) --------------------------------------------------------------------------------------
  * With the flag set, every env that resets in as_step_fused has its episode outcome added to a (grid_bins x

@@ -835,3 +835,47 @@ def test_nan_inputs_propagate_like_torch():
         st = mdp.export_state()
         exact(st["curr_target_index"], orc.curr_target_index, f"step {step} idx")
         exact(st["target_reach_count"], orc.target_reach_count, f"step {step} count")
+
+
+def test_stone_poses_in_physx_view_layout():
+    """as_export_stone_poses against a torch restatement of the reference egress: ENV:119-120 builds (N,S,7) w,x,y,z
+    poses, RigidObjectCollection.write_object_pose_to_sim (rigid_object_collection.py:295-301) scatters them into
+    object_state_w, converts the WHOLE tensor to x,y,z,w, transposes it to object-major (S*N,7)
+    (reshape_data_to_view, :650-659) and passes the view ids object*N + env (:675)."""
+    N, seed = 777, 5
+    sc = Scenario(N, seed=seed)
+    mdp = make_cuda(N, seed)
+    origins = sc.env_origins.cuda()
+    mdp.generate_stones(origins)
+    steps_pos = mdp.export_state()["steps_pos"]
+    S = steps_pos.shape[1]
+
+    def reference_egress(object_state_w, env_ids):
+        full = torch.cat((steps_pos, torch.tensor([1.0, 0, 0, 0], device="cuda").repeat(N, S, 1)), dim=-1)
+        object_state_w[env_ids[:, None], torch.arange(S, device="cuda"), :7] = full[env_ids].clone()
+        poses_xyzw = object_state_w[..., :7].clone()
+        poses_xyzw[..., 3:] = poses_xyzw[..., 3:][..., [1, 2, 3, 0]]  # convert_quat(to="xyzw"), MATH:118-155
+        view = torch.einsum("ijk -> jik", poses_xyzw).reshape(S * N, 7)
+        view_ids = (torch.arange(S, device="cuda").unsqueeze(1) * N + env_ids).flatten()
+        return view, view_ids
+
+    # all envs (what __init__ does, ENV:71)
+    state = torch.zeros(N, S, 13, device="cuda")
+    state[..., 3] = 1.0
+    want, want_ids = reference_egress(state, torch.arange(N, device="cuda"))
+    got, got_ids = mdp.export_stone_poses()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert torch.equal(got_ids.long(), want_ids)
+    # a subset, unordered, into a persistent buffer: other rows stay as they are
+    ids = torch.tensor([5, 700, 3, 64, 776, 0], device="cuda")
+    buf = torch.full((S * N, 7), -7.0, device="cuda")
+    got, got_ids = mdp.export_stone_poses(ids, buf)
+    torch.cuda.synchronize()
+    assert torch.equal(got_ids.long(), (torch.arange(S, device="cuda").unsqueeze(1) * N + ids).flatten())
+    assert torch.equal(got[got_ids.long()], want[got_ids.long()])
+    untouched = torch.ones(S * N, dtype=torch.bool, device="cuda")
+    untouched[got_ids.long()] = False
+    assert (got[untouched] == -7.0).all()
+    _, none_ids = mdp.export_stone_poses(torch.empty(0, dtype=torch.int64, device="cuda"), buf)
+    assert none_ids.numel() == 0
