@@ -15,6 +15,7 @@ OBS_DIM = 59
 NUM_LEVELS = 10
 ROOT_STATE_DIM = 13
 NUM_REWARD_TERMS = 10
+PEER_HANDLE_BYTES = 64  # AS_PEER_HANDLE_BYTES (sizeof(cudaIpcMemHandle_t))
 TILE_ENVS = 128
 ABI_VERSION = 1
 
@@ -111,6 +112,10 @@ SIGNATURES = {
     "as_read_stats": (C.c_int, [_ptr, C.POINTER(AsStats), _ptr]),
     "as_apply_action": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr]),
     "as_mirror_rows": (C.c_int, [_ptr, _ptr, _ptr, _i64, _i32, _ptr]),
+    "as_peer_create": (C.c_int, [_ptr, C.c_int, C.c_int, _ptr]),
+    "as_peer_connect": (C.c_int, [_ptr, _ptr]),
+    "as_peer_status": (C.c_int, [_ptr, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64), _ptr]),
+    "as_global_stats_device_ptr": (C.c_int, [_ptr, C.POINTER(_ptr)]),
     "as_export_state": (C.c_int, [_ptr, C.POINTER(AsMdpState), _ptr]),
     "as_export_stone_poses": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "as_import_state": (C.c_int, [_ptr, C.POINTER(AsMdpState), _ptr]),

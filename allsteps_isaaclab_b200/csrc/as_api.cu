@@ -26,6 +26,8 @@ struct AsHandle {
                        // kernel after the gather kernel (ALLSTEPS_PDL, default 2; 0 = plain stream order)
   int prefetch_tiles;  // L2 prefetch distance of the step kernel, in 128-env tiles (about one wave of CTAs)
   cudaEvent_t ev_start, ev_stop;  // optional timing hook around k_step<fused>
+  PeerArgs peer;        // world > 0 after as_peer_create; buf[] complete after as_peer_connect
+  bool peer_connected;
   bool pass1_done;
   bool pending_valid;   // a fused step was launched and still needs as_finish_step
   StepArgs pending;     // its arguments: the conditional fix-up re-reads the same inputs
@@ -218,6 +220,22 @@ int grid_for(int64_t items, int per_block, int sm_count, int max_waves) {
   return static_cast<int>(blocks);
 }
 
+// A kernel launch that may start under the tail of the kernel before it in the stream (programmatic dependent launch).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s,
+                             bool programmatic, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = programmatic ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 }  // namespace
 
 extern "C" {
@@ -272,6 +290,8 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->launches = 0;
   h->pass1_done = false;
   h->obs_clip_pass1 = 0.0f;
+  std::memset(&h->peer, 0, sizeof(h->peer));
+  h->peer_connected = false;
   h->pending_valid = false;
   h->ev_start = h->ev_stop = nullptr;
   {
@@ -322,7 +342,18 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   return AS_OK;
 }
 
-void as_destroy(AsHandle* h) { delete h; }
+void as_destroy(AsHandle* h) {
+  if (!h) return;
+  if (h->peer.world > 0) {
+    cudaSetDevice(h->device);
+    for (int r = 0; r < h->peer.world; ++r) {
+      if (!h->peer.buf[r]) continue;
+      if (r == h->peer.rank) cudaFree(h->peer.buf[r]);
+      else cudaIpcCloseMemHandle(h->peer.buf[r]);
+    }
+  }
+  delete h;
+}
 
 int as_generate_stones(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids,
                        const float* uniforms, void* stream) {
@@ -357,24 +388,12 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   if (want_rows) a.rows = *reset_out;  // start-pose rows are written by the step kernel itself
   if (int rc = launch_contact_gather(h, in, s)) return rc;
   if (h->ev_start) AS_CUDA(cudaEventRecord(h->ev_start, s));
-  if (h->pdl >= 2 && a.use_pre && !h->ev_start) {
-    // dependent of the gather kernel: tiles, state words and windows are loaded while the gather's last wave runs;
-    // the MDP role waits for the gather (griddepcontrol.wait) right before it reads the contact norms
-    a.pdl_wait = 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(a.num_tiles));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    AS_CUDA(cudaLaunchKernelEx(&cfg, k_step<kModeFused>, a));
-  } else {
-    k_step<kModeFused><<<a.num_tiles, kThreads, kSmemBytes, s>>>(a);
-  }
+  // dependent of the gather kernel: tiles, state words and windows are loaded while the gather's last wave runs;
+  // the MDP role waits for the gather (griddepcontrol.wait) right before it reads the contact norms
+  const bool dep = h->pdl >= 2 && a.use_pre && !h->ev_start;
+  a.pdl_wait = dep ? 1 : 0;
+  AS_CUDA(launch_dependent(k_step<kModeFused>, static_cast<unsigned>(a.num_tiles), static_cast<unsigned>(kThreads),
+                           kSmemBytes, s, dep, a));
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
   if (h->ev_stop) AS_CUDA(cudaEventRecord(h->ev_stop, s));
   if (grid) {  // kernel (c): outcomes into the difficulty histogram, then new bins by inverse-CDF sampling
@@ -403,31 +422,85 @@ int as_fold_stats(AsHandle* h, void* stream) {
   return check_launch(h, "k_fold_early");
 }
 
+int as_peer_create(AsHandle* h, int world, int rank, void* ipc_handle_out) {
+  AS_REQUIRE(h && ipc_handle_out, "null argument");
+  AS_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "world/rank out of range");
+  AS_REQUIRE(h->peer.world == 0, "as_peer_create was already called on this handle");
+  static_assert(sizeof(cudaIpcMemHandle_t) == AS_PEER_HANDLE_BYTES, "IPC handle size");
+  AS_CUDA(cudaSetDevice(h->device));
+  void* buf = nullptr;
+  AS_CUDA(cudaMalloc(&buf, static_cast<size_t>(kPeerBufferBytes)));
+  cudaError_t e = cudaMemset(buf, 0, static_cast<size_t>(kPeerBufferBytes));
+  cudaIpcMemHandle_t ipc;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&ipc, buf);
+  if (e != cudaSuccess) {
+    cudaFree(buf);
+    return cuda_fail(e, "peer buffer");
+  }
+  std::memcpy(ipc_handle_out, &ipc, sizeof(ipc));
+  h->peer.world = world;
+  h->peer.rank = rank;
+  h->peer.buf[rank] = static_cast<PeerSlot*>(buf);
+  h->peer_connected = false;
+  return AS_OK;
+}
+
+int as_peer_connect(AsHandle* h, const void* ipc_handles_in_rank_order) {
+  AS_REQUIRE(h && ipc_handles_in_rank_order, "null argument");
+  AS_REQUIRE(h->peer.world > 0, "as_peer_connect without as_peer_create");
+  AS_REQUIRE(!h->peer_connected, "peers are already connected");
+  AS_CUDA(cudaSetDevice(h->device));
+  const unsigned char* all = static_cast<const unsigned char*>(ipc_handles_in_rank_order);
+  for (int r = 0; r < h->peer.world; ++r) {
+    if (r == h->peer.rank) continue;
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, all + static_cast<size_t>(r) * AS_PEER_HANDLE_BYTES, sizeof(ipc));
+    void* p = nullptr;
+    AS_CUDA(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->peer.buf[r] = static_cast<PeerSlot*>(p);
+  }
+  h->peer_connected = true;
+  return AS_OK;
+}
+
+int as_peer_status(AsHandle* h, int* world, int* rank, int64_t* timeouts, void* stream) {
+  AS_REQUIRE(h, "handle is null");
+  if (world) *world = h->peer_connected ? h->peer.world : 0;
+  if (rank) *rank = h->peer.rank;
+  if (timeouts) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned long long t = 0;
+    AS_CUDA(cudaMemcpyAsync(&t, &h->ws.ctrl->peer_timeouts, sizeof(t), cudaMemcpyDeviceToHost, s));
+    AS_CUDA(cudaStreamSynchronize(s));
+    *timeouts = static_cast<int64_t>(t);
+  }
+  return AS_OK;
+}
+
+int as_global_stats_device_ptr(AsHandle* h, AsStats** device_stats) {
+  AS_REQUIRE(h && device_stats, "null argument");
+  *device_stats = &h->ws.ctrl->gstats;
+  return AS_OK;
+}
+
 int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream) {
   AS_REQUIRE(h, "handle is null");
   if (!h->pending_valid) return fail(AS_ERR_STATE, "as_finish_step without a preceding as_step_fused");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   StepArgs a = h->pending;  // the fix-up re-reads the inputs of the step it closes
   a.global_stats = global_stats;
-  const int grid = grid_for(a.num_tiles, 1, h->sm_count, 1);
-  if (h->pdl) {
-    // programmatic dependent launch: the step kernel releases its dependents as soon as its last wave of CTAs is
-    // resident, so this kernel's launch and prologue overlap that wave; it waits (griddepcontrol.wait) for the
-    // step kernel to complete and flush before it reads anything
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    AS_CUDA(cudaLaunchKernelEx(&cfg, k_fixup_finish, a));
-  } else {
-    k_fixup_finish<<<grid, kThreads, kSmemBytes, s>>>(a);
+  if (h->peer_connected && global_stats == nullptr) {
+    // fold + sum over the shards through NVLink peer memory, in one small kernel under the step kernel's tail
+    AS_CUDA(launch_dependent(k_peer_exchange, 1u, 128u, 0, s, h->pdl >= 1, h->ws.ctrl, h->peer, h->num_envs));
+    if (int rc = check_launch(h, "k_peer_exchange")) return rc;
+    a.global_stats = &h->ws.ctrl->gstats;
   }
+  const int grid = grid_for(a.num_tiles, 1, h->sm_count, 1);
+  // programmatic dependent launch: the step kernel releases its dependents as soon as its last wave of CTAs is
+  // resident, so this kernel's launch and prologue overlap that wave; it waits (griddepcontrol.wait) for the kernel
+  // before it to complete and flush before it reads anything
+  AS_CUDA(launch_dependent(k_fixup_finish, static_cast<unsigned>(grid), static_cast<unsigned>(kThreads), kSmemBytes, s,
+                           h->pdl >= 1, a));
   h->pending_valid = false;
   return check_launch(h, "k_fixup_finish");
 }

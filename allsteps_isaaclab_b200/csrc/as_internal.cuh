@@ -74,7 +74,7 @@ struct Ctrl {
   uint32_t fixup_ran;     // diagnostics: how many steps needed the no-reset fix-up
   uint32_t last_adv2;     // pass-2 index advances of the last step (discarded again if the fix-up runs)
   uint32_t stats_folded;  // as_fold_stats already folded this step's counters (the finish kernel must not redo it)
-  uint32_t _pad1;
+  uint32_t peer_epoch;    // steps closed through the peer exchange (its flag value is peer_epoch + 1, never 0)
   unsigned long long step_counter;
   AsStats stats;          // folded statistics of the last step (this shard)
   unsigned int slots[kSlots][kNumCounters];
@@ -82,6 +82,23 @@ struct Ctrl {
   unsigned int grid_attempts[kMaxGridBins];   // grid curriculum extension: episodes ended per difficulty bin
   unsigned int grid_successes[kMaxGridBins];  // ... of which the env had passed half of the stones
   unsigned long long dbg_t[16];               // -DAS_TIMING builds only: summed clock64() phase durations per CTA
+  AsStats gstats;                             // step counters summed over all shards (peer exchange)
+  unsigned long long peer_timeouts;           // peers that did not deliver within the time limit (diagnostics)
+};
+
+// Peer exchange buffer of one rank: for each of the two epoch parities one 128-byte slot per sending rank.
+constexpr int kMaxPeers = AS_MAX_PEERS;
+constexpr int kPeerCounters = 10;  // the additive head of AsStats
+struct PeerSlot {
+  unsigned long long flag;  // epoch the counters belong to; written last (release), polled by the owner
+  long long counters[kPeerCounters];
+  unsigned long long pad[5];
+};
+static_assert(sizeof(PeerSlot) == 128, "one slot per 128-byte line");
+constexpr int64_t kPeerBufferBytes = 2 * kMaxPeers * static_cast<int64_t>(sizeof(PeerSlot));
+struct PeerArgs {
+  PeerSlot* buf[kMaxPeers];  // buf[r]: rank r's buffer as seen from this GPU (own: local pointer, others: IPC mappings)
+  int32_t world, rank;
 };
 
 struct Workspace {

@@ -1062,6 +1062,81 @@ __global__ void __launch_bounds__(128) k_fold_early(Ctrl* ctrl, int64_t num_envs
   if (threadIdx.x == 0) ctrl->stats_folded = 1;
 }
 
+// Fold + cross-shard sum in one kernel over NVLink peer memory (replaces k_fold_early + NCCL all-reduce of 80 bytes).
+// One CTA.  Lane r of warp 0 talks to rank r: it stores this shard's ten counters into OUR slot of rank r's buffer,
+// fences, then stores the epoch as the flag; it then polls rank r's slot in OUR buffer for the same epoch and reads
+// the counters.  Two slots per sender (epoch parity): a rank can run at most one step ahead of a peer that has not
+// yet read, because it cannot close step t+1 without that peer's step-t+1 counters.
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void __launch_bounds__(128) k_peer_exchange(Ctrl* ctrl, const __grid_constant__ PeerArgs peer,
+                                                       int64_t num_envs) {
+  __shared__ unsigned int fold[kNumCounters];
+  asm volatile("griddepcontrol.launch_dependents;");  // the finish kernel may become resident; it waits for us
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the step kernel has completed and flushed
+  fold_stats(ctrl, fold, num_envs);
+  const int tid = threadIdx.x;
+  if (tid == 0) ctrl->stats_folded = 1;
+  __syncthreads();
+  if (tid >= 32) return;
+  const unsigned long long epoch = static_cast<unsigned long long>(ctrl->peer_epoch) + 1ull;
+  const int par = static_cast<int>(epoch & 1ull);
+  const long long* mine = reinterpret_cast<const long long*>(&ctrl->stats);
+  long long got[kPeerCounters];
+#pragma unroll
+  for (int k = 0; k < kPeerCounters; ++k) got[k] = 0;
+  bool timed_out = false;
+  if (tid < peer.world) {
+    PeerSlot* dst = peer.buf[tid] + par * kMaxPeers + peer.rank;
+#pragma unroll
+    for (int k = 0; k < kPeerCounters; ++k) {
+      asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(&dst->counters[k]), "l"(mine[k]) : "memory");
+    }
+    st_release_sys_u64(&dst->flag, epoch);  // release: the counters are visible before the flag
+    const PeerSlot* src = peer.buf[peer.rank] + par * kMaxPeers + tid;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u64(&src->flag) != epoch) {
+      if (global_timer_ns() - t0 > 2000000000ull) {
+        timed_out = true;
+        break;
+      }
+      __nanosleep(100);
+    }
+    if (!timed_out) {
+#pragma unroll
+      for (int k = 0; k < kPeerCounters; ++k) {
+        asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(got[k]) : "l"(&src->counters[k]) : "memory");
+      }
+    }
+  }
+  const unsigned n_to = __popc(__ballot_sync(0xffffffffu, timed_out));
+#pragma unroll
+  for (int k = 0; k < kPeerCounters; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) got[k] += __shfl_xor_sync(0xffffffffu, got[k], o);
+  }
+  if (tid == 0) {
+    AsStats g = ctrl->stats;  // level, step counter, reward sum: this shard's
+    long long* gs = reinterpret_cast<long long*>(&g);
+#pragma unroll
+    for (int k = 0; k < kPeerCounters; ++k) gs[k] = got[k];
+    ctrl->gstats = g;
+    ctrl->peer_epoch = static_cast<uint32_t>(epoch == 0xFFFFFFFFull ? 0ull : epoch);
+    if (n_to) ctrl->peer_timeouts += n_to;
+  }
+}
+
 // 3-call path: folds the statistics of pass 1, consumes the promotion every CTA applied, advances the counter.
 __global__ void __launch_bounds__(128) k_fold_pass1(Ctrl* ctrl, int64_t num_envs) {
   __shared__ unsigned int fold[kNumCounters];
@@ -1086,7 +1161,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
   asm volatile("griddepcontrol.wait;" ::: "memory");  // (returns at once unless launched as a programmatic dependent)
   const bool prefolded = ctrl->stats_folded != 0;  // as_fold_stats ran: the slots are empty, the totals are in stats
   if (tid < 32) {
-    const unsigned n = prefolded ? static_cast<unsigned>(ctrl->stats.n_reset) : slot_sum(ctrl, kCntReset);
+    // "did any env reset" (DRL:359-360) is a property of ALL envs: with a global sum at hand, that one decides
+    unsigned n;
+    if (a.global_stats) n = a.global_stats->n_reset > 0 ? 1u : 0u;
+    else n = prefolded ? static_cast<unsigned>(ctrl->stats.n_reset) : slot_sum(ctrl, kCntReset);
     if (tid == 0) misc->is_last = n;  // reused as "number of resets this step"
   }
   if (tid == 0) {

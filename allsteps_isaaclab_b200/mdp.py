@@ -233,6 +233,50 @@ class AllstepsMDP:
         launch-latency bound.  The producer of the physics tensors must write into the same storage every step."""
         return CapturedStep(self, views, actions, out, global_stats)
 
+    # ------------------------------------------------------------------ cross-shard promotion over NVLink peer memory
+    def connect_peers(self, group=None):
+        """One process per GPU, every rank owning one env-id shard: after this call `step()` / `finish_step()` decide
+        the promotion rule (ENV:471) and the "did any env reset" test (DRL:359) on the sum over ALL shards.  The sum is
+        formed by one small kernel that stores this shard's ten step counters into every peer's exchange buffer
+        through NVLink and reads theirs -- no NCCL call on the step path.  torch.distributed is used once, here, to
+        hand round the 64-byte CUDA IPC handles.  Every rank must step in lockstep from now on."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = (C.c_ubyte * _cabi.PEER_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.as_peer_create(self.handle, world, rank, mine), "as_peer_create")
+            on_gpu = dist.get_backend(group) == "nccl"
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device if on_gpu else "cpu")
+            gathered = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(gathered, t, group=group)
+            blob = b"".join(bytes(g.cpu().tolist()) for g in gathered)
+            _cabi.check(self.lib.as_peer_connect(self.handle, blob), "as_peer_connect")
+        self._bind_global_stats()
+        dist.barrier(group)  # nobody steps before every mapping exists
+        return world, rank
+
+    def connect_self(self):
+        """World of one (tests, single-GPU runs of a sharded script): the exchange kernel talks to itself."""
+        mine = (C.c_ubyte * _cabi.PEER_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.as_peer_create(self.handle, 1, 0, mine), "as_peer_create")
+            _cabi.check(self.lib.as_peer_connect(self.handle, bytes(mine)), "as_peer_connect")
+        self._bind_global_stats()
+
+    def _bind_global_stats(self):
+        ptr = C.c_void_p()
+        _cabi.check(self.lib.as_global_stats_device_ptr(self.handle, C.byref(ptr)), "as_global_stats_device_ptr")
+        off = ptr.value - self.workspace.data_ptr()
+        # device view of the step counters summed over all shards (int64 fields; see _cabi.AsStats)
+        self.global_stats_tensor = self.workspace[off: off + C.sizeof(_cabi.AsStats)].view(torch.int64)
+
+    def peer_status(self) -> Dict[str, int]:
+        world, rank, timeouts = C.c_int(), C.c_int(), C.c_int64()
+        _cabi.check(self.lib.as_peer_status(self.handle, C.byref(world), C.byref(rank), C.byref(timeouts),
+                                            self._stream()), "as_peer_status")
+        return {"world": world.value, "rank": rank.value, "timeouts": timeouts.value}
+
     def fold_stats(self):
         """Between `step(..., finish=False)` and `finish_step(global)`: make this step's counters available in
         `stats_tensor` so they can be all-reduced over the shards first (promotion on the global mean)."""

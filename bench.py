@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 24)")
     ap.add_argument("--stats-interval", type=int, default=16, help="all-reduce step statistics every k steps")
+    ap.add_argument("--global-promotion", action="store_true",
+                    help="N > 1: all-reduce the step statistics EVERY step (NCCL, on the step's stream) and apply the "
+                         "promotion rule ENV:471 to the global mean (config 4); default is shard-local promotion")
     ap.add_argument("--small-sizes", default="4096,65536", help="extra env counts timed for latency (N=1 only)")
     # other BASELINE.json configs (the default flags are the headline workload)
     ap.add_argument("--fall-fraction", type=float, default=0.02, help="fraction of envs dying per step (0.3 = config 5)")
@@ -196,11 +199,24 @@ def build_pool(torch, syn, cfg, mdp, origins, sets, device, seed, fall_fraction=
     return pool
 
 
-def time_steps(torch, mdp, pool, out, steps, warmup, dist=None, stats_interval=0, stats_buf=None, side=None):
+def time_steps(torch, mdp, pool, out, steps, warmup, dist=None, stats_interval=0, stats_buf=None, side=None,
+               global_promotion=False):
     dev = mdp.device
+
+    def one_step(v, d):
+        if global_promotion and dist is not None:
+            # the one cross-env dependency of the path, ENV:471 -- the additive counters of all shards
+            mdp.step(v, d["actions"], out, finish=False)
+            mdp.fold_stats()
+            stats_buf.copy_(mdp.stats_tensor)      # a whole AsStats; its first 10 int64 are the additive counters
+            dist.all_reduce(stats_buf[:10])
+            mdp.finish_step(stats_buf)
+        else:
+            mdp.step(v, d["actions"], out)
+
     for i in range(warmup):
         v, d = pool[i % len(pool)]
-        mdp.step(v, d["actions"], out)
+        one_step(v, d)
     torch.cuda.synchronize(dev)
     if dist is not None:
         dist.barrier()
@@ -210,13 +226,13 @@ def time_steps(torch, mdp, pool, out, steps, warmup, dist=None, stats_interval=0
     e0.record()
     for i in range(steps):
         v, d = pool[i % len(pool)]
-        mdp.step(v, d["actions"], out)
-        if dist is not None and stats_interval and (i + 1) % stats_interval == 0:
+        one_step(v, d)
+        if dist is not None and stats_interval and not global_promotion and (i + 1) % stats_interval == 0:
             # episode / curriculum statistics: summed over ranks off the step path (side stream, NCCL)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                stats_buf.copy_(mdp.stats_tensor[:10])
-                dist.all_reduce(stats_buf)
+                stats_buf.copy_(mdp.stats_tensor)
+                dist.all_reduce(stats_buf[:10])
     e1.record()
     torch.cuda.synchronize(dev)
     if dist is not None:
@@ -395,11 +411,11 @@ def main_b200(args):
 
     mdp, origins, pool, out = make(N)
     side = torch.cuda.Stream(dev) if dist is not None else None
-    stats_buf = torch.zeros(10, dtype=torch.int64, device=dev) if dist is not None else None
+    stats_buf = torch.zeros_like(mdp.stats_tensor) if dist is not None else None
 
     with ClockSampler(local_rank) as clocks:
         ms_total, launches = time_steps(torch, mdp, pool, out, args.steps, args.warmup, dist,
-                                        args.stats_interval, stats_buf, side)
+                                        args.stats_interval, stats_buf, side, args.global_promotion)
         # roofline of the dominant kernel (rank-local, timed alone on its stream), same clock record
         k_avg, k_med = time_kernel_only(torch, mdp, pool, out, min(args.steps, 200))
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -468,7 +484,9 @@ def main_b200(args):
                        "envs_per_gpu": N, "global_envs": N * world, "parallelism": f"env-id shards x{world}",
                        "l2_policy": f"{args.input_sets} rotating input sets of {N * 808 / 1e6:.0f} MB each "
                                     "(larger than the 126 MB L2)",
-                       "promotion": "shard-local (reference --distributed semantics)",
+                       "promotion": ("global mean, NCCL all-reduce of the step counters every step"
+                                     if (args.global_promotion and world > 1)
+                                     else "shard-local (reference --distributed semantics)"),
                        "stats_allreduce_interval": args.stats_interval if world > 1 else 0},
             "e2e": e2e,
             "gpu_launches": launches,

@@ -204,6 +204,25 @@ int as_fold_stats(AsHandle* h, void* stream);
 int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream);
 int as_read_stats(AsHandle* h, AsStats* host_out, void* stream); /* synchronises `stream` */
 
+/* ---- the promotion rule's cross-shard sum over NVLink peer memory (the ONE cross-env dependency of the
+ * path, `mean(curr_target_index) > 12` over ALL envs, ENV:471) --------------------------------------------------
+ * One process per GPU.  as_peer_create allocates this shard's 4-KB exchange buffer and returns its CUDA IPC handle
+ * (AS_PEER_HANDLE_BYTES bytes); the caller gathers the handles of all ranks (any transport, e.g.
+ * torch.distributed.all_gather) and hands them, in rank order, to as_peer_connect.  From then on
+ * as_finish_step(h, NULL, stream) launches ONE small kernel that folds this shard's step counters, stores them into
+ * every peer's buffer through NVLink, waits for the peers' stores of the same step and sums them, followed by the
+ * finish kernel deciding on that global sum -- the fused replacement of as_fold_stats + NCCL all-reduce +
+ * as_finish_step(global).  Every rank must call as_step_fused / as_finish_step the same number of times.  A peer that
+ * does not show up within 2 s is counted in AsStats-independent `*timeouts` of as_peer_status and its counters are
+ * taken as zero (no hang).  world == 1 is allowed (self-exchange).  as_global_stats_device_ptr: the summed AsStats
+ * (first 10 fields; the rest is this shard's). */
+#define AS_PEER_HANDLE_BYTES 64
+#define AS_MAX_PEERS 16
+int as_peer_create(AsHandle* h, int world, int rank, void* ipc_handle_out);
+int as_peer_connect(AsHandle* h, const void* ipc_handles_in_rank_order);
+int as_peer_status(AsHandle* h, int* world, int* rank, int64_t* timeouts, void* stream); /* synchronises `stream` */
+int as_global_stats_device_ptr(AsHandle* h, AsStats** device_stats);
+
 /* ---- action path: ENV:257-274 `_pre_physics_step` + `_apply_action` --------------------------------------
  * efforts[n,j] = applied_gain[level[n]] * joint_gears[j] * clamp(actions[n,j], -1, 1) */
 int as_apply_action(AsHandle* h, const float* actions, int64_t actions_stride, float* efforts, void* stream);

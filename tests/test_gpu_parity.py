@@ -879,3 +879,36 @@ def test_stone_poses_in_physx_view_layout():
     assert (got[untouched] == -7.0).all()
     _, none_ids = mdp.export_stone_poses(torch.empty(0, dtype=torch.int64, device="cuda"), buf)
     assert none_ids.numel() == 0
+
+
+def test_peer_exchange_world_of_one_equals_the_plain_step():
+    """The peer-memory route with a single rank (the exchange kernel stores to and reads from its own buffer) must
+    change nothing: same outputs, same levels (promotions included), global counters == local counters."""
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+
+    N, seed = 3000, 19
+    sc = Scenario(N, seed=seed)
+    (plain, peer), origins, st0 = _twin_mdps(N, seed, sc)
+    hi = torch.randint(11, 20, (N,), generator=sc.gen)
+    for m in (plain, peer):
+        m.import_state({"curr_target_index": hi})
+    peer.connect_self()
+    outs = [StepBuffers(N, "cuda:0"), StepBuffers(N, "cuda:0")]
+    levels = set()
+    for step in range(10):
+        st = plain.export_state()
+        phys = sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+        views, keep = to_views(phys, origins, sc.body_indices)
+        plain.step(views, keep["actions"], outs[0])
+        peer.step(views, keep["actions"], outs[1])
+        torch.cuda.synchronize()
+        for name in ("obs", "reward", "terminated", "time_out", "dones", "reset_joint_pos"):
+            assert torch.equal(getattr(outs[0], name), getattr(outs[1], name)), f"step {step}: {name}"
+        a, b = plain.export_state(), peer.export_state()
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"step {step}: state {k}"
+        assert torch.equal(peer.global_stats_tensor[:10], peer.stats_tensor[:10])
+        assert plain.read_stats() == peer.read_stats()
+        levels.add(int(b["curriculum"].max()))
+    assert len(levels) > 1, "no promotion happened"
+    assert peer.peer_status() == {"world": 1, "rank": 0, "timeouts": 0}
