@@ -47,9 +47,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 24)")
     ap.add_argument("--stats-interval", type=int, default=16, help="all-reduce step statistics every k steps")
-    ap.add_argument("--global-promotion", action="store_true",
-                    help="N > 1: all-reduce the step statistics EVERY step (NCCL, on the step's stream) and apply the "
-                         "promotion rule ENV:471 to the global mean (config 4); default is shard-local promotion")
+    ap.add_argument("--global-promotion", nargs="?", const="peer", default=None, choices=["peer", "nccl"],
+                    help="N > 1: apply the promotion rule ENV:471 to the mean over ALL shards every step (config 4). "
+                         "peer (default when given): one exchange kernel over NVLink peer memory; nccl: as_fold_stats + "
+                         "NCCL all-reduce + as_finish_step(global). Without the flag promotion is shard-local.")
     ap.add_argument("--small-sizes", default="4096,65536", help="extra env counts timed for latency (N=1 only)")
     # other BASELINE.json configs (the default flags are the headline workload)
     ap.add_argument("--fall-fraction", type=float, default=0.02, help="fraction of envs dying per step (0.3 = config 5)")
@@ -204,14 +205,14 @@ def time_steps(torch, mdp, pool, out, steps, warmup, dist=None, stats_interval=0
     dev = mdp.device
 
     def one_step(v, d):
-        if global_promotion and dist is not None:
+        if global_promotion == "nccl" and dist is not None:
             # the one cross-env dependency of the path, ENV:471 -- the additive counters of all shards
             mdp.step(v, d["actions"], out, finish=False)
             mdp.fold_stats()
             stats_buf.copy_(mdp.stats_tensor)      # a whole AsStats; its first 10 int64 are the additive counters
             dist.all_reduce(stats_buf[:10])
             mdp.finish_step(stats_buf)
-        else:
+        else:  # shard-local, or peers connected: the exchange kernel is part of the step
             mdp.step(v, d["actions"], out)
 
     for i in range(warmup):
@@ -410,6 +411,8 @@ def main_b200(args):
         return mdp, origins, pool, StepBuffers(num_envs, dev)
 
     mdp, origins, pool, out = make(N)
+    if args.global_promotion == "peer" and dist is not None:
+        mdp.connect_peers()
     side = torch.cuda.Stream(dev) if dist is not None else None
     stats_buf = torch.zeros_like(mdp.stats_tensor) if dist is not None else None
 
@@ -484,10 +487,15 @@ def main_b200(args):
                        "envs_per_gpu": N, "global_envs": N * world, "parallelism": f"env-id shards x{world}",
                        "l2_policy": f"{args.input_sets} rotating input sets of {N * 808 / 1e6:.0f} MB each "
                                     "(larger than the 126 MB L2)",
-                       "promotion": ("global mean, NCCL all-reduce of the step counters every step"
+                       "promotion": ({"nccl": "global mean, NCCL all-reduce of the step counters every step",
+                                      "peer": "global mean, step counters summed by one kernel over NVLink peer "
+                                              "memory every step"}[args.global_promotion]
                                      if (args.global_promotion and world > 1)
                                      else "shard-local (reference --distributed semantics)"),
-                       "stats_allreduce_interval": args.stats_interval if world > 1 else 0},
+                       "stats_allreduce_interval": (args.stats_interval if world > 1 and not args.global_promotion
+                                                    else 0),
+                       **({"peer_exchange_timeouts": mdp.peer_status()["timeouts"]}
+                          if (args.global_promotion == "peer" and world > 1) else {})},
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
