@@ -17,7 +17,7 @@ ROOT_STATE_DIM = 13
 NUM_REWARD_TERMS = 10
 PEER_HANDLE_BYTES = 64  # AS_PEER_HANDLE_BYTES (sizeof(cudaIpcMemHandle_t))
 TILE_ENVS = 128
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FLAG_INTENDED_REGEN = 1 << 0
 FLAG_SKIP_PASS2 = 1 << 1

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AS_ABI_VERSION 1
+#define AS_ABI_VERSION 2
 
 #define AS_NUM_JOINTS 21  /* CFG:57  action_space            */
 #define AS_NUM_STONES 20  /* CFG:90  num_steps               */
