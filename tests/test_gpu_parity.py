@@ -912,3 +912,39 @@ def test_peer_exchange_world_of_one_equals_the_plain_step():
         levels.add(int(b["curriculum"].max()))
     assert len(levels) > 1, "no promotion happened"
     assert peer.peer_status() == {"world": 1, "rank": 0, "timeouts": 0}
+
+
+def test_programmatic_launch_chain_changes_nothing(monkeypatch):
+    """gather -> step -> finish are chained by programmatic dependent launch (each kernel starts under the tail of the
+    one before and waits with griddepcontrol.wait before it reads what that one wrote).  Against a handle created
+    with ALLSTEPS_PDL=0 (plain stream order) every output and the whole MDP state must be bit-identical."""
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+
+    N, seed = (1 << 17) + 37, 47
+    sc = Scenario(N, seed=seed)
+    st0 = sc.initial_mdp_state()
+    origins = sc.env_origins.cuda()
+    monkeypatch.setenv("ALLSTEPS_PDL", "0")
+    plain = make_cuda(N, seed)
+    monkeypatch.delenv("ALLSTEPS_PDL")
+    chained = make_cuda(N, seed)
+    for m in (plain, chained):
+        m.generate_stones(origins)
+        m.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                            "episode_length_buf", "potentials")})
+    outs = [StepBuffers(N, "cuda:0"), StepBuffers(N, "cuda:0")]
+    for step in range(4):
+        st = plain.export_state()
+        phys = sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+        views, keep = to_views(phys, origins, sc.body_indices)
+        for o in outs:
+            o.obs.fill_(float("nan"))
+        plain.step(views, keep["actions"], outs[0])
+        chained.step(views, keep["actions"], outs[1])
+        torch.cuda.synchronize()
+        assert not torch.isnan(outs[1].obs).any()
+        for name in ("obs", "reward", "terminated", "time_out", "dones", "reset_root_state", "reset_joint_pos"):
+            assert torch.equal(getattr(outs[0], name), getattr(outs[1], name)), f"step {step}: {name}"
+        a, b = plain.export_state(), chained.export_state()
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"step {step}: state {k}"

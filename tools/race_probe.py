@@ -17,13 +17,21 @@ from scenario import Scenario
 NAMES = ("obs", "reward", "terminated", "time_out", "dones")
 
 
-def run(N, steps, seed, use_graph):
+def run(N, steps, seed, use_graph, pdl_vs_plain=False):
+    """pdl_vs_plain: the first instance is created with ALLSTEPS_PDL=0 (plain stream order between the step's kernels),
+    the second with the default programmatic dependent launches -- any read that runs ahead of the kernel it depends
+    on shows up as a difference."""
     sc = Scenario(N, seed=seed)
     st0 = sc.initial_mdp_state()
     origins = sc.env_origins.cuda()
     junk = torch.full((64 << 20,), float("nan"), device="cuda")  # poison the caching allocator's free blocks
     del junk
-    mdps = [AllstepsMDP(N, device="cuda:0", seed=seed) for _ in range(2)]
+    mdps = []
+    for i in range(2):
+        if pdl_vs_plain and i == 0:
+            os.environ["ALLSTEPS_PDL"] = "0"
+        mdps.append(AllstepsMDP(N, device="cuda:0", seed=seed))
+        os.environ.pop("ALLSTEPS_PDL", None)
     for m in mdps:
         m.generate_stones(origins)
         m.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
@@ -91,4 +99,8 @@ if __name__ == "__main__":
     for N in (4096, 5000, 300, 20000):
         for g in (True, False):
             total += run(N, 40, seed=41, use_graph=g)
+    # the sizes that use the separate gather kernel and the programmatic launch chain gather -> step -> finish
+    for N in ((1 << 17) + 37, 1 << 20):
+        total += run(N, 12, seed=43, use_graph=False, pdl_vs_plain=True)
+        total += run(N, 12, seed=43, use_graph=True, pdl_vs_plain=True)
     sys.exit(1 if total else 0)
