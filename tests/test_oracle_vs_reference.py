@@ -51,6 +51,55 @@ def test_port_is_bit_identical_to_live_reference(num_envs, steps, high):
                            * ref.actions, orc.joint_efforts())
 
 
+def test_port_propagates_nan_inputs_like_the_live_reference():
+    """NaN in actions / joint state / foot height / root quaternion / root velocity: the port must show NaN exactly
+    where the executed reference does (torch.clamp / torch.minimum hand NaN through, comparisons with NaN are false).
+    This pins the oracle that tests/test_gpu_parity.py::test_nan_inputs_propagate_like_torch holds the kernels to."""
+    from allsteps_isaaclab_b200.config import BODY_NAMES, JOINT_NAMES
+    from oracle import allsteps_oracle as ao
+    from oracle import ref_fake_env as rf
+    from scenario import Scenario, install_mdp_state
+
+    num_envs = 256
+    sc = Scenario(num_envs, seed=77, full_bodies=True, fall_fraction=0.0)
+    su = sc.stone_uniforms(0)
+    st0 = sc.initial_mdp_state()
+    orc = ao.AllstepsOracle(sc.cfg, num_envs, sc.env_origins, sc.joint_limits, sc.body_indices, su)
+    phys = sc.physics(orc.steps_pos, st0["curr_target_index"], st0["swing_leg"])
+    world = dict(phys)
+    world["env_origins"] = sc.env_origins
+    world["joint_pos_limits"] = sc.joint_limits.unsqueeze(0).repeat(num_envs, 1, 1)
+    ref = rf.make_reference_env(world, sc.cfg, BODY_NAMES, JOINT_NAMES, su)
+    install_mdp_state(ref, st0)
+    install_mdp_state(orc, st0)
+    nan = float("nan")
+    saw_nan = False
+    for step in range(3):
+        phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+        phys["actions"][3, 2] = nan
+        phys["joint_vel"][7, 5] = nan
+        phys["joint_pos"][9, 0] = nan
+        phys["body_pos_w"][11, sc.body_indices[0], 2] = nan
+        phys["body_pos_w"][12, sc.body_indices[1], 2] = nan
+        phys["root_quat_w"][13, 1] = nan
+        phys["root_lin_vel_w"][14, 0] = nan
+        m, n = sc.reset_uniforms(step)
+        rf.load_physics(ref, phys)
+        r = rf.step_mdp(ref, phys["actions"], rf.UniformTables(m, n, sc.stone_uniforms(step)))
+        o = orc.step(phys, phys["actions"], m, n, sc.stone_uniforms(step))
+        for a, b, what in zip(r, o, ("obs", "reward", "terminated", "time_out", "reset ids")):
+            assert torch.equal(torch.isnan(a), torch.isnan(b)) if a.dtype.is_floating_point else True, what
+            if a.dtype.is_floating_point:
+                saw_nan |= bool(torch.isnan(a).any())
+                ok = ~torch.isnan(a)
+                assert torch.equal(a[ok], b[ok]), f"step {step}: {what}"
+            else:
+                assert torch.equal(a, b), f"step {step}: {what}"
+        for k in ("curr_target_index", "swing_leg", "target_reach_count", "episode_length_buf"):
+            assert torch.equal(getattr(ref, k), getattr(orc, k)), f"step {step}: {k}"
+    assert saw_nan
+
+
 def test_reference_cfg_constants_match_product_config():
     """The product's constants (allsteps_isaaclab_b200/config.py) against the reference's own cfg class / env."""
     from allsteps_isaaclab_b200.config import AllstepsCfg
