@@ -19,6 +19,7 @@
 //   DRL:351 episode counter, ENV:276-324 pass, ENV:396-405 dones, ENV:347-394 rewards, ENV:469-567 reset + pass 2
 //   for ALL envs when any env resets, ENV:326-345 observations.
 #pragma once
+#include <type_traits>
 #include "as_internal.cuh"
 #include "as_math.cuh"
 #include "philox.cuh"
@@ -35,7 +36,10 @@ constexpr int kOffRv = kOffRq + kTile * 4 * 4;
 constexpr int kOffBody = kOffRv + kTile * 3 * 4;
 constexpr int kOffOrg = kOffBody + kTile * 9 * 4;   // env origins of the tile (needed by the envs that reset)
 constexpr int kOffMisc = kOffOrg + kTile * 3 * 4;
-constexpr int kSmemBytes = kOffMisc + 6144;
+constexpr int kMiscBytes = 6400;
+constexpr int kOffW3 = kOffMisc + kMiscBytes;     // float4 per env: the stone entering the window record (see write-back)
+constexpr int kSmemBytes = kOffW3 + kTile * 16;
+static_assert(4 * (kSmemBytes + 1024) <= 233472, "four CTAs per SM");
 static_assert(kTile * kObs * 4 <= kOffRp, "observation tile must fit over the joint/action tiles it aliases");
 static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffRq % 16 == 0 &&
                   kOffRv % 16 == 0 && kOffBody % 16 == 0 && kOffOrg % 16 == 0 && kOffMisc % 16 == 0,
@@ -61,12 +65,13 @@ struct Misc {  // lives at kOffMisc, never aliased
   float red_energy[kTile];   // sum_j |joint_vel * action|, ENV:365
   float red_actsq[kTile];    // sum_j action^2, ENV:364
   int red_limit[kTile];      // count_j |joint_pos_scaled| > 0.99, ENV:367
-  unsigned int flags[kTile]; // bit 0: env resets this step, bit 1: its start pose is mirrored
+  unsigned int flags[kTile]; // bit 0: env resets this step
+  unsigned char coin[kTile]; // the mirror coin of ENV:518 for this step (used only if the env resets)
   // orientation results computed by the joint role from the root tile while its own tiles are in flight
   float x_roll[kTile], x_pitch[kTile];
   float x_inv[4][kTile];     // quat_inv(root_quat), MATH:238-248
 };
-static_assert(sizeof(Misc) <= 6144, "misc block");
+static_assert(sizeof(Misc) <= kMiscBytes, "misc block");
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -118,6 +123,13 @@ __device__ __forceinline__ void joint_rows_consumed() { asm volatile("bar.sync 3
 // Named barrier 4: "rows consumed + reward sums written", joint role (producer) -> MDP role (consumer).
 __device__ __forceinline__ void sums_arrive() { asm volatile("bar.arrive 4, %0;" ::"n"(2 * kTile) : "memory"); }
 __device__ __forceinline__ void sums_wait() { asm volatile("bar.sync 4, %0;" ::"n"(2 * kTile) : "memory"); }
+// Asynchronous 16-byte copy global -> shared (LDGSTS): the issuing thread does not wait for the data.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 // TMA prefetch of a contiguous global range into L2 (no shared memory involved).
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
@@ -278,9 +290,12 @@ __device__ __forceinline__ void first_three_stones(const AsParams& P, const Vec3
 // (2*(x - offset)) / range is produced by the two-FMA correction q = fma(fma(-q0, range, n), inv, q0), which is the
 // correctly rounded quotient when inv = RN(1/range) (Markstein); as_create falls back to a true division for a
 // joint whose range has an all-ones significand (the theorem's excluded case).
+// EXACT is a template parameter so that the (uniform, practically never taken) choice is made once per tile and
+// not by a branch inside each of the 21 unrolled iterations -- every taken branch costs an instruction refetch.
+template <bool EXACT>
 __device__ __forceinline__ float scale_joint(const JointConsts& C, int j, float x) {
   const float n = 2.0f * (x - C.offset[j]);
-  if (C.exact_div) return n / C.range[j];
+  if (EXACT) return n / C.range[j];
   const float q0 = n * C.inv_range[j];
   const float e = fmaf(-q0, C.range[j], n);
   return fmaf(e, C.inv_range[j], q0);
@@ -396,7 +411,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   const int64_t env0 = static_cast<int64_t>(tile) * kTile;
   const int64_t rem = a.num_envs - env0;
   const int n_valid = rem < kTile ? static_cast<int>(rem) : kTile;
+#ifdef AS_ASSUME_FULL_TILES
+  const bool active = true;  // diagnostic build only
+#else
   const bool active = t < n_valid;
+#endif
   const int64_t e = env0 + t;
 
   float* s_jp = reinterpret_cast<float*>(smem + kOffJp);
@@ -489,7 +508,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   Mdp m{1, 0, 0, 0.0f};
   int level = 0, ep = 0;
   float4 s_prev = make_float4(0, 0, 0, 0), s_curr = s_prev, s_next = s_prev;
-  bool win_valid = false, win_dirty = false;
+  bool win_valid = false, win_dirty = false, w3_pending = false;
+  float4* s_w3 = reinterpret_cast<float4*>(smem + kOffW3);
   float f_r = 0.0f, f_l = 0.0f;
   const float* cr_row = nullptr;
   const float* cl_row = nullptr;
@@ -534,7 +554,14 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   auto slide_window = [&]() {
     s_prev = s_curr;
     s_curr = s_next;
-    s_next = stone_at(min(m.idx + 1, kS - 1));  // == window entry 3 when the cache is valid; a 16-byte gather
+    // The stone that enters is entry 3 of the window record.  Its 32-byte sector came in with entry 2 above, so this
+    // load is answered by L1/L2; gathering it from the stone row instead is a DRAM miss in the middle of the MDP
+    // role's critical path (almost every warp has a lane that slides).  A second slide in one step (possible only
+    // with stop_frames == 1) or a stale record falls back to the gather.
+#ifndef AS_SLIDE_FROM_WINDOW
+#define AS_SLIDE_FROM_WINDOW 1
+#endif
+    s_next = (AS_SLIDE_FROM_WINDOW && win_valid && !win_dirty) ? wrow[3] : stone_at(min(m.idx + 1, kS - 1));
     win_dirty = true;
   };
 
@@ -608,13 +635,16 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       // pulling it in now, it is read after pass 1
       if (MODE == kModeFused && is_reset) {
         prefetch_l1(stones);
-        const uint4 rblk = philox_block(P.seed, step_now, kStreamReset, gid, 0);
-        mirror = u32_to_unit(rblk.x) > 0.5f;  // ENV:518
       }
     }
+    unsigned rmask = 0, rbase = 0;
     if (MODE == kModeFused) {  // the joint role finishes the envs that reset: tell it early which ones they are
-      misc->flags[t] = (is_reset ? 1u : 0u) | (mirror ? 2u : 0u);
+      misc->flags[t] = is_reset ? 1u : 0u;
       flags_arrive();
+      // reserve this warp's range of the reset-id list now: the atomic's round trip to L2 (the ids are written at
+      // the end) then hides behind pass 1 instead of sitting in front of the hand-off to the joint role
+      rmask = __ballot_sync(0xffffffffu, is_reset);
+      if (rmask && a.want_reset_list && lane == __ffs(rmask) - 1) rbase = atomicAdd(&ctrl->n_reset_list, __popc(rmask));
     }
     bool moved1 = false;
     if (active) {
@@ -646,6 +676,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 
     if (MODE == kModeFused && active) {
       if (is_reset) {
+        mirror = misc->coin[t] != 0;  // drawn by the joint role in its idle time (ordered by the orientation barrier)
         // ---- masked reset, ENV:487-538.  Pass 2 on the post-reset state: identity orientation (vector part +-0),
         // zero velocity, zero contacts (contact_sensor.py:155), stale body positions; so roll = pitch = v_b = 0 and
         // targets_b = stone - root.  The start-pose joints are produced by the joint-role warps.
@@ -695,7 +726,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       st_out[e] = sw;
       if ((win_dirty || !win_valid) && !regen) {  // (a regenerated env's window is written by the regeneration kernel)
         s_prev.w = __int_as_float(m.idx);  // tag
-        wrow[0] = s_prev; wrow[1] = s_curr; wrow[2] = s_next; wrow[3] = stone_at(window_slot_stone(m.idx, 3));
+        wrow[0] = s_prev; wrow[1] = s_curr; wrow[2] = s_next;
+        // Entry 3 is a stone this step never looked at: a gather out of the stone row.  Loading it into a register
+        // and storing it would park the warp on the store until DRAM answers (in-order issue), in the middle of the
+        // MDP role's critical path and for nearly every warp; instead it travels global -> shared asynchronously
+        // and is written back at the very end of the tile.
+        cp_async16(smem_u32(s_w3 + t), stones + window_slot_stone(m.idx, 3));
+        w3_pending = true;
       }
     }
 #ifdef AS_TIMING
@@ -703,12 +740,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 #endif
     if (MODE == kModeFused) {
       // ---- reset / regeneration id lists (warp ballots)
-      const unsigned rmask = __ballot_sync(0xffffffffu, is_reset);
       if (rmask && a.want_reset_list) {
-        const int leader = __ffs(rmask) - 1;
-        unsigned base = 0;
-        if (lane == leader) base = atomicAdd(&ctrl->n_reset_list, __popc(rmask));
-        base = __shfl_sync(0xffffffffu, base, leader);
+        const unsigned base = __shfl_sync(0xffffffffu, rbase, __ffs(rmask) - 1);
         int32_t* ids_dst = a.rows.reset_ids ? a.rows.reset_ids : a.ws.reset_ids;
         if (is_reset) ids_dst[base + __popc(rmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
       }
@@ -729,6 +762,14 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     // ================================================================ joint role, before the barrier
     // The root tile is small and lands first: do the orientation math of this env (ENV:285,293; MATH:238-248) while
     // the three joint tiles are still in flight, and hand roll / pitch / quat_inv to the MDP role.
+    // The mirror coin of every env (ENV:518; draw 0 of the reset stream): ten Philox rounds that the MDP role would
+    // otherwise run, in three warps out of four, on its critical path; here they fill the wait for the first tiles.
+    bool my_coin = false;
+    if (MODE == kModeFused && active) {
+      const uint4 rblk = philox_block(P.seed, step_now, kStreamReset, static_cast<uint32_t>(e + a.env_id_offset), 0);
+      my_coin = u32_to_unit(rblk.x) > 0.5f;
+      misc->coin[t] = my_coin ? 1 : 0;
+    }
     if (bulk_root) mbar_wait(bar_root, phase_root);
     Quat q{1, 0, 0, 0};
     if (active) {
@@ -753,19 +794,23 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       const float* my_jp = s_jp + t * kJ;
       const float* my_jv = s_jv + t * kJ;
       const float* my_act = s_act + t * kJ;
+      auto joint_rows = [&](auto exact) {
 #pragma unroll
-      for (int j = 0; j < kJ; ++j) {
-        const float jv = my_jv[j];
-        const float sc = scale_joint(JC, j, my_jp[j]);  // ENV:287-291
-        if (kNeedActions) {
-          const float act = clamp_nan(my_act[j], -1.0f, 1.0f);  // ENV:268
-          at_limit += fabsf(sc) > 0.99f ? 1 : 0;                   // ENV:367
-          energy += fabsf(jv * act);                               // ENV:365
-          act_sq = fmaf(act, act, act_sq);                         // ENV:364
+        for (int j = 0; j < kJ; ++j) {
+          const float jv = my_jv[j];
+          const float sc = scale_joint<decltype(exact)::value>(JC, j, my_jp[j]);  // ENV:287-291
+          if (kNeedActions) {
+            const float act = clamp_nan(my_act[j], -1.0f, 1.0f);  // ENV:268
+            at_limit += fabsf(sc) > 0.99f ? 1 : 0;                   // ENV:367
+            energy += fabsf(jv * act);                               // ENV:365
+            act_sq = fmaf(act, act, act_sq);                         // ENV:364
+          }
+          o_jp[j] = sc;
+          o_jv[j] = clamp_nan(jv * P.dof_vel_scale, -5.0f, 5.0f);  // ENV:337
         }
-        o_jp[j] = sc;
-        o_jv[j] = clamp_nan(jv * P.dof_vel_scale, -5.0f, 5.0f);  // ENV:337
-      }
+      };
+      if (JC.exact_div) joint_rows(std::true_type{});
+      else joint_rows(std::false_type{});
     }
 #ifdef AS_TIMING
     if (tid == kTile) { AS_T(t_j1); AS_TACC(8, t_start, t_j0); AS_TACC(9, t_j0, t_j1); }
@@ -813,7 +858,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       while (todo) {
         const int r = __ffs(todo) - 1;
         todo &= todo - 1u;
-        const bool mirror_r = (__shfl_sync(0xffffffffu, fl, r) & 2u) != 0;
+        const bool mirror_r = __shfl_sync(0xffffffffu, my_coin ? 1u : 0u, r) != 0;
         const int64_t e_r = env0 + row0 + r;
         const uint32_t gid_r = static_cast<uint32_t>(e_r + a.env_id_offset);
         if (lane < kJ) {
@@ -971,6 +1016,10 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 #ifdef AS_TIMING
   AS_T(t_w0);
 #endif
+  if (!joint_role) {  // deferred write-back of window entry 3 (the copy was issued microseconds ago)
+    cp_async_wait_all();
+    if (w3_pending) wrow[3] = s_w3[t];
+  }
   if (tid == 0 && b_obs) bulk_wait_read_all();  // shared memory must stay intact until the engine has read it
 #ifdef AS_TIMING
   if (tid == 0) { AS_T(t_w1); AS_TACC(6, t_w0, t_w1); AS_TACC(7, t_start, t_w1); atomicAdd(&ctrl->dbg_t[15], 1ull); }
