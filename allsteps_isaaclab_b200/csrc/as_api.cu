@@ -21,6 +21,7 @@ struct AsHandle {
   int64_t launches;
   MirrorTable mirror_obs, mirror_act;
   JointConsts jc;
+  float inv_step_dt;
   float obs_clip_pass1;  // AsStepOut.obs_clip of the last as_step_pass1 (applied by as_step_pass2 too)
   int pdl;             // programmatic dependent launch: >= 1 k_fixup_finish after the step kernel, >= 2 also the step
                        // kernel after the gather kernel (ALLSTEPS_PDL, default 2; 0 = plain stream order)
@@ -153,14 +154,16 @@ void build_joint_consts(AsHandle* h) {
     // same fp32 roundings as MATH:36-40: offset = (lower + upper) * 0.5 ; denominator = upper - lower
     volatile float sum = P.joint_lower[j] + P.joint_upper[j];
     volatile float range = P.joint_upper[j] - P.joint_lower[j];
-    c.offset[j] = sum * 0.5f;
-    c.range[j] = range;
-    c.inv_range[j] = rn_reciprocal(range);
+    c.c[j] = make_float4(sum * 0.5f, range, rn_reciprocal(range), 0.0f);
     uint32_t bits;
     const float r = range;
     std::memcpy(&bits, &r, sizeof(bits));
     if ((bits & 0x7FFFFFu) == 0x7FFFFFu) c.exact_div = 1;  // Markstein's excluded case
   }
+  uint32_t dt_bits;
+  std::memcpy(&dt_bits, &P.step_dt, sizeof(dt_bits));
+  if ((dt_bits & 0x7FFFFFu) == 0x7FFFFFu) c.exact_div = 1;  // the same for the divisor of ENV:416
+  h->inv_step_dt = rn_reciprocal(P.step_dt);
 }
 
 StepArgs make_step_args(AsHandle* h, const AsStateIn* in, const float* actions, int64_t actions_stride,
@@ -169,6 +172,7 @@ StepArgs make_step_args(AsHandle* h, const AsStateIn* in, const float* actions, 
   std::memset(&a, 0, sizeof(a));
   a.P = h->params;
   a.jc = h->jc;
+  a.inv_step_dt = h->inv_step_dt;
   if (in) a.in = *in;
   a.actions = actions;
   a.actions_stride = actions_stride;
@@ -236,6 +240,24 @@ cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned b
   cfg.numAttrs = programmatic ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
+
+// Launches k_step over all tiles: a one-CTA launch of the ragged instantiation for a tail tile (first, so that in a
+// programmatic chain the full-tile kernel, whose CTAs wait for their primary before they read the contact norms,
+// cannot complete before it), then the full-tile instantiation.  `full` / `ragged` are the two instantiations.
+template <typename K>
+cudaError_t launch_step(AsHandle* h, K full, K ragged, StepArgs& a, cudaStream_t s, bool programmatic) {
+  const int n_full = static_cast<int>(a.num_envs / kTile);
+  if (n_full < a.num_tiles) {
+    a.tile_base = n_full;
+    cudaError_t rc = launch_dependent(ragged, 1u, static_cast<unsigned>(kThreads), kSmemBytes, s, programmatic, a);
+    if (rc != cudaSuccess) return rc;
+    if (n_full > 0) h->launches += 1;  // (check_launch counts one launch per call)
+  }
+  a.tile_base = 0;
+  if (n_full == 0) return cudaSuccess;
+  return launch_dependent(full, static_cast<unsigned>(n_full), static_cast<unsigned>(kThreads), kSmemBytes, s,
+                          programmatic, a);
+}
 }  // namespace
 
 extern "C" {
@@ -276,9 +298,13 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
                                  std::to_string(prop.minor));
   }
   // the step kernels stage more than the default 48 KB of dynamic shared memory
-  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_fixup_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AsHandle* h = new (std::nothrow) AsHandle();
   AS_REQUIRE(h != nullptr, "out of host memory");
@@ -392,8 +418,9 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   // the MDP role waits for the gather (griddepcontrol.wait) right before it reads the contact norms
   const bool dep = h->pdl >= 2 && a.use_pre && !h->ev_start;
   a.pdl_wait = dep ? 1 : 0;
-  AS_CUDA(launch_dependent(k_step<kModeFused>, static_cast<unsigned>(a.num_tiles), static_cast<unsigned>(kThreads),
-                           kSmemBytes, s, dep, a));
+  // (the host knows whether any divisor needs a true division: the hot kernel has no branch for it)
+  AS_CUDA(launch_step(h, h->jc.exact_div ? k_step<kModeFused, 1, true> : k_step<kModeFused, 0, true>,
+                      k_step<kModeFused, 2, false>, a, s, dep));
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
   if (h->ev_stop) AS_CUDA(cudaEventRecord(h->ev_stop, s));
   if (grid) {  // kernel (c): outcomes into the difficulty histogram, then new bins by inverse-CDF sampling
@@ -518,7 +545,7 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   h->obs_clip_pass1 = out->obs_clip;  // as_step_pass2 rewrites the same observation buffer: same epilogue
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (int rc = launch_contact_gather(h, in, s)) return rc;
-  k_step<kModePass1><<<a.num_tiles, kThreads, kSmemBytes, s>>>(a);
+  AS_CUDA(launch_step(h, k_step<kModePass1, 2, true>, k_step<kModePass1, 2, false>, a, s, false));
   if (int rc = check_launch(h, "k_step<pass1>")) return rc;
   k_fold_pass1<<<1, 128, 0, s>>>(h->ws.ctrl, h->num_envs);
   h->pass1_done = true;
@@ -555,7 +582,8 @@ int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
   out.obs_clip = h->obs_clip_pass1;
   StepArgs a = make_step_args(h, in, nullptr, 0, &out);
   if (int rc = launch_contact_gather(h, in, static_cast<cudaStream_t>(stream))) return rc;
-  k_step<kModePass2><<<a.num_tiles, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
+  AS_CUDA(launch_step(h, k_step<kModePass2, 2, true>, k_step<kModePass2, 2, false>, a, static_cast<cudaStream_t>(stream),
+                      false));
   return check_launch(h, "k_step<pass2>");
 }
 

@@ -34,11 +34,11 @@ enum Counter {
 };
 
 // Per-joint constants of MATH:22-40 scale_transform, precomputed by as_create.
-struct JointConsts {
-  float offset[AS_NUM_JOINTS];     // (lower + upper) * 0.5
-  float range[AS_NUM_JOINTS];      // upper - lower
-  float inv_range[AS_NUM_JOINTS];  // RN(1 / range)
-  int32_t exact_div;               // 1: use a true division (a range with an all-ones significand)
+// One 16-byte record per joint, so that the three constants of a joint reach the uniform registers with ONE constant
+// load (LDCU.128) instead of three.
+struct alignas(16) JointConsts {
+  float4 c[AS_NUM_JOINTS];  // .x offset = (lower + upper) * 0.5   .y range = upper - lower   .z RN(1 / range)
+  int32_t exact_div;        // 1: use true divisions (a joint range, or step_dt, has an all-ones significand)
 };
 
 // Packed per-env MDP state word (state.x); state.y holds the bits of `potentials`.
@@ -162,11 +162,13 @@ struct StepArgs {
   int64_t num_envs;
   int64_t env_id_offset;
   int32_t num_tiles;
+  int32_t tile_base;                  // first tile of this launch (k_step: 0 for the full tiles, the last tile's index for a ragged tail)
   int32_t want_reset_list;            // fused: compact the ids of the envs that reset
   int32_t use_pre;                    // 1: contact norms come from k_contact_gather (large batches), 0: gather here
   int32_t pdl_wait;                   // 1: launched as a programmatic dependent of k_contact_gather*
   int32_t prefetch_tiles;             // the step kernel pulls the inputs of tile + prefetch_tiles into L2 (0 = off)
   uint32_t dense16;                   // per-array "dense and 16-byte aligned" bits (DenseBit), evaluated by the host
+  float inv_step_dt;                  // RN(1 / P.step_dt) for the two-FMA quotient of ENV:416 (see JointConsts::exact_div)
   AsResetOut rows;                    // fused: start-pose rows for PhysX, written at the env's own row (optional)
 };
 

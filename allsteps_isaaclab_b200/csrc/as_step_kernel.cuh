@@ -36,7 +36,7 @@ constexpr int kOffRv = kOffRq + kTile * 4 * 4;
 constexpr int kOffBody = kOffRv + kTile * 3 * 4;
 constexpr int kOffOrg = kOffBody + kTile * 9 * 4;   // env origins of the tile (needed by the envs that reset)
 constexpr int kOffMisc = kOffOrg + kTile * 3 * 4;
-constexpr int kMiscBytes = 6400;
+constexpr int kMiscBytes = 6656;
 constexpr int kOffW3 = kOffMisc + kMiscBytes;     // float4 per env: the stone entering the window record (see write-back)
 constexpr int kSmemBytes = kOffW3 + kTile * 16;
 static_assert(4 * (kSmemBytes + 1024) <= 233472, "four CTAs per SM");
@@ -48,7 +48,8 @@ static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffR
 // Per-joint tables of the reset pose, one entry per lane.  Lane-indexed reads of kernel parameters would go
 // through the constant bank, which serialises divergent addresses; shared memory / registers do not.
 struct ResetTables {
-  float lower[32], upper[32], pose[32], pose_mirrored[32], vel_mirrored[32];
+  float4 jc[32];  // JointConsts record of joint `lane`
+  float pose[32], pose_mirrored[32], vel_mirrored[32];
 };
 
 constexpr int kThreads = 2 * kTile;  // two threads per env: one MDP-role and one joint-role warp per 32 envs
@@ -255,15 +256,19 @@ __device__ __forceinline__ bool foot_update(const AsParams& P, const FootGeom& g
 }
 
 // ENV:459-467 + ENV:302-316 + ENV:407-416 for a general root orientation (`inv` = quat_inv(root_quat)).
-__device__ __forceinline__ void targets_and_potential(const AsParams& P, const Vec3& p, const Quat& inv,
-                                                      const float4& s_prev, const float4& s_curr,
+// ENV:416 potentials = -dist / step_dt
+__device__ __forceinline__ float potential_of(const AsParams& P, float inv_step_dt, float dist, bool exact) {
+  return exact ? (-dist) / P.step_dt : div_by_const(-dist, P.step_dt, inv_step_dt);
+}
+__device__ __forceinline__ void targets_and_potential(const AsParams& P, float inv_step_dt, bool exact, const Vec3& p,
+                                                      const Quat& inv, const float4& s_prev, const float4& s_curr,
                                                       const float4& s_next, Mdp& m, PassOut& o) {
   o.tb0 = point_in_frame(p, inv, Vec3{s_prev.x, s_prev.y, s_prev.z});
   o.tb1 = point_in_frame(p, inv, Vec3{s_curr.x, s_curr.y, s_curr.z});
   o.tb2 = point_in_frame(p, inv, Vec3{s_next.x, s_next.y, s_next.z});
   o.body_dist = norm2(s_next.x - p.x, s_next.y - p.y);
   o.old_pot = m.pot;
-  m.pot = (-o.body_dist) / P.step_dt;
+  m.pot = potential_of(P, inv_step_dt, o.body_dist, exact);
 }
 
 // First three stones of ANY generated sequence are fixed (ENV:144-150): the pass after a regeneration needs
@@ -290,32 +295,53 @@ __device__ __forceinline__ void first_three_stones(const AsParams& P, const Vec3
 // (2*(x - offset)) / range is produced by the two-FMA correction q = fma(fma(-q0, range, n), inv, q0), which is the
 // correctly rounded quotient when inv = RN(1/range) (Markstein); as_create falls back to a true division for a
 // joint whose range has an all-ones significand (the theorem's excluded case).
-// EXACT is a template parameter so that the (uniform, practically never taken) choice is made once per tile and
-// not by a branch inside each of the 21 unrolled iterations -- every taken branch costs an instruction refetch.
-template <bool EXACT>
-__device__ __forceinline__ float scale_joint(const JointConsts& C, int j, float x) {
-  const float n = 2.0f * (x - C.offset[j]);
-  if (EXACT) return n / C.range[j];
-  const float q0 = n * C.inv_range[j];
-  const float e = fmaf(-q0, C.range[j], n);
-  return fmaf(e, C.inv_range[j], q0);
+// `exact` (true division) is a compile-time choice in the fused kernel: the host knows whether any divisor is an
+// excluded case and launches the matching instantiation, so the hot code has no branch for it -- every branch ends a
+// basic block and, when taken, costs an instruction refetch; with one inside each of the 21 unrolled joint
+// iterations the joint loop ran 2.5x slower.
+__device__ __forceinline__ float scale_joint(const float4& c, float x, bool exact) {  // c = offset, range, 1 / range
+  const float n = 2.0f * (x - c.x);
+  return exact ? n / c.y : div_by_const(n, c.y, c.z);
+}
+// EXACT template argument of process_tile / k_step: 0 two-FMA quotients, 1 true divisions, 2 decided at run time
+// (the modes off the hot path, to keep the number of instantiations down).
+template <int EXACT>
+__device__ __forceinline__ bool use_exact_div(const JointConsts& C) {
+  return EXACT == 2 ? C.exact_div != 0 : EXACT == 1;
 }
 
 // Start-pose joint value of a reset env (ENV:505-560): running-start pose (already mirrored or not), uniform
 // noise, clip in the unit range.  `base`, `lo`, `hi` are this joint's table entries.
+// (offset and range of the record are (lo + hi) * 0.5 and hi - lo with the roundings of MATH:36-40 / MATH:57-61.)
+__device__ __forceinline__ float reset_joint_value(const AsParams& P, float base, const float4& c, float u, bool exact) {
+  const float noisy = base + (u * P.noise_span + P.noise_lower);
+  float unit = scale_joint(c, noisy, exact);
+  unit = clamp_nan(unit, P.clip_lower, P.clip_upper);
+  return (unit * c.y) * 0.5f + c.x;  // MATH:43-61 unscale_transform
+}
+
+// The same with the joint limits themselves and a true division (k_reset_rows, off the hot path); identical results.
 __device__ __forceinline__ float reset_joint_value(const AsParams& P, float base, float lo, float hi, float u) {
   const float noisy = base + (u * P.noise_span + P.noise_lower);
   float unit = scale_to_unit(noisy, lo, hi);
   unit = clamp_nan(unit, P.clip_lower, P.clip_upper);
   return unscale_from_unit(unit, lo, hi);
 }
-
-// Fills one lane's entries of the reset tables (called once per CTA by the first warp, or kept in registers).
 __device__ __forceinline__ void load_reset_tables(const AsParams& P, int lane, float& lo, float& hi, float& pose,
                                                   float& pose_m, float& vel_m) {
   const int j = lane < kJ ? lane : 0;
   lo = P.joint_lower[j];
   hi = P.joint_upper[j];
+  pose = P.reset_pose[j];
+  pose_m = P.reset_pose[P.mirror_src[j]] * P.mirror_sign[j];  // ENV:522-526
+  vel_m = 0.0f * P.mirror_sign[j];                             // default_joint_vel is zero, ENV:513,528-532
+}
+
+// Fills one lane's entries of the reset tables (called once per CTA by the first warp, or kept in registers).
+__device__ __forceinline__ void load_reset_tables(const AsParams& P, const JointConsts& C, int lane, float4& jc,
+                                                  float& pose, float& pose_m, float& vel_m) {
+  const int j = lane < kJ ? lane : 0;
+  jc = C.c[j];
   pose = P.reset_pose[j];
   pose_m = P.reset_pose[P.mirror_src[j]] * P.mirror_sign[j];  // ENV:522-526
   vel_m = 0.0f * P.mirror_sign[j];                             // default_joint_vel is zero, ENV:513,528-532
@@ -398,11 +424,15 @@ __device__ __forceinline__ uint32_t promotion_decision(const AsParams& P, const 
 #define AS_TACC(slot, from, to)
 #endif
 
-template <int MODE>
+// FULL: the tile has all kTile envs (every tile but a ragged last one).  A template parameter because the
+// `active` guards it removes are not free: each one ends a basic block, and the step is bound by how well the
+// instruction streams of its two roles schedule, not by DRAM.
+template <int MODE, bool FULL, int EXACT>
 __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32_t& phase_root,
                                              uint32_t& phase_joint, unsigned char* smem) {
   const AsParams& P = a.P;
   const JointConsts& JC = a.jc;
+  const bool exact = use_exact_div<EXACT>(JC);
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -410,12 +440,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   const int t = tid & (kTile - 1);  // env row inside the tile (both roles)
   const int64_t env0 = static_cast<int64_t>(tile) * kTile;
   const int64_t rem = a.num_envs - env0;
-  const int n_valid = rem < kTile ? static_cast<int>(rem) : kTile;
-#ifdef AS_ASSUME_FULL_TILES
-  const bool active = true;  // diagnostic build only
-#else
-  const bool active = t < n_valid;
-#endif
+  const int n_valid = FULL ? kTile : (rem < kTile ? static_cast<int>(rem) : kTile);
+  const bool active = FULL ? true : t < n_valid;
   const int64_t e = env0 + t;
 
   float* s_jp = reinterpret_cast<float*>(smem + kOffJp);
@@ -656,7 +682,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     orient_wait();  // roll / pitch / quat_inv of this env were computed by the joint role (ENV:285, MATH:238-248)
     if (active) {
       inv = Quat{misc->x_inv[0][t], misc->x_inv[1][t], misc->x_inv[2][t], misc->x_inv[3][t]};
-      targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
+      targets_and_potential(P, a.inv_step_dt, exact, p, inv, s_prev, s_curr, s_next, m, po);
       adv1 = po.advanced;
       idx_after_pass1 = m.idx;
       if (MODE != kModePass2) {
@@ -701,7 +727,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         po.tb1 = Vec3{s_curr.x - p.x, s_curr.y - p.y, s_curr.z - p.z};
         po.tb2 = Vec3{s_next.x - p.x, s_next.y - p.y, s_next.z - p.z};
         po.body_dist = norm2(s_next.x - p.x, s_next.y - p.y);
-        m.pot = (-po.body_dist) / P.step_dt;  // ENV:487-488 zero both potentials, ENV:415-416 in pass 2
+        m.pot = potential_of(P, a.inv_step_dt, po.body_dist, exact);  // ENV:487-488, then ENV:415-416 in pass 2
       } else if (!(P.flags & AS_FLAG_SKIP_PASS2)) {
         // ---- pass 2 over ALL envs, ENV:567, on unchanged physics: only the foot state machine can
         // change anything.  Assumed to happen; the fix-up kernel undoes the assumption when no env reset.
@@ -714,7 +740,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         adv2 = po.advanced;
         if (moved) {
           slide_window();
-          targets_and_potential(P, p, inv, s_prev, s_curr, s_next, m, po);
+          targets_and_potential(P, a.inv_step_dt, exact, p, inv, s_prev, s_curr, s_next, m, po);
         }
         // (unmoved: targets, body distance and potential are recomputed to the same values; old_potentials is dead)
       }
@@ -794,11 +820,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       const float* my_jp = s_jp + t * kJ;
       const float* my_jv = s_jv + t * kJ;
       const float* my_act = s_act + t * kJ;
-      auto joint_rows = [&](auto exact) {
+      auto joint_rows = [&](auto ex) {
 #pragma unroll
         for (int j = 0; j < kJ; ++j) {
           const float jv = my_jv[j];
-          const float sc = scale_joint<decltype(exact)::value>(JC, j, my_jp[j]);  // ENV:287-291
+          const float sc = scale_joint(JC.c[j], my_jp[j], decltype(ex)::value);  // ENV:287-291
           if (kNeedActions) {
             const float act = clamp_nan(my_act[j], -1.0f, 1.0f);  // ENV:268
             at_limit += fabsf(sc) > 0.99f ? 1 : 0;                   // ENV:367
@@ -809,7 +835,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
           o_jv[j] = clamp_nan(jv * P.dof_vel_scale, -5.0f, 5.0f);  // ENV:337
         }
       };
-      if (JC.exact_div) joint_rows(std::true_type{});
+      // (one copy of the loop per choice: with EXACT == 2 the choice is made here, once, not in every iteration)
+      if (exact) joint_rows(std::true_type{});
       else joint_rows(std::false_type{});
     }
 #ifdef AS_TIMING
@@ -855,6 +882,9 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       unsigned todo = __ballot_sync(0xffffffffu, (fl & 1u) != 0);
       __syncwarp();
       const int row0 = (warp - kTile / 32) * 32;
+      const ResetTables& T = misc->rt;
+      const float4 jc_l = T.jc[lane];
+      const float pose_l = T.pose[lane], pose_m_l = T.pose_mirrored[lane], vel_m_l = T.vel_mirrored[lane];
       while (todo) {
         const int r = __ffs(todo) - 1;
         todo &= todo - 1u;
@@ -862,13 +892,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         const int64_t e_r = env0 + row0 + r;
         const uint32_t gid_r = static_cast<uint32_t>(e_r + a.env_id_offset);
         if (lane < kJ) {
-          const ResetTables& T = misc->rt;
           const float u = philox_uniform(P.seed, step_now, kStreamReset, gid_r, 1 + lane);
-          const float val = reset_joint_value(P, mirror_r ? T.pose_mirrored[lane] : T.pose[lane], T.lower[lane],
-                                              T.upper[lane], u);
+          const float val = reset_joint_value(P, mirror_r ? pose_m_l : pose_l, jc_l, u, exact);
           float* row = s_obs + (row0 + r) * kObs;
-          row[6 + lane] = scale_to_unit(val, T.lower[lane], T.upper[lane]);
-          const float jv0 = mirror_r ? T.vel_mirrored[lane] : 0.0f;
+          row[6 + lane] = scale_joint(jc_l, val, exact);
+          const float jv0 = mirror_r ? vel_m_l : 0.0f;
           row[6 + kJ + lane] = clamp_nan(jv0 * P.dof_vel_scale, -5.0f, 5.0f);
           if (a.rows.joint_pos) a.rows.joint_pos[e_r * kJ + lane] = val;
           if (a.rows.joint_vel) a.rows.joint_vel[e_r * kJ + lane] = jv0;
@@ -904,7 +932,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 #endif
     if (MODE != kModePass2 && active) {  // reward, ENV:377-394
       const float r_energy = P.energy_cost_scale * misc->red_energy[t];
-      const float r_action = P.actions_cost_scale * sqrtf(misc->red_actsq[t]);
+      const float r_action = P.actions_cost_scale * sqrt_rn(misc->red_actsq[t]);
       const float r_limit = static_cast<float>(misc->red_limit[t]) * P.joint_at_limit_cost_scale;
       // roll / pitch were written by the joint role before it signalled the sums (ENV:356-359)
       const float roll_j = misc->x_roll[t], pitch_j = misc->x_pitch[t];
@@ -1083,7 +1111,10 @@ __global__ void __launch_bounds__(256) k_contact_gather_paired(const AsStateIn i
 #ifndef AS_STEP_MIN_CTAS
 #define AS_STEP_MIN_CTAS (512 / AS_KTILE)
 #endif
-template <int MODE>
+// FULL = true: the grid covers the full tiles; FULL = false: a one-CTA launch for the ragged last tile (tile_base =
+// its index).  Two kernels, not a branch in one: compiled together, the ragged instantiation more than doubles the
+// code and its register needs leak into the allocation of the hot one (ptxas: 246 instead of 56 spilled bytes).
+template <int MODE, int EXACT, bool FULL>
 __global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
@@ -1097,11 +1128,12 @@ __global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __gri
   if (MODE == kModeFused && threadIdx.x < 32) {
     ResetTables& T = misc->rt;
     const int l = threadIdx.x;
-    load_reset_tables(a.P, l, T.lower[l], T.upper[l], T.pose[l], T.pose_mirrored[l], T.vel_mirrored[l]);
+    load_reset_tables(a.P, a.jc, l, T.jc[l], T.pose[l], T.pose_mirrored[l], T.vel_mirrored[l]);
   }
   __syncthreads();
   uint32_t phase_root = 0, phase_joint = 0;
-  process_tile<MODE>(a, blockIdx.x, phase_root, phase_joint, smem);
+  const int tile = FULL ? static_cast<int>(blockIdx.x) : a.tile_base;  // (full tiles start at 0; the ragged launch is one CTA)
+  process_tile<MODE, FULL, EXACT>(a, tile, phase_root, phase_joint, smem);
 }
 
 // as_fold_stats: fold early so that the caller can all-reduce the statistics before as_finish_step.
@@ -1226,7 +1258,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
   if (need_fixup) {
     uint32_t phase_root = 0, phase_joint = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      process_tile<kModeFixup>(a, tile, phase_root, phase_joint, smem);
+      process_tile<kModeFixup, false, 2>(a, tile, phase_root, phase_joint, smem);
       __syncthreads();
     }
     __threadfence();
