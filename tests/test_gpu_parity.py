@@ -377,6 +377,29 @@ def test_joint_scaling_is_bit_exact():
         assert torch.equal(got[keep_rows], expect[keep_rows]), "joint_pos_scaled is not bit-identical to torch"
 
 
+def test_straight_line_math_is_exact(tmp_path):
+    """The kernels compute sqrt and the constant-divisor quotients as straight-line code (csrc/as_math.cuh: no range
+    check, no branch to a slow path).  tools/exact_math_check.cu compares them on the device with the IEEE operations
+    they replace: sqrt_rn against sqrtf for ALL 2^32 inputs, div_by_const against `/` for step_dt and the task's joint
+    ranges, div_with_rcp against `/` for quaternion-like operands.  Zero mismatches required."""
+    import os
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(nvcc):
+        pytest.skip("nvcc not available on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "exact_math_check")
+    build = subprocess.run([nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false",
+                            "-o", exe, os.path.join(root, "tools", "exact_math_check.cu")],
+                           capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert run.stdout.count(" 0 mismatches") == 4, run.stdout
+
+
 def test_cuda_graph_replay_is_identical_to_eager_steps():
     """The launch-bound small-N regime runs the step as one captured CUDA graph; results must not change."""
     from allsteps_isaaclab_b200.mdp import PhysicsViews, StepBuffers
