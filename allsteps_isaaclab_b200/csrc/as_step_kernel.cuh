@@ -36,9 +36,10 @@ constexpr int kOffRv = kOffRq + kTile * 4 * 4;
 constexpr int kOffBody = kOffRv + kTile * 3 * 4;
 constexpr int kOffOrg = kOffBody + kTile * 9 * 4;   // env origins of the tile (needed by the envs that reset)
 constexpr int kOffMisc = kOffOrg + kTile * 3 * 4;
-constexpr int kMiscBytes = 6656;
+constexpr int kMiscBytes = 8192;
 constexpr int kOffW3 = kOffMisc + kMiscBytes;     // float4 per env: the stone entering the window record (see write-back)
-constexpr int kSmemBytes = kOffW3 + kTile * 16;
+constexpr int kOffPhx = kOffW3 + kTile * 16;  // uint4 per joint-role lane: Philox blocks of five envs of a warp that reset
+constexpr int kSmemBytes = kOffPhx + kTile * 16;
 static_assert(4 * (kSmemBytes + 1024) <= 233472, "four CTAs per SM");
 static_assert(kTile * kObs * 4 <= kOffRp, "observation tile must fit over the joint/action tiles it aliases");
 static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffRq % 16 == 0 &&
@@ -70,6 +71,7 @@ struct Misc {  // lives at kOffMisc, never aliased
   unsigned char coin[kTile]; // the mirror coin of ENV:518 for this step (used only if the env resets)
   // orientation results computed by the joint role from the root tile while its own tiles are in flight
   float x_roll[kTile], x_pitch[kTile];
+  float x_vb[3][kTile];      // root velocity in the root frame, parked here across the joint loop (registers are short)
   float x_inv[4][kTile];     // quat_inv(root_quat), MATH:238-248
 };
 static_assert(sizeof(Misc) <= kMiscBytes, "misc block");
@@ -641,7 +643,6 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       lf = Vec3{s_body[t * 9 + 3], s_body[t * 9 + 4], s_body[t * 9 + 5]};
       torso_z = s_body[t * 9 + 8];
     }
-    const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
     FootGeom geom{};
     Quat inv{1, 0, 0, 0};
     const int idx_before = m.idx;
@@ -811,7 +812,10 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       vb = rotate_by_inverse(q, v);
       misc->x_roll[t] = roll;
       misc->x_pitch[t] = pitch;
+      misc->x_vb[0][t] = vb.x; misc->x_vb[1][t] = vb.y; misc->x_vb[2][t] = vb.z;
     }
+    // (nothing but the loop's own 42 outputs and three sums stays in registers across it: roll / pitch / v_b and the
+    // coin are read back from shared memory afterwards -- a spilled value costs more than the round trip)
     if (bulk_joint) mbar_wait(bar_joint, phase_joint);
     AS_T(t_j0);
     float energy = 0.0f, act_sq = 0.0f;
@@ -863,11 +867,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       float* row = s_obs + t * kObs;
       // an env that reset is observed in its start pose: identity orientation, zero velocity (pass 2, ENV:567)
       const bool was_reset = MODE == kModeFused && (misc->flags[t] & 1u);
-      row[1] = was_reset ? 0.0f : roll;
-      row[2] = was_reset ? 0.0f : pitch;
-      row[3] = was_reset ? 0.0f : vb.x;
-      row[4] = was_reset ? 0.0f : vb.y;
-      row[5] = was_reset ? 0.0f : vb.z;
+      row[1] = was_reset ? 0.0f : misc->x_roll[t];
+      row[2] = was_reset ? 0.0f : misc->x_pitch[t];
+      row[3] = was_reset ? 0.0f : misc->x_vb[0][t];
+      row[4] = was_reset ? 0.0f : misc->x_vb[1][t];
+      row[5] = was_reset ? 0.0f : misc->x_vb[2][t];
 #pragma unroll
       for (int j = 0; j < kJ; ++j) {
         row[6 + j] = o_jp[j];
@@ -882,17 +886,45 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       unsigned todo = __ballot_sync(0xffffffffu, (fl & 1u) != 0);
       __syncwarp();
       const int row0 = (warp - kTile / 32) * 32;
+      // The joint noise of an env (ENV:542-560) is draws 1..21 of its reset stream: six Philox blocks.  They are drawn
+      // for FIVE envs per pass -- lane (slot, block) = (lane / 6, lane % 6) -- and parked in shared memory, where lane j
+      // picks up draw 1 + j: a warp with n resets runs ceil(n / 5) passes of ten rounds instead of n.  The warp with
+      // the most resets is the one its CTA waits for.
+      uint4* phx = reinterpret_cast<uint4*>(smem + kOffPhx) + row0;
+      const uint32_t* phx_w = reinterpret_cast<const uint32_t*>(phx);
+      auto philox_group = [&](unsigned mask) {  // blocks of the first five set bits of `mask`
+        const int slot = lane / 6, blk = lane - slot * 6;
+        int my_r = -1;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          if (k == slot && mask) my_r = __ffs(mask) - 1;
+          mask &= mask - 1u;
+        }
+        uint4 b = make_uint4(0u, 0u, 0u, 0u);
+        if (my_r >= 0 && lane < 30) {
+          const uint32_t gid_g = static_cast<uint32_t>(env0 + row0 + my_r + a.env_id_offset);
+          b = philox_block(P.seed, step_now, kStreamReset, gid_g, static_cast<uint32_t>(blk));
+        }
+        phx[lane] = b;
+      };
+      int k5 = 5;  // position of the next env in its group of five (5: draw a new group first)
       const ResetTables& T = misc->rt;
       const float4 jc_l = T.jc[lane];
       const float pose_l = T.pose[lane], pose_m_l = T.pose_mirrored[lane], vel_m_l = T.vel_mirrored[lane];
       while (todo) {
+        if (k5 == 5) {
+          __syncwarp();
+          philox_group(todo);
+          __syncwarp();
+          k5 = 0;
+        }
         const int r = __ffs(todo) - 1;
         todo &= todo - 1u;
-        const bool mirror_r = __shfl_sync(0xffffffffu, my_coin ? 1u : 0u, r) != 0;
+        const bool mirror_r = misc->coin[row0 + r] != 0;
         const int64_t e_r = env0 + row0 + r;
-        const uint32_t gid_r = static_cast<uint32_t>(e_r + a.env_id_offset);
         if (lane < kJ) {
-          const float u = philox_uniform(P.seed, step_now, kStreamReset, gid_r, 1 + lane);
+          const int d = 1 + lane;  // draw d = component d % 4 of block d / 4
+          const float u = u32_to_unit(phx_w[(k5 * 6 + (d >> 2)) * 4 + (d & 3)]);
           const float val = reset_joint_value(P, mirror_r ? pose_m_l : pose_l, jc_l, u, exact);
           float* row = s_obs + (row0 + r) * kObs;
           row[6 + lane] = scale_joint(jc_l, val, exact);
@@ -914,6 +946,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
           }
           a.rows.root_state[e_r * AS_ROOT_STATE_DIM + lane] = val;
         }
+        ++k5;
       }
     }
   }
