@@ -36,11 +36,11 @@ constexpr int kOffRv = kOffRq + kTile * 4 * 4;
 constexpr int kOffBody = kOffRv + kTile * 3 * 4;
 constexpr int kOffOrg = kOffBody + kTile * 9 * 4;   // env origins of the tile (needed by the envs that reset)
 constexpr int kOffMisc = kOffOrg + kTile * 3 * 4;
-constexpr int kMiscBytes = 8192;
+constexpr int kMiscBytes = AS_KTILE == 128 ? 8192 : 4864;
 constexpr int kOffW3 = kOffMisc + kMiscBytes;     // float4 per env: the stone entering the window record (see write-back)
 constexpr int kOffPhx = kOffW3 + kTile * 16;  // uint4 per joint-role lane: Philox blocks of five envs of a warp that reset
 constexpr int kSmemBytes = kOffPhx + kTile * 16;
-static_assert(4 * (kSmemBytes + 1024) <= 233472, "four CTAs per SM");
+static_assert((512 / AS_KTILE) * (kSmemBytes + 1024) <= 233472 || AS_KTILE != 128, "four CTAs per SM");
 static_assert(kTile * kObs * 4 <= kOffRp, "observation tile must fit over the joint/action tiles it aliases");
 static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffRq % 16 == 0 &&
                   kOffRv % 16 == 0 && kOffBody % 16 == 0 && kOffOrg % 16 == 0 && kOffMisc % 16 == 0,
