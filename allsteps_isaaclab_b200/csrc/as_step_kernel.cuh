@@ -1,16 +1,22 @@
 // Kernel (a): the fused Allsteps-v0 MDP step for sm_100a.
 //
-// One CTA of 128 threads owns a tile of 128 consecutive envs, one thread per env.
+// One CTA of 256 threads owns a tile of 128 consecutive envs, TWO threads per env in two warp roles (warps 0-3 "MDP
+// role", warps 4-7 "joint role"; see process_tile).
 //
 //   HBM -> SMEM   the row-major PhysX views of the tile (joint_pos/joint_vel/actions (128,21), root pos/quat/vel,
 //                 feet+torso positions) are contiguous byte ranges, so one elected thread moves each of them with a
 //                 single TMA bulk copy (cp.async.bulk.shared.global, completion on an mbarrier).  A thread then
 //                 reads ITS row from shared memory: row strides 21, 3, 9 are odd => bank-conflict free, and the
 //                 global side is perfectly coalesced although the layout is array-of-structs.
-//   gathers       the packed 8-byte MDP state word is a coalesced load; the two 12-byte contact-force vectors of
-//                 the current stone and the three 16-byte stones are data-dependent gathers issued before the
-//                 mbarrier wait so their latency overlaps the bulk copies.
-//   compute       pass 1 -> dones -> rewards -> masked reset (Philox) -> pass 2 -> observations, all in registers.
+//   gathers       the packed 8-byte MDP state word and the 64-byte stone-window record are coalesced loads; the two
+//                 contact norms of the current stone come as one coalesced record from k_contact_gather* (large
+//                 batches) or are gathered here (small, launch-bound batches); stones a step has to fetch out of the
+//                 320-byte stone rows travel global -> shared asynchronously (cp.async) when nothing waits for them.
+//   compute       dones -> pass 1 -> rewards -> masked reset (Philox) -> pass 2 -> observations.  The code of both
+//                 roles is kept STRAIGHT-LINE on purpose: the kernel is bound by how its two instruction streams
+//                 schedule, every branch ends a basic block and a taken one refetches
+//                 instructions -- hence the template parameters instead of run-time choices, the branch-free sqrt /
+//                 quotients of as_math.cuh, and full and ragged tiles as separate kernels.
 //   SMEM -> HBM   the (128,59) observation tile is assembled in shared memory (row stride 59, odd) on top of the
 //                 consumed input tiles and leaves with one TMA bulk store; reward / flags / state word are
 //                 coalesced per-thread stores.
@@ -586,10 +592,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     // load is answered by L1/L2; gathering it from the stone row instead is a DRAM miss in the middle of the MDP
     // role's critical path (almost every warp has a lane that slides).  A second slide in one step (possible only
     // with stop_frames == 1) or a stale record falls back to the gather.
-#ifndef AS_SLIDE_FROM_WINDOW
-#define AS_SLIDE_FROM_WINDOW 1
-#endif
-    s_next = (AS_SLIDE_FROM_WINDOW && win_valid && !win_dirty) ? wrow[3] : stone_at(min(m.idx + 1, kS - 1));
+    s_next = (win_valid && !win_dirty) ? wrow[3] : stone_at(min(m.idx + 1, kS - 1));
     win_dirty = true;
   };
 
