@@ -154,7 +154,7 @@ void build_joint_consts(AsHandle* h) {
     // same fp32 roundings as MATH:36-40: offset = (lower + upper) * 0.5 ; denominator = upper - lower
     volatile float sum = P.joint_lower[j] + P.joint_upper[j];
     volatile float range = P.joint_upper[j] - P.joint_lower[j];
-    c.c[j] = make_float4(sum * 0.5f, range, rn_reciprocal(range), 0.0f);
+    c.c[j] = make_float4(sum * 0.5f, range * 0.5f, 2.0f * rn_reciprocal(range), 0.99f);  // (the factors 2 are exact)
     uint32_t bits;
     const float r = range;
     std::memcpy(&bits, &r, sizeof(bits));

@@ -37,7 +37,8 @@ enum Counter {
 // One 16-byte record per joint, so that the three constants of a joint reach the uniform registers with ONE constant
 // load (LDCU.128) instead of three.
 struct alignas(16) JointConsts {
-  float4 c[AS_NUM_JOINTS];  // .x offset = (lower + upper) * 0.5   .y range = upper - lower   .z RN(1 / range)
+  float4 c[AS_NUM_JOINTS];  // .x offset = (lower + upper) * 0.5   .y (upper - lower) / 2   .z 2 * RN(1 / (upper - lower))
+                            // .w 0.99, the at-limit threshold of ENV:367 (so that all four words are used and load as one)
   int32_t exact_div;        // 1: use true divisions (a joint range, or step_dt, has an all-ones significand)
 };
 

@@ -307,9 +307,12 @@ __device__ __forceinline__ void first_three_stones(const AsParams& P, const Vec3
 // excluded case and launches the matching instantiation, so the hot code has no branch for it -- every branch ends a
 // basic block and, when taken, costs an instruction refetch; with one inside each of the 21 unrolled joint
 // iterations the joint loop ran 2.5x slower.
-__device__ __forceinline__ float scale_joint(const float4& c, float x, bool exact) {  // c = offset, range, 1 / range
-  const float n = 2.0f * (x - c.x);
-  return exact ? n / c.y : div_by_const(n, c.y, c.z);
+// The factor 2 of MATH:39 is folded into the constants (c = offset, range / 2, 2 / range): scaling by a power of two is
+// exact, so (2 d) / range and d / (range / 2) are the same real quotient and every rounding of the two-FMA sequence
+// lands on the same value (outside the denormal range) -- one multiplication per joint less.
+__device__ __forceinline__ float scale_joint(const float4& c, float x, bool exact) {
+  const float d = x - c.x;
+  return exact ? d / c.y : div_by_const(d, c.y, c.z);
 }
 // EXACT template argument of process_tile / k_step: 0 two-FMA quotients, 1 true divisions, 2 decided at run time
 // (the modes off the hot path, to keep the number of instantiations down).
@@ -325,7 +328,7 @@ __device__ __forceinline__ float reset_joint_value(const AsParams& P, float base
   const float noisy = base + (u * P.noise_span + P.noise_lower);
   float unit = scale_joint(c, noisy, exact);
   unit = clamp_nan(unit, P.clip_lower, P.clip_upper);
-  return (unit * c.y) * 0.5f + c.x;  // MATH:43-61 unscale_transform
+  return unit * c.y + c.x;  // MATH:43-61 unscale_transform: (unit * range) * 0.5 + offset, the halving being exact
 }
 
 // The same with the joint limits themselves and a true division (k_reset_rows, off the hot path); identical results.
@@ -834,7 +837,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
           const float sc = scale_joint(JC.c[j], my_jp[j], decltype(ex)::value);  // ENV:287-291
           if (kNeedActions) {
             const float act = clamp_nan(my_act[j], -1.0f, 1.0f);  // ENV:268
-            at_limit += fabsf(sc) > 0.99f ? 1 : 0;                   // ENV:367
+            at_limit += fabsf(sc) > JC.c[j].w ? 1 : 0;               // ENV:367 (0.99; rides in the record's 4th word)
             energy += fabsf(jv * act);                               // ENV:365
             act_sq = fmaf(act, act, act_sq);                         // ENV:364
           }
