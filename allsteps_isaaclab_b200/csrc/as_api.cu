@@ -300,6 +300,8 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   // the step kernels stage more than the default 48 KB of dynamic shared memory
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -419,8 +421,11 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   const bool dep = h->pdl >= 2 && a.use_pre && !h->ev_start;
   a.pdl_wait = dep ? 1 : 0;
   // (the host knows whether any divisor needs a true division: the hot kernel has no branch for it)
-  AS_CUDA(launch_step(h, h->jc.exact_div ? k_step<kModeFused, 1, true> : k_step<kModeFused, 0, true>,
-                      k_step<kModeFused, 2, false>, a, s, dep));
+  // the common launch shape has its own instantiation (process_tile: FAST)
+  const bool fast = !a.in.quat_xyzw && !a.out.reward_terms && a.out.obs_clip == 0.0f && a.prefetch_tiles == 0;
+  auto* full_kernel = fast ? (h->jc.exact_div ? k_step<kModeFused, 1, true, true> : k_step<kModeFused, 0, true, true>)
+                           : (h->jc.exact_div ? k_step<kModeFused, 1, true> : k_step<kModeFused, 0, true>);
+  AS_CUDA(launch_step(h, full_kernel, k_step<kModeFused, 2, false>, a, s, dep));
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
   if (h->ev_stop) AS_CUDA(cudaEventRecord(h->ev_stop, s));
   if (grid) {  // kernel (c): outcomes into the difficulty histogram, then new bins by inverse-CDF sampling
