@@ -619,7 +619,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         const int b = c / 3;
         const int k = c - b * 3;
         const int row = b == 0 ? a.in.right_foot_row : (b == 1 ? a.in.left_foot_row : a.in.torso_row);
-        s_body[i] = __ldg(a.in.body_pos + (env0 + r) * a.in.body_env_stride + row * a.in.body_row_stride + k);
+        // (12 bytes out of a 52-byte body row, three rows out of an 884-byte env record: L2 fills of 64 bytes, not 128)
+        s_body[i] = ldg64_f(a.in.body_pos + (env0 + r) * a.in.body_env_stride + row * a.in.body_row_stride + k);
       }
     }
     __syncthreads();

@@ -21,9 +21,21 @@ def probe(N, steps=50, sets=4, warmup=10):
                                           "episode_length_buf", "potentials")})
     st = mdp.export_state()
     pool = []
+    isaac = "--isaac-views" in sys.argv  # slices of root_state_w (N,13) and body_state_w (N,17,13), as Isaac Lab hands out
     for s in range(sets):
         d = syn.random_physics_state(cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen)
-        pool.append((PhysicsViews.from_dict(d, origins), d))
+        rows = (0, 1, 2)
+        if isaac:
+            root_state = torch.zeros(N, 13, device=dev)
+            root_state[:, 0:3], root_state[:, 3:7], root_state[:, 7:10] = d["root_pos_w"], d["root_quat_w"], d["root_lin_vel_w"]
+            rows = (16, 13, 0)  # right_foot, left_foot, torso among 17 bodies
+            body_state = torch.zeros(N, 17, 13, device=dev)
+            for k, r in enumerate(rows):
+                body_state[:, r, 0:3] = d["body_pos_w"][:, k]
+            d["root_pos_w"], d["root_quat_w"], d["root_lin_vel_w"] = root_state[:, 0:3], root_state[:, 3:7], root_state[:, 7:10]
+            d["body_pos_w"] = body_state[..., 0:3]
+            d["_keep"] = (root_state, body_state)
+        pool.append((PhysicsViews.from_dict(d, origins, rows), d))
     out = StepBuffers(N, dev, reset_rows=("--rows" in sys.argv))
     for i in range(warmup):
         v, d = pool[i % sets]
