@@ -245,7 +245,8 @@ cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned b
 // programmatic chain the full-tile kernel, whose CTAs wait for their primary before they read the contact norms,
 // cannot complete before it), then the full-tile instantiation.  `full` / `ragged` are the two instantiations.
 template <typename K>
-cudaError_t launch_step(AsHandle* h, K full, K ragged, StepArgs& a, cudaStream_t s, bool programmatic) {
+cudaError_t launch_step(AsHandle* h, K full, K ragged, StepArgs& a, cudaStream_t s, bool programmatic,
+                        size_t full_smem = kSmemBytes) {
   const int n_full = static_cast<int>(a.num_envs / kTile);
   if (n_full < a.num_tiles) {
     a.tile_base = n_full;
@@ -255,7 +256,7 @@ cudaError_t launch_step(AsHandle* h, K full, K ragged, StepArgs& a, cudaStream_t
   }
   a.tile_base = 0;
   if (n_full == 0) return cudaSuccess;
-  return launch_dependent(full, static_cast<unsigned>(n_full), static_cast<unsigned>(kThreads), kSmemBytes, s,
+  return launch_dependent(full, static_cast<unsigned>(n_full), static_cast<unsigned>(kThreads), full_smem, s,
                           programmatic, a);
 }
 }  // namespace
@@ -303,6 +304,10 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -423,9 +428,21 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   // (the host knows whether any divisor needs a true division: the hot kernel has no branch for it)
   // the common launch shape has its own instantiation (process_tile: FAST)
   const bool fast = !a.in.quat_xyzw && !a.out.reward_terms && a.out.obs_clip == 0.0f && a.prefetch_tiles == 0;
-  auto* full_kernel = fast ? (h->jc.exact_div ? k_step<kModeFused, 1, true, true> : k_step<kModeFused, 0, true, true>)
-                           : (h->jc.exact_div ? k_step<kModeFused, 1, true> : k_step<kModeFused, 0, true>);
-  AS_CUDA(launch_step(h, full_kernel, k_step<kModeFused, 2, false>, a, s, dep));
+  // root pos / quat / lin vel handed over as slices of one (N,13) root_state_w tensor (Isaac Lab's own layout): the
+  // full tiles take the whole rows with one bulk copy (process_tile: PACKED)
+  const bool packed = in->root_pos_stride == AS_ROOT_STATE_DIM && in->root_quat_stride == AS_ROOT_STATE_DIM &&
+                      in->root_lin_vel_stride == AS_ROOT_STATE_DIM && in->root_quat == in->root_pos + 3 &&
+                      in->root_lin_vel == in->root_pos + 7 && (reinterpret_cast<uintptr_t>(in->root_pos) & 15u) == 0;
+  using StepKernel = void (*)(StepArgs);
+  const int ex = h->jc.exact_div ? 1 : 0;
+  static const StepKernel kFull[2][2][2] = {  // [exact][fast][packed]
+      {{k_step<kModeFused, 0, true, false, false>, k_step<kModeFused, 0, true, false, true>},
+       {k_step<kModeFused, 0, true, true, false>, k_step<kModeFused, 0, true, true, true>}},
+      {{k_step<kModeFused, 1, true, false, false>, k_step<kModeFused, 1, true, false, true>},
+       {k_step<kModeFused, 1, true, true, false>, k_step<kModeFused, 1, true, true, true>}}};
+  const StepKernel ragged_kernel = k_step<kModeFused, 2, false>;
+  AS_CUDA(launch_step(h, kFull[ex][fast ? 1 : 0][packed ? 1 : 0], ragged_kernel, a, s, dep,
+                      packed ? kSmemBytesPacked : kSmemBytes));
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
   if (h->ev_stop) AS_CUDA(cudaEventRecord(h->ev_stop, s));
   if (grid) {  // kernel (c): outcomes into the difficulty histogram, then new bins by inverse-CDF sampling

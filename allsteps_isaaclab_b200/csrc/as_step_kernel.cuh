@@ -47,6 +47,15 @@ constexpr int kOffW3 = kOffMisc + kMiscBytes;     // float4 per env: the stone e
 constexpr int kOffPhx = kOffW3 + kTile * 16;  // uint4 per joint-role lane: Philox blocks of five envs of a warp that reset
 constexpr int kSmemBytes = kOffPhx + kTile * 16;
 static_assert((512 / AS_KTILE) * (kSmemBytes + 1024) <= 233472 || AS_KTILE != 128, "four CTAs per SM");
+// PACKED instantiations (root pos / quat / lin vel are slices of ONE (N,13) root_state_w tensor, which is what Isaac
+// Lab hands out): the (kTile,13) tile is a single contiguous 16-byte aligned range and travels as one bulk copy
+// into the place of the three root tiles; the body tile moves up behind it and the env-origin tile to the very end.
+constexpr int kRootRow = AS_ROOT_STATE_DIM;  // 13 floats: pos 0..2, quat 3..6, lin vel 7..9, ang vel 10..12
+constexpr int kOffBodyPacked = kOffRp + kTile * kRootRow * 4;
+constexpr int kOffOrgPacked = kSmemBytes;
+constexpr int kSmemBytesPacked = kSmemBytes + kTile * 3 * 4;
+static_assert(kOffBodyPacked + kTile * 9 * 4 <= kOffMisc && kOffBodyPacked % 16 == 0 && kOffOrgPacked % 16 == 0, "packed layout");
+static_assert((512 / AS_KTILE) * (kSmemBytesPacked + 1024) <= 233472 || AS_KTILE != 128, "four CTAs per SM (packed)");
 static_assert(kTile * kObs * 4 <= kOffRp, "observation tile must fit over the joint/action tiles it aliases");
 static_assert(kOffJv % 16 == 0 && kOffAct % 16 == 0 && kOffRp % 16 == 0 && kOffRq % 16 == 0 &&
                   kOffRv % 16 == 0 && kOffBody % 16 == 0 && kOffOrg % 16 == 0 && kOffMisc % 16 == 0,
@@ -442,7 +451,7 @@ __device__ __forceinline__ uint32_t promotion_decision(const AsParams& P, const 
 // no L2 prefetch.  The host checks that (as_step_fused) and the instantiation drops their uniform branches.
 // (Measured: 179.3 -> 176.7 us per 1M-env step.  Also making the per-array "dense" bits compile-time constants
 // removes 45 more instructions per warp but ptxas then spills 56 instead of 20 bytes in the MDP role: 184 us.)
-template <int MODE, bool FULL, int EXACT, bool FAST = false>
+template <int MODE, bool FULL, int EXACT, bool FAST = false, bool PACKED = false>
 __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32_t& phase_root,
                                              uint32_t& phase_joint, unsigned char* smem) {
   const AsParams& P = a.P;
@@ -465,8 +474,9 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   float* s_rp = reinterpret_cast<float*>(smem + kOffRp);
   float* s_rq = reinterpret_cast<float*>(smem + kOffRq);
   float* s_rv = reinterpret_cast<float*>(smem + kOffRv);
-  float* s_body = reinterpret_cast<float*>(smem + kOffBody);
-  float* s_org = reinterpret_cast<float*>(smem + kOffOrg);
+  float* s_body = reinterpret_cast<float*>(smem + (PACKED ? kOffBodyPacked : kOffBody));
+  const float* s_root = s_rp;  // PACKED: (kTile, 13) rows of root_state_w
+  float* s_org = reinterpret_cast<float*>(smem + (PACKED ? kOffOrgPacked : kOffOrg));
   float* s_obs = reinterpret_cast<float*>(smem);
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
   const uint32_t bar_root = smem_u32(&misc->mbar_root);
@@ -484,9 +494,9 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   const bool b_jp = bm & kDenseJp;
   const bool b_jv = bm & kDenseJv;
   const bool b_act = kNeedActions && (bm & kDenseAct);
-  const bool b_rp = bm & kDenseRp;
-  const bool b_rq = bm & kDenseRq;
-  const bool b_rv = bm & kDenseRv;
+  const bool b_rp = PACKED || (bm & kDenseRp);  // (PACKED: the three arrive together, see below)
+  const bool b_rq = PACKED || (bm & kDenseRq);
+  const bool b_rv = PACKED || (bm & kDenseRv);
   const bool b_body = bm & kDenseBody;
   const bool b_org = MODE == kModeFused && (bm & kDenseOrg);
   const bool bulk_root = b_rp || b_rq || b_rv || b_body || b_org;
@@ -496,12 +506,17 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   if (tid == 0) {
     const uint32_t nv = static_cast<uint32_t>(n_valid);
     if (bulk_root) {
-      mbar_arrive_expect_tx(bar_root, (b_rp ? nv * 12 : 0) + (b_rq ? nv * 16 : 0) + (b_rv ? nv * 12 : 0) +
-                                          (b_body ? nv * 36 : 0) + (b_org ? nv * 12 : 0));
+      const uint32_t root_bytes = PACKED ? nv * kRootRow * 4
+                                         : (b_rp ? nv * 12 : 0) + (b_rq ? nv * 16 : 0) + (b_rv ? nv * 12 : 0);
+      mbar_arrive_expect_tx(bar_root, root_bytes + (b_body ? nv * 36 : 0) + (b_org ? nv * 12 : 0));
       if (b_org) bulk_g2s(smem_u32(s_org), a.in.env_origins + env0 * 3, nv * 12, bar_root);
-      if (b_rp) bulk_g2s(smem_u32(s_rp), a.in.root_pos + env0 * 3, nv * 12, bar_root);
-      if (b_rq) bulk_g2s(smem_u32(s_rq), a.in.root_quat + env0 * 4, nv * 16, bar_root);
-      if (b_rv) bulk_g2s(smem_u32(s_rv), a.in.root_lin_vel + env0 * 3, nv * 12, bar_root);
+      if (PACKED) {  // root_pos points at column 0 of the (N,13) rows: one copy brings pos, quat, lin vel (and ang vel)
+        bulk_g2s(smem_u32(s_rp), a.in.root_pos + env0 * kRootRow, nv * kRootRow * 4, bar_root);
+      } else {
+        if (b_rp) bulk_g2s(smem_u32(s_rp), a.in.root_pos + env0 * 3, nv * 12, bar_root);
+        if (b_rq) bulk_g2s(smem_u32(s_rq), a.in.root_quat + env0 * 4, nv * 16, bar_root);
+        if (b_rv) bulk_g2s(smem_u32(s_rv), a.in.root_lin_vel + env0 * 3, nv * 12, bar_root);
+      }
       if (b_body) bulk_g2s(smem_u32(s_body), a.in.body_pos + env0 * 9, nv * 36, bar_root);
     }
     if (bulk_joint) {
@@ -648,8 +663,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     Vec3 p{0, 0, 0}, v{0, 0, 0}, rf{0, 0, 0}, lf{0, 0, 0};
     float torso_z = 0.0f;
     if (active) {
-      p = Vec3{s_rp[t * 3], s_rp[t * 3 + 1], s_rp[t * 3 + 2]};
-      v = Vec3{s_rv[t * 3], s_rv[t * 3 + 1], s_rv[t * 3 + 2]};
+      if (PACKED) {  // row stride 13 (odd): conflict-free
+        p = Vec3{s_root[t * kRootRow], s_root[t * kRootRow + 1], s_root[t * kRootRow + 2]};
+        v = Vec3{s_root[t * kRootRow + 7], s_root[t * kRootRow + 8], s_root[t * kRootRow + 9]};
+      } else {
+        p = Vec3{s_rp[t * 3], s_rp[t * 3 + 1], s_rp[t * 3 + 2]};
+        v = Vec3{s_rv[t * 3], s_rv[t * 3 + 1], s_rv[t * 3 + 2]};
+      }
       rf = Vec3{s_body[t * 9 + 0], s_body[t * 9 + 1], s_body[t * 9 + 2]};
       lf = Vec3{s_body[t * 9 + 3], s_body[t * 9 + 4], s_body[t * 9 + 5]};
       torso_z = s_body[t * 9 + 8];
@@ -811,14 +831,17 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     if (bulk_root) mbar_wait(bar_root, phase_root);
     Quat q{1, 0, 0, 0};
     if (active) {
-      const float4 q4 = *reinterpret_cast<const float4*>(s_rq + t * 4);
+      const float4 q4 = PACKED ? make_float4(s_root[t * kRootRow + 3], s_root[t * kRootRow + 4], s_root[t * kRootRow + 5],
+                                             s_root[t * kRootRow + 6])
+                               : *reinterpret_cast<const float4*>(s_rq + t * 4);
       q = (!FAST && a.in.quat_xyzw) ? Quat{q4.w, q4.x, q4.y, q4.z} : Quat{q4.x, q4.y, q4.z, q4.w};
       const Quat inv = quat_inverse(q);  // first: the MDP role is waiting for it to transform the targets
       misc->x_inv[0][t] = inv.w; misc->x_inv[1][t] = inv.x; misc->x_inv[2][t] = inv.y; misc->x_inv[3][t] = inv.z;
     }
     orient_arrive();  // (warp-convergent: outside the `active` branch)
     if (active) {
-      const Vec3 v{s_rv[t * 3], s_rv[t * 3 + 1], s_rv[t * 3 + 2]};
+      const Vec3 v = PACKED ? Vec3{s_root[t * kRootRow + 7], s_root[t * kRootRow + 8], s_root[t * kRootRow + 9]}
+                            : Vec3{s_rv[t * 3], s_rv[t * 3 + 1], s_rv[t * 3 + 2]};
       euler_roll_pitch(q, roll, pitch);  // read by the MDP role only after the sums hand-off further down
       vb = rotate_by_inverse(q, v);
       misc->x_roll[t] = roll;
@@ -1158,7 +1181,7 @@ __global__ void __launch_bounds__(256) k_contact_gather_paired(const AsStateIn i
 // FULL = true: the grid covers the full tiles; FULL = false: a one-CTA launch for the ragged last tile (tile_base =
 // its index).  Two kernels, not a branch in one: compiled together, the ragged instantiation more than doubles the
 // code and its register needs leak into the allocation of the hot one (ptxas: 246 instead of 56 spilled bytes).
-template <int MODE, int EXACT, bool FULL, bool FAST = false>
+template <int MODE, int EXACT, bool FULL, bool FAST = false, bool PACKED = false>
 __global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
@@ -1177,7 +1200,8 @@ __global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __gri
   __syncthreads();
   uint32_t phase_root = 0, phase_joint = 0;
   const int tile = FULL ? static_cast<int>(blockIdx.x) : a.tile_base;  // (full tiles start at 0; the ragged launch is one CTA)
-  process_tile<MODE, FULL, EXACT, FAST>(a, tile, phase_root, phase_joint, smem);
+  static_assert(!PACKED || FULL, "a packed root tile needs a full tile (its byte count must be a multiple of 16)");
+  process_tile<MODE, FULL, EXACT, FAST, PACKED>(a, tile, phase_root, phase_joint, smem);
 }
 
 // as_fold_stats: fold early so that the caller can all-reduce the statistics before as_finish_step.
