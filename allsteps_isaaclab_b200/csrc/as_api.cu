@@ -346,6 +346,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->ws.regen_info = reinterpret_cast<uint8_t*>(base + l.regen_info_off);
   h->ws.bin = reinterpret_cast<uint8_t*>(base + l.bin_off);
   h->ws.contact_pre = reinterpret_cast<float2*>(base + l.contact_pre_off);
+  h->ws.body_dense = reinterpret_cast<float*>(base + l.body_dense_off);
   build_mirror_tables(h);
   build_joint_consts(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -419,6 +420,21 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   const bool regen_enabled = grid || (h->params.flags & AS_FLAG_INTENDED_REGEN) != 0;
   a.want_reset_list = (reset_out && reset_out->reset_ids) ? 1 : 0;
   if (want_rows) a.rows = *reset_out;  // start-pose rows are written by the step kernel itself
+  if (!(a.dense16 & kDenseBody) && h->num_envs >= kSeparateGatherMinEnvs) {
+    // The three body rows the task reads (12 bytes each out of Isaac Lab's (N,B,13) body_state_w) are scattered
+    // reads like the contact vectors: gathered by a kernel of their own into a dense (N,3,3) array, which the step
+    // kernel (and the fix-up, which re-reads the inputs) then takes by bulk copy.
+    const unsigned blocks = static_cast<unsigned>((h->num_envs * 3 + 255) / 256);
+    k_body_gather<<<blocks, 256, 0, s>>>(*in, h->ws.body_dense, h->num_envs);
+    if (int rc = check_launch(h, "k_body_gather")) return rc;
+    a.in.body_pos = h->ws.body_dense;
+    a.in.body_env_stride = 9;
+    a.in.body_row_stride = 3;
+    a.in.right_foot_row = 0;
+    a.in.left_foot_row = 1;
+    a.in.torso_row = 2;
+    a.dense16 |= kDenseBody;
+  }
   if (int rc = launch_contact_gather(h, in, s)) return rc;
   if (h->ev_start) AS_CUDA(cudaEventRecord(h->ev_start, s));
   // dependent of the gather kernel: tiles, state words and windows are loaded while the gather's last wave runs;

@@ -112,11 +112,12 @@ struct Workspace {
   uint8_t* regen_info;// (N) curr_target_index at the end of the episode, parallel to regen_ids (grid curriculum)
   uint8_t* bin;       // (N) difficulty-grid bin of each env (grid curriculum extension)
   float2* contact_pre;// (N) |F_right|, |F_left| of each env's current stone, gathered by k_contact_gather
+  float* body_dense;  // (N,3,3) right foot, left foot, torso positions gathered out of a strided body tensor (k_body_gather)
 };
 
 struct WorkspaceLayout {
   int64_t ctrl_off, state0_off, state1_off, stones_off, window_off, reset_ids_off, regen_ids_off, regen_info_off,
-      bin_off, contact_pre_off, total;
+      bin_off, contact_pre_off, body_dense_off, total;
 };
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -144,6 +145,8 @@ inline WorkspaceLayout workspace_layout(int64_t n) {
   off = align_up(off + n, 256);
   l.contact_pre_off = off;
   off = align_up(off + n * 8, 256);
+  l.body_dense_off = off;
+  off = align_up(off + n * 36, 256);
   l.total = off;
   return l;
 }

@@ -1139,6 +1139,22 @@ __global__ void __launch_bounds__(256) k_contact_gather(const AsStateIn in, Work
   ws.contact_pre[e] = make_float2(f_r, f_l);
 }
 
+// The body rows of the task (right foot, left foot, torso: 12 bytes each) out of a strided body tensor, one thread per
+// (env, body), into a dense (N,3,3) array.  From 131 072 envs up this replaces the cooperative strided loads inside
+// the step kernel (which end in a CTA barrier): Isaac Lab's (N,17,13) body_state_w costs 192 B of DRAM fills per env
+// for 36 B either way, but here they are hidden by full occupancy.
+__global__ void __launch_bounds__(256) k_body_gather(const AsStateIn in, float* __restrict__ dense, int64_t num_envs) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= num_envs * 3) return;
+  const int64_t e = i / 3;
+  const int b = static_cast<int>(i - e * 3);
+  const int row = b == 0 ? in.right_foot_row : (b == 1 ? in.left_foot_row : in.torso_row);
+  const float* src = in.body_pos + e * in.body_env_stride + row * in.body_row_stride;
+  dense[i * 3 + 0] = ldg64_f(src);
+  dense[i * 3 + 1] = ldg64_f(src + 1);
+  dense[i * 3 + 2] = ldg64_f(src + 2);
+}
+
 // Same gather with TWO lanes per env: the even lane fetches the 16-byte chunk the vector starts in, the odd lane the
 // following chunk when the vector runs into it, in ONE load instruction.  The two chunks then travel as one request
 // whenever they share a 128-byte line, which is what counts when the matrices live in pinned host memory: PCIe reads

@@ -178,11 +178,14 @@ def run_replay(num_envs, steps, seed, full_bodies=False, layout="contiguous", fa
     return totals, worst_obs, worst_rew
 
 
-@pytest.mark.parametrize("layout", ["contiguous", "unaligned_contact", "pinned_contact"])
+@pytest.mark.parametrize("layout", ["contiguous", "unaligned_contact", "pinned_contact", "isaac"])
 def test_separate_contact_gather_kernels(layout):
     """From 2^17 envs on the current stone's contact vectors are gathered by a kernel of their own: two lanes per env
-    on 16-byte aligned rows (device or pinned host memory), one lane per env otherwise."""
-    totals, _, _ = run_replay((1 << 17) + 37, 2, seed=29, layout=layout, high_index=(layout == "contiguous"))
+    on 16-byte aligned rows (device or pinned host memory), one lane per env otherwise.  "isaac": slices of one (N,13)
+    root_state_w and of the full (N,17,13) body_state_w -- the root rows travel as one bulk copy (packed tile), the
+    three body rows are gathered by k_body_gather into a dense array first."""
+    totals, _, _ = run_replay((1 << 17) + 37, 2, seed=29, layout=layout, high_index=(layout == "contiguous"),
+                              full_bodies=(layout == "isaac"))
     assert totals["advanced"] > 0
 
 
