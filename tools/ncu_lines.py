@@ -1,6 +1,9 @@
 """Per-source-line stall breakdown of one kernel out of an .ncu-rep (run here, no GPU needed).
 
-  python tools/ncu_lines.py gpurun_out/step.ncu-rep path/to/lib.so '_ZN2as6k_stepILi0ELi0ELb1EEEvNS_8StepArgsE' [top]
+  python tools/ncu_lines.py gpurun_out/step.ncu-rep path/to/lib.so '_ZN2as6k_stepILi0ELi0ELb1EEEvNS_8StepArgsE' [top] [name]
+
+`name` (a substring of the demangled kernel name, default "k_step") picks the launch when the report holds several
+kernels; the first launch that matches is analysed.
 
 The report gives stall samples per SASS instruction; `nvdisasm -g` of the same cubin gives the source line of every
 instruction (both list the kernel's instructions in address order).  Prints the kernel's headline metrics, the stall
@@ -45,8 +48,11 @@ def line_map(lib, mangled):
 def main():
     rep, lib, mangled = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+    want = sys.argv[5] if len(sys.argv) > 5 else "k_step"
     raw = list(csv.reader(io.StringIO(run(["ncu", "-i", rep, "--page", "raw", "--csv"]))))
-    h, u, r = raw[0], raw[1], raw[2]
+    h, u = raw[0], raw[1]
+    kcol = h.index("Kernel Name")
+    r = next((x for x in raw[2:] if want in x[kcol]), raw[2])
     for n in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
               "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
               "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -55,7 +61,11 @@ def main():
         if n in h:
             print(f"{n:70s} {r[h.index(n)]:>24s} {u[h.index(n)]}")
     src = list(csv.reader(io.StringIO(run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"]))))
-    hdr, data = src[1], src[2:]
+    # one section per launch: a "Kernel Name" row, the column header, then one row per instruction
+    starts = [i for i, x in enumerate(src) if x and x[0] == "Kernel Name"]
+    pick = next((i for i in starts if want in src[i][1]), starts[0])
+    end = next((i for i in starts if i > pick), len(src))
+    hdr, data = src[pick + 1], [x for x in src[pick + 2:end] if x]
     ix = {n: i for i, n in enumerate(hdr)}
 
     def g(row, n):
