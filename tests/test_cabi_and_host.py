@@ -54,6 +54,7 @@ def test_workspace_size_is_monotonic_and_aligned(lib):
         prev = b
     assert lib.as_workspace_bytes(0) == 0
     # 1M envs: stones 320 B + stone window 64 B + 2 x 8 B state + 2 x 4 B lists + 8 B contact norms + 2 B grid
+    # + 36 B dense body rows (used when the caller's body tensor is strided)
     assert lib.as_workspace_bytes(1 << 20) < (1 << 20) * 480
 
 
