@@ -17,7 +17,7 @@ ROOT_STATE_DIM = 13
 NUM_REWARD_TERMS = 10
 PEER_HANDLE_BYTES = 64  # AS_PEER_HANDLE_BYTES (sizeof(cudaIpcMemHandle_t))
 TILE_ENVS = 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 FLAG_INTENDED_REGEN = 1 << 0
 FLAG_SKIP_PASS2 = 1 << 1
@@ -119,6 +119,9 @@ SIGNATURES = {
     "as_export_state": (C.c_int, [_ptr, C.POINTER(AsMdpState), _ptr]),
     "as_export_stone_poses": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "as_import_state": (C.c_int, [_ptr, C.POINTER(AsMdpState), _ptr]),
+    "as_snapshot_bytes": (_i64, [_ptr, _i32]),
+    "as_snapshot": (C.c_int, [_ptr, _ptr, _i32, _ptr]),
+    "as_restore": (C.c_int, [_ptr, _ptr, _i32, _ptr]),
     "as_grid_state": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "as_set_timing_events": (C.c_int, [_ptr, _ptr, _ptr]),
     "as_debug_timing": (C.c_int, [_ptr, _ptr, C.c_int, _ptr]),

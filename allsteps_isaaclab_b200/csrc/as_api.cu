@@ -29,6 +29,7 @@ struct AsHandle {
   cudaEvent_t ev_start, ev_stop;  // optional timing hook around k_step<fused>
   PeerArgs peer;        // world > 0 after as_peer_create; buf[] complete after as_peer_connect
   bool peer_connected;
+  volatile uint32_t* peer_host_error;  // mapped pinned host word the exchange kernel sets when a peer timed out
   bool pass1_done;
   bool pending_valid;   // a fused step was launched and still needs as_finish_step
   StepArgs pending;     // its arguments: the conditional fix-up re-reads the same inputs
@@ -60,6 +61,16 @@ int check_launch(AsHandle* h, const char* what) {
   h->launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, what);
+  return AS_OK;
+}
+
+// A peer exchange that timed out is fatal and sticky (the shards may have decided the promotion rule on different
+// sums): the exchange kernel raised the mapped host word, every later step is refused.  A plain host read, no sync.
+int check_peer(const AsHandle* h) {
+  if (h->peer_host_error && *h->peer_host_error != 0u) {
+    return fail(AS_ERR_PEER, "peer exchange timed out at epoch " + std::to_string(*h->peer_host_error & 0x7FFFFFFFu) +
+                                 ": a shard did not deliver its step counters in time; the shards may have diverged");
+  }
   return AS_OK;
 }
 
@@ -325,6 +336,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->obs_clip_pass1 = 0.0f;
   std::memset(&h->peer, 0, sizeof(h->peer));
   h->peer_connected = false;
+  h->peer_host_error = nullptr;
   h->pending_valid = false;
   h->ev_start = h->ev_stop = nullptr;
   {
@@ -385,6 +397,7 @@ void as_destroy(AsHandle* h) {
       if (r == h->peer.rank) cudaFree(h->peer.buf[r]);
       else cudaIpcCloseMemHandle(h->peer.buf[r]);
     }
+    if (h->peer_host_error) cudaFreeHost(const_cast<uint32_t*>(h->peer_host_error));
   }
   delete h;
 }
@@ -412,6 +425,7 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   AS_REQUIRE(out->obs && out->reward && out->terminated && out->time_out, "step outputs must be set");
   AS_REQUIRE(out->obs_clip >= 0.0f, "obs_clip must be >= 0");
   if (h->pending_valid) return fail(AS_ERR_STATE, "previous fused step was not closed with as_finish_step");
+  if (int rc = check_peer(h)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   StepArgs a = make_step_args(h, in, actions, actions_stride, out);
   const bool want_rows = reset_out && (reset_out->root_state || reset_out->joint_pos || reset_out->joint_vel ||
@@ -503,6 +517,26 @@ int as_peer_create(AsHandle* h, int world, int rank, void* ipc_handle_out) {
     return cuda_fail(e, "peer buffer");
   }
   std::memcpy(ipc_handle_out, &ipc, sizeof(ipc));
+  {
+    void* host_word = nullptr;
+    void* dev_view = nullptr;
+    e = cudaHostAlloc(&host_word, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+      std::memset(host_word, 0, 64);
+      e = cudaHostGetDevicePointer(&dev_view, host_word, 0);
+    }
+    if (e != cudaSuccess) {
+      if (host_word) cudaFreeHost(host_word);
+      cudaFree(buf);
+      return cuda_fail(e, "peer error word");
+    }
+    h->peer_host_error = static_cast<volatile uint32_t*>(host_word);
+    h->peer.host_error = static_cast<uint32_t*>(dev_view);
+    // how long the exchange kernel polls for a peer: ALLSTEPS_PEER_TIMEOUT_MS (default 10 s; 0 = without limit)
+    const char* to = std::getenv("ALLSTEPS_PEER_TIMEOUT_MS");
+    const long long ms = to ? std::atoll(to) : 10000;
+    h->peer.timeout_ns = ms > 0 ? static_cast<unsigned long long>(ms) * 1000000ull : 0ull;
+  }
   h->peer.world = world;
   h->peer.rank = rank;
   h->peer.buf[rank] = static_cast<PeerSlot*>(buf);
@@ -551,6 +585,10 @@ int as_global_stats_device_ptr(AsHandle* h, AsStats** device_stats) {
 int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream) {
   AS_REQUIRE(h, "handle is null");
   if (!h->pending_valid) return fail(AS_ERR_STATE, "as_finish_step without a preceding as_step_fused");
+  if (int rc = check_peer(h)) {
+    h->pending_valid = false;
+    return rc;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   StepArgs a = h->pending;  // the fix-up re-reads the inputs of the step it closes
   a.global_stats = global_stats;
@@ -596,7 +634,16 @@ int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int6
   AS_REQUIRE(n_ids >= 0 && n_ids <= h->num_envs, "id count out of range");
   if (n_ids == 0) return AS_OK;  // DRL:360: `_reset_idx` is not entered (an empty id tensor has a null pointer)
   AS_REQUIRE(env_origins && env_ids, "env_origins/env_ids is null");
+  if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->pass1_done) {
+    // `_reset_idx` outside a step (DirectRLEnv.reset(), DRL:256-279): the promotion rule of ENV:471 looks at the
+    // indices as they are now, and the draws must not repeat those of an earlier reset -- sum the indices and
+    // advance the Philox step counter, which as_step_pass1 would have done
+    k_prepare_reset<<<1, 1024, 0, s>>>(h->ws, h->num_envs);
+    if (int rc = check_launch(h, "k_prepare_reset")) return rc;
+  }
+  h->pass1_done = false;  // consumed: a second reset without a pass in between prepares for itself
   k_decide_promotion<<<1, 32, 0, s>>>(h->params, h->ws.ctrl, nullptr, 1);
   if (int rc = check_launch(h, "k_decide_promotion")) return rc;
   ResetArgs r = make_reset_args(h, env_origins);
@@ -613,7 +660,9 @@ int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int6
 int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
   AS_REQUIRE(h && obs, "handle/obs is null");
   if (int rc = validate_state_in(in, false)) return rc;
-  if (!h->pass1_done) return fail(AS_ERR_STATE, "as_step_pass2 without a preceding as_step_pass1");
+  // (no call-order precondition: the reference runs `_compute_useful_values` at the end of `_reset_idx` whether or
+  // not a pass preceded it -- DirectRLEnv.reset() calls `_reset_idx(all ids)` before the first step, DRL:256-279)
+  if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
   AsStepOut out;
   std::memset(&out, 0, sizeof(out));
   out.obs = obs;
@@ -676,6 +725,65 @@ int as_import_state(AsHandle* h, const AsMdpState* src, void* stream) {
   if (int rc = check_launch(h, "k_import")) return rc;
   k_clear_promotion<<<1, 32, 0, s>>>(h->ws.ctrl);
   return check_launch(h, "k_clear_promotion");
+}
+
+// Snapshot layout: [Ctrl | state words, both buffers | stone windows | grid bins | stones (optional)].
+namespace {
+struct SnapshotLayout {
+  int64_t ctrl, state, window, bin, stones, total;
+};
+SnapshotLayout snapshot_layout(int64_t n, bool with_stones) {
+  const WorkspaceLayout w = workspace_layout(n);
+  SnapshotLayout l;
+  int64_t off = 0;
+  l.ctrl = off;   off += w.state0_off - w.ctrl_off;
+  l.state = off;  off += w.stones_off - w.state0_off;
+  l.window = off; off += w.reset_ids_off - w.window_off;
+  l.bin = off;    off += w.contact_pre_off - w.bin_off;
+  l.stones = off; off += with_stones ? (w.window_off - w.stones_off) : 0;
+  l.total = off;
+  return l;
+}
+}  // namespace
+
+int64_t as_snapshot_bytes(const AsHandle* h, int32_t include_stones) {
+  if (!h) return 0;
+  return snapshot_layout(h->num_envs, include_stones != 0).total;
+}
+
+int as_snapshot(AsHandle* h, void* dst, int32_t include_stones, void* stream) {
+  AS_REQUIRE(h && dst, "null argument");
+  if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const WorkspaceLayout w = workspace_layout(h->num_envs);
+  const SnapshotLayout l = snapshot_layout(h->num_envs, include_stones != 0);
+  unsigned char* d = static_cast<unsigned char*>(dst);
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(h->ws.ctrl);
+  AS_CUDA(cudaMemcpyAsync(d + l.ctrl, base + w.ctrl_off, static_cast<size_t>(l.window - l.ctrl), cudaMemcpyDeviceToDevice, s));
+  AS_CUDA(cudaMemcpyAsync(d + l.window, base + w.window_off, static_cast<size_t>(l.bin - l.window), cudaMemcpyDeviceToDevice, s));
+  AS_CUDA(cudaMemcpyAsync(d + l.bin, base + w.bin_off, static_cast<size_t>(l.stones - l.bin), cudaMemcpyDeviceToDevice, s));
+  if (include_stones)
+    AS_CUDA(cudaMemcpyAsync(d + l.stones, base + w.stones_off, static_cast<size_t>(l.total - l.stones), cudaMemcpyDeviceToDevice, s));
+  return AS_OK;
+}
+
+int as_restore(AsHandle* h, const void* src, int32_t include_stones, void* stream) {
+  AS_REQUIRE(h && src, "null argument");
+  if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const WorkspaceLayout w = workspace_layout(h->num_envs);
+  const SnapshotLayout l = snapshot_layout(h->num_envs, include_stones != 0);
+  const unsigned char* d = static_cast<const unsigned char*>(src);
+  unsigned char* base = reinterpret_cast<unsigned char*>(h->ws.ctrl);
+  k_restore_ctrl<<<1, 256, 0, s>>>(h->ws.ctrl, reinterpret_cast<const Ctrl*>(d + l.ctrl));
+  if (int rc = check_launch(h, "k_restore_ctrl")) return rc;
+  AS_CUDA(cudaMemcpyAsync(base + w.state0_off, d + l.state, static_cast<size_t>(l.window - l.state), cudaMemcpyDeviceToDevice, s));
+  AS_CUDA(cudaMemcpyAsync(base + w.window_off, d + l.window, static_cast<size_t>(l.bin - l.window), cudaMemcpyDeviceToDevice, s));
+  AS_CUDA(cudaMemcpyAsync(base + w.bin_off, d + l.bin, static_cast<size_t>(l.stones - l.bin), cudaMemcpyDeviceToDevice, s));
+  if (include_stones)
+    AS_CUDA(cudaMemcpyAsync(base + w.stones_off, d + l.stones, static_cast<size_t>(l.total - l.stones), cudaMemcpyDeviceToDevice, s));
+  h->pass1_done = false;
+  return AS_OK;
 }
 
 int as_grid_state(AsHandle* h, uint8_t* bins_dst, const uint8_t* bins_src, uint32_t* hist_dst, const uint32_t* hist_src,

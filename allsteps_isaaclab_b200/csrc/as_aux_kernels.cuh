@@ -446,6 +446,52 @@ __global__ void __launch_bounds__(256) k_grid_state(Workspace ws, uint8_t* bins_
   }
 }
 
+// `_reset_idx` called outside a step (as_reset without a preceding as_step_pass1): the numerator of ENV:471 from the
+// state words as they are, and a fresh Philox step counter for the draws of this reset.  One CTA.
+__global__ void __launch_bounds__(1024) k_prepare_reset(Workspace ws, int64_t num_envs) {
+  __shared__ unsigned long long s_sum[32];
+  Ctrl* ctrl = ws.ctrl;
+  const uint2* st = ws.state[ctrl->parity];
+  unsigned long long sum = 0;
+  for (int64_t e = threadIdx.x; e < num_envs; e += blockDim.x) sum += static_cast<unsigned long long>(state_idx(st[e].x));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFullMask, sum, o);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) tot += s_sum[w];
+    ctrl->stats.n_envs = num_envs;
+    ctrl->stats.sum_target_index = static_cast<int64_t>(tot);
+    ctrl->step_counter += 1ull;
+    ctrl->stats.step_counter = static_cast<int64_t>(ctrl->step_counter);
+  }
+}
+
+// as_restore: the fields of a saved control block that are MDP state (parity of the state buffers, pending promotion,
+// Philox step counter, folded statistics, difficulty-grid histograms).  Live bookkeeping stays: the peer-exchange
+// epoch (the peers' slots hold flags of the live epoch), diagnostics counters.
+__global__ void k_restore_ctrl(Ctrl* ctrl, const Ctrl* saved) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    ctrl->parity = saved->parity;
+    ctrl->promote_cur = saved->promote_cur;
+    ctrl->step_counter = saved->step_counter;
+    ctrl->stats = saved->stats;
+    ctrl->gstats = saved->gstats;
+    ctrl->last_adv2 = saved->last_adv2;
+    ctrl->stats_folded = 0;
+    ctrl->blocks_done = ctrl->blocks_done2 = 0;
+    ctrl->n_reset_list = ctrl->n_regen_list = 0;
+  }
+  for (int i = t; i < kMaxGridBins; i += blockDim.x) {
+    ctrl->grid_attempts[i] = saved->grid_attempts[i];
+    ctrl->grid_successes[i] = saved->grid_successes[i];
+  }
+  for (int i = t; i < kSlots * kNumCounters; i += blockDim.x) (&ctrl->slots[0][0])[i] = 0u;
+  for (int i = t; i < kSlots; i += blockDim.x) ctrl->slot_reward[i] = 0.0f;
+}
+
 __global__ void k_clear_promotion(Ctrl* ctrl) {
   if (threadIdx.x == 0 && blockIdx.x == 0) ctrl->promote_cur = 0;
 }

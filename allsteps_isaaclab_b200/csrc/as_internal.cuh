@@ -84,7 +84,9 @@ struct Ctrl {
   unsigned int grid_successes[kMaxGridBins];  // ... of which the env had passed half of the stones
   unsigned long long dbg_t[16];               // -DAS_TIMING builds only: summed clock64() phase durations per CTA
   AsStats gstats;                             // step counters summed over all shards (peer exchange)
-  unsigned long long peer_timeouts;           // peers that did not deliver within the time limit (diagnostics)
+  unsigned long long peer_timeouts;           // peers that did not deliver within the time limit (sticky: see peer_error)
+  uint32_t peer_error;                        // != 0: a peer exchange timed out; the shards may have diverged (AS_ERR_PEER)
+  uint32_t reserved0;
 };
 
 // Peer exchange buffer of one rank: for each of the two epoch parities one 128-byte slot per sending rank.
@@ -100,6 +102,8 @@ constexpr int64_t kPeerBufferBytes = 2 * kMaxPeers * static_cast<int64_t>(sizeof
 struct PeerArgs {
   PeerSlot* buf[kMaxPeers];  // buf[r]: rank r's buffer as seen from this GPU (own: local pointer, others: IPC mappings)
   int32_t world, rank;
+  unsigned long long timeout_ns;  // how long to poll for a peer's counters; 0 = without limit
+  uint32_t* host_error;           // mapped pinned host word, set to the epoch when a peer timed out (read by the API, no sync)
 };
 
 struct Workspace {

@@ -1272,7 +1272,7 @@ __global__ void __launch_bounds__(128) k_peer_exchange(Ctrl* ctrl, const __grid_
     const PeerSlot* src = peer.buf[peer.rank] + par * kMaxPeers + tid;
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys_u64(&src->flag) != epoch) {
-      if (global_timer_ns() - t0 > 2000000000ull) {
+      if (peer.timeout_ns != 0ull && global_timer_ns() - t0 > peer.timeout_ns) {
         timed_out = true;
         break;
       }
@@ -1293,12 +1293,23 @@ __global__ void __launch_bounds__(128) k_peer_exchange(Ctrl* ctrl, const __grid_
   }
   if (tid == 0) {
     AsStats g = ctrl->stats;  // level, step counter, reward sum: this shard's
-    long long* gs = reinterpret_cast<long long*>(&g);
+    if (n_to == 0) {
+      long long* gs = reinterpret_cast<long long*>(&g);
 #pragma unroll
-    for (int k = 0; k < kPeerCounters; ++k) gs[k] = got[k];
+      for (int k = 0; k < kPeerCounters; ++k) gs[k] = got[k];
+    } else {
+      // A peer did not deliver in time.  A sum over some of the shards is never published: this step closes on the
+      // shard's own counters, and the error is STICKY -- ctrl->peer_error on the device, the mapped host word for the
+      // API, which refuses every further step with AS_ERR_PEER (the shards may have promoted differently).
+      ctrl->peer_timeouts += n_to;
+      ctrl->peer_error = 1u;
+      if (peer.host_error) {
+        *reinterpret_cast<volatile uint32_t*>(peer.host_error) = static_cast<uint32_t>(epoch) | 0x80000000u;
+        __threadfence_system();
+      }
+    }
     ctrl->gstats = g;
     ctrl->peer_epoch = static_cast<uint32_t>(epoch == 0xFFFFFFFFull ? 0ull : epoch);
-    if (n_to) ctrl->peer_timeouts += n_to;
   }
 }
 

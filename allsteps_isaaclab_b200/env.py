@@ -18,8 +18,34 @@ from typing import Dict, Optional
 
 import torch
 
-from .config import AllstepsCfg, NUM_STONES
+from .config import AllstepsCfg, JOINT_NAMES, NUM_JOINTS, NUM_STONES
 from .mdp import AllstepsMDP, PhysicsViews, StepBuffers
+
+
+def resolve_robot_tables(robot, cfg: AllstepsCfg):
+    """What the reference resolves from the live articulation at run time (ENV:87-92, 287-291), checked against what
+    the kernels assume: returns ((right_foot, left_foot, torso) body rows, joint limits (21,2) or None).
+
+    The kernels' joint tables (gears CFG:133-155, reset pose ENV:505-511, mirror permutation CFG:217-219) are indexed in
+    the PhysX joint order the reference documents; an articulation that enumerates its joints differently would be
+    scaled, mirrored and actuated wrongly without any error, so a different order is refused here.  Joint limits are
+    taken from `robot.data.joint_pos_limits` (what ENV:287-291 reads; PhysX' own degree -> radian conversion need not
+    round like the table's) and must not differ between envs (they are O(1) constants of the kernels)."""
+    names = list(robot.data.body_names)
+    body_rows = (names.index(cfg.foot_names[0]), names.index(cfg.foot_names[1]), names.index(cfg.torso_name))
+    jn = list(robot.data.joint_names)
+    if jn != list(JOINT_NAMES):
+        raise ValueError("robot.data.joint_names differs from the joint order the Allsteps kernels are built for "
+                         f"(CFG:133-155):\n  robot:   {jn}\n  kernels: {list(JOINT_NAMES)}")
+    limits = getattr(robot.data, "joint_pos_limits", None)
+    if limits is None:
+        return body_rows, None
+    limits = torch.as_tensor(limits)
+    if limits.dim() != 3 or tuple(limits.shape[1:]) != (NUM_JOINTS, 2):
+        raise ValueError(f"robot.data.joint_pos_limits must be (N,{NUM_JOINTS},2), got {tuple(limits.shape)}")
+    if limits.shape[0] > 1 and not bool((limits == limits[:1]).all()):
+        raise ValueError("robot.data.joint_pos_limits differ between envs; the Allsteps kernels take one limit table")
+    return body_rows, limits[0].detach().to(torch.float32).cpu()
 
 
 class AllstepsHooksB200:
@@ -29,11 +55,12 @@ class AllstepsHooksB200:
         """Call at the end of `__init__` (replaces ENV:40-102)."""
         self.task_cfg = task_cfg or AllstepsCfg()
         dev = torch.device(self.device)
-        self.mdp = AllstepsMDP(self.num_envs, device=dev, cfg=self.task_cfg, seed=seed, **mdp_kwargs)
+        body_rows, joint_limits = resolve_robot_tables(self.robot, self.task_cfg)
+        self.mdp = AllstepsMDP(self.num_envs, device=dev, cfg=self.task_cfg, seed=seed, joint_limits=joint_limits,
+                               **mdp_kwargs)
         self.buf = StepBuffers(self.num_envs, dev, reward_terms=True)
-        names = list(self.robot.data.body_names)
-        self.foot_indices = [names.index(n) for n in self.task_cfg.foot_names]  # ENV:87
-        self.torso_index = names.index(self.task_cfg.torso_name)  # ENV:88
+        self.foot_indices = [body_rows[0], body_rows[1]]  # ENV:87
+        self.torso_index = body_rows[2]  # ENV:88
         jn = list(self.robot.data.joint_names)
         as_idx = lambda ns: torch.tensor([jn.index(n) for n in ns], dtype=torch.int64, device=dev)  # noqa: E731
         self.right_body_indices = as_idx(self.task_cfg.right_body_names)  # ENV:90
@@ -137,6 +164,12 @@ class StandaloneAllstepsEnv(AllstepsHooksB200, _StandaloneBase):
         self.common_step_counter = 0
         self.extras = {}
         self._init_allsteps_b200(task_cfg, seed, **mdp_kwargs)
+
+    def reset(self):
+        """DRL:256-279: `_reset_idx(all ids)` before any step, then the observations (no physics here)."""
+        self._reset_idx(torch.arange(self.num_envs, dtype=torch.int64, device=self.episode_length_buf.device))
+        self.obs_buf = self._get_observations()
+        return self.obs_buf, self.extras
 
     def post_physics_step(self, actions: torch.Tensor):
         """DRL:326 + DRL:351-375."""

@@ -150,7 +150,9 @@ class CapturedStep:
 class AllstepsMDP:
     def __init__(self, num_envs: int, device="cuda:0", cfg: Optional[AllstepsCfg] = None, seed: int = 0,
                  env_id_offset: int = 0, intended_regen: bool = False, skip_pass2: bool = False,
-                 grid_bins: int = 0):
+                 grid_bins: int = 0, joint_limits: Optional[torch.Tensor] = None):
+        """joint_limits: optional (21,2) [lower, upper] in radians as the simulator reports them
+        (`robot.data.joint_pos_limits[0]`, ENV:287-291); default = the MJCF table of config.py."""
         self.lib = _cabi.load()  # raises if the CUDA library was not built: there is no fallback
         self.cfg = cfg or AllstepsCfg()
         self.device = torch.device(device)
@@ -161,7 +163,9 @@ class AllstepsMDP:
         flags = (_cabi.FLAG_INTENDED_REGEN if intended_regen else 0) | (_cabi.FLAG_SKIP_PASS2 if skip_pass2 else 0)
         flags |= _cabi.FLAG_GRID_CURRICULUM if grid_bins else 0
         self.grid_bins = int(grid_bins)
-        self.params = make_params(self.cfg, seed=seed, flags=flags, grid_bins=self.grid_bins)
+        self.seed = int(seed)
+        self.params = make_params(self.cfg, seed=seed, flags=flags, grid_bins=self.grid_bins,
+                                  joint_limits=joint_limits)
         nbytes = self.lib.as_workspace_bytes(self.num_envs)
         with torch.cuda.device(self.device):
             self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -415,11 +419,47 @@ class AllstepsMDP:
                     "as_grid_state")
         self._keepalive = (b, hist)
 
+    # ------------------------------------------------------------------ exact checkpoint / resume
+    def snapshot(self, include_stones: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Opaque device blob of the whole MDP state: packed state words, stone windows (and rows), grid bins and
+        histograms, pending promotion, Philox step counter.  Stream-ordered, no synchronisation."""
+        n = int(self.lib.as_snapshot_bytes(self.handle, 1 if include_stones else 0))
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        if out.numel() != n or out.dtype != torch.uint8 or out.device != self.device or not out.is_contiguous():
+            raise ValueError(f"snapshot buffer must be a contiguous uint8 tensor of {n} bytes on {self.device}")
+        _cabi.check(self.lib.as_snapshot(self.handle, out.data_ptr(), 1 if include_stones else 0, self._stream()),
+                    "as_snapshot")
+        return out
+
+    def restore(self, blob: torch.Tensor, include_stones: bool = True):
+        """Put a `snapshot()` back (same num_envs; `include_stones` as it was taken)."""
+        n = int(self.lib.as_snapshot_bytes(self.handle, 1 if include_stones else 0))
+        if blob.numel() != n or blob.dtype != torch.uint8:
+            raise ValueError(f"snapshot of {blob.numel()} bytes does not fit this handle ({n} bytes expected)")
+        blob = blob.to(self.device).contiguous()
+        _cabi.check(self.lib.as_restore(self.handle, blob.data_ptr(), 1 if include_stones else 0, self._stream()),
+                    "as_restore")
+        self._keepalive = blob
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
-        """Checkpoint: MDP buffers + the Philox position (seed is in the params, step counter in the stats)."""
+        """Checkpoint for an exact resume: `snapshot` is what `load_state_dict` restores (it holds the Philox position,
+        the pending promotion and the grid-curriculum state too); the reference-layout buffers of `export_state()` ride
+        along for inspection."""
         d = {k: v.cpu() for k, v in self.export_state().items()}
-        d["step_counter"] = torch.tensor(self.read_stats()["step_counter"], dtype=torch.int64)
+        d["snapshot"] = self.snapshot(include_stones=True).cpu()
+        d["meta"] = torch.tensor([_cabi.ABI_VERSION, self.num_envs, self.env_id_offset, self.seed,
+                                  int(self.params.flags), self.grid_bins], dtype=torch.int64)
         return d
+
+    def load_state_dict(self, d: Dict[str, torch.Tensor]):
+        meta = [int(x) for x in d["meta"].tolist()]
+        mine = [_cabi.ABI_VERSION, self.num_envs, self.env_id_offset, self.seed, int(self.params.flags), self.grid_bins]
+        names = ["abi", "num_envs", "env_id_offset", "seed", "flags", "grid_bins"]
+        for name, a, b in zip(names, meta, mine):
+            if a != b:
+                raise ValueError(f"checkpoint was taken with {name}={a}, this handle has {name}={b}")
+        self.restore(d["snapshot"], include_stones=True)
 
     def read_stats(self) -> Dict[str, float]:
         s = _cabi.AsStats()

@@ -15,7 +15,10 @@ def _f32(x: float) -> float:
     return float(torch.tensor(x, dtype=torch.float64).to(torch.float32))
 
 
-def make_params(cfg: AllstepsCfg, seed: int = 0, flags: int = 0, grid_bins: int = 0) -> _cabi.AsParams:
+def make_params(cfg: AllstepsCfg, seed: int = 0, flags: int = 0, grid_bins: int = 0,
+                joint_limits=None) -> _cabi.AsParams:
+    """joint_limits: optional (J,2) tensor / nested list [lower, upper] in radians, as the simulator reports them
+    (`robot.data.joint_pos_limits[0]`); default: the MJCF ranges converted in double (config.py)."""
     p = _cabi.AsParams()
     n_levels = cfg.max_curriculum + 1
     assert n_levels <= _cabi.NUM_LEVELS
@@ -54,6 +57,11 @@ def make_params(cfg: AllstepsCfg, seed: int = 0, flags: int = 0, grid_bins: int 
     for i in range(3):
         p.default_root_pos[i] = cfg.default_root_pos[i]
     limits = cfg.joint_limits_rad()
+    if joint_limits is not None:
+        jl = torch.as_tensor(joint_limits, dtype=torch.float32).cpu()
+        if tuple(jl.shape) != (NUM_JOINTS, 2):
+            raise ValueError(f"joint_limits must be ({NUM_JOINTS},2), got {tuple(jl.shape)}")
+        limits = [(float(a), float(b)) for a, b in jl.tolist()]
     pose = cfg.reset_joint_pose()
     src, sign = cfg.mirror_permutation()
     for j in range(NUM_JOINTS):

@@ -44,12 +44,11 @@ class _Binding:
         self.cfg = task_cfg or AllstepsCfg()
         self.names = (robot, left, right)
         dev = torch.device(env.device)
-        self.mdp = AllstepsMDP(env.num_envs, device=dev, cfg=self.cfg, seed=seed)
+        from .env import resolve_robot_tables
+
+        self.body_rows, joint_limits = resolve_robot_tables(env.scene[robot], self.cfg)
+        self.mdp = AllstepsMDP(env.num_envs, device=dev, cfg=self.cfg, seed=seed, joint_limits=joint_limits)
         self.buf = StepBuffers(env.num_envs, dev, reward_terms=True)
-        rob = env.scene[robot]
-        bn = list(rob.data.body_names)
-        self.body_rows = (bn.index(self.cfg.foot_names[0]), bn.index(self.cfg.foot_names[1]),
-                          bn.index(self.cfg.torso_name))
         self.mdp.generate_stones(env.scene.env_origins)
         self.epoch = None
         self.fell = self.so_fast = self.died = None

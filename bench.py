@@ -9,11 +9,19 @@ rewards, masked reset incl. the PhysX start-pose rows, pass 2, observations) ove
 articulation state.  Workload at every N: 1,048,576 envs per GPU (weak scaling; envs are
 sharded by env id, no collective on the step path; step statistics are all-reduced over NCCL off the step path).
 
+The timed state stays on SURVEY 8(d)'s distribution: the input sets form a cycle, set k generated from the MDP state k
+steps of the cycle lead to, and the MDP state is rewound every `--input-sets` steps INSIDE the timed region
+(allsteps_isaaclab_b200/workload.py); the advance / reset rates that result are printed in the line.
+
 JSON keys: `value` = env-steps/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` = the same metric
 through the public API with HOST buffers (pinned host -> device copy of every step's inputs and device -> host
-read of its results inside the timed region); `roofline` = algorithmic bytes (652 B per env-step)
-over the live-measured duration of the fused step kernel against the measured HBM copy peak; `cpu_baseline` = the
-CPU oracle port on a bounded sample.
+read of its results inside the timed region); `roofline` = SURVEY 8(d)'s 652 algorithmic bytes per env-step over the
+WHOLE step's time against the measured HBM copy peak (`roofline.kernel` = the dominant kernel alone, timed live by
+CUDA events on its stream); `cpu_baseline` = the CPU oracle port on a bounded sample.  First-class blocks for the
+other BASELINE.json configs: `c2_4096` (rl_games' default scale), `c3_65536_grid`, `c5_reset_heavy`, and at N > 1
+`c4` (1,048,576 envs SPLIT over the N ranks, promotion on the global mean over NVLink peer memory, with a
+peer == NCCL == single-handle bit-identity self-check); `three_call` = the pass1 / reset / pass2 path the DirectRLEnv
+hooks use under PhysX; `isaac_layout` = the fused step on the (N,13) / (N,B,13) views Isaac Lab hands out.
 """
 from __future__ import annotations
 
@@ -31,6 +39,7 @@ sys.path.insert(0, ROOT)
 B_ALG = 652  # algorithmic bytes per env-step (BASELINE.md section 4 / SURVEY.md section 8d)
 ENVS_PER_GPU = 1 << 20
 CPU_SAMPLE_ENVS = 1 << 16
+C4_GLOBAL_ENVS = 1 << 20
 METRIC = "MDP env-steps/sec"
 UNIT = "env-steps/s"
 
@@ -42,7 +51,11 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
-    ap.add_argument("--input-sets", type=int, default=4, help="distinct synthetic states rotated through")
+    ap.add_argument("--input-sets", type=int, default=16,
+                    help="length of the cycle of synthetic states (each generated from the MDP state it meets; the MDP "
+                         "state is rewound when the cycle restarts)")
+    ap.add_argument("--no-extra-blocks", action="store_true",
+                    help="skip c2/c3/c5/three_call/isaac_layout (N=1) and c4 (N>1): headline numbers only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 24)")
@@ -51,7 +64,6 @@ def parse_args():
                     help="N > 1: apply the promotion rule ENV:471 to the mean over ALL shards every step (config 4). "
                          "peer (default when given): one exchange kernel over NVLink peer memory; nccl: as_fold_stats + "
                          "NCCL all-reduce + as_finish_step(global). Without the flag promotion is shard-local.")
-    ap.add_argument("--small-sizes", default="4096,65536", help="extra env counts timed for latency (N=1 only)")
     # other BASELINE.json configs (the default flags are the headline workload)
     ap.add_argument("--fall-fraction", type=float, default=0.02, help="fraction of envs dying per step (0.3 = config 5)")
     ap.add_argument("--intended-regen", action="store_true", help="regenerate stones of reset envs past S/2 (extension)")
@@ -131,8 +143,13 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def run_cpu_port(num_envs: int, steps: int, warmup: int, seed: int = 1234):
-    """Times the CPU oracle port (the reference's algorithm, op for op in torch) on all host cores."""
+def run_cpu_port(num_envs: int, steps: int, warmup: int, seed: int = 1234, period: int = 4):
+    """Times the CPU oracle port (the reference's algorithm, op for op in torch) on all host cores.  Same cycle of
+    synthetic states as the CUDA arm: set k is generated from the MDP state k steps lead to, the oracle's MDP buffers
+    are rewound (outside the per-step timers) when the cycle restarts.  The port leaves out the six debug clones of
+    ENV:257-266, i.e. it is slightly FASTER than the reference itself."""
+    import copy
+
     import torch
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -142,13 +159,25 @@ def run_cpu_port(num_envs: int, steps: int, warmup: int, seed: int = 1234):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sc = Scenario(num_envs, seed=seed)
-    orc = ao.AllstepsOracle(sc.cfg, num_envs, sc.env_origins, sc.joint_limits, sc.body_indices, sc.stone_uniforms(0))
+    # (level 0: the stone draws have zero-width ranges, ENV:126-133 -- no table of uniforms needed)
+    orc = ao.AllstepsOracle(sc.cfg, num_envs, sc.env_origins, sc.joint_limits, sc.body_indices, None)
     install_mdp_state(orc, sc.initial_mdp_state())
-    pool = [sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg) for _ in range(4)]
-    mirror_u, noise_u = sc.reset_uniforms(0)
-    times = []
+    mirror_u = torch.rand(num_envs, generator=sc.gen)
+    noise_u = torch.rand(num_envs, 21, generator=sc.gen)
+    state_keys = ("curr_target_index", "prev_target_index", "next_target_index", "swing_leg", "target_reach_count",
+                  "episode_length_buf", "curriculum", "potentials", "old_potentials")
+    snap = {k: getattr(orc, k).clone() for k in state_keys}
+    pool = []
+    for _ in range(period):
+        phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+        pool.append(phys)
+        orc.step(phys, phys["actions"], mirror_u, noise_u, None)
+    times, adv = [], 0
     for i in range(warmup + steps):
-        phys = pool[i % len(pool)]
+        if i % period == 0:
+            for k in state_keys:
+                setattr(orc, k, snap[k].clone())
+        phys = pool[i % period]
         t0 = time.perf_counter()
         orc.step(phys, phys["actions"], mirror_u, noise_u, None)
         t1 = time.perf_counter()
@@ -161,22 +190,26 @@ def run_cpu_port(num_envs: int, steps: int, warmup: int, seed: int = 1234):
 
 def main_reference(args):
     """The reference arm: the reference's own CPU implementation of the path (it is pure Python/torch and cannot be
-    installed on the GPU box, so the bit-identical oracle port stands in -- kind "port"), all host threads."""
+    installed on the GPU box, so the bit-identical oracle port stands in -- kind "port"), all host threads, on the
+    same config as the CUDA arm: 1,048,576 envs per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample per step: ~1.1 us of host time per env-step => keep K steps within about a minute
-    envs = CPU_SAMPLE_ENVS
-    while envs > 4096 and envs * args.steps * 1.1e-6 > 60.0:
+    envs = args.envs_per_gpu
+    # ~0.5 us of host time per env-step on 16 cores: K steps of 1M envs stay within a few minutes up to K ~ 200
+    while envs > 4096 and envs * (args.steps + max(args.warmup, 3)) * 1.0e-6 > 240.0:
         envs //= 2
     r = run_cpu_port(envs, args.steps, max(args.warmup, 3))
-    sample = f"{envs} envs per step (1/{ENVS_PER_GPU // envs} of the 1,048,576-env workload), {args.steps} steps"
+    frac = "" if envs == args.envs_per_gpu else f" (1/{args.envs_per_gpu // envs} of the workload: bounded sample)"
+    sample = (f"{envs} envs per step{frac}, {args.steps} steps; the port omits the reference's six debug clones "
+              "(ENV:257-266), so it is slightly faster than the reference")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Allsteps-v0 fused MDP step, 1,048,576 envs per GPU (reference arm: bounded "
-                               "sample per step on host cores)", "envs_per_step": envs},
+        "config": {"workload": f"Allsteps-v0 fused MDP step, {args.envs_per_gpu} envs per GPU (reference arm: the "
+                               "reference's algorithm on the host cores of rank 0)", "envs_per_gpu": args.envs_per_gpu,
+                   "envs_per_step": envs},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -185,39 +218,13 @@ def main_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- CUDA arm
-def build_pool(torch, syn, cfg, mdp, origins, sets, device, seed, fall_fraction=0.02):
-    """`sets` distinct synthetic post-physics states, generated on the device (throughput only)."""
-    from allsteps_isaaclab_b200.mdp import PhysicsViews
-
-    gen = torch.Generator(device=device).manual_seed(seed)
-    st = mdp.export_state()
-    pool = []
-    for _ in range(sets):
-        d = syn.random_physics_state(cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen,
-                                     fall_fraction=fall_fraction)
-        d.pop("root_ang_vel_w", None)
-        pool.append((PhysicsViews.from_dict(d, origins), d))
-    return pool
-
-
-def time_steps(torch, mdp, pool, out, steps, warmup, dist=None, stats_interval=0, stats_buf=None, side=None,
-               global_promotion=False):
+def time_cycle(torch, wl, steps, warmup, dist=None, after_step=None):
+    """K steps of the workload cycle between CUDA events (the rewind at each cycle start is inside)."""
+    mdp = wl.mdp
     dev = mdp.device
-
-    def one_step(v, d):
-        if global_promotion == "nccl" and dist is not None:
-            # SURVEY 8(e): the one cross-env dependency of the path, ENV:471 -- the additive counters of all shards
-            mdp.step(v, d["actions"], out, finish=False)
-            mdp.fold_stats()
-            stats_buf.copy_(mdp.stats_tensor)      # a whole AsStats; its first 10 int64 are the additive counters
-            dist.all_reduce(stats_buf[:10])
-            mdp.finish_step(stats_buf)
-        else:  # shard-local, or peers connected: the exchange kernel is part of the step
-            mdp.step(v, d["actions"], out)
-
-    for i in range(warmup):
-        v, d = pool[i % len(pool)]
-        one_step(v, d)
+    wl.rewind()
+    for _ in range(warmup):
+        wl.step()
     torch.cuda.synchronize(dev)
     if dist is not None:
         dist.barrier()
@@ -226,14 +233,9 @@ def time_steps(torch, mdp, pool, out, steps, warmup, dist=None, stats_interval=0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        v, d = pool[i % len(pool)]
-        one_step(v, d)
-        if dist is not None and stats_interval and not global_promotion and (i + 1) % stats_interval == 0:
-            # episode / curriculum statistics: summed over ranks off the step path (side stream, NCCL)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                stats_buf.copy_(mdp.stats_tensor)
-                dist.all_reduce(stats_buf[:10])
+        wl.step()
+        if after_step is not None:
+            after_step(i)
     e1.record()
     torch.cuda.synchronize(dev)
     if dist is not None:
@@ -242,62 +244,111 @@ def time_steps(torch, mdp, pool, out, steps, warmup, dist=None, stats_interval=0
     return e0.elapsed_time(e1), mdp.launch_count - launches0
 
 
-def time_steps_graph(torch, mdp, pool, out, steps, warmup):
-    """Same loop with every input set's step captured once as a CUDA graph and replayed."""
-    dev = mdp.device
-    graphs = [mdp.capture_step(v, d["actions"], out) for v, d in pool]
-    for i in range(warmup):
-        graphs[i % len(graphs)].replay()
+def time_cycle_graph(torch, wl, steps, warmup):
+    """Same loop with every set's step captured once as a CUDA graph and replayed (the rewind stays an API call)."""
+    mdp, dev = wl.mdp, wl.mdp.device
+    wl.rewind()
+    graphs = [mdp.capture_step(v, d["actions"], wl.out) for v, d in wl.sets]
+    per_replay = graphs[0].kernels_per_replay
+
+    def run(n):
+        for _ in range(n):
+            k = wl.j % wl.period
+            if k == 0 and wl.j > 0:
+                wl.rewind()
+            graphs[k].replay()
+            wl.j += 1
+
+    wl.rewind()
+    run(warmup)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(steps):
-        graphs[i % len(graphs)].replay()
+    run(steps)
     e1.record()
     torch.cuda.synchronize(dev)
-    return e0.elapsed_time(e1), steps * graphs[0].kernels_per_replay
+    return e0.elapsed_time(e1), steps * per_replay
 
 
-def time_kernel_only(torch, mdp, pool, out, steps):
+def time_kernel_only(torch, wl, steps):
     """Average duration of the dominant kernel alone, k_step<fused>: the library records a pair of CUDA events on the
-    launching stream immediately around that launch (as_set_timing_events).  Also returns the duration of the whole
-    device-side step (contact-gather kernel + step kernel + finish kernel) from events around the two API calls."""
+    launching stream immediately around that launch (as_set_timing_events)."""
     from allsteps_isaaclab_b200 import _cabi
 
-    dev = mdp.device
+    mdp, dev = wl.mdp, wl.mdp.device
     pairs = []
     for _ in range(steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); b.record()  # creates the underlying cudaEvent_t
         pairs.append((a, b))
     torch.cuda.synchronize(dev)
+    wl.rewind()
     for i in range(steps):
-        v, d = pool[i % len(pool)]
         a, b = pairs[i]
         _cabi.check(mdp.lib.as_set_timing_events(mdp.handle, a.cuda_event, b.cuda_event), "as_set_timing_events")
-        mdp.step(v, d["actions"], out)
+        wl.step()
     _cabi.check(mdp.lib.as_set_timing_events(mdp.handle, None, None), "as_set_timing_events")
     torch.cuda.synchronize(dev)
     ms = sorted(a.elapsed_time(b) for a, b in pairs)
     return sum(ms) / len(ms), ms[len(ms) // 2]
 
 
-def time_e2e(torch, mdp, pool, origins, out, steps, warmup, zero_copy_contact=False):
+def time_three_call(torch, wl, origins, steps, warmup, device_reset_list=False):
+    """DRL:351-375 as the DirectRLEnv hooks run it under PhysX: as_step_pass1, the host's `.nonzero()` on reset_buf
+    (DRL:359, a device->host sync), as_reset on those ids, as_step_pass2.  (No PhysX here: pass 2 sees unchanged
+    physics.)  Device time between events, host gaps included."""
+    mdp, dev, out = wl.mdp, wl.mdp.device, wl.out
+    N = mdp.num_envs
+    ep_len = torch.zeros(N, dtype=torch.int64, device=dev)
+
+    def one(v, d):
+        ep_len.add_(1)
+        mdp.pass1(v, d["actions"], out, episode_length=ep_len)
+        ids = out.dones.nonzero(as_tuple=False).squeeze(-1)  # DRL:359
+        if len(ids) > 0:
+            mdp.reset(origins, ids, out, episode_length=ep_len)
+            mdp.pass2(v, out)
+
+    def run(n):
+        for _ in range(n):
+            k = wl.j % wl.period
+            if k == 0 and wl.j > 0:
+                wl.rewind()
+            one(*wl.sets[k])
+            wl.j += 1
+
+    wl.rewind()
+    run(warmup)
+    torch.cuda.synchronize(dev)
+    l0 = mdp.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    run(steps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    wall = (time.perf_counter() - t0) * 1e3
+    return max(e0.elapsed_time(e1), wall), mdp.launch_count - l0
+
+
+def time_e2e(torch, wl, origins, steps, warmup, zero_copy_contact=False):
     """Same metric through the public API with HOST buffers: every step copies that step's inputs from pinned host
     memory, runs the fused step, and reads the results back to pinned host memory.  Copies of step t+1 / t-1
-    overlap the kernel of step t on separate streams (double-buffered device inputs and outputs).
+    overlap the kernel of step t on separate streams (double-buffered device inputs and outputs).  The host holds the
+    first two states of the cycle; the MDP state is rewound every two steps.
 
     zero_copy_contact: the two (N,1,20,3) contact matrices (59 % of the input bytes, of which the step needs 24 B per
     env) are NOT copied; the C ABI is handed the pinned host tensors themselves (device-accessible under unified
     addressing) and the contact-gather kernel fetches just the current stone's vectors across PCIe."""
     from allsteps_isaaclab_b200.mdp import PhysicsViews, StepBuffers
 
+    mdp = wl.mdp
     dev = mdp.device
     N = mdp.num_envs
     keys = ["root_pos_w", "root_quat_w", "root_lin_vel_w", "body_pos_w", "joint_pos", "joint_vel",
             "force_matrix_right", "force_matrix_left", "actions"]
     host_sets = []
-    for _, d in pool[:2]:
+    for _, d in wl.sets[:2]:
         host_sets.append({k: d[k].cpu().pin_memory() for k in keys})
     copied = [k for k in keys if not (zero_copy_contact and k.startswith("force_matrix"))]
     h2d_bytes = sum(host_sets[0][k].numel() * host_sets[0][k].element_size() for k in copied)
@@ -310,7 +361,7 @@ def time_e2e(torch, mdp, pool, origins, out, steps, warmup, zero_copy_contact=Fa
                   for hs in host_sets] for b in range(2)]
     else:
         views = [[PhysicsViews.from_dict(dev_in[b], origins)] * len(host_sets) for b in range(2)]
-    outs = [out, StepBuffers(N, dev)]
+    outs = [wl.out, StepBuffers(N, dev)]
     host_out = [{"obs": torch.empty(N, 59).pin_memory(), "reward": torch.empty(N).pin_memory(),
                  "terminated": torch.empty(N, dtype=torch.bool).pin_memory(),
                  "time_out": torch.empty(N, dtype=torch.bool).pin_memory()} for _ in range(2)]
@@ -333,6 +384,8 @@ def time_e2e(torch, mdp, pool, origins, out, steps, warmup, zero_copy_contact=Fa
         b = i % 2
         s_main.wait_event(in_ready[b])
         s_main.wait_event(out_free[b])
+        if i % 2 == 0:
+            wl.rewind()  # the two host-resident states belong to the first two steps of the cycle
         mdp.step(views[b][i % len(host_sets)], dev_in[b]["actions"], outs[b])
         in_free[b].record(s_main)
         out_ready[b].record(s_main)
@@ -350,6 +403,7 @@ def time_e2e(torch, mdp, pool, origins, out, steps, warmup, zero_copy_contact=Fa
     for b in range(2):
         in_free[b].record(s_main)
         out_free[b].record(s_main)
+    warmup += warmup % 2  # keep the timed region on the cycle's phase
     total = warmup + steps
     t_start = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -373,6 +427,77 @@ def time_e2e(torch, mdp, pool, origins, out, steps, warmup, zero_copy_contact=Fa
     return ms, h2d_bytes, d2h_bytes, checksum
 
 
+def selfcheck_global_promotion(torch, dist, dev, rank, world, per=8192, steps=10, seed=17):
+    """BASELINE config 4 correctness inside the bench run (the driver's test box has one GPU): every rank steps its
+    env-id shard three ways from the same seeded state -- global promotion over NVLink peer memory, the same through
+    as_fold_stats + NCCL all-reduce + as_finish_step(global), and rank 0 additionally ONE handle with all envs --
+    and all outputs and MDP state must be bit-identical.  The state sits near the promotion threshold so that
+    promotions actually happen."""
+    from allsteps_isaaclab_b200 import synthetic as syn
+    from allsteps_isaaclab_b200.config import AllstepsCfg
+    from allsteps_isaaclab_b200.mdp import AllstepsMDP, PhysicsViews, StepBuffers
+
+    cfg = AllstepsCfg()
+    N = per * world
+    sl = slice(rank * per, (rank + 1) * per)
+    g0 = torch.Generator().manual_seed(seed)            # same on every rank
+    st0 = syn.random_mdp_state(cfg, N, g0)
+    st0["curr_target_index"] = torch.randint(11, 20, (N,), generator=g0)
+    origins_all = syn.env_origins_grid(N, cfg.env_spacing).to(dev)
+    origins = origins_all[sl].contiguous()
+    keys = ("curr_target_index", "swing_leg", "target_reach_count", "episode_length_buf", "potentials")
+
+    def make(n, off, o, state):
+        m = AllstepsMDP(n, device=dev, seed=seed, env_id_offset=off)
+        m.generate_stones(o)
+        m.import_state(state)
+        return m
+
+    shard_state = {k: st0[k][sl] for k in keys}
+    peer = make(per, rank * per, origins, shard_state)
+    nccl = make(per, rank * per, origins, shard_state)
+    peer.connect_peers()
+    single = make(N, 0, origins_all, {k: st0[k] for k in keys})  # every rank steps the whole thing: no broadcast needed
+    o_p, o_n, o_s = StepBuffers(per, dev), StepBuffers(per, dev), StepBuffers(N, dev)
+    gbuf = torch.zeros_like(nccl.stats_tensor)
+    gen = torch.Generator(device=dev).manual_seed(seed)  # same sequence on every rank
+    ok_pn = ok_single = True
+    level0, promotions = 0, 0
+    for _ in range(steps):
+        st = single.export_state()
+        d = syn.random_physics_state(cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen,
+                                     fall_fraction=0.05)
+        d.pop("root_ang_vel_w", None)
+        ds = {k: v[sl].contiguous() for k, v in d.items()}
+        v_all, v_sh = PhysicsViews.from_dict(d, origins_all), PhysicsViews.from_dict(ds, origins)
+        single.step(v_all, d["actions"], o_s)
+        peer.step(v_sh, ds["actions"], o_p)
+        nccl.step(v_sh, ds["actions"], o_n, finish=False)
+        nccl.fold_stats()
+        gbuf.copy_(nccl.stats_tensor)
+        dist.all_reduce(gbuf[:10])
+        nccl.finish_step(gbuf)
+        torch.cuda.synchronize(dev)
+        for name in ("obs", "reward", "terminated", "time_out"):
+            a, b, c = getattr(o_p, name), getattr(o_n, name), getattr(o_s, name)[sl]
+            ok_pn &= bool(torch.equal(a, b))
+            ok_single &= bool(torch.equal(a, c))
+        sa, sb, sc_ = peer.export_state(), nccl.export_state(), single.export_state()
+        for k in ("curr_target_index", "swing_leg", "target_reach_count", "curriculum", "potentials"):
+            ok_pn &= bool(torch.equal(sa[k], sb[k]))
+            ok_single &= bool(torch.equal(sa[k], sc_[k][sl]))
+        lvl = int(sc_["curriculum"].max())
+        promotions += int(lvl != level0)
+        level0 = lvl
+    flags = torch.tensor([int(ok_pn), int(ok_single), int(peer.peer_status()["timeouts"] == 0)], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    res = {"peer_eq_nccl": bool(flags[0]), "shards_eq_single_handle": bool(flags[1]),
+           "no_peer_timeouts": bool(flags[2]), "promotions": promotions, "global_envs": N, "steps": steps}
+    res["ok"] = res["peer_eq_nccl"] and res["shards_eq_single_handle"] and res["no_peer_timeouts"] and promotions > 0
+    del peer, nccl, single
+    return res
+
+
 def main_b200(args):
     import torch
 
@@ -381,6 +506,8 @@ def main_b200(args):
     from allsteps_isaaclab_b200 import synthetic as syn
     from allsteps_isaaclab_b200.config import AllstepsCfg
     from allsteps_isaaclab_b200.mdp import AllstepsMDP, StepBuffers
+    from allsteps_isaaclab_b200.sharding import StatsReducer
+    from allsteps_isaaclab_b200.workload import ChainedWorkload
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -399,83 +526,195 @@ def main_b200(args):
     cfg = AllstepsCfg()
     N = args.envs_per_gpu
 
-    def make(num_envs, seed=1234):
+    def make(num_envs, seed=1234, period=None, fall_fraction=None, intended_regen=None, grid_bins=None,
+             layout="dense", env_id_offset=None, peers=False, close_step=None):
+        fall_fraction = args.fall_fraction if fall_fraction is None else fall_fraction
+        intended_regen = args.intended_regen if intended_regen is None else intended_regen
+        grid_bins = args.grid_bins if grid_bins is None else grid_bins
         origins = syn.env_origins_grid(num_envs, cfg.env_spacing).to(dev)
-        mdp = AllstepsMDP(num_envs, device=dev, seed=seed, env_id_offset=rank * num_envs,
-                          intended_regen=args.intended_regen, grid_bins=args.grid_bins)
+        mdp = AllstepsMDP(num_envs, device=dev, seed=seed,
+                          env_id_offset=rank * num_envs if env_id_offset is None else env_id_offset,
+                          intended_regen=intended_regen, grid_bins=grid_bins)
         mdp.generate_stones(origins)
         st0 = syn.random_mdp_state(cfg, num_envs, torch.Generator().manual_seed(seed + rank))
         mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
                                               "episode_length_buf", "potentials")})
-        pool = build_pool(torch, syn, cfg, mdp, origins, args.input_sets, dev, seed + rank, args.fall_fraction)
-        return mdp, origins, pool, StepBuffers(num_envs, dev)
+        if peers:
+            mdp.connect_peers()
+        out = StepBuffers(num_envs, dev)
+        wl = ChainedWorkload(mdp, origins, out, period or args.input_sets, seed + rank, cfg, fall_fraction, layout,
+                             stones_change=bool(intended_regen or grid_bins), close_step=close_step)
+        return wl, origins
 
-    mdp, origins, pool, out = make(N)
-    if args.global_promotion == "peer" and dist is not None:
-        mdp.connect_peers()
+    def reduce_max(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     side = torch.cuda.Stream(dev) if dist is not None else None
-    stats_buf = torch.zeros_like(mdp.stats_tensor) if dist is not None else None
+    reducer = StatsReducer(dev) if dist is not None else None
+    gbuf = torch.zeros(13, dtype=torch.int64, device=dev)  # a whole AsStats; its first 10 int64 are the additive counters
+
+    def nccl_close(m, v, d, o):  # config-4 semantics through the plain library route (--global-promotion nccl)
+        m.step(v, d["actions"], o, finish=False)
+        m.fold_stats()
+        gbuf.copy_(m.stats_tensor)
+        dist.all_reduce(gbuf[:10])
+        m.finish_step(gbuf)
+
+    if args.global_promotion and dist is not None:  # the headline workload itself with a global promotion route
+        wl, origins = make(N, peers=args.global_promotion == "peer",
+                           close_step=nccl_close if args.global_promotion == "nccl" else None)
+    else:
+        wl, origins = make(N)
+    mdp, out = wl.mdp, wl.out
+    wl_rates = (wl.advance_rate, wl.reset_rate, wl.set_bytes, wl.rewind_bytes)
+
+    def stats_hook(i):
+        if dist is not None and args.stats_interval and not args.global_promotion and (i + 1) % args.stats_interval == 0:
+            # episode / curriculum statistics: summed over ranks off the step path (side stream, NCCL)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                reducer.start(mdp.stats_tensor)
 
     with ClockSampler(local_rank) as clocks:
-        ms_total, launches = time_steps(torch, mdp, pool, out, args.steps, args.warmup, dist,
-                                        args.stats_interval, stats_buf, side, args.global_promotion)
-        # roofline of the dominant kernel (rank-local, timed alone on its stream), same clock record
-        k_avg, k_med = time_kernel_only(torch, mdp, pool, out, min(args.steps, 200))
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+        ms_total, launches = time_cycle(torch, wl, args.steps, args.warmup, dist, stats_hook)
+        # the dominant kernel alone (rank-local, timed by events on its stream), same clock record
+        k_avg, k_med = time_kernel_only(torch, wl, min(args.steps, 200))
+    ms_total = reduce_max(ms_total)
     ms_step = ms_total / args.steps
     value = N * world * args.steps / (ms_total * 1e-3)
+    if reducer is not None and reducer.work is not None:
+        reducer.wait()
     stats = mdp.read_stats()
 
     peak, peak_src = measured_peaks()
     # k_step<fused> moves everything except the 24 B/env of contact vectors, which k_contact_gather fetches for it
     b_kernel = B_ALG - 24
-    achieved = N * b_kernel / (k_avg * 1e-3) / 1e9
+    achieved_kernel = N * b_kernel / (k_avg * 1e-3) / 1e9
     achieved_step = N * B_ALG / (ms_step * 1e-3) / 1e9
     traffic = profiled_traffic()
 
     e2e = None
     if not args.no_e2e:
         e_steps = args.e2e_steps or min(args.steps, 24)
+        e_steps += e_steps % 2
         variants = {}
         for name, zc in (("copy_all_inputs", False), ("zero_copy_contact_matrices", True)):
-            e_ms, h2d_b, d2h_b, _ = time_e2e(torch, mdp, pool, origins, out, e_steps, 3, zero_copy_contact=zc)
-            te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
-            if dist is not None:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            variants[name] = {"value": N * world * e_steps / (float(te.item()) * 1e-3), "h2d_bytes_per_step": h2d_b,
-                              "d2h_bytes_per_step": d2h_b, "ms_per_step": float(te.item()) / e_steps}
+            e_ms, h2d_b, d2h_b, _ = time_e2e(torch, wl, origins, e_steps, 4, zero_copy_contact=zc)
+            e_ms = reduce_max(e_ms)
+            variants[name] = {"value": N * world * e_steps / (e_ms * 1e-3), "h2d_bytes_per_step": h2d_b,
+                              "d2h_bytes_per_step": d2h_b, "ms_per_step": e_ms / e_steps,
+                              "host_link_GBps_per_gpu": (h2d_b + d2h_b) / (e_ms / e_steps * 1e-3) / 1e9}
         best = max(variants, key=lambda k: variants[k]["value"])
         e2e = {"value": variants[best]["value"], "unit": UNIT,
                "h2d_bytes_per_step": variants[best]["h2d_bytes_per_step"],
                "d2h_bytes_per_step": variants[best]["d2h_bytes_per_step"], "steps": e_steps,
                "ms_per_step": variants[best]["ms_per_step"], "mode": best, "variants": variants,
+               "bound": "host<->device copies (PCIe; at N > 1 all ranks share the host's memory system / one NUMA "
+                        f"node): {variants[best]['host_link_GBps_per_gpu'] * world:.0f} GB/s aggregate over "
+                        f"{world} GPU(s).  Under Isaac Lab the state is device resident; this leg is synthetic.",
                "note": "pinned host buffers; H2D of step t+1 and D2H of step t-1 overlap the kernel of step t; in "
                        "zero_copy_contact_matrices the (N,1,20,3) contact tensors stay in pinned host memory and "
                        "k_contact_gather_paired reads the current stone's vectors through PCIe"}
 
-    small = {}
-    if rank == 0 and world == 1 and args.small_sizes:
-        for n in [int(x) for x in args.small_sizes.split(",") if x]:
-            m2, _, p2, o2 = make(n, seed=99)
-            k2 = max(args.steps, 500)
-            ms2, l2 = time_steps(torch, m2, p2, o2, k2, args.warmup)
-            ms3, l3 = time_steps_graph(torch, m2, p2, o2, k2, args.warmup)
-            best = min(ms2, ms3)  # since the kernels are chained by programmatic dependent launch the two are close
-            small[str(n)] = {"us_per_step": 1e3 * best / k2, "env_steps_per_s": n * k2 / (best * 1e-3),
-                             "kernels_per_step": l3 / k2,
-                             "mode": "library calls" if ms2 <= ms3 else "one CUDA-graph replay per step",
-                             "us_per_step_library_calls": 1e3 * ms2 / k2, "us_per_step_graph_replay": 1e3 * ms3 / k2,
-                             "bound": "launch latency (working set is L2 resident)"}
+    blocks = {}
+    extra = not args.no_extra_blocks
+    if extra and world > 1:
+        # ---- BASELINE config 4: 1,048,576 envs SPLIT over the ranks, promotion on the global mean (peer memory)
+        del wl
+        torch.cuda.empty_cache()
+        per = C4_GLOBAL_ENVS // world
+        w4, _ = make(per, seed=4321, peers=True)
+        ms4, l4 = time_cycle(torch, w4, max(args.steps, 200), args.warmup, dist)
+        ms4 = reduce_max(ms4) / max(args.steps, 200)
+        status = w4.mdp.peer_status()
+        blocks["c4"] = {"value": C4_GLOBAL_ENVS / (ms4 * 1e-3), "unit": UNIT, "us_per_step": ms4 * 1e3,
+                        "global_envs": C4_GLOBAL_ENVS, "envs_per_gpu": per, "scaling": "strong",
+                        "promotion": "global mean; step counters summed by one kernel over NVLink peer memory every step",
+                        "efficiency_vs_one_gpu_at_1M": (C4_GLOBAL_ENVS / (ms4 * 1e-3)) / value,
+                        "peer_exchange_timeouts": status["timeouts"], "kernels_per_step": l4 / max(args.steps, 200),
+                        "advance_rate": w4.advance_rate, "reset_rate": w4.reset_rate}
+        del w4
+        blocks["c4"]["selfcheck"] = selfcheck_global_promotion(torch, dist, dev, rank, world)
+
+    if extra and rank == 0 and world == 1:
+        del wl
+        torch.cuda.empty_cache()
+        k_small = max(args.steps, 500)
+
+        def small_block(n, **kw):
+            w, w_org = make(n, seed=99, **kw)
+            ms2, l2 = time_cycle(torch, w, k_small, args.warmup)
+            ms3, l3 = time_cycle_graph(torch, w, k_small, args.warmup)
+            best = min(ms2, ms3)
+            return {"us_per_step": 1e3 * best / k_small, "value": n * k_small / (best * 1e-3), "unit": UNIT,
+                    "envs": n, "kernels_per_step": l3 / k_small,
+                    "mode": "library calls" if ms2 <= ms3 else "one CUDA-graph replay per step",
+                    "us_per_step_library_calls": 1e3 * ms2 / k_small, "us_per_step_graph_replay": 1e3 * ms3 / k_small,
+                    "advance_rate": w.advance_rate, "reset_rate": w.reset_rate,
+                    "bound": "launch latency (working set is L2 resident)"}, w, w_org
+
+        # ---- BASELINE config 2: 4096 envs, rl_games' default batch scale
+        blocks["c2_4096"], w2, o2 = small_block(4096)
+        ms_t, l_t = time_three_call(torch, w2, o2, k_small, args.warmup)
+        three = {"4096": {"us_per_step": 1e3 * ms_t / k_small, "kernels_per_step": l_t / k_small}}
+        del w2
+        # ---- BASELINE config 3: 65536 envs with the pitch x yaw grid curriculum (extension)
+        blocks["c3_65536_grid"], w3, _ = small_block(65536, grid_bins=11)
+        blocks["c3_65536_grid"]["bound"] = "launch latency (5 launches; working set is L2 resident)"
+        del w3
+        w65, o65 = make(65536, seed=99)
+        ms_f, _ = time_cycle(torch, w65, k_small, args.warmup)
+        ms_t, l_t = time_three_call(torch, w65, o65, k_small, args.warmup)
+        three["65536"] = {"us_per_step": 1e3 * ms_t / k_small, "kernels_per_step": l_t / k_small,
+                          "fused_us_per_step": 1e3 * ms_f / k_small}
+        del w65
+        # ---- the 3-call path at the headline size
+        k_big = min(max(args.steps, 40), 200)
+        w1m, o1m = make(N, seed=77)
+        ms_f, _ = time_cycle(torch, w1m, k_big, args.warmup)
+        ms_t, l_t = time_three_call(torch, w1m, o1m, k_big, args.warmup)
+        three[str(N)] = {"us_per_step": 1e3 * ms_t / k_big, "kernels_per_step": l_t / k_big,
+                         "fused_us_per_step": 1e3 * ms_f / k_big, "ratio_to_fused": ms_t / ms_f}
+        three["what"] = ("as_step_pass1 -> host .nonzero() of reset_buf (DRL:359, a device->host sync) -> as_reset -> "
+                         "as_step_pass2: the path the DirectRLEnv hooks take when PhysX sits between the writes of "
+                         "ENV:563-565 and pass 2")
+        blocks["three_call"] = three
+        del w1m
+        torch.cuda.empty_cache()
+        # ---- BASELINE config 5: reset-heavy stress with stone regeneration
+        w5, _ = make(N, seed=55, period=4, fall_fraction=0.3, intended_regen=True)
+        ms5, l5 = time_cycle(torch, w5, k_big, args.warmup)
+        b5 = B_ALG + w5.reset_rate * 244 + (w5.mdp.read_stats()["n_regenerated"] / N) * 320
+        blocks["c5_reset_heavy"] = {"us_per_step": 1e3 * ms5 / k_big, "value": N * k_big / (ms5 * 1e-3), "unit": UNIT,
+                                    "envs": N, "reset_rate": w5.reset_rate, "advance_rate": w5.advance_rate,
+                                    "regenerated_per_step": w5.mdp.read_stats()["n_regenerated"],
+                                    "kernels_per_step": l5 / k_big, "algorithmic_bytes_per_env_step": b5,
+                                    "roofline_frac": N * b5 / (ms5 / k_big * 1e-3) / 1e9 / peak,
+                                    "state_rewind": "every 4 steps incl. the 320 B/env stone rows"}
+        del w5
+        torch.cuda.empty_cache()
+        # ---- the layout Isaac Lab hands out: (N,13) root_state_w slices, (N,17,13) body_state_w slice
+        wi, _ = make(N, seed=66, period=4, layout="isaac")
+        msi, li = time_cycle(torch, wi, k_big, args.warmup)
+        blocks["isaac_layout"] = {"us_per_step": 1e3 * msi / k_big, "value": N * k_big / (msi * 1e-3), "unit": UNIT,
+                                  "envs": N, "kernels_per_step": li / k_big,
+                                  "roofline_frac": N * B_ALG / (msi / k_big * 1e-3) / 1e9 / peak,
+                                  "what": "root pos/quat/lin vel as slices of one (N,13) root_state_w tensor, body "
+                                          "positions as a slice of the (N,17,13) body_state_w tensor "
+                                          "(articulation_data.py:366-380,430-449)"}
+        del wi
+        torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N=1 only (rank 0 host cores)
         r = run_cpu_port(CPU_SAMPLE_ENVS, 24, 3)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"{CPU_SAMPLE_ENVS} envs x 24 steps of the same synthetic workload "
-                         f"({r['ms_per_step']:.1f} ms/step), torch {torch.__version__} CPU"}
+                         f"({r['ms_per_step']:.1f} ms/step), torch {torch.__version__} CPU; the port omits the "
+                         "reference's six debug clones (ENV:257-266)"}
 
     if rank == 0:
         line = {
@@ -483,35 +722,41 @@ def main_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"Allsteps-v0 fused MDP step, {N} envs per GPU, "
-                                   f"{100.0 * stats['n_reset'] / N:.0f}% of envs resetting per step"
+                                   f"{100.0 * wl_rates[1]:.1f}% of envs resetting and {100.0 * wl_rates[0]:.1f}% "
+                                   "advancing a stone per step"
                                    + (", stone regeneration on reset" if args.intended_regen else "")
                                    + (f", {args.grid_bins}x{args.grid_bins} grid curriculum" if args.grid_bins else ""),
                        "envs_per_gpu": N, "global_envs": N * world, "parallelism": f"env-id shards x{world}",
-                       "l2_policy": f"{args.input_sets} rotating input sets of {N * 808 / 1e6:.0f} MB each "
-                                    "(larger than the 126 MB L2)",
+                       "advance_rate": wl_rates[0], "reset_rate": wl_rates[1],
+                       "l2_policy": f"cycle of {args.input_sets} input sets of {wl_rates[2] / 1e6:.0f} MB each "
+                                    "(larger than the 126 MB L2), each generated from the MDP state it meets",
+                       "state_rewind": f"every {args.input_sets} steps, inside the timed region "
+                                       f"({wl_rates[3] / 1e6:.0f} MB device-to-device)",
                        "promotion": ({"nccl": "global mean, NCCL all-reduce of the step counters every step",
                                       "peer": "global mean, step counters summed by one kernel over NVLink peer "
                                               "memory every step"}[args.global_promotion]
                                      if (args.global_promotion and world > 1)
                                      else "shard-local (reference --distributed semantics)"),
                        "stats_allreduce_interval": (args.stats_interval if world > 1 and not args.global_promotion
-                                                    else 0),
-                       **({"peer_exchange_timeouts": mdp.peer_status()["timeouts"]}
-                          if (args.global_promotion == "peer" and world > 1) else {})},
+                                                    else 0)},
             "e2e": e2e,
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                         "kernel": "as::k_step<fused>", "kernel_ms_avg": k_avg, "kernel_ms_median": k_med,
-                         "algorithmic_bytes_per_env_step": b_kernel, "peak_source": peak_src,
-                         "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "whole_step": {"achieved": achieved_step, "frac": achieved_step / peak,
-                                        "algorithmic_bytes_per_env_step": B_ALG,
-                                        "kernels": "k_contact_gather_paired + k_step<fused> + k_fixup_finish"}},
+            "roofline": {"bound": "hbm", "achieved": achieved_step, "peak": peak, "unit": "GB/s",
+                         "frac": achieved_step / peak,
+                         "traffic": traffic["dram_bytes_per_step"] if traffic and "dram_bytes_per_step" in traffic
+                         else None,
+                         "what": "whole step (SURVEY 8d): 652 algorithmic bytes per env-step over ms_per_step; "
+                                 "kernels k_contact_gather_paired + k_step<fused> + k_fixup_finish",
+                         "algorithmic_bytes_per_env_step": B_ALG, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved_step / 8000.0,
+                         "kernel": {"name": "as::k_step<fused>", "achieved": achieved_kernel,
+                                    "frac": achieved_kernel / peak, "ms_avg": k_avg, "ms_median": k_med,
+                                    "algorithmic_bytes_per_env_step": b_kernel,
+                                    "traffic": traffic["dram_bytes_per_launch"] if traffic else None}},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
             "step_stats": {k: stats[k] for k in ("n_reset", "n_terminated", "n_time_out", "n_advanced", "level")},
-            "other_sizes": small,
+            **blocks,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

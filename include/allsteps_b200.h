@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AS_ABI_VERSION 2
+#define AS_ABI_VERSION 3
 
 #define AS_NUM_JOINTS 21  /* CFG:57  action_space            */
 #define AS_NUM_STONES 20  /* CFG:90  num_steps               */
@@ -41,7 +41,8 @@ enum {
   AS_OK = 0,
   AS_ERR_INVALID = -1, /* bad argument (null pointer, bad size, unsupported stride ...) */
   AS_ERR_CUDA = -2,    /* a CUDA runtime call failed; as_last_error() has the CUDA message  */
-  AS_ERR_STATE = -3    /* call sequence violated (e.g. pass2 without pass1)                */
+  AS_ERR_STATE = -3,   /* call sequence violated (e.g. a fused step left open)             */
+  AS_ERR_PEER = -4     /* a peer exchange timed out earlier: sticky, the shards may have diverged */
 };
 
 /* AsParams.flags */
@@ -182,7 +183,11 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
  *         NULL = the library keeps and increments its own counter.
  * reset:  `_reset_idx(env_ids)` minus the PhysX writes: promotion rule, MDP state reset, start pose rows.
  *         Compact outputs: row i of the AsResetOut buffers belongs to env_ids[i].
- * pass2:  the second `_compute_useful_values` over ALL envs + `_get_observations`, on the post-write state. */
+ *         Called without a preceding as_step_pass1 (DirectRLEnv.reset() runs `_reset_idx(all ids)` before the first
+ *         step, DRL:256-279) it evaluates the promotion rule on the indices as they are and advances the Philox
+ *         step counter itself.
+ * pass2:  the second `_compute_useful_values` over ALL envs + `_get_observations`, on the post-write state.  No
+ *         call-order precondition (ENV:567 runs whether or not a pass preceded the reset). */
 int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_t actions_stride,
                   const int64_t* episode_length, const AsStepOut* out, void* stream);
 int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids,
@@ -246,6 +251,16 @@ typedef struct AsMdpState {
 } AsMdpState;
 int as_export_state(AsHandle* h, const AsMdpState* dst, void* stream);
 int as_import_state(AsHandle* h, const AsMdpState* src, void* stream);
+
+/* ---- exact checkpoint / resume -----------------------------------------------------------
+ * A snapshot is one opaque device blob: control block (state parity, pending promotion, Philox step counter, folded
+ * statistics, difficulty-grid histograms), the packed state words, the stone windows, the grid bins and -- with
+ * include_stones -- the stone rows (needed whenever stones can change: regeneration extensions, or a restore into a
+ * fresh handle).  as_restore puts it back; a run continued from a restored snapshot is bit-identical to the
+ * uninterrupted one (same seed / env_id_offset / num_envs).  Stream-ordered, no synchronisation. */
+int64_t as_snapshot_bytes(const AsHandle* h, int32_t include_stones);
+int as_snapshot(AsHandle* h, void* dst, int32_t include_stones, void* stream);
+int as_restore(AsHandle* h, const void* src, int32_t include_stones, void* stream);
 
 /* Stone poses in the layout PhysX takes them.  Replaces the egress of `_generate_foot_steps`,
  * ENV:119-120 -> RigidObjectCollection.write_object_pose_to_sim, rigid_object_collection.py:295-301: instead of

@@ -1023,3 +1023,80 @@ def test_programmatic_launch_chain_changes_nothing(monkeypatch):
         a, b = plain.export_state(), chained.export_state()
         for k in a:
             assert torch.equal(a[k], b[k]), f"step {step}: state {k}"
+
+
+def test_resume_from_a_checkpoint_is_bit_identical():
+    """state_dict() / load_state_dict() incl. the Philox position, the pending promotion and the
+    grid-curriculum state -- a run resumed in a FRESH handle continues bit for bit like the uninterrupted one."""
+    from allsteps_isaaclab_b200.mdp import AllstepsMDP, PhysicsViews, StepBuffers
+
+    for kw in (dict(), dict(grid_bins=5), dict(intended_regen=True)):
+        N, seed = 3000, 41
+        sc = Scenario(N, seed=seed, fall_fraction=0.2)
+        origins = sc.env_origins.cuda()
+        st0 = sc.initial_mdp_state()
+        st0["curr_target_index"] = torch.randint(11, 20, (N,), generator=sc.gen)  # promotions will happen
+
+        def fresh():
+            m = AllstepsMDP(N, device="cuda:0", seed=seed, **kw)
+            m.generate_stones(origins)
+            return m
+
+        mdp = fresh()
+        mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                              "episode_length_buf", "potentials")})
+        out = StepBuffers(N, "cuda:0")
+
+        def physics_for(m):
+            st = m.export_state()
+            phys = sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+            d = {k: v.cuda() for k, v in phys.items()}
+            return PhysicsViews.from_dict(d, origins, sc.body_indices), d
+
+        for _ in range(5):
+            v, d = physics_for(mdp)
+            mdp.step(v, d["actions"], out)
+        ckpt = mdp.state_dict()
+        assert int(ckpt["meta"][1]) == N
+        tail = [physics_for(mdp)]
+        record = []
+        for i in range(6):
+            v, d = tail[-1]
+            mdp.step(v, d["actions"], out)
+            torch.cuda.synchronize()
+            record.append({k: getattr(out, k).clone() for k in ("obs", "reward", "terminated", "time_out",
+                                                                "reset_joint_pos", "reset_root_state")})
+            record[-1]["state"] = mdp.export_state()
+            tail.append(physics_for(mdp))
+        levels = int(record[-1]["state"]["curriculum"].max())
+        resumed = fresh()
+        with pytest.raises(ValueError):
+            AllstepsMDP(N, device="cuda:0", seed=seed + 1, **kw).load_state_dict(ckpt)
+        resumed.load_state_dict(ckpt)
+        out2 = StepBuffers(N, "cuda:0")
+        for i in range(6):
+            v, d = tail[i]
+            resumed.step(v, d["actions"], out2)
+            torch.cuda.synchronize()
+            for k in ("obs", "reward", "terminated", "time_out"):
+                assert torch.equal(getattr(out2, k), record[i][k]), f"{kw} step {i}: {k} differs after the resume"
+            ids = record[i]["terminated"] | record[i]["time_out"]
+            assert torch.equal(out2.reset_joint_pos[ids], record[i]["reset_joint_pos"][ids])
+            st = resumed.export_state()
+            for k, ref in record[i]["state"].items():
+                assert torch.equal(st[k], ref), f"{kw} step {i}: state {k} differs after the resume"
+        if not kw:
+            assert levels > 0, "no promotion in the replay: the pending-promotion part of the checkpoint went untested"
+        if kw.get("grid_bins"):
+            a, b = mdp.grid_state(), resumed.grid_state()
+            for x, y in zip(a, b):
+                assert torch.equal(x, y)
+        # an in-place rewind of a live handle (what bench.py does to keep its input sets on the state they were made for)
+        snap = mdp.snapshot(include_stones=True)
+        before = mdp.export_state()
+        v, d = tail[-1]
+        mdp.step(v, d["actions"], out)
+        mdp.restore(snap, include_stones=True)
+        after = mdp.export_state()
+        for k in before:
+            assert torch.equal(before[k], after[k]), k

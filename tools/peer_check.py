@@ -3,9 +3,15 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/peer_check.py
 
 Every rank owns one env-id shard of the same seeded scenario and steps it twice per step: once closing the step with
-as_fold_stats -> NCCL all-reduce -> as_finish_step(global) and once with the peer-memory exchange kernel
+as_fold_stats -> all-reduce -> as_finish_step(global) and once with the peer-memory exchange kernel
 (AllstepsMDP.connect_peers).  Outputs, MDP state and levels must be bit-identical between the two on every rank, the
-global counters must equal the NCCL sum, and promotions must actually occur.  Then both routes are timed.
+global counters must equal the all-reduced sum, promotions must actually occur, and rank 0 also steps ONE handle
+holding all envs: every rank's shard must equal its slice of that single handle.  Then the routes are timed.
+
+PEER_CHECK_BACKEND=gloo runs the ranks as processes sharing GPU (rank % device_count) -- CUDA IPC peer memory works
+between processes on one device too -- with the all-reduce going through gloo on host copies: the same check on a
+one-GPU box.  PEER_CHECK_MODE=timeout: rank 1 connects but never steps; rank 0's exchange must time out, close the
+step on its own counters and make every later step fail with AS_ERR_PEER.
 """
 import os
 import sys
@@ -23,9 +29,32 @@ from scenario import Scenario
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    backend = os.environ.get("PEER_CHECK_BACKEND", "nccl")
+    if backend == "gloo":
+        local = rank % torch.cuda.device_count()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo")
+
+    def all_reduce(t, op=dist.ReduceOp.SUM):
+        if backend == "nccl":
+            dist.all_reduce(t, op=op)
+        else:
+            c = t.cpu()
+            dist.all_reduce(c, op=op)
+            t.copy_(c)
+
+    def all_gather_cat(t):
+        src = t.contiguous() if backend == "nccl" else t.contiguous().cpu()
+        parts = [torch.empty_like(src) for _ in range(world)]
+        dist.all_gather(parts, src)
+        return torch.cat(parts).cpu()
+
+    if os.environ.get("PEER_CHECK_MODE") == "timeout":
+        return timeout_mode(rank, world, dev)
     per = int(os.environ.get("PEER_CHECK_ENVS", "4096"))
     steps = int(os.environ.get("PEER_CHECK_STEPS", "24"))
     N, seed = per * world, 17
@@ -41,6 +70,13 @@ def main():
                                                 "episode_length_buf", "potentials")})
     nccl_mdp, peer_mdp = mdps
     assert peer_mdp.connect_peers() == (world, rank)
+    single = None
+    if rank == 0:  # ONE handle with all envs: what every shard has to reproduce
+        single = AllstepsMDP(N, device=dev, seed=seed)
+        single.generate_stones(sc.env_origins.to(dev))
+        single.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                                 "episode_length_buf", "potentials")})
+        out_single = StepBuffers(N, dev)
     outs = [StepBuffers(per, dev), StepBuffers(per, dev)]
     g = torch.zeros_like(nccl_mdp.stats_tensor)
     promotions = 0
@@ -48,21 +84,37 @@ def main():
     for step in range(steps):
         st = nccl_mdp.export_state()
         # the scenario needs the stones / indices of ALL envs: gather the shards
-        full = {}
-        for k in ("steps_pos", "curr_target_index", "swing_leg"):
-            parts = [torch.empty_like(st[k]) for _ in range(world)]
-            dist.all_gather(parts, st[k].contiguous())
-            full[k] = torch.cat(parts).cpu()
+        full = {k: all_gather_cat(st[k]) for k in ("steps_pos", "curr_target_index", "swing_leg")}
         phys = sc.physics(full["steps_pos"], full["curr_target_index"], full["swing_leg"])
         d = {k: v[sl].to(dev) for k, v in phys.items()}
         views = PhysicsViews.from_dict(d, origins, sc.body_indices)
         nccl_mdp.step(views, d["actions"], outs[0], finish=False)
         nccl_mdp.fold_stats()
         g.copy_(nccl_mdp.stats_tensor)
-        dist.all_reduce(g[:10])
+        all_reduce(g[:10])
         nccl_mdp.finish_step(g)
         peer_mdp.step(views, d["actions"], outs[1])
         torch.cuda.synchronize()
+        if single is not None:
+            dall = {k: v.to(dev) for k, v in phys.items()}
+            single.step(PhysicsViews.from_dict(dall, sc.env_origins.to(dev), sc.body_indices), dall["actions"],
+                        out_single)
+            torch.cuda.synchronize()
+        # every rank's shard against its slice of the single handle (rank 0 broadcasts the whole result)
+        for name in ("obs", "reward", "terminated", "time_out"):
+            mine = getattr(outs[1], name)
+            shape = (N,) + tuple(mine.shape[1:])
+            whole = getattr(out_single, name) if rank == 0 else torch.empty(shape, dtype=mine.dtype, device=dev)
+            whole = whole.view(torch.uint8) if whole.dtype == torch.bool else whole
+            if backend == "nccl":
+                dist.broadcast(whole, src=0)
+                whole = whole.cpu()
+            else:
+                whole = whole.cpu()
+                dist.broadcast(whole, src=0)
+            ref = whole[sl]
+            got = mine.view(torch.uint8).cpu() if mine.dtype == torch.bool else mine.cpu()
+            assert torch.equal(got, ref), f"rank {rank} step {step}: {name} differs from the single handle"
         for name in ("obs", "reward", "terminated", "time_out", "dones", "reset_joint_pos"):
             a, b = getattr(outs[0], name), getattr(outs[1], name)
             assert torch.equal(a, b), f"rank {rank} step {step}: {name} differs between the NCCL and the peer route"
@@ -93,7 +145,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
     local_mdp = AllstepsMDP(per, device=dev, seed=seed, env_id_offset=rank * per)
@@ -104,7 +156,7 @@ def main():
         nccl_mdp.step(views, d["actions"], outs[0], finish=False)
         nccl_mdp.fold_stats()
         g.copy_(nccl_mdp.stats_tensor)
-        dist.all_reduce(g[:10])
+        all_reduce(g[:10])
         nccl_mdp.finish_step(g)
 
     t_local = timed(lambda: local_mdp.step(views, d["actions"], out_l))
@@ -112,9 +164,53 @@ def main():
     t_peer = timed(lambda: peer_mdp.step(views, d["actions"], outs[1]))
     assert peer_mdp.peer_status()["timeouts"] == 0
     if rank == 0:
-        print(f"peer_check OK: world {world}, {per} envs per rank, {steps} steps, {promotions} promotions; "
-              f"us/step: shard-local {t_local:.1f}, NCCL all-reduce {t_nccl:.1f}, peer-memory exchange {t_peer:.1f}",
+        print(f"peer_check OK: world {world} ({backend}), {per} envs per rank, {steps} steps, {promotions} promotions, "
+              f"shards == single handle; us/step: shard-local {t_local:.1f}, {backend} all-reduce {t_nccl:.1f}, "
+              f"peer-memory exchange {t_peer:.1f}", flush=True)
+    dist.destroy_process_group()
+
+
+def timeout_mode(rank, world, dev):
+    """Rank 1 connects and then stays away; rank 0 must not hang, must not use a partial sum, and must refuse to go on."""
+    from allsteps_isaaclab_b200._cabi import AllstepsLibraryError
+
+    per, seed = 2048, 5
+    sc = Scenario(per * world, seed=seed)
+    sl = slice(rank * per, (rank + 1) * per)
+    origins = sc.env_origins[sl].to(dev)
+    st0 = sc.initial_mdp_state()
+    mdp = AllstepsMDP(per, device=dev, seed=seed, env_id_offset=rank * per)
+    mdp.generate_stones(origins)
+    mdp.import_state({k: st0[k][sl] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                              "episode_length_buf", "potentials")})
+    mdp.connect_peers()
+    if rank == 0:
+        twin = AllstepsMDP(per, device=dev, seed=seed, env_id_offset=0)   # same shard, shard-local promotion
+        twin.generate_stones(origins)
+        twin.import_state({k: st0[k][sl] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                                   "episode_length_buf", "potentials")})
+        st = mdp.export_state()
+        phys = sc.physics(torch.cat([st["steps_pos"].cpu()] * world), torch.cat([st["curr_target_index"].cpu()] * world),
+                          torch.cat([st["swing_leg"].cpu()] * world))
+        d = {k: v[sl].to(dev) for k, v in phys.items()}
+        views = PhysicsViews.from_dict(d, origins, sc.body_indices)
+        out, out_t = StepBuffers(per, dev), StepBuffers(per, dev)
+        mdp.step(views, d["actions"], out)        # the exchange waits ALLSTEPS_PEER_TIMEOUT_MS, then gives up
+        twin.step(views, d["actions"], out_t)
+        torch.cuda.synchronize()
+        assert torch.equal(out.obs, out_t.obs), "the timed-out step must close on the shard's own counters"
+        a, b = mdp.export_state(), twin.export_state()
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+        assert mdp.peer_status()["timeouts"] >= 1
+        try:
+            mdp.step(views, d["actions"], out)
+            raise SystemExit("a step after a peer timeout must fail")
+        except AllstepsLibraryError as e:
+            assert "(-4)" in str(e) and "timed out" in str(e), str(e)
+        print("peer_check timeout OK: the exchange gave up, the step closed shard-locally, later steps are refused",
               flush=True)
+    dist.barrier()
     dist.destroy_process_group()
 
 

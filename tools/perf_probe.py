@@ -10,42 +10,46 @@ B_ALG = 652
 
 
 def probe(N, steps=50, sets=4, warmup=10):
+    from allsteps_isaaclab_b200.workload import ChainedWorkload
+
     cfg = AllstepsCfg()
     dev = torch.device("cuda:0")
-    gen = torch.Generator(device=dev).manual_seed(1234)
     origins = syn.env_origins_grid(N, cfg.env_spacing).to(dev)
     mdp = AllstepsMDP(N, device=dev, seed=1, skip_pass2=("--skip-pass2" in sys.argv))
     mdp.generate_stones(origins)
     st0 = syn.random_mdp_state(cfg, N, torch.Generator().manual_seed(1))
     mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
                                           "episode_length_buf", "potentials")})
-    st = mdp.export_state()
-    pool = []
     isaac = "--isaac-views" in sys.argv  # slices of root_state_w (N,13) and body_state_w (N,17,13), as Isaac Lab hands out
-    for s in range(sets):
-        d = syn.random_physics_state(cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen)
-        rows = (0, 1, 2)
-        if isaac:
-            root_state = torch.zeros(N, 13, device=dev)
-            root_state[:, 0:3], root_state[:, 3:7], root_state[:, 7:10] = d["root_pos_w"], d["root_quat_w"], d["root_lin_vel_w"]
-            rows = (16, 13, 0)  # right_foot, left_foot, torso among 17 bodies
-            body_state = torch.zeros(N, 17, 13, device=dev)
-            for k, r in enumerate(rows):
-                body_state[:, r, 0:3] = d["body_pos_w"][:, k]
-            d["root_pos_w"], d["root_quat_w"], d["root_lin_vel_w"] = root_state[:, 0:3], root_state[:, 3:7], root_state[:, 7:10]
-            d["body_pos_w"] = body_state[..., 0:3]
-            d["_keep"] = (root_state, body_state)
-        pool.append((PhysicsViews.from_dict(d, origins, rows), d))
-    out = StepBuffers(N, dev, reset_rows=("--rows" in sys.argv))
+    out = StepBuffers(N, dev, reset_rows=("--no-rows" not in sys.argv))
+    # every input set is generated from the MDP state it meets; the state is rewound when the cycle restarts
+    wl = ChainedWorkload(mdp, origins, out, sets, 1234, cfg, layout="isaac" if isaac else "dense")
+    pool = wl.sets
+    l0 = mdp.launch_count
+    if "--three-call" in sys.argv:
+        ep_len = torch.zeros(N, dtype=torch.int64, device=dev)
+
+        def one():
+            k = wl.j % wl.period
+            if k == 0 and wl.j > 0:
+                wl.rewind()
+            v, d = wl.sets[k]
+            ep_len.add_(1)
+            mdp.pass1(v, d["actions"], out, episode_length=ep_len)
+            ids = out.dones.nonzero(as_tuple=False).squeeze(-1)
+            if len(ids):
+                mdp.reset(origins, ids, out, episode_length=ep_len)
+                mdp.pass2(v, out)
+            wl.j += 1
+    else:
+        one = wl.step
     for i in range(warmup):
-        v, d = pool[i % sets]
-        mdp.step(v, d["actions"], out)
+        one()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        v, d = pool[i % sets]
-        mdp.step(v, d["actions"], out)
+        one()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -54,7 +58,7 @@ def probe(N, steps=50, sets=4, warmup=10):
         buf = (ctypes.c_uint64 * 16)()
         mdp.lib.as_debug_timing(mdp.handle, buf, 1, mdp._stream())
         for i in range(warmup):
-            v, d = pool[i % sets]; mdp.step(v, d["actions"], out)
+            one()
         mdp.lib.as_debug_timing(mdp.handle, buf, 0, mdp._stream())
         n = max(buf[15], 1)
         names = ["M: start->state/window regs", "M: wait root tiles", "M: pass1+reset+pass2+stores", "M: wait at CTA barrier",
@@ -65,7 +69,8 @@ def probe(N, steps=50, sets=4, warmup=10):
             print(f"   {nm:42s} {buf[i] / n / 1965.0:7.2f} us")
     stats = mdp.read_stats()
     print(f"N={N:>8}  {ms*1e3:9.1f} us/step  {N/ms/1e6:9.3f} G env-steps/s  {N*B_ALG/ms/1e6:8.1f} GB/s alg  "
-          f"resets/step={stats['n_reset']}  launches/step={mdp.launch_count/(steps+warmup):.1f}", flush=True)
+          f"reset {100*wl.reset_rate:.1f}%  advance {100*wl.advance_rate:.1f}%  "
+          f"launches/step={(mdp.launch_count-l0)/(steps+warmup):.1f}", flush=True)
 
 
 def set_l2_fetch_granularity(nbytes):
