@@ -93,6 +93,10 @@ class AsMdpState(C.Structure):
                 ("steps_dphi", _ptr)]
 
 
+class AsMirrorJob(C.Structure):
+    _fields_ = [("in_", _ptr), ("out", _ptr), ("rows", _i64), ("kind", _i32), ("_pad", _i32)]
+
+
 # name -> (restype, argtypes); every symbol the header declares
 SIGNATURES = {
     "as_abi_version": (C.c_int, []),
@@ -112,6 +116,7 @@ SIGNATURES = {
     "as_read_stats": (C.c_int, [_ptr, C.POINTER(AsStats), _ptr]),
     "as_apply_action": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr]),
     "as_mirror_rows": (C.c_int, [_ptr, _ptr, _ptr, _i64, _i32, _ptr]),
+    "as_mirror_batch": (C.c_int, [_ptr, C.POINTER(AsMirrorJob), _i32, _ptr]),
     "as_peer_create": (C.c_int, [_ptr, C.c_int, C.c_int, _ptr]),
     "as_peer_connect": (C.c_int, [_ptr, _ptr]),
     "as_peer_status": (C.c_int, [_ptr, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64), _ptr]),

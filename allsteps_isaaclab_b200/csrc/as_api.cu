@@ -694,6 +694,30 @@ int as_mirror_rows(AsHandle* h, const float* in, float* out, int64_t rows, int32
   return check_launch(h, "k_mirror_rows");
 }
 
+int as_mirror_batch(AsHandle* h, const AsMirrorJob* jobs, int32_t n_jobs, void* stream) {
+  AS_REQUIRE(h && jobs, "null argument");
+  AS_REQUIRE(n_jobs >= 1 && n_jobs <= 4, "1..4 jobs per launch");
+  MirrorJobs mj;
+  std::memset(&mj, 0, sizeof(mj));
+  int64_t most = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    AS_REQUIRE(jobs[i].in && jobs[i].out, "job with a null pointer");
+    AS_REQUIRE(jobs[i].rows >= 0, "negative row count");
+    AS_REQUIRE(jobs[i].kind == 0 || jobs[i].kind == 1, "kind must be 0 (observations) or 1 (actions / mus)");
+    mj.in[i] = jobs[i].in;
+    mj.out[i] = jobs[i].out;
+    mj.rows[i] = jobs[i].rows;
+    mj.kind[i] = jobs[i].kind;
+    const int64_t items = jobs[i].rows * (jobs[i].kind == 0 ? kObs : kJ);
+    most = items > most ? items : most;
+  }
+  mj.n = n_jobs;
+  if (most == 0) return AS_OK;
+  const dim3 grid(static_cast<unsigned>(grid_for(most, 256 * 4, h->sm_count, 8)), static_cast<unsigned>(n_jobs));
+  k_mirror_batch<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->mirror_obs, h->mirror_act, mj);
+  return check_launch(h, "k_mirror_batch");
+}
+
 int as_export_state(AsHandle* h, const AsMdpState* dst, void* stream) {
   AS_REQUIRE(h && dst, "null argument");
   if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
@@ -823,6 +847,7 @@ int64_t as_sizeof(int32_t which) {
     case 3: return sizeof(AsResetOut);
     case 4: return sizeof(AsStats);
     case 5: return sizeof(AsMdpState);
+    case 6: return sizeof(AsMirrorJob);
     default: return -1;
   }
 }

@@ -253,18 +253,41 @@ struct MirrorTable {
   int32_t dim;
 };
 
-// ENV:570-660: rows [0,R) copy, rows [R,2R) = sign[c] * in[r][src[c]]
-__global__ void __launch_bounds__(256) k_mirror_rows(const __grid_constant__ MirrorTable t,
-                                                     const float* __restrict__ in, float* __restrict__ out,
-                                                     int64_t rows) {
+// ENV:570-660: rows [0,R) copy, rows [R,2R) = +-in[r][src[c]].  The sign is applied as a NEGATION (`-x`, what
+// ENV:593,634 do), not as a product with -1: the two differ in the bits they give a NaN.
+__device__ __forceinline__ void mirror_rows_body(const MirrorTable& t, const float* __restrict__ in,
+                                                 float* __restrict__ out, int64_t rows) {
   const int64_t total = rows * t.dim;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / t.dim;
     const int c = static_cast<int>(i - r * t.dim);
     out[i] = in[i];
-    out[total + i] = t.sign[c] * in[r * t.dim + t.src[c]];
+    const float v = in[r * t.dim + t.src[c]];
+    out[total + i] = t.sign[c] < 0.0f ? -v : v;
   }
+}
+__global__ void __launch_bounds__(256) k_mirror_rows(const __grid_constant__ MirrorTable t,
+                                                     const float* __restrict__ in, float* __restrict__ out,
+                                                     int64_t rows) {
+  mirror_rows_body(t, in, out, rows);
+}
+
+// The three tensors A2CAgentSymmetry.play_steps mirrors (obses, actions, mus: learning/a2c_ppo_mirroring.py:32-34)
+// in ONE launch: blockIdx.y picks the job.
+struct MirrorJobs {
+  const float* in[4];
+  float* out[4];
+  int64_t rows[4];
+  int32_t kind[4];  // 0 observations (dim 59), 1 actions / mus (dim 21)
+  int32_t n;
+};
+__global__ void __launch_bounds__(256) k_mirror_batch(const __grid_constant__ MirrorTable t_obs,
+                                                      const __grid_constant__ MirrorTable t_act,
+                                                      const __grid_constant__ MirrorJobs jobs) {
+  const int j = blockIdx.y;
+  if (j >= jobs.n) return;
+  mirror_rows_body(jobs.kind[j] == 0 ? t_obs : t_act, jobs.in[j], jobs.out[j], jobs.rows[j]);
 }
 
 __global__ void __launch_bounds__(256) k_export(const __grid_constant__ AsParams P, Workspace ws, AsMdpState dst,

@@ -236,6 +236,16 @@ int as_apply_action(AsHandle* h, const float* actions, int64_t actions_stride, f
  * out (2*rows, dim): rows [0,rows) = copy of `in`, rows [rows, 2*rows) = mirrored.  kind: 0 = observations
  * (dim 59), 1 = actions / mus (dim 21). */
 int as_mirror_rows(AsHandle* h, const float* in, float* out, int64_t rows, int32_t kind, void* stream);
+/* The same for up to four tensors in ONE launch -- what A2CAgentSymmetry.play_steps does to `obses`, `actions` and
+ * `mus` every PPO epoch (learning/a2c_ppo_mirroring.py:32-38 -> get_symmetric_states_rl_games, ENV:611-660). */
+typedef struct AsMirrorJob {
+  const float* in;   /* (rows, dim)                                             */
+  float* out;        /* (2*rows, dim): rows [0,rows) copy, [rows,2*rows) mirror */
+  int64_t rows;
+  int32_t kind;      /* 0 observations (dim 59), 1 actions / mus (dim 21)       */
+  int32_t _pad;
+} AsMirrorJob;
+int as_mirror_batch(AsHandle* h, const AsMirrorJob* jobs, int32_t n_jobs, void* stream);
 
 /* ---- state exchange in the reference's own layouts (checkpoint / replay / tests) -------------------------
  * All pointers device, optional (NULL = skip).  int64 arrays as in ENV:48,74-78 and DRL:179. */
@@ -291,7 +301,8 @@ int as_set_timing_events(AsHandle* h, void* start_event, void* stop_event);
 int as_debug_timing(AsHandle* h, uint64_t* host16, int reset, void* stream);
 
 /* Host-side introspection used by the tests: number of kernel launches issued by this handle so far, and
- * sizeof() of the public structs (0 AsParams, 1 AsStateIn, 2 AsStepOut, 3 AsResetOut, 4 AsStats, 5 AsMdpState)
+ * sizeof() of the public structs (0 AsParams, 1 AsStateIn, 2 AsStepOut, 3 AsResetOut, 4 AsStats, 5 AsMdpState,
+ * 6 AsMirrorJob)
  * so that a foreign-language binding can verify its struct layout. */
 int64_t as_launch_count(const AsHandle* h);
 int64_t as_sizeof(int32_t which);

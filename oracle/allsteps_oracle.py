@@ -115,6 +115,29 @@ def generate_stones(cfg, level: torch.Tensor, uniforms: torch.Tensor) -> Tuple[t
 
 
 # --------------------------------------------------------------------------------------------- the MDP
+# --------------------------------------------------------------------------------------------- mirror symmetry
+def symmetric_states(x, right_ids, left_ids, negate_ids, kind: str, num_joints: int = 21):
+    """ENV:570-660 for one tensor: `kind` "obs" (N,59) or "actions" (N,21; also used for `mus`).  Returns
+    vstack((x, mirrored(x))), or None for None."""
+    if x is None:
+        return None
+    right_ids, left_ids, negate_ids = (torch.as_tensor(t, dtype=torch.int64) for t in (right_ids, left_ids, negate_ids))
+    if kind == "obs":
+        J = num_joints
+        steps_neg = torch.tensor([3 * i + 1 for i in range(3)], dtype=torch.int64)  # y of prev / curr / next, ENV:620
+        root_neg = torch.tensor([1, 4], dtype=torch.int64)  # roll, v_y, ENV:621
+        right = torch.cat((right_ids + 6, right_ids + 6 + J, torch.tensor([6 + 2 * J])))  # ENV:623
+        left = torch.cat((left_ids + 6, left_ids + 6 + J, torch.tensor([6 + 2 * J + 1])))  # ENV:624
+        neg = torch.cat((root_neg, 6 + negate_ids, 6 + J + negate_ids, 6 + 2 * J + 2 + steps_neg))  # ENV:625
+    else:
+        right, left, neg = right_ids, left_ids, negate_ids
+    m = x.clone()
+    m[:, right] = x[:, left]
+    m[:, left] = x[:, right]
+    m[:, neg] = -x[:, neg]
+    return torch.vstack((x, m))
+
+
 class AllstepsOracle:
     """Reference-exact MDP state machine on CPU tensors (reference dtypes: int64 indices, bool masks)."""
 

@@ -6,6 +6,8 @@ allsteps_replay_n64.npz   16 consecutive MDP steps of 64 envs through the refere
                           (oracle/ref_fake_env.py hosts them): per-step synthetic physics inputs, injected uniforms,
                           and every output / MDP buffer after the step, plus the arguments of the three PhysX writes.
 stones_levels.npz         `_generate_foot_steps_allsteps` at curriculum levels 0..9 for given uniforms.
+mirror_symmetry.npz       `get_symmetric_states_rl_games` / `get_symmetric_states_rsl_rl` (ENV:570-660) on random
+                          observation / action / mu batches (incl. -0.0, inf and NaN entries).
 math_helpers.npz          euler_xyz_from_quat / quat_rotate_inverse / subtract_frame_transforms / scale_transform /
                           unscale_transform of the reference's utils/math.py on random inputs.
 """
@@ -133,6 +135,43 @@ def math_helpers(n=256, seed=11):
             "unscaled": M.unscale_transform(x, lo, hi).numpy()}
 
 
+def fake_wrapped_env(cfg, num_envs=8, device="cpu"):
+    """What the reference's symmetry helpers read from `env` (ENV:574-584): three index tensors and two batched spaces."""
+    import types
+
+    base = types.SimpleNamespace(
+        right_body_indices=torch.tensor(cfg.right_joint_indices, dtype=torch.int64, device=device),
+        left_body_indices=torch.tensor(cfg.left_joint_indices, dtype=torch.int64, device=device),
+        negation_body_indices=torch.tensor(cfg.negation_joint_indices, dtype=torch.int64, device=device),
+        observation_space=types.SimpleNamespace(shape=(num_envs, 59)),
+        action_space=types.SimpleNamespace(shape=(num_envs, 21)), device=device)
+    return types.SimpleNamespace(unwrapped=base, device=device)
+
+
+def mirror_symmetry(rows=96, seed=31):
+    ref = ref_loader.load_reference()
+    from allsteps_isaaclab_b200.config import AllstepsCfg
+
+    g = torch.Generator().manual_seed(seed)
+    obs = 3.0 * torch.randn(rows, 59, generator=g)
+    actions = torch.randn(rows, 21, generator=g)
+    mus = torch.randn(rows, 21, generator=g)
+    specials = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), float("nan")])
+    for r in range(5):   # special values in every column kind: kept / swapped / negated
+        obs[r, :] = specials[r]
+        actions[r, :] = specials[r]
+        mus[r, ::2] = specials[r]
+    env = fake_wrapped_env(AllstepsCfg())
+    o2, a2, m2 = ref.env_module.get_symmetric_states_rl_games(obs, actions, env, False, mus)
+    o3, a3 = ref.env_module.get_symmetric_states_rsl_rl(obs, actions, env)
+    n1, n2, n3 = ref.env_module.get_symmetric_states_rl_games(None, actions, env, False, None)
+    assert n1 is None and n3 is None
+    as_bits = lambda t: t.numpy().view(np.uint32).copy()  # noqa: E731  (bit patterns: NaN-safe comparisons)
+    return {"obs": as_bits(obs), "actions": as_bits(actions), "mus": as_bits(mus),
+            "rl_games_obs": as_bits(o2), "rl_games_actions": as_bits(a2), "rl_games_mus": as_bits(m2),
+            "rsl_rl_obs": as_bits(o3), "rsl_rl_actions": as_bits(a3), "actions_only": as_bits(n2)}
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "needs the reference checkout under /root/reference"
     torch.set_num_threads(1)
@@ -142,6 +181,7 @@ if __name__ == "__main__":
                         **replay(num_envs=16, steps=12, seed=5, high_index_from=-1, fall_fraction=0.0))
     np.savez_compressed(os.path.join(HERE, "stones_levels.npz"), **stones_levels())
     np.savez_compressed(os.path.join(HERE, "math_helpers.npz"), **math_helpers())
+    np.savez_compressed(os.path.join(HERE, "mirror_symmetry.npz"), **mirror_symmetry())
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -327,26 +327,77 @@ def test_action_path_and_mirror_rows():
     mdp.import_state({"curriculum": levels})
     eff = mdp.apply_action(actions.cuda())
     close(eff, orc.joint_efforts(), "joint efforts")
-    # mirror augmentation, ENV:611-660 restated with index tables
+    # mirror augmentation, ENV:570-660: against the oracle's restatement (pinned to the live reference functions in
+    # tests/test_oracle_vs_reference.py and to tests/golden/mirror_symmetry.npz)
     cfg = sc.cfg
-    right = torch.tensor(cfg.right_joint_indices)
-    left = torch.tensor(cfg.left_joint_indices)
-    neg = torch.tensor(cfg.negation_joint_indices)
+    tabs = (cfg.right_joint_indices, cfg.left_joint_indices, cfg.negation_joint_indices)
     obs = torch.randn(N, 59, generator=sc.gen)
-    steps_neg = torch.tensor([3 * i + 1 for i in range(3)])
-    right_obs = torch.cat((right + 6, right + 6 + 21, torch.tensor([6 + 42])))
-    left_obs = torch.cat((left + 6, left + 6 + 21, torch.tensor([6 + 42 + 1])))
-    neg_obs = torch.cat((torch.tensor([1, 4]), 6 + neg, 6 + 21 + neg, 6 + 42 + 2 + steps_neg))
-    m = obs.clone()
-    m[:, right_obs] = obs[:, left_obs]
-    m[:, left_obs] = obs[:, right_obs]
-    m[:, neg_obs] = -obs[:, neg_obs]
-    exact(mdp.mirror_rows(obs.cuda(), "obs"), torch.vstack((obs, m)), "mirrored observations")
-    ma = actions.clone()
-    ma[:, right] = actions[:, left]
-    ma[:, left] = actions[:, right]
-    ma[:, neg] = -actions[:, neg]
-    exact(mdp.mirror_rows(actions.cuda(), "actions"), torch.vstack((actions, ma)), "mirrored actions")
+    exact(mdp.mirror_rows(obs.cuda(), "obs"), ao.symmetric_states(obs, *tabs, "obs"), "mirrored observations")
+    exact(mdp.mirror_rows(actions.cuda(), "actions"), ao.symmetric_states(actions, *tabs, "actions"),
+          "mirrored actions")
+
+
+def test_symmetry_functions_match_the_reference_fixture():
+    """the drop-ins with the reference's signatures (ENV:570, ENV:611) and the play_steps-shaped call
+    (learning/a2c_ppo_mirroring.py:20-40) against outputs of the reference's own functions (mirror_symmetry.npz),
+    bit for bit (-0.0, inf and NaN entries included)."""
+    import types
+
+    import numpy as np
+
+    import golden_util as gu
+    from allsteps_isaaclab_b200 import symmetry
+    from allsteps_isaaclab_b200.config import AllstepsCfg
+
+    d = gu.load("mirror_symmetry.npz")
+    bits = lambda t: t.detach().cpu().contiguous().numpy().view(np.uint32)  # noqa: E731
+    f = lambda k: torch.from_numpy(d[k].view(np.float32).copy()).cuda()  # noqa: E731
+    cfg = AllstepsCfg()
+    base = types.SimpleNamespace(
+        right_body_indices=torch.tensor(cfg.right_joint_indices, device="cuda"),
+        left_body_indices=torch.tensor(cfg.left_joint_indices, device="cuda"),
+        negation_body_indices=torch.tensor(cfg.negation_joint_indices, device="cuda"),
+        observation_space=types.SimpleNamespace(shape=(8, 59)), action_space=types.SimpleNamespace(shape=(8, 21)),
+        device="cuda:0")
+    env = types.SimpleNamespace(unwrapped=base, device="cuda:0")
+    obs, actions, mus = f("obs"), f("actions"), f("mus")
+    mdp0 = symmetry._mdp_for(env)
+    l0 = mdp0.launch_count
+    o, a, m = symmetry.get_symmetric_states_rl_games(obs, actions, env, False, mus)
+    assert mdp0.launch_count == l0 + 1, "obses, actions and mus must be mirrored by ONE launch"
+    assert np.array_equal(bits(o), d["rl_games_obs"]) and np.array_equal(bits(a), d["rl_games_actions"])
+    assert np.array_equal(bits(m), d["rl_games_mus"])
+    o, a = symmetry.get_symmetric_states_rsl_rl(obs, actions, env)
+    assert np.array_equal(bits(o), d["rsl_rl_obs"]) and np.array_equal(bits(a), d["rsl_rl_actions"])
+    o, a, m = symmetry.get_symmetric_states_rl_games(None, actions, env, False, None)
+    assert o is None and m is None and np.array_equal(bits(a), d["actions_only"])
+    # A2CAgentSymmetry.play_steps, learning/a2c_ppo_mirroring.py:23-38
+    R = obs.shape[0]
+    batch = {"returns": torch.randn(R, 1, device="cuda"), "dones": torch.zeros(R, device="cuda"),
+             "values": torch.randn(R, 1, device="cuda"), "sigmas": torch.randn(R, 21, device="cuda"),
+             "neglogpacs": torch.randn(R, device="cuda"), "obses": obs, "actions": actions, "mus": mus,
+             "played_frames": R}
+    ret0 = batch["returns"].clone()
+    out = symmetry.augment_play_steps_batch(batch, env)
+    assert out["returns"].shape == (2 * R, 1) and torch.equal(out["returns"][R:], ret0)
+    assert out["dones"].shape == (2 * R,) and out["neglogpacs"].shape == (2 * R,) and out["sigmas"].shape == (2 * R, 21)
+    assert np.array_equal(bits(out["obses"]), d["rl_games_obs"]) and np.array_equal(bits(out["mus"]), d["rl_games_mus"])
+    # an env whose index tensors are not the ones the kernels are built with is refused
+    bad = types.SimpleNamespace(unwrapped=types.SimpleNamespace(**{**base.__dict__,
+                                "right_body_indices": base.left_body_indices}), device="cuda:0")
+    with pytest.raises(ValueError, match="mirror tables"):
+        symmetry.get_symmetric_states_rsl_rl(obs, actions, bad)
+    # the hooks' env serves its own handle
+    big = torch.randn(32 * 4096, 59, device="cuda")
+    o2, _ = symmetry.get_symmetric_states_rsl_rl(big, None, env)
+    torch.cuda.synchronize()
+    exact(o2, ao_sym(big.cpu(), cfg), "32 x 4096 observation rows (one PPO epoch at rl_games' default scale)")
+
+
+def ao_sym(x, cfg):
+    from oracle import allsteps_oracle as ao
+
+    return ao.symmetric_states(x, cfg.right_joint_indices, cfg.left_joint_indices, cfg.negation_joint_indices, "obs")
 
 
 def test_joint_scaling_is_bit_exact():
@@ -572,9 +623,10 @@ def test_api_misuse_is_reported():
                                                st["swing_leg"].cpu()).items()}
     views = PhysicsViews.from_dict(phys, origins)
     out = StepBuffers(N, "cuda:0")
-    with pytest.raises(_cabi.AllstepsLibraryError, match="pass1"):
-        mdp.pass2(views, out)  # pass 2 without pass 1
+    mdp.pass2(views, out)  # pass 2 without pass 1 is legal: DirectRLEnv.reset() -> _reset_idx -> ENV:567
     mdp.step(views, phys["actions"], out, finish=False)
+    with pytest.raises(_cabi.AllstepsLibraryError, match="as_finish_step"):
+        mdp.pass2(views, out)  # ... but not while a fused step is open
     with pytest.raises(_cabi.AllstepsLibraryError, match="as_finish_step"):
         mdp.step(views, phys["actions"], out)  # a fused step is still open
     with pytest.raises(_cabi.AllstepsLibraryError):

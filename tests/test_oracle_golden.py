@@ -104,3 +104,20 @@ def test_quat_rotate_inverse_known_answers():
     p = torch.randn(1024, 3, generator=g)
     local = ao.point_in_frame(p, q.float(), p + torch.einsum("nij,nj->ni", R.float(), v.float()))
     assert torch.allclose(local, v.float(), atol=1e-4)
+
+
+def test_symmetric_states_port_against_the_reference_fixture():
+    """tests/golden/mirror_symmetry.npz = outputs of the reference's own get_symmetric_states_* (ENV:570-660)."""
+    from allsteps_isaaclab_b200.config import AllstepsCfg
+    from oracle import allsteps_oracle as ao
+
+    d = gu.load("mirror_symmetry.npz")
+    cfg = AllstepsCfg()
+    tabs = (cfg.right_joint_indices, cfg.left_joint_indices, cfg.negation_joint_indices)
+    f = lambda k: torch.from_numpy(d[k].view(np.float32).copy())  # noqa: E731
+    bits = lambda t: t.numpy().view(np.uint32)  # noqa: E731
+    assert np.array_equal(bits(ao.symmetric_states(f("obs"), *tabs, "obs")), d["rl_games_obs"])
+    assert np.array_equal(bits(ao.symmetric_states(f("actions"), *tabs, "actions")), d["rl_games_actions"])
+    assert np.array_equal(bits(ao.symmetric_states(f("mus"), *tabs, "actions")), d["rl_games_mus"])
+    assert np.array_equal(d["rsl_rl_obs"], d["rl_games_obs"]) and np.array_equal(d["rsl_rl_actions"], d["rl_games_actions"])
+    assert ao.symmetric_states(None, *tabs, "obs") is None

@@ -117,3 +117,45 @@ def test_reference_cfg_constants_match_product_config():
     assert tuple(R.initial_joint_angle_range) == C.initial_joint_angle_range
     assert tuple(R.initial_joint_angle_clip_range) == C.initial_joint_angle_clip_range
     assert ref.env_module.EPSILON == C.contact_epsilon
+
+
+def test_symmetric_states_port_equals_the_live_reference_functions():
+    """`get_symmetric_states_rl_games` / `_rsl_rl` (ENV:570-660) executed from the reference checkout on
+    a fake wrapped env (three index tensors + two batched spaces) against the oracle's restatement, bit for bit."""
+    import numpy as np
+
+    from allsteps_isaaclab_b200.config import AllstepsCfg
+    from oracle import allsteps_oracle as ao
+
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as mg
+
+    ref = ref_loader.load_reference()
+    cfg = AllstepsCfg()
+    env = mg.fake_wrapped_env(cfg)
+    g = torch.Generator().manual_seed(77)
+    obs, actions, mus = torch.randn(333, 59, generator=g), torch.randn(333, 21, generator=g), torch.randn(333, 21, generator=g)
+    obs[0, :] = float("nan")
+    obs[1, :] = -0.0
+    tabs = (cfg.right_joint_indices, cfg.left_joint_indices, cfg.negation_joint_indices)
+    bits = lambda t: t.numpy().view(np.uint32)  # noqa: E731
+    o, a, m = ref.env_module.get_symmetric_states_rl_games(obs, actions, env, False, mus)
+    assert np.array_equal(bits(o), bits(ao.symmetric_states(obs, *tabs, "obs")))
+    assert np.array_equal(bits(a), bits(ao.symmetric_states(actions, *tabs, "actions")))
+    assert np.array_equal(bits(m), bits(ao.symmetric_states(mus, *tabs, "actions")))
+    o, a = ref.env_module.get_symmetric_states_rsl_rl(obs, actions, env)
+    assert np.array_equal(bits(o), bits(ao.symmetric_states(obs, *tabs, "obs")))
+    assert np.array_equal(bits(a), bits(ao.symmetric_states(actions, *tabs, "actions")))
+    # the env's index tensors are what config.py derives from the names (CFG:217-219)
+    assert env.unwrapped.right_body_indices.tolist() == [2, 3, 4, 9, 11, 12, 13, 17, 19]
+    assert env.unwrapped.left_body_indices.tolist() == [5, 6, 7, 10, 14, 15, 16, 18, 20]
+    assert env.unwrapped.negation_body_indices.tolist() == [0, 8]
+    # and the committed fixture is what the live reference produces now
+    import golden_util as gu
+
+    d = gu.load("mirror_symmetry.npz")
+    fresh = mg.mirror_symmetry()
+    for k in fresh:
+        assert np.array_equal(fresh[k], d[k]), k
