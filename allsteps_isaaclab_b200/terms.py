@@ -15,6 +15,13 @@ All terms of one env step are slices of ONE kernel launch: the first term that n
 buffer.  `env` needs: `num_envs`, `device`, `common_step_counter`, `episode_length_buf`, `scene` holding
 `env_origins` and the entities named by the params (`scene["robot"]`, `scene["foot_contacts_left/right"]`), and
 `action_manager.action` (or `env.actions`).
+
+No term steps the MDP before the first env step: `ObservationManager._prepare_terms` calls every observation term
+once AT CONSTRUCTION to read its shape (observation_manager.py:411), and `ManagerBasedRLEnv.reset()` computes
+observations after the reset events with `common_step_counter == 0`; in both cases the terms hand out the buffers as
+they are (zeros, or what `reset_allsteps` left there) and launch nothing.  Every term takes the optional parameters
+`asset_cfg` / `left_sensor_cfg` / `right_sensor_cfg` (a `SceneEntityCfg` or a name) to name its scene entities, the
+way Isaac Lab's stock terms do; `manager_cfg.py` assembles the term configurations the managers take.
 """
 from __future__ import annotations
 
@@ -34,6 +41,14 @@ OBS_SLICES = {"torso_to_feet_height": (0, 1), "root_roll_pitch": (1, 3), "root_l
 # AsStepOut.reward_terms columns (costs are positive numbers)
 REWARD_COLUMNS = {"alive": 0, "progress": 1, "roll_cost": 2, "pitch_cost": 3, "speed_cost": 4, "energy_cost": 5,
                   "action_cost": 6, "joint_at_limit_cost": 7, "step_reward": 8, "target_bonus": 9}
+DEFAULT_ENTITIES = ("robot", "foot_contacts_left", "foot_contacts_right")
+
+
+def _entity_name(cfg, default: str) -> str:
+    """A `SceneEntityCfg` (manager_base.py:250-266 resolves it against env.scene), a plain name, or None."""
+    if cfg is None:
+        return default
+    return cfg if isinstance(cfg, str) else cfg.name
 
 
 class _Binding:
@@ -41,17 +56,19 @@ class _Binding:
 
     def __init__(self, env, robot="robot", left="foot_contacts_left", right="foot_contacts_right", seed=0,
                  task_cfg: Optional[AllstepsCfg] = None):
+        from .env import resolve_robot_tables
+
         self.cfg = task_cfg or AllstepsCfg()
         self.names = (robot, left, right)
         dev = torch.device(env.device)
-        from .env import resolve_robot_tables
-
         self.body_rows, joint_limits = resolve_robot_tables(env.scene[robot], self.cfg)
         self.mdp = AllstepsMDP(env.num_envs, device=dev, cfg=self.cfg, seed=seed, joint_limits=joint_limits)
         self.buf = StepBuffers(env.num_envs, dev, reward_terms=True)
+        self.buf.obs.zero_()
+        self.buf.reward.zero_()
+        self.buf.reward_terms.zero_()
         self.mdp.generate_stones(env.scene.env_origins)
         self.epoch = None
-        self.fell = self.so_fast = self.died = None
 
     def views(self, env) -> PhysicsViews:
         robot, left, right = (env.scene[n] for n in self.names)
@@ -62,7 +79,9 @@ class _Binding:
                             env_origins=env.scene.env_origins, body_rows=self.body_rows)
 
     def ensure_pass1(self, env):
-        if self.epoch == env.common_step_counter:
+        """Pass 1 of the env step in progress, once.  Before the first step (`common_step_counter == 0`: the shape
+        probe at manager construction, the observations of the initial `reset()`) nothing is launched."""
+        if env.common_step_counter == 0 or self.epoch == env.common_step_counter:
             return
         am = getattr(env, "action_manager", None)
         actions = am.action if am is not None else env.actions
@@ -70,48 +89,50 @@ class _Binding:
         self.epoch = env.common_step_counter
 
 
-def binding(env, **kw) -> _Binding:
+def binding(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None, **kw) -> _Binding:
     b = getattr(env, _KEY, None)
     if b is None:
-        b = _Binding(env, **kw)
+        names = (_entity_name(asset_cfg, DEFAULT_ENTITIES[0]), _entity_name(left_sensor_cfg, DEFAULT_ENTITIES[1]),
+                 _entity_name(right_sensor_cfg, DEFAULT_ENTITIES[2]))
+        b = _Binding(env, *names, **kw)
         setattr(env, _KEY, b)
     return b
 
 
 # ---------------------------------------------------------------------------------------------- observations
-def _obs(env, name: str) -> torch.Tensor:
-    b = binding(env)
+def _obs(env, name: str, ent) -> torch.Tensor:
+    b = binding(env, *ent)
     b.ensure_pass1(env)  # no-op when termination/reward terms already ran this step (the usual order)
     lo, hi = OBS_SLICES[name]
     return b.buf.obs[:, lo:hi]
 
 
-def torso_to_feet_height(env) -> torch.Tensor:  # ENV:332
-    return _obs(env, "torso_to_feet_height")
+def torso_to_feet_height(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:  # ENV:332
+    return _obs(env, "torso_to_feet_height", (asset_cfg, left_sensor_cfg, right_sensor_cfg))
 
 
-def root_roll_pitch(env) -> torch.Tensor:  # ENV:333-334
-    return _obs(env, "root_roll_pitch")
+def root_roll_pitch(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:  # ENV:333-334
+    return _obs(env, "root_roll_pitch", (asset_cfg, left_sensor_cfg, right_sensor_cfg))
 
 
-def root_lin_vel_b(env) -> torch.Tensor:  # ENV:335
-    return _obs(env, "root_lin_vel_b")
+def root_lin_vel_b(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:  # ENV:335
+    return _obs(env, "root_lin_vel_b", (asset_cfg, left_sensor_cfg, right_sensor_cfg))
 
 
-def joint_pos_scaled(env) -> torch.Tensor:  # ENV:336
-    return _obs(env, "joint_pos_scaled")
+def joint_pos_scaled(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:  # ENV:336
+    return _obs(env, "joint_pos_scaled", (asset_cfg, left_sensor_cfg, right_sensor_cfg))
 
 
-def joint_vel_scaled_clipped(env) -> torch.Tensor:  # ENV:337
-    return _obs(env, "joint_vel_scaled_clipped")
+def joint_vel_scaled_clipped(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:  # ENV:337
+    return _obs(env, "joint_vel_scaled_clipped", (asset_cfg, left_sensor_cfg, right_sensor_cfg))
 
 
-def foot_contact(env) -> torch.Tensor:  # ENV:338
-    return _obs(env, "foot_contact")
+def foot_contact(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:  # ENV:338
+    return _obs(env, "foot_contact", (asset_cfg, left_sensor_cfg, right_sensor_cfg))
 
 
-def stone_targets_b(env) -> torch.Tensor:  # ENV:339
-    return _obs(env, "stone_targets_b")
+def stone_targets_b(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:  # ENV:339
+    return _obs(env, "stone_targets_b", (asset_cfg, left_sensor_cfg, right_sensor_cfg))
 
 
 OBSERVATION_TERMS = (torso_to_feet_height, root_roll_pitch, root_lin_vel_b, joint_pos_scaled,
@@ -119,43 +140,46 @@ OBSERVATION_TERMS = (torso_to_feet_height, root_roll_pitch, root_lin_vel_b, join
 
 
 # ---------------------------------------------------------------------------------------------- rewards
-def allsteps_total_reward(env) -> torch.Tensor:
+def allsteps_total_reward(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:
     """ENV:377-394 in one term.  RewardManager multiplies by `weight * dt` (reward_manager.py:148): use
-    weight = 1 / env.step_dt to reproduce the DirectRLEnv reward."""
-    b = binding(env)
+    weight = 1 / env.step_dt to reproduce the DirectRLEnv reward (to within the two roundings of `x * w * dt`)."""
+    b = binding(env, asset_cfg, left_sensor_cfg, right_sensor_cfg)
     b.ensure_pass1(env)
     return b.buf.reward
 
 
-def reward_term(env, name: str) -> torch.Tensor:
+def reward_term(env, name: str, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:
     """One of the ten terms of ENV:350-375 (see REWARD_COLUMNS; costs are returned positive, give them a negative
     weight).  Their signed sum equals `allsteps_total_reward` for envs that did not terminate."""
-    b = binding(env)
+    b = binding(env, asset_cfg, left_sensor_cfg, right_sensor_cfg)
     b.ensure_pass1(env)
     return b.buf.reward_terms[:, REWARD_COLUMNS[name]]
 
 
 # ---------------------------------------------------------------------------------------------- terminations
-def allsteps_terminated(env) -> torch.Tensor:  # ENV:401-405 fell | so_fast | died
-    b = binding(env)
+def allsteps_terminated(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:
+    """ENV:401-405 fell | so_fast | died."""
+    b = binding(env, asset_cfg, left_sensor_cfg, right_sensor_cfg)
     b.ensure_pass1(env)
     return b.buf.terminated
 
 
-def allsteps_time_out(env) -> torch.Tensor:
+def allsteps_time_out(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> torch.Tensor:
     """ENV:399: `episode_length_buf >= max_episode_length - 1` (the stock mdp.time_out uses `>= max`)."""
-    b = binding(env)
+    b = binding(env, asset_cfg, left_sensor_cfg, right_sensor_cfg)
     b.ensure_pass1(env)
     return b.buf.time_out
 
 
 # ---------------------------------------------------------------------------------------------- reset event
-def reset_allsteps(env, env_ids: torch.Tensor, write_to_sim: bool = True):
-    """EventManager `mode="reset"` term, ENV:469-567: MDP reset + start pose + PhysX writes + pass 2."""
-    b = binding(env)
+def reset_allsteps(env, env_ids, write_to_sim: bool = True, asset_cfg=None, left_sensor_cfg=None,
+                   right_sensor_cfg=None):
+    """EventManager `mode="reset"` term, ENV:469-567: MDP reset + start pose + PhysX writes + pass 2.  `env_ids` is
+    what EventManager.apply hands over (event_manager.py:219-240): an index tensor, `slice(None)` or None."""
+    b = binding(env, asset_cfg, left_sensor_cfg, right_sensor_cfg)
     b.ensure_pass1(env)
-    if env_ids is None:
-        env_ids = torch.arange(env.num_envs, device=env.device)
+    if env_ids is None or isinstance(env_ids, slice):
+        env_ids = torch.arange(env.num_envs, device=env.device)[env_ids if isinstance(env_ids, slice) else slice(None)]
     if len(env_ids) == 0:
         return
     b.mdp.reset(env.scene.env_origins, env_ids, b.buf, episode_length=env.episode_length_buf)
@@ -170,10 +194,12 @@ def reset_allsteps(env, env_ids: torch.Tensor, write_to_sim: bool = True):
 
 
 # ---------------------------------------------------------------------------------------------- curriculum
-def allsteps_level(env, env_ids: torch.Tensor) -> Dict[str, float]:
-    """CurriculumManager term (logged under Curriculum/<name>, curriculum_manager.py:103-117): the current level
-    and the statistic the promotion rule of ENV:471 looks at.  The promotion itself happens inside `reset`."""
-    b = binding(env)
-    s = b.mdp.read_stats()
-    n = max(int(s["n_envs"]), 1)
-    return {"level": float(s["level"]), "mean_target_index": float(s["sum_target_index"]) / n}
+def allsteps_level(env, env_ids, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None) -> Dict[str, torch.Tensor]:
+    """CurriculumManager term (logged under Curriculum/<name>/<key>, curriculum_manager.py:103-117): the current
+    level and the statistic the promotion rule of ENV:471 looks at, as 0-dim device tensors (the manager's `reset()`
+    does the `.item()` when it logs; computing the term itself does not synchronise).  The promotion itself happens
+    inside `reset_allsteps`."""
+    b = binding(env, asset_cfg, left_sensor_cfg, right_sensor_cfg)
+    s = b.mdp.stats_tensor  # int64 view of the device AsStats: 0 n_envs ... 8 sum_target_index ... 10 level
+    n = torch.clamp(s[0], min=1).to(torch.float32)
+    return {"level": s[10].to(torch.float32), "mean_target_index": s[8].to(torch.float32) / n}
