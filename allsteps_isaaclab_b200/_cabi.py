@@ -22,6 +22,7 @@ ABI_VERSION = 3
 FLAG_INTENDED_REGEN = 1 << 0
 FLAG_SKIP_PASS2 = 1 << 1
 FLAG_GRID_CURRICULUM = 1 << 2
+STEP_DEFER_FINISH = 1 << 0  # AsStepOut.flags
 
 LIB_NAME = "liballsteps_b200.so"
 LIB_PATH = os.environ.get("ALLSTEPS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
@@ -65,7 +66,7 @@ class AsStateIn(C.Structure):
 
 class AsStepOut(C.Structure):
     _fields_ = [("obs", _ptr), ("reward", _ptr), ("terminated", _ptr), ("time_out", _ptr), ("reward_terms", _ptr),
-                ("dones", _ptr), ("obs_clip", _f), ("_reserved", C.c_uint32)]
+                ("dones", _ptr), ("obs_clip", _f), ("flags", C.c_uint32)]
 
 
 class AsResetOut(C.Structure):

@@ -25,6 +25,7 @@ struct AsHandle {
   float obs_clip_pass1;  // AsStepOut.obs_clip of the last as_step_pass1 (applied by as_step_pass2 too)
   int pdl;             // programmatic dependent launch: >= 1 k_fixup_finish after the step kernel, >= 2 also the step
                        // kernel after the gather kernel (ALLSTEPS_PDL, default 2; 0 = plain stream order)
+  int allow_self_finish, allow_pre;  // A/B knobs (ALLSTEPS_SELF_FINISH, ALLSTEPS_PRE; default 1)
   int prefetch_tiles;  // L2 prefetch distance of the step kernel, in 128-env tiles (about one wave of CTAs)
   cudaEvent_t ev_start, ev_stop;  // optional timing hook around k_step<fused>
   PeerArgs peer;        // world > 0 after as_peer_create; buf[] complete after as_peer_connect
@@ -80,18 +81,25 @@ int num_tiles(int64_t n) { return static_cast<int>((n + kTile - 1) / kTile); }
 // fewer beats the better latency hiding of the separate gather kernel.
 constexpr int64_t kSeparateGatherMinEnvs = 1 << 17;
 
-int launch_contact_gather(AsHandle* h, const AsStateIn* in, cudaStream_t s) {
+// k_prepare*: contact norms of the current / following stone, stale stone windows, optionally the three body rows out
+// of a strided body tensor (`gather_body`), for batches that are not launch-bound.
+int launch_prepare(AsHandle* h, const AsStateIn* in, cudaStream_t s, bool gather_body = false) {
   if (h->num_envs < kSeparateGatherMinEnvs) return AS_OK;
+  PrepareArgs p;
+  p.in = *in;
+  p.ws = h->ws;
+  p.num_envs = h->num_envs;
+  p.body_dense = gather_body ? h->ws.body_dense : nullptr;
   const bool aligned = ((reinterpret_cast<uintptr_t>(in->contact_right) | reinterpret_cast<uintptr_t>(in->contact_left)) &
                         15u) == 0 && ((in->contact_right_stride | in->contact_left_stride) & 3) == 0;
   if (aligned) {  // two lanes per env: one memory request per force vector
     const unsigned blocks = static_cast<unsigned>((2 * h->num_envs + 255) / 256);
-    k_contact_gather_paired<<<blocks, 256, 0, s>>>(*in, h->ws, h->num_envs);
-    return check_launch(h, "k_contact_gather_paired");
+    k_prepare_paired<<<blocks, 256, 0, s>>>(p);
+    return check_launch(h, "k_prepare_paired");
   }
   const unsigned blocks = static_cast<unsigned>((h->num_envs + 255) / 256);
-  k_contact_gather<<<blocks, 256, 0, s>>>(*in, h->ws, h->num_envs);
-  return check_launch(h, "k_contact_gather");
+  k_prepare<<<blocks, 256, 0, s>>>(p);
+  return check_launch(h, "k_prepare");
 }
 
 int validate_state_in(const AsStateIn* in, bool need_origins) {
@@ -319,6 +327,10 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -346,6 +358,10 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
     h->prefetch_tiles = pf ? std::atoi(pf) : 0;
     const char* pdl = std::getenv("ALLSTEPS_PDL");
     h->pdl = pdl ? std::atoi(pdl) : 2;
+    const char* sf = std::getenv("ALLSTEPS_SELF_FINISH");
+    h->allow_self_finish = sf ? std::atoi(sf) : 1;
+    const char* pre = std::getenv("ALLSTEPS_PRE");
+    h->allow_pre = pre ? std::atoi(pre) : 1;
   }
   unsigned char* base = static_cast<unsigned char*>(workspace);
   h->ws.ctrl = reinterpret_cast<Ctrl*>(base + l.ctrl_off);
@@ -357,7 +373,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->ws.regen_ids = reinterpret_cast<int32_t*>(base + l.regen_ids_off);
   h->ws.regen_info = reinterpret_cast<uint8_t*>(base + l.regen_info_off);
   h->ws.bin = reinterpret_cast<uint8_t*>(base + l.bin_off);
-  h->ws.contact_pre = reinterpret_cast<float2*>(base + l.contact_pre_off);
+  h->ws.contact_pre = reinterpret_cast<float4*>(base + l.contact_pre_off);
   h->ws.body_dense = reinterpret_cast<float*>(base + l.body_dense_off);
   build_mirror_tables(h);
   build_joint_consts(h);
@@ -434,13 +450,12 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   const bool regen_enabled = grid || (h->params.flags & AS_FLAG_INTENDED_REGEN) != 0;
   a.want_reset_list = (reset_out && reset_out->reset_ids) ? 1 : 0;
   if (want_rows) a.rows = *reset_out;  // start-pose rows are written by the step kernel itself
+  bool gather_body = false;
   if (!(a.dense16 & kDenseBody) && h->num_envs >= kSeparateGatherMinEnvs) {
     // The three body rows the task reads (12 bytes each out of Isaac Lab's (N,B,13) body_state_w) are scattered
-    // reads like the contact vectors: gathered by a kernel of their own into a dense (N,3,3) array, which the step
-    // kernel (and the fix-up, which re-reads the inputs) then takes by bulk copy.
-    const unsigned blocks = static_cast<unsigned>((h->num_envs * 3 + 255) / 256);
-    k_body_gather<<<blocks, 256, 0, s>>>(*in, h->ws.body_dense, h->num_envs);
-    if (int rc = check_launch(h, "k_body_gather")) return rc;
+    // reads like the contact vectors: k_prepare* gathers them into a dense (N,3,3) array, which the step kernel (and
+    // the fix-up, which re-reads the inputs) then takes by bulk copy.
+    gather_body = true;
     a.in.body_pos = h->ws.body_dense;
     a.in.body_env_stride = 9;
     a.in.body_row_stride = 3;
@@ -449,7 +464,7 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
     a.in.torso_row = 2;
     a.dense16 |= kDenseBody;
   }
-  if (int rc = launch_contact_gather(h, in, s)) return rc;
+  if (int rc = launch_prepare(h, in, s, gather_body)) return rc;
   if (h->ev_start) AS_CUDA(cudaEventRecord(h->ev_start, s));
   // dependent of the gather kernel: tiles, state words and windows are loaded while the gather's last wave runs;
   // the MDP role waits for the gather (griddepcontrol.wait) right before it reads the contact norms
@@ -470,9 +485,18 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
        {k_step<kModeFused, 0, true, true, false>, k_step<kModeFused, 0, true, true, true>}},
       {{k_step<kModeFused, 1, true, false, false>, k_step<kModeFused, 1, true, false, true>},
        {k_step<kModeFused, 1, true, true, false>, k_step<kModeFused, 1, true, true, true>}}};
+  // behind k_prepare* (large batches, two-FMA quotients): the instantiation without any scattered access of its own
+  static const StepKernel kFullPre[2][2] = {  // [fast][packed]
+      {k_step<kModeFused, 0, true, false, false, true>, k_step<kModeFused, 0, true, false, true, true>},
+      {k_step<kModeFused, 0, true, true, false, true>, k_step<kModeFused, 0, true, true, true, true>}};
   const StepKernel ragged_kernel = k_step<kModeFused, 2, false>;
-  AS_CUDA(launch_step(h, kFull[ex][fast ? 1 : 0][packed ? 1 : 0], ragged_kernel, a, s, dep,
-                      packed ? kSmemBytesPacked : kSmemBytes));
+  const bool pre = a.use_pre && ex == 0 && h->allow_pre;
+  // the last CTA closes the step itself unless somebody else has to see the open step: the cross-shard exchange, an
+  // all-reduce the caller announced (AS_STEP_DEFER_FINISH), or the regeneration kernels launched below
+  a.self_finish = (h->allow_self_finish && !h->peer_connected && !regen_enabled &&
+                   !(out->flags & AS_STEP_DEFER_FINISH)) ? 1 : 0;
+  AS_CUDA(launch_step(h, pre ? kFullPre[fast ? 1 : 0][packed ? 1 : 0] : kFull[ex][fast ? 1 : 0][packed ? 1 : 0],
+                      ragged_kernel, a, s, dep, packed ? kSmemBytesPacked : kSmemBytes));
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
   if (h->ev_stop) AS_CUDA(cudaEventRecord(h->ev_stop, s));
   if (grid) {  // kernel (c): outcomes into the difficulty histogram, then new bins by inverse-CDF sampling
@@ -620,7 +644,7 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   a.ext_episode_length = episode_length;
   h->obs_clip_pass1 = out->obs_clip;  // as_step_pass2 rewrites the same observation buffer: same epilogue
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (int rc = launch_contact_gather(h, in, s)) return rc;
+  if (int rc = launch_prepare(h, in, s)) return rc;
   AS_CUDA(launch_step(h, k_step<kModePass1, 2, true>, k_step<kModePass1, 2, false>, a, s, false));
   if (int rc = check_launch(h, "k_step<pass1>")) return rc;
   k_fold_pass1<<<1, 128, 0, s>>>(h->ws.ctrl, h->num_envs);
@@ -668,7 +692,7 @@ int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
   out.obs = obs;
   out.obs_clip = h->obs_clip_pass1;
   StepArgs a = make_step_args(h, in, nullptr, 0, &out);
-  if (int rc = launch_contact_gather(h, in, static_cast<cudaStream_t>(stream))) return rc;
+  if (int rc = launch_prepare(h, in, static_cast<cudaStream_t>(stream))) return rc;
   AS_CUDA(launch_step(h, k_step<kModePass2, 2, true>, k_step<kModePass2, 2, false>, a, static_cast<cudaStream_t>(stream),
                       false));
   return check_launch(h, "k_step<pass2>");

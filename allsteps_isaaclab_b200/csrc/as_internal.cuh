@@ -86,7 +86,8 @@ struct Ctrl {
   AsStats gstats;                             // step counters summed over all shards (peer exchange)
   unsigned long long peer_timeouts;           // peers that did not deliver within the time limit (sticky: see peer_error)
   uint32_t peer_error;                        // != 0: a peer exchange timed out; the shards may have diverged (AS_ERR_PEER)
-  uint32_t reserved0;
+  uint32_t step_state;                        // written by the LAST CTA of every fused step kernel: 2 = it closed the step itself
+                                              // (statistics folded, promotion decided, parity flipped), 1 = k_fixup_finish has to
 };
 
 // Peer exchange buffer of one rank: for each of the two epoch parities one 128-byte slot per sending rank.
@@ -115,7 +116,8 @@ struct Workspace {
   int32_t* regen_ids; // (N)
   uint8_t* regen_info;// (N) curr_target_index at the end of the episode, parallel to regen_ids (grid curriculum)
   uint8_t* bin;       // (N) difficulty-grid bin of each env (grid curriculum extension)
-  float2* contact_pre;// (N) |F_right|, |F_left| of each env's current stone, gathered by k_contact_gather
+  float4* contact_pre;// (N) |F_right|, |F_left| under each foot for the env's CURRENT stone (.x, .y) and for the stone after it
+                      // (.z, .w: what pass 2 needs when pass 1 advances the index), gathered by k_prepare*
   float* body_dense;  // (N,3,3) right foot, left foot, torso positions gathered out of a strided body tensor (k_body_gather)
 };
 
@@ -148,7 +150,7 @@ inline WorkspaceLayout workspace_layout(int64_t n) {
   l.bin_off = off;
   off = align_up(off + n, 256);
   l.contact_pre_off = off;
-  off = align_up(off + n * 8, 256);
+  off = align_up(off + n * 16, 256);
   l.body_dense_off = off;
   off = align_up(off + n * 36, 256);
   l.total = off;
@@ -172,7 +174,8 @@ struct StepArgs {
   int32_t num_tiles;
   int32_t tile_base;                  // first tile of this launch (k_step: 0 for the full tiles, the last tile's index for a ragged tail)
   int32_t want_reset_list;            // fused: compact the ids of the envs that reset
-  int32_t use_pre;                    // 1: contact norms come from k_contact_gather (large batches), 0: gather here
+  int32_t use_pre;                    // 1: contact norms come from k_prepare* (large batches), 0: gather here
+  int32_t self_finish;                // fused: the last CTA closes the step when at least one env reset (no peers, no regeneration)
   int32_t pdl_wait;                   // 1: launched as a programmatic dependent of k_contact_gather*
   int32_t prefetch_tiles;             // the step kernel pulls the inputs of tile + prefetch_tiles into L2 (0 = off)
   uint32_t dense16;                   // per-array "dense and 16-byte aligned" bits (DenseBit), evaluated by the host

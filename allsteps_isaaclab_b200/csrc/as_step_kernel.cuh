@@ -425,6 +425,71 @@ __device__ __forceinline__ uint32_t promotion_decision(const AsParams& P, const 
   return promotion_rule(P, s.n_reset, s.sum_target_index, s.n_envs);
 }
 
+// One-warp version of fold_stats (the last CTA of the fused step kernel folds with the warp that took the ticket).
+__device__ __forceinline__ void fold_stats_warp(Ctrl* ctrl, int64_t num_envs, int lane, unsigned& n_reset_out) {
+  unsigned tot[kNumCounters];
+#pragma unroll
+  for (int c = 0; c < kNumCounters; ++c) {
+    const unsigned v = __ldcg(&ctrl->slots[lane][c]);
+    __stcg(&ctrl->slots[lane][c], 0u);
+    tot[c] = c == kCntLevelMax ? __reduce_max_sync(0xffffffffu, v) : __reduce_add_sync(0xffffffffu, v);
+  }
+  float rsum = __ldcg(&ctrl->slot_reward[lane]);
+  __stcg(&ctrl->slot_reward[lane], 0.0f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+  n_reset_out = tot[kCntReset];
+  if (lane == 0) {
+    AsStats& st = ctrl->stats;
+    st.n_envs = num_envs;
+    st.n_reset = tot[kCntReset];
+    st.n_terminated = tot[kCntTerminated];
+    st.n_time_out = tot[kCntTimeOut];
+    st.n_fell = tot[kCntFell];
+    st.n_so_fast = tot[kCntSoFast];
+    st.n_died = tot[kCntDied];
+    st.n_advanced = static_cast<int64_t>(tot[kCntAdvanced1]) + tot[kCntAdvanced2];
+    st.sum_target_index = tot[kCntSumIndex];
+    st.n_regenerated = tot[kCntRegen];
+    st.level = tot[kCntLevelMax];
+    st.step_counter = static_cast<int64_t>(ctrl->step_counter);
+    st.sum_reward = static_cast<double>(rsum);
+    ctrl->last_adv2 = tot[kCntAdvanced2];
+  }
+}
+
+// The last CTA of a fused step kernel (every CTA takes a ticket once its counters are out).  When the launch is
+// allowed to close its own step (StepArgs::self_finish: shard-local promotion, no regeneration kernels behind it) and
+// at least one env reset -- so that pass 2 for everybody was the right assumption (DRL:360) -- it does what
+// k_fixup_finish's finisher does: fold the statistics, decide the promotion of ENV:471 for the next step, flip the state
+// parity, advance the Philox step counter.  k_fixup_finish then finds step_state == 2 and returns at once.
+__device__ __forceinline__ void close_step_by_last_cta(const StepArgs& a, Ctrl* ctrl, int lane) {
+  __threadfence();
+  unsigned state = 1u;
+  if (a.self_finish) {
+    const unsigned n_reset = slot_sum(ctrl, kCntReset);
+    if (n_reset > 0 || (a.P.flags & AS_FLAG_SKIP_PASS2)) {
+      unsigned nr;
+      fold_stats_warp(ctrl, a.num_envs, lane, nr);
+      __syncwarp();
+      if (lane == 0) {
+        ctrl->stats_folded = 0;
+        ctrl->promote_cur = promotion_decision(a.P, ctrl->stats);
+        if (a.rows.n_reset) *a.rows.n_reset = static_cast<int32_t>(a.want_reset_list ? ctrl->n_reset_list : nr);
+        ctrl->parity ^= 1u;
+        ctrl->step_counter += 1ull;
+        ctrl->n_reset_list = 0;
+        ctrl->n_regen_list = 0;
+      }
+      state = 2u;
+    }
+  }
+  if (lane == 0) {
+    ctrl->blocks_done = 0;
+    ctrl->step_state = state;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ the tile
 // A CTA is 8 warps on one 128-env tile, two threads per env:
 //   warps 0-3  "MDP role"    thread t owns env t: state word, stone window, contact gathers, pass 1, dones, reward,
@@ -451,7 +516,11 @@ __device__ __forceinline__ uint32_t promotion_decision(const AsParams& P, const 
 // no L2 prefetch.  The host checks that (as_step_fused) and the instantiation drops their uniform branches.
 // (Measured: 179.3 -> 176.7 us per 1M-env step.  Also making the per-array "dense" bits compile-time constants
 // removes 45 more instructions per warp but ptxas then spills 56 instead of 20 bytes in the MDP role: 184 us.)
-template <int MODE, bool FULL, int EXACT, bool FAST = false, bool PACKED = false>
+// PRE: the launch follows k_prepare* (large batches): the contact norms of the current stone AND of the stone after it
+// come as one coalesced 16-byte record, the stone window is known to be valid and is never written here (k_prepare* of
+// the next step refreshes the records whose tag went stale) -- no scattered access is left in the hot kernel but the
+// stones 0..2 of an env that resets.
+template <int MODE, bool FULL, int EXACT, bool FAST = false, bool PACKED = false, bool PRE = false>
 __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32_t& phase_root,
                                              uint32_t& phase_joint, unsigned char* smem) {
   const AsParams& P = a.P;
@@ -566,7 +635,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   float4 s_prev = make_float4(0, 0, 0, 0), s_curr = s_prev, s_next = s_prev;
   bool win_valid = false, win_dirty = false, w3_pending = false;
   float4* s_w3 = reinterpret_cast<float4*>(smem + kOffW3);
-  float f_r = 0.0f, f_l = 0.0f;
+  float f_r = 0.0f, f_l = 0.0f, f_r_next = 0.0f, f_l_next = 0.0f;
   const float* cr_row = nullptr;
   const float* cl_row = nullptr;
   if (!joint_role && active) {
@@ -588,16 +657,18 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
     cr_row = a.in.contact_right + e * a.in.contact_right_stride;
     cl_row = a.in.contact_left + e * a.in.contact_left_stride;
-    if (a.use_pre) {  // |F| of the current stone under each foot, gathered by k_contact_gather just before
+    if (PRE || a.use_pre) {  // |F| of the current (and the following) stone under each foot, gathered by k_prepare* just before
       if (a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
-      const float2 pre = a.ws.contact_pre[e];
+      const float4 pre = a.ws.contact_pre[e];
       f_r = pre.x;
       f_l = pre.y;
+      f_r_next = pre.z;
+      f_l_next = pre.w;
     } else {  // small batches are launch-bound: the gathers stay in this kernel and a launch is saved
       f_r = contact_norm(cr_row, m.idx, contact_aligned);
       f_l = contact_norm(cl_row, m.idx, contact_aligned);
     }
-    win_valid = __float_as_int(w0.w) == m.idx;
+    win_valid = PRE || __float_as_int(w0.w) == m.idx;
     if (win_valid) {
       s_prev = w0; s_curr = w1; s_next = w2;
     } else {  // stale cache (first use, or the fix-up re-reading an env the step already advanced): gather
@@ -764,8 +835,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         // ---- pass 2 over ALL envs, ENV:567, on unchanged physics: only the foot state machine can
         // change anything.  Assumed to happen; the fix-up kernel undoes the assumption when no env reset.
         if (idx_after_pass1 != idx_before) {  // the current stone changed in pass 1: new contact column
-          f_r = contact_norm(cr_row, m.idx, contact_aligned);
-          f_l = contact_norm(cl_row, m.idx, contact_aligned);
+          if (PRE) {  // (the index moved by exactly one: the record's second pair)
+            f_r = f_r_next;
+            f_l = f_l_next;
+          } else {
+            f_r = contact_norm(cr_row, m.idx, contact_aligned);
+            f_l = contact_norm(cl_row, m.idx, contact_aligned);
+          }
           geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
         }
         const bool moved = foot_update(P, geom, m, po);
@@ -782,7 +858,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       sw.x = pack_state(m.idx, m.leg, m.count, level, ep);
       sw.y = __float_as_uint(m.pot);
       st_out[e] = sw;
-      if ((win_dirty || !win_valid) && !regen) {  // (a regenerated env's window is written by the regeneration kernel)
+      if (!PRE && (win_dirty || !win_valid) && !regen) {  // (a regenerated env's window is written by the regeneration kernel)
         s_prev.w = __int_as_float(m.idx);  // tag
         wrow[0] = s_prev; wrow[1] = s_curr; wrow[2] = s_next;
         // Entry 3 is a stone this step never looked at: a gather out of the stone row.  Loading it into a register
@@ -1092,103 +1168,173 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     __syncthreads();
     for (int i = tid; i < n_valid * kObs; i += kThreads) obs_dst[i] = s_obs[i];
   }
-  if (kStats && tid <= kCntLevelMax) {  // CTA totals -> one replicated global slot (fire and forget)
-    unsigned tot = 0;
-#pragma unroll
-    for (int w = 0; w < kTile / 32; ++w) tot = tid == kCntLevelMax ? max(tot, misc->wcnt[w][tid]) : tot + misc->wcnt[w][tid];
+  unsigned ticket = 0;
+  if (kStats && warp == 0) {  // CTA totals -> one replicated global slot (fire and forget), by the first warp
     const int slot = blockIdx.x & (kSlots - 1);
-    if (tot) {
-      if (tid == kCntLevelMax) atomicMax(&ctrl->slots[slot][tid], tot);
-      else atomicAdd(&ctrl->slots[slot][tid], tot);
-    }
-  }
-  if (kStats && tid == 32) {
-    float rs = 0.0f;
+    if (lane <= kCntLevelMax) {
+      unsigned tot = 0;
 #pragma unroll
-    for (int w = 0; w < kTile / 32; ++w) rs += misc->wreward[w];
-    atomicAdd(&ctrl->slot_reward[blockIdx.x & (kSlots - 1)], rs);
+      for (int w = 0; w < kTile / 32; ++w) tot = lane == kCntLevelMax ? max(tot, misc->wcnt[w][lane]) : tot + misc->wcnt[w][lane];
+      if (tot) {
+        if (lane == kCntLevelMax) atomicMax(&ctrl->slots[slot][lane], tot);
+        else atomicAdd(&ctrl->slots[slot][lane], tot);
+      }
+    } else if (lane == kCntLevelMax + 1) {
+      float rs = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kTile / 32; ++w) rs += misc->wreward[w];
+      atomicAdd(&ctrl->slot_reward[slot], rs);
+    }
+    if (MODE == kModeFused) {
+      // "last CTA closes the step": a ticket per CTA, taken after this CTA's counters are out (fence), by the one
+      // thread that has to wait for the bulk store anyway -- the atomic's round trip hides behind that wait
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        ticket = atomicAdd(&ctrl->blocks_done, 1u) + 1u;
+      }
+    }
   }
 #ifdef AS_TIMING
   AS_T(t_w0);
 #endif
-  if (!joint_role) {  // deferred write-back of window entry 3 (the copy was issued microseconds ago)
+  if (!PRE && !joint_role) {  // deferred write-back of window entry 3 (the copy was issued microseconds ago)
     cp_async_wait_all();
     if (w3_pending) wrow[3] = s_w3[t];
   }
   if (tid == 0 && b_obs) bulk_wait_read_all();  // shared memory must stay intact until the engine has read it
+  if (MODE == kModeFused && warp == 0) {
+    const bool last = __shfl_sync(0xffffffffu, ticket, 0) == static_cast<unsigned>(a.num_tiles);
+    if (last) close_step_by_last_cta(a, ctrl, lane);
+  }
 #ifdef AS_TIMING
   if (tid == 0) { AS_T(t_w1); AS_TACC(6, t_w0, t_w1); AS_TACC(7, t_start, t_w1); atomicAdd(&ctrl->dbg_t[15], 1ull); }
 #endif
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-// The data-dependent part of the step's input: for every env the 12-byte contact-force vectors of its CURRENT stone
-// out of the two (N,1,S,3) PhysX matrices (ENV:421-425).  These random DRAM reads are what floors the step
-// (profiles/r01_membound_probe.txt); as a kernel of their own they run at full occupancy with nothing else on the
-// critical path -- state word (coalesced) -> two gathers -> one coalesced 8-byte store -- instead of stalling a
-// 46-KB CTA of the step kernel, which then reads the two norms as a coalesced record.
-__global__ void __launch_bounds__(256) k_contact_gather(const AsStateIn in, Workspace ws, int64_t num_envs) {
+// k_prepare*: everything data-dependent and scattered that a step reads, done by a kernel of its own at full occupancy
+// with nothing else on its critical path, and handed to the step kernel as coalesced records:
+//   * for every env the norms of the 12-byte contact-force vectors of its CURRENT stone and of the stone AFTER it (the
+//     one pass 2 looks at when pass 1 advances the index) out of the two (N,1,S,3) PhysX matrices, ENV:421-425 -- the
+//     two vectors are neighbours in the row, so the second one rides in the same 64-byte fills as the first;
+//   * the stone window of every env whose record went stale (the index moved or the env reset in the last step):
+//     stones idx-1 .. idx+2 out of its 320-byte stone row, tagged with idx -- the step kernel only reads windows;
+//   * optionally the three body rows the task reads (right foot, left foot, torso: 12 bytes each) out of a strided
+//     (N,B,13) body_state_w tensor into a dense (N,3,3) array the step kernel takes by bulk copy.
+// These random DRAM reads are what floors the step (profiles/r01_membound_probe.txt); issued from inside the step
+// kernel they stall a 46-KB CTA each.
+struct PrepareArgs {
+  AsStateIn in;
+  Workspace ws;
+  int64_t num_envs;
+  float* body_dense;  // non-null: gather the body rows
+};
+
+__device__ __forceinline__ void refresh_window_entry(const Workspace& ws, int64_t e, int idx, int slot) {
+  float4 v = ldg64_f4(ws.stones + e * kS + window_slot_stone(idx, slot));
+  if (slot == 0) v.w = __int_as_float(idx);  // tag
+  ws.window[e * 4 + slot] = v;
+}
+
+// One lane per env (rows that are not 16-byte aligned).
+__global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ PrepareArgs a) {
   asm volatile("griddepcontrol.launch_dependents;");
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (e >= num_envs) return;
-  const bool aligned = ((reinterpret_cast<uintptr_t>(in.contact_right) | reinterpret_cast<uintptr_t>(in.contact_left)) &
-                        15u) == 0 && ((in.contact_right_stride | in.contact_left_stride) & 3) == 0;
-  const int idx = state_idx(ws.state[ws.ctrl->parity][e].x);
-  const float f_r = contact_norm(in.contact_right + e * in.contact_right_stride, idx, aligned);
-  const float f_l = contact_norm(in.contact_left + e * in.contact_left_stride, idx, aligned);
-  ws.contact_pre[e] = make_float2(f_r, f_l);
+  if (e >= a.num_envs) return;
+  const AsStateIn& in = a.in;
+  const int idx = state_idx(a.ws.state[a.ws.ctrl->parity][e].x);
+  const int nxt = min(idx + 1, kS - 1);
+  const float4 w0 = a.ws.window[e * 4];
+  const float* rr = in.contact_right + e * in.contact_right_stride;
+  const float* lr = in.contact_left + e * in.contact_left_stride;
+  a.ws.contact_pre[e] = make_float4(contact_norm(rr, idx, false), contact_norm(lr, idx, false),
+                                    contact_norm(rr, nxt, false), contact_norm(lr, nxt, false));
+  if (__float_as_int(w0.w) != idx) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) refresh_window_entry(a.ws, e, idx, k);
+  }
+  if (a.body_dense) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int row = b == 0 ? in.right_foot_row : (b == 1 ? in.left_foot_row : in.torso_row);
+      const float* src = in.body_pos + e * in.body_env_stride + row * in.body_row_stride;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) a.body_dense[e * 9 + b * 3 + k] = ldg64_f(src + k);
+    }
+  }
 }
 
-// The body rows of the task (right foot, left foot, torso: 12 bytes each) out of a strided body tensor, one thread per
-// (env, body), into a dense (N,3,3) array.  From 131 072 envs up this replaces the cooperative strided loads inside
-// the step kernel (which end in a CTA barrier): Isaac Lab's (N,17,13) body_state_w costs 192 B of DRAM fills per env
-// for 36 B either way, but here they are hidden by full occupancy.
-__global__ void __launch_bounds__(256) k_body_gather(const AsStateIn in, float* __restrict__ dense, int64_t num_envs) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= num_envs * 3) return;
-  const int64_t e = i / 3;
-  const int b = static_cast<int>(i - e * 3);
-  const int row = b == 0 ? in.right_foot_row : (b == 1 ? in.left_foot_row : in.torso_row);
-  const float* src = in.body_pos + e * in.body_env_stride + row * in.body_row_stride;
-  dense[i * 3 + 0] = ldg64_f(src);
-  dense[i * 3 + 1] = ldg64_f(src + 1);
-  dense[i * 3 + 2] = ldg64_f(src + 2);
-}
-
-// Same gather with TWO lanes per env: the even lane fetches the 16-byte chunk the vector starts in, the odd lane the
-// following chunk when the vector runs into it, in ONE load instruction.  The two chunks then travel as one request
-// whenever they share a 128-byte line, which is what counts when the matrices live in pinned host memory: PCIe reads
-// are bound by the number of requests in flight, not by their size (tools/e2e_probe.py).  Needs 16-byte aligned rows.
-__global__ void __launch_bounds__(256) k_contact_gather_paired(const AsStateIn in, Workspace ws, int64_t num_envs) {
+// TWO lanes per env: the even lane fetches the 16-byte chunk the current stone's vector starts in, the odd lane the
+// following chunk, in ONE load instruction per foot -- the two chunks travel as one request whenever they share a
+// 128-byte line, which is what counts when the matrices live in pinned host memory: PCIe reads are bound by the number
+// of requests in flight, not by their size (tools/e2e_probe.py).  The six floats of the two vectors start at float
+// k = (3 idx) & 3 of the first chunk: for k = 3 they run into a third chunk, which the even lane fetches too.
+// Needs 16-byte aligned rows.
+__global__ void __launch_bounds__(256) k_prepare_paired(const __grid_constant__ PrepareArgs a) {
   asm volatile("griddepcontrol.launch_dependents;");  // the step kernel may stage its tiles under our last wave
+  const AsStateIn& in = a.in;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t e = t >> 1;
-  const bool live = e < num_envs;  // both lanes of a pair agree; no early exit, the shuffles below need the warp
+  const bool live = e < a.num_envs;  // both lanes of a pair agree; no early exit, the shuffles below need the warp
   const int half = static_cast<int>(t & 1);
-  const int idx = live ? state_idx(ws.state[ws.ctrl->parity][e].x) : 0;
+  const int idx = live ? state_idx(a.ws.state[a.ws.ctrl->parity][e].x) : 0;
+  float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) w0 = a.ws.window[e * 4];  // (both lanes: one request)
   const int o = idx * 3;
   const int k = o & 3;
-  const bool fetch = live && (half == 0 || k >= 2);
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f), l = r;
-  if (fetch) {
-    r = ldg64_f4(reinterpret_cast<const float4*>(in.contact_right + e * in.contact_right_stride) + (o >> 2) + half);
-    l = ldg64_f4(reinterpret_cast<const float4*>(in.contact_left + e * in.contact_left_stride) + (o >> 2) + half);
+  const bool has_next = idx < kS - 1;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f), l = r, r2 = r, l2 = r;
+  if (live) {
+    const float4* rrow = reinterpret_cast<const float4*>(in.contact_right + e * in.contact_right_stride) + (o >> 2);
+    const float4* lrow = reinterpret_cast<const float4*>(in.contact_left + e * in.contact_left_stride) + (o >> 2);
+    // chunk 1 is needed unless the row ends with this stone's vector (idx = S-1 has k = 1: inside chunk 0)
+    if (half == 0 || has_next || k >= 2) {
+      r = ldg64_f4(rrow + half);
+      l = ldg64_f4(lrow + half);
+    }
+    if (half == 0 && k == 3 && has_next) {  // floats 3..8: the tail of the second vector sits in a third chunk
+      r2 = ldg64_f4(rrow + 2);
+      l2 = ldg64_f4(lrow + 2);
+    }
   }
-  // the odd lane's first two floats are all the even lane can need from the second chunk
-  const float r1x = __shfl_down_sync(0xffffffffu, r.x, 1), r1y = __shfl_down_sync(0xffffffffu, r.y, 1);
-  const float l1x = __shfl_down_sync(0xffffffffu, l.x, 1), l1y = __shfl_down_sync(0xffffffffu, l.y, 1);
+  // the six floats as f[k .. k+5] of the concatenation chunk0 (even lane) | chunk1 (odd lane) | chunk2 (even lane)
+  float rc[12], lc[12];
+  rc[0] = r.x; rc[1] = r.y; rc[2] = r.z; rc[3] = r.w;
+  lc[0] = l.x; lc[1] = l.y; lc[2] = l.z; lc[3] = l.w;
+  rc[4] = __shfl_down_sync(0xffffffffu, r.x, 1); rc[5] = __shfl_down_sync(0xffffffffu, r.y, 1);
+  rc[6] = __shfl_down_sync(0xffffffffu, r.z, 1); rc[7] = __shfl_down_sync(0xffffffffu, r.w, 1);
+  lc[4] = __shfl_down_sync(0xffffffffu, l.x, 1); lc[5] = __shfl_down_sync(0xffffffffu, l.y, 1);
+  lc[6] = __shfl_down_sync(0xffffffffu, l.z, 1); lc[7] = __shfl_down_sync(0xffffffffu, l.w, 1);
+  rc[8] = r2.x; rc[9] = 0.f; rc[10] = 0.f; rc[11] = 0.f;
+  lc[8] = l2.x; lc[9] = 0.f; lc[10] = 0.f; lc[11] = 0.f;
+  if (live) {
+    const bool stale = __float_as_int(w0.w) != idx;
+    if (stale) {  // lane h rewrites entries 2h, 2h+1 of the record
+      refresh_window_entry(a.ws, e, idx, 2 * half);
+      refresh_window_entry(a.ws, e, idx, 2 * half + 1);
+    }
+    if (a.body_dense) {  // even lane: the two feet, odd lane: the torso
+      const int b0 = half ? 2 : 0, b1 = half ? 3 : 2;
+      for (int b = b0; b < b1; ++b) {
+        const int row = b == 0 ? in.right_foot_row : (b == 1 ? in.left_foot_row : in.torso_row);
+        const float* src = in.body_pos + e * in.body_env_stride + row * in.body_row_stride;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a.body_dense[e * 9 + b * 3 + c] = ldg64_f(src + c);
+      }
+    }
+  }
   if (!live || half) return;
-  float rx, ry, rz, lx, ly, lz;
-  if (k == 0) {
-    rx = r.x; ry = r.y; rz = r.z; lx = l.x; ly = l.y; lz = l.z;
-  } else if (k == 1) {
-    rx = r.y; ry = r.z; rz = r.w; lx = l.y; ly = l.z; lz = l.w;
-  } else if (k == 2) {
-    rx = r.z; ry = r.w; rz = r1x; lx = l.z; ly = l.w; lz = l1x;
-  } else {
-    rx = r.w; ry = r1x; rz = r1y; lx = l.w; ly = l1x; lz = l1y;
+  float v[6], u[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {  // select by k without dynamic indexing of the register arrays
+    v[i] = k == 0 ? rc[i] : (k == 1 ? rc[i + 1] : (k == 2 ? rc[i + 2] : rc[i + 3]));
+    u[i] = k == 0 ? lc[i] : (k == 1 ? lc[i + 1] : (k == 2 ? lc[i + 2] : lc[i + 3]));
   }
-  ws.contact_pre[e] = make_float2(norm3(rx, ry, rz), norm3(lx, ly, lz));  // ENV:421-424
+  const float f_r = norm3(v[0], v[1], v[2]), f_l = norm3(u[0], u[1], u[2]);  // ENV:421-424
+  const float f_r2 = has_next ? norm3(v[3], v[4], v[5]) : f_r;
+  const float f_l2 = has_next ? norm3(u[3], u[4], u[5]) : f_l;
+  a.ws.contact_pre[e] = make_float4(f_r, f_l, f_r2, f_l2);
 }
 
 #ifndef AS_STEP_MIN_CTAS
@@ -1197,7 +1343,7 @@ __global__ void __launch_bounds__(256) k_contact_gather_paired(const AsStateIn i
 // FULL = true: the grid covers the full tiles; FULL = false: a one-CTA launch for the ragged last tile (tile_base =
 // its index).  Two kernels, not a branch in one: compiled together, the ragged instantiation more than doubles the
 // code and its register needs leak into the allocation of the hot one (ptxas: 246 instead of 56 spilled bytes).
-template <int MODE, int EXACT, bool FULL, bool FAST = false, bool PACKED = false>
+template <int MODE, int EXACT, bool FULL, bool FAST = false, bool PACKED = false, bool PRE = false>
 __global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + kOffMisc);
@@ -1217,12 +1363,14 @@ __global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __gri
   uint32_t phase_root = 0, phase_joint = 0;
   const int tile = FULL ? static_cast<int>(blockIdx.x) : a.tile_base;  // (full tiles start at 0; the ragged launch is one CTA)
   static_assert(!PACKED || FULL, "a packed root tile needs a full tile (its byte count must be a multiple of 16)");
-  process_tile<MODE, FULL, EXACT, FAST, PACKED>(a, tile, phase_root, phase_joint, smem);
+  static_assert(!PRE || (FULL && MODE == kModeFused), "the prepared path is the full-tile fused step");
+  process_tile<MODE, FULL, EXACT, FAST, PACKED, PRE>(a, tile, phase_root, phase_joint, smem);
 }
 
 // as_fold_stats: fold early so that the caller can all-reduce the statistics before as_finish_step.
 __global__ void __launch_bounds__(128) k_fold_early(Ctrl* ctrl, int64_t num_envs) {
   __shared__ unsigned int fold[kNumCounters];
+  if (__ldcg(&ctrl->step_state) == 2u) return;  // (the step closed itself: the totals are in ctrl->stats already)
   fold_stats(ctrl, fold, num_envs);
   if (threadIdx.x == 0) ctrl->stats_folded = 1;
 }
@@ -1335,6 +1483,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
   Ctrl* ctrl = a.ws.ctrl;
   const int tid = threadIdx.x;
   asm volatile("griddepcontrol.wait;" ::: "memory");  // (returns at once unless launched as a programmatic dependent)
+  if (__ldcg(&ctrl->step_state) == 2u) return;  // the step kernel's last CTA closed the step itself (the common case)
   const bool prefolded = ctrl->stats_folded != 0;  // as_fold_stats ran: the slots are empty, the totals are in stats
   if (tid < 32) {
     // "did any env reset" (DRL:359-360) is a property of ALL envs: with a global sum at hand, that one decides

@@ -223,6 +223,8 @@ class AllstepsMDP:
         if actions.dim() != 2 or actions.shape != (self.num_envs, NUM_JOINTS) or actions.stride(1) != 1:
             raise ValueError("actions must be (N,21) with unit inner stride")
         stride = actions.stride(0) if self.num_envs > 1 else NUM_JOINTS
+        # finish=False announces as_fold_stats + an all-reduce + as_finish_step(global): the step must stay open
+        out.step_out.flags = 0 if finish else _cabi.STEP_DEFER_FINISH
         _cabi.check(self.lib.as_step_fused(self.handle, C.byref(views.struct), actions.data_ptr(), stride,
                                            C.byref(out.step_out), C.byref(out.reset_out), self._stream()),
                     "as_step_fused")

@@ -122,8 +122,15 @@ typedef struct AsStepOut {
                             RlGamesVecEnvWrapper._process_obs (isaaclab_rl/rl_games.py:293; NaN is kept, like
                             torch.clamp), so the wrapper can hand the buffer on as it is.  0: raw (ENV:326-345).
                             as_step_pass2 applies the value given to the as_step_pass1 before it.           */
-  uint32_t _reserved;
+  uint32_t flags;        /* AS_STEP_* bits                                                                 */
 } AsStepOut;
+/* AsStepOut.flags */
+enum {
+  AS_STEP_DEFER_FINISH = 1u << 0  /* as_step_fused: the caller is going to call as_fold_stats and hand the summed
+                                     statistics to as_finish_step(global_stats) -- the step kernel must leave the step
+                                     open (by default its last CTA closes the step itself and as_finish_step only
+                                     checks a flag) */
+};
 
 /* What `_reset_idx` hands to PhysX (ENV:563-565).  Rows are written AT THE ENV'S OWN ROW (full-size buffers),
  * only for envs that reset; `reset_ids[0 .. *n_reset)` lists them (unordered).  All optional. */
