@@ -22,6 +22,7 @@ ABI_VERSION = 3
 FLAG_INTENDED_REGEN = 1 << 0
 FLAG_SKIP_PASS2 = 1 << 1
 FLAG_GRID_CURRICULUM = 1 << 2
+FLAG_MISSED_STEP = 1 << 3
 STEP_DEFER_FINISH = 1 << 0  # AsStepOut.flags
 
 LIB_NAME = "liballsteps_b200.so"
@@ -45,7 +46,7 @@ class AsParams(C.Structure):
         ("clip_lower", _f), ("clip_upper", _f), ("default_root_pos", _f * 3),
         ("joint_lower", _f * NUM_JOINTS), ("joint_upper", _f * NUM_JOINTS), ("joint_gears", _f * NUM_JOINTS),
         ("reset_pose", _f * NUM_JOINTS), ("mirror_src", _i32 * NUM_JOINTS), ("mirror_sign", _f * NUM_JOINTS),
-        ("flags", C.c_uint32), ("grid_bins", C.c_uint32), ("seed", C.c_uint64),
+        ("missed_step_height", _f), ("flags", C.c_uint32), ("grid_bins", C.c_uint32), ("seed", C.c_uint64),
     ]
 
 
@@ -79,6 +80,7 @@ class AsStats(C.Structure):
         ("n_envs", _i64), ("n_reset", _i64), ("n_terminated", _i64), ("n_time_out", _i64), ("n_fell", _i64),
         ("n_so_fast", _i64), ("n_died", _i64), ("n_advanced", _i64), ("sum_target_index", _i64),
         ("n_regenerated", _i64), ("level", _i64), ("step_counter", _i64), ("sum_reward", C.c_double),
+        ("n_missed", _i64),
     ]
 
     def as_dict(self):

@@ -89,6 +89,8 @@ class AllstepsCfg:
     # --- terminations (CFG:228, ENV:402) ----------------------------------------------------------------
     termination_height_absolute: float = 0.4
     max_root_speed: float = 5.0
+    # extension (no reference counterpart): missed-step termination, used when AS_FLAG_MISSED_STEP is set
+    missed_step_height: float = 0.05
     # --- reset (CFG:232-233, ENV:505-511, WALKER:36-39) -------------------------------------------------
     initial_joint_angle_range: Tuple[float, float] = (-0.1, 0.1)
     initial_joint_angle_clip_range: Tuple[float, float] = (-0.95, 0.95)

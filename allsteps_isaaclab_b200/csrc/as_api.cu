@@ -456,6 +456,7 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
     // reads like the contact vectors: k_prepare* gathers them into a dense (N,3,3) array, which the step kernel (and
     // the fix-up, which re-reads the inputs) then takes by bulk copy.
     gather_body = true;
+    a.body_from_prepare = 1;
     a.in.body_pos = h->ws.body_dense;
     a.in.body_env_stride = 9;
     a.in.body_row_stride = 3;

@@ -30,6 +30,7 @@ enum Counter {
   kCntSumIndex,   // sum of curr_target_index after pass 1 (numerator of ENV:471)
   kCntRegen,
   kCntLevelMax,   // max curriculum level seen (combined with max, not add)
+  kCntMissed,     // AS_FLAG_MISSED_STEP: envs terminated by a missed step
   kNumCounters = 12
 };
 
@@ -176,7 +177,8 @@ struct StepArgs {
   int32_t want_reset_list;            // fused: compact the ids of the envs that reset
   int32_t use_pre;                    // 1: contact norms come from k_prepare* (large batches), 0: gather here
   int32_t self_finish;                // fused: the last CTA closes the step when at least one env reset (no peers, no regeneration)
-  int32_t pdl_wait;                   // 1: launched as a programmatic dependent of k_contact_gather*
+  int32_t pdl_wait;                   // 1: launched as a programmatic dependent of k_prepare*
+  int32_t body_from_prepare;          // 1: in.body_pos is the dense array k_prepare* of this step writes
   int32_t prefetch_tiles;             // the step kernel pulls the inputs of tile + prefetch_tiles into L2 (0 = off)
   uint32_t dense16;                   // per-array "dense and 16-byte aligned" bits (DenseBit), evaluated by the host
   float inv_step_dt;                  // RN(1 / P.step_dt) for the two-FMA quotient of ENV:416 (see JointConsts::exact_div)

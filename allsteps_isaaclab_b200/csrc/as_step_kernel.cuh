@@ -408,6 +408,7 @@ __device__ __forceinline__ void fold_stats(Ctrl* ctrl, unsigned int* fold, int64
     st.n_regenerated = fold[kCntRegen];
     st.level = fold[kCntLevelMax];
     st.step_counter = static_cast<int64_t>(ctrl->step_counter);
+    st.n_missed = fold[kCntMissed];
     ctrl->last_adv2 = fold[kCntAdvanced2];
   }
   if (t == 32) ctrl->stats.sum_reward = static_cast<double>(rsum);
@@ -454,6 +455,7 @@ __device__ __forceinline__ void fold_stats_warp(Ctrl* ctrl, int64_t num_envs, in
     st.level = tot[kCntLevelMax];
     st.step_counter = static_cast<int64_t>(ctrl->step_counter);
     st.sum_reward = static_cast<double>(rsum);
+    st.n_missed = tot[kCntMissed];
     ctrl->last_adv2 = tot[kCntAdvanced2];
   }
 }
@@ -586,13 +588,19 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         if (b_rq) bulk_g2s(smem_u32(s_rq), a.in.root_quat + env0 * 4, nv * 16, bar_root);
         if (b_rv) bulk_g2s(smem_u32(s_rv), a.in.root_lin_vel + env0 * 3, nv * 12, bar_root);
       }
-      if (b_body) bulk_g2s(smem_u32(s_body), a.in.body_pos + env0 * 9, nv * 36, bar_root);
+      if (b_body && !a.body_from_prepare) bulk_g2s(smem_u32(s_body), a.in.body_pos + env0 * 9, nv * 36, bar_root);
     }
     if (bulk_joint) {
       mbar_arrive_expect_tx(bar_joint, (b_jp ? nv * kJ * 4 : 0) + (b_jv ? nv * kJ * 4 : 0) + (b_act ? nv * kJ * 4 : 0));
       if (b_jp) bulk_g2s(smem_u32(s_jp), a.in.joint_pos + env0 * kJ, nv * kJ * 4, bar_joint);
       if (b_jv) bulk_g2s(smem_u32(s_jv), a.in.joint_vel + env0 * kJ, nv * kJ * 4, bar_joint);
       if (b_act) bulk_g2s(smem_u32(s_act), a.actions + env0 * kJ, nv * kJ * 4, bar_joint);
+    }
+    if (b_body && a.body_from_prepare) {
+      // the dense body rows are being written by k_prepare*, whose last wave this kernel may overlap (programmatic
+      // dependent launch): everything else is in flight, this one copy waits for the primary to complete
+      if (a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+      bulk_g2s(smem_u32(s_body), a.in.body_pos + env0 * 9, nv * 36, bar_root);
     }
   }
 
@@ -639,10 +647,12 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   const float* cr_row = nullptr;
   const float* cl_row = nullptr;
   if (!joint_role && active) {
-    // the stone window does not depend on the state word: its four coalesced loads go out first
+    const uint2 sw = st_in[e];
+    // k_prepare* -- whose last wave this kernel may overlap as its programmatic dependent -- refreshes stale window
+    // records and writes the contact norms: both are read only once it has completed
+    if (a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     // (entry 3, the stone that enters when the window slides, is fetched only by the few envs that do slide)
     const float4 w0 = wrow[0], w1 = wrow[1], w2 = wrow[2];
-    const uint2 sw = st_in[e];
     m.idx = state_idx(sw.x);
     m.leg = state_leg(sw.x);
     m.count = state_count(sw.x);
@@ -658,7 +668,6 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     cr_row = a.in.contact_right + e * a.in.contact_right_stride;
     cl_row = a.in.contact_left + e * a.in.contact_left_stride;
     if (PRE || a.use_pre) {  // |F| of the current (and the following) stone under each foot, gathered by k_prepare* just before
-      if (a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
       const float4 pre = a.ws.contact_pre[e];
       f_r = pre.x;
       f_l = pre.y;
@@ -717,7 +726,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   Vec3 vb{0, 0, 0};
   PassOut po{};
   bool terminated = false, time_out = false, is_reset = false, mirror = false, regen = false;
-  bool fell = false, so_fast = false, died = false, adv1 = false, adv2 = false;
+  bool fell = false, so_fast = false, died = false, missed = false, adv1 = false, adv2 = false;
   float r_partial = 0.0f, r_speed = 0.0f, r_step = 0.0f, r_bonus = 0.0f;
   int idx_after_pass1 = 0;
   const unsigned long long step_now = ctrl->step_counter;
@@ -758,7 +767,13 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       speed = norm3(v.x, v.y, v.z);
       so_fast = speed > P.max_root_speed;
       died = p.z < P.termination_height_absolute;
-      terminated = fell || so_fast || died;
+      if (P.flags & AS_FLAG_MISSED_STEP) {
+        // extension: the swing foot is down (below the stone it heads for) outside that stone's footprint; leg and
+        // stone as they are before this pass updates them
+        const float dsw = m.leg ? norm2(lf.x - s_curr.x, lf.y - s_curr.y) : norm2(rf.x - s_curr.x, rf.y - s_curr.y);
+        missed = ((m.leg ? lf.z : rf.z) < s_curr.z + P.missed_step_height) && dsw >= P.step_radius;
+      }
+      terminated = fell || so_fast || died || missed;
       is_reset = terminated || time_out;
       // an env that resets restarts on stones 0..3 (one 64-byte record at the head of its stone row): start
       // pulling it in now, it is read after pass 1
@@ -1114,7 +1129,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
                           (fell ? 1u << 24 : 0u);
       const unsigned w1 = (so_fast ? 1u : 0u) | (died ? 1u << 8 : 0u) | (adv1 ? 1u << 16 : 0u) |
                           (adv2 ? 1u << 24 : 0u);
-      const unsigned w2 = (regen ? 1u : 0u) | (static_cast<unsigned>(active ? idx_after_pass1 : 0) << 8);
+      const unsigned w2 = (regen ? 1u : 0u) | (static_cast<unsigned>(active ? idx_after_pass1 : 0) << 8) |
+                          (missed ? 1u << 20 : 0u);
       const unsigned s0 = __reduce_add_sync(0xffffffffu, w0);
       const unsigned s1 = __reduce_add_sync(0xffffffffu, w1);
       const unsigned s2 = __reduce_add_sync(0xffffffffu, w2);
@@ -1133,7 +1149,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         wc[kCntAdvanced1] = (s1 >> 16) & 255u;
         wc[kCntAdvanced2] = s1 >> 24;
         wc[kCntRegen] = s2 & 255u;
-        wc[kCntSumIndex] = s2 >> 8;
+        wc[kCntSumIndex] = (s2 >> 8) & 4095u;
+        wc[kCntMissed] = s2 >> 20;
         wc[kCntLevelMax] = lmax;
         misc->wreward[warp] = rs;
       }
@@ -1171,7 +1188,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   unsigned ticket = 0;
   if (kStats && warp == 0) {  // CTA totals -> one replicated global slot (fire and forget), by the first warp
     const int slot = blockIdx.x & (kSlots - 1);
-    if (lane <= kCntLevelMax) {
+    if (lane < kNumCounters) {
       unsigned tot = 0;
 #pragma unroll
       for (int w = 0; w < kTile / 32; ++w) tot = lane == kCntLevelMax ? max(tot, misc->wcnt[w][lane]) : tot + misc->wcnt[w][lane];
@@ -1179,7 +1196,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         if (lane == kCntLevelMax) atomicMax(&ctrl->slots[slot][lane], tot);
         else atomicAdd(&ctrl->slots[slot][lane], tot);
       }
-    } else if (lane == kCntLevelMax + 1) {
+    } else if (lane == kNumCounters) {
       float rs = 0.0f;
 #pragma unroll
       for (int w = 0; w < kTile / 32; ++w) rs += misc->wreward[w];

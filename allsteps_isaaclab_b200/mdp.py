@@ -150,7 +150,7 @@ class CapturedStep:
 class AllstepsMDP:
     def __init__(self, num_envs: int, device="cuda:0", cfg: Optional[AllstepsCfg] = None, seed: int = 0,
                  env_id_offset: int = 0, intended_regen: bool = False, skip_pass2: bool = False,
-                 grid_bins: int = 0, joint_limits: Optional[torch.Tensor] = None):
+                 grid_bins: int = 0, joint_limits: Optional[torch.Tensor] = None, missed_step: bool = False):
         """joint_limits: optional (21,2) [lower, upper] in radians as the simulator reports them
         (`robot.data.joint_pos_limits[0]`, ENV:287-291); default = the MJCF table of config.py."""
         self.lib = _cabi.load()  # raises if the CUDA library was not built: there is no fallback
@@ -162,6 +162,7 @@ class AllstepsMDP:
         self.env_id_offset = int(env_id_offset)
         flags = (_cabi.FLAG_INTENDED_REGEN if intended_regen else 0) | (_cabi.FLAG_SKIP_PASS2 if skip_pass2 else 0)
         flags |= _cabi.FLAG_GRID_CURRICULUM if grid_bins else 0
+        flags |= _cabi.FLAG_MISSED_STEP if missed_step else 0  # extension: AllstepsCfg.missed_step_height
         self.grid_bins = int(grid_bins)
         self.seed = int(seed)
         self.params = make_params(self.cfg, seed=seed, flags=flags, grid_bins=self.grid_bins,

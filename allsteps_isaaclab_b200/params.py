@@ -50,6 +50,7 @@ def make_params(cfg: AllstepsCfg, seed: int = 0, flags: int = 0, grid_bins: int 
     p.death_cost = cfg.death_cost
     p.termination_height_absolute = cfg.termination_height_absolute
     p.max_root_speed = cfg.max_root_speed
+    p.missed_step_height = cfg.missed_step_height
     lo, hi = cfg.initial_joint_angle_range
     p.noise_span = hi - lo  # MATH:1331 evaluates (upper - lower) in Python double, then rounds to fp32
     p.noise_lower = lo

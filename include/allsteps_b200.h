@@ -52,7 +52,14 @@ enum {
                                        ENV:497 runs after ENV:492 and is never true.            */
   AS_FLAG_SKIP_PASS2 = 1u << 1,     /* extension: never run the second `_compute_useful_values` pass
                                        (ENV:567) for envs that did not reset.  Off = reference. */
-  AS_FLAG_GRID_CURRICULUM = 1u << 2 /* extension: pitch x yaw difficulty grid sampling at regeneration.   */
+  AS_FLAG_GRID_CURRICULUM = 1u << 2,/* extension: pitch x yaw difficulty grid sampling at regeneration.   */
+  AS_FLAG_MISSED_STEP = 1u << 3     /* extension (BASELINE north_star "missed-step termination"; the reference's
+                                       ENV:396-405 has none): an env also terminates when its swing foot
+                                       has come down below the top of the stone it is heading for, outside that stone's
+                                       footprint -- swing_foot_z < stone_z + missed_step_height  and
+                                       |swing_foot_xy - stone_xy| >= step_radius, swing leg and current stone taken as
+                                       they are BEFORE the pass updates them.  Specification: AllstepsOracle(
+                                       missed_step_height=...) in oracle/allsteps_oracle.py.  Off = reference.  */
 };
 
 /* Constants of the task: CFG:52-235 plus the values hard-coded in ENV:41-59.  Tables that the reference builds
@@ -84,6 +91,8 @@ typedef struct AsParams {
   float reset_pose[AS_NUM_JOINTS]; /* ENV:505-511                                                       */
   int32_t mirror_src[AS_NUM_JOINTS]; /* ENV:522-526: joint j takes the value of joint mirror_src[j] ... */
   float mirror_sign[AS_NUM_JOINTS];  /* ... times mirror_sign[j]                                        */
+  float missed_step_height;        /* AS_FLAG_MISSED_STEP: metres above the stone's position below which the swing
+                                      foot's body origin counts as "down" (extension, no reference counterpart) */
   uint32_t flags;
   uint32_t grid_bins;              /* AS_FLAG_GRID_CURRICULUM: bins per axis (<= 16), else 0            */
   uint64_t seed;                   /* Philox key                                                        */
@@ -152,6 +161,7 @@ typedef struct AsStats {
   int64_t level;         /* current curriculum level (max over envs when per-env levels are in use)        */
   int64_t step_counter;
   double sum_reward;
+  int64_t n_missed;      /* AS_FLAG_MISSED_STEP: envs terminated by a missed step (this shard)             */
 } AsStats;
 
 typedef struct AsHandle AsHandle;

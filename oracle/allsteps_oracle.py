@@ -143,7 +143,8 @@ class AllstepsOracle:
 
     def __init__(self, cfg, num_envs: int, env_origins: torch.Tensor, joint_limits: torch.Tensor,
                  body_indices=(0, 1, 2), stone_uniforms: Optional[torch.Tensor] = None,
-                 intended_regen: bool = False, grid=None, seed: int = 0):
+                 intended_regen: bool = False, grid=None, seed: int = 0,
+                 missed_step_height: Optional[float] = None):
         self.cfg = cfg
         self.N = N = num_envs
         self.S = S = cfg.num_steps
@@ -158,6 +159,11 @@ class AllstepsOracle:
         self.grid = grid  # extension: oracle.grid_curriculum.GridCurriculum (every reset env is re-binned + regenerated)
         self.seed = seed
         self.step_index = 0
+        # EXTENSION, no reference counterpart (BASELINE north_star "missed-step termination") -- this
+        # method IS its specification, parity unpinned in the reference.  None = off = reference behaviour.
+        # An env also terminates when its swing foot has come down below the top of the stone it is heading for,
+        # outside that stone's footprint; swing leg and current stone as they are BEFORE the pass updates them.
+        self.missed_step_height = missed_step_height
         # ENV:45-48
         self.termination_curriculum = torch.linspace(*cfg.termination_height_range, cfg.max_curriculum + 1)
         self.applied_gain_curriculum = torch.linspace(*cfg.applied_gain_range, cfg.max_curriculum + 1)
@@ -226,6 +232,12 @@ class AllstepsOracle:
         stone_xy = self.steps_pos[rows, self.curr_target_index, :2]
         feet_xy = torch.stack((right_foot[:, :2], left_foot[:, :2]), dim=1)  # body_pos_w[:, foot_indices, :2]
         self.foot_to_target_dist_xy = torch.linalg.vector_norm(feet_xy - stone_xy[:, None, :], dim=-1)
+        if self.missed_step_height is not None:  # extension (see __init__): evaluated on the pre-update leg / stone
+            feet_z = torch.stack((right_foot[:, 2], left_foot[:, 2]), dim=1)
+            swing_z = feet_z[rows, self.swing_leg]
+            stone_z = self.steps_pos[rows, self.curr_target_index, 2]
+            swing_d = self.foot_to_target_dist_xy[rows, self.swing_leg]
+            self.missed_step = (swing_z < stone_z + self.missed_step_height) & (swing_d >= self.cfg.step_radius)
         self.target_reached = (pressed[rows, self.swing_leg] > 0) & (
             (self.foot_to_target_dist_xy < self.cfg.step_radius)[rows, self.swing_leg])
         self.target_reach_count[self.target_reached] += 1
@@ -262,6 +274,9 @@ class AllstepsOracle:
         so_fast = torch.linalg.vector_norm(p["root_lin_vel_w"], dim=-1) > self.cfg.max_root_speed
         died = p["root_pos_w"][:, 2] < self.cfg.termination_height_absolute
         self.fell, self.so_fast, self.died = fell, so_fast, died
+        if self.missed_step_height is not None:
+            self.missed_step_pass1 = self.missed_step.clone()
+            return fell | so_fast | died | self.missed_step, time_out
         return fell | so_fast | died, time_out
 
     # ------------------------------------------------------------------ rewards, ENV:347-394

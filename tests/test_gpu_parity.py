@@ -101,18 +101,25 @@ def compare_state(mdp, orc, what):
 
 
 def run_replay(num_envs, steps, seed, full_bodies=False, layout="contiguous", fall_fraction=0.02,
-               high_index=False, per_env_levels=False, intended_regen=False, env_id_offset=0):
+               high_index=False, per_env_levels=False, intended_regen=False, env_id_offset=0, missed_step=None):
     from allsteps_isaaclab_b200.mdp import StepBuffers
     from oracle import allsteps_oracle as ao
 
+    cfg = None
+    if missed_step is not None:  # extension: missed-step termination at the given foot height
+        from allsteps_isaaclab_b200.config import AllstepsCfg
+
+        cfg = AllstepsCfg(missed_step_height=missed_step)
     sc = Scenario(num_envs, seed=seed, full_bodies=full_bodies, fall_fraction=fall_fraction,
-                  env_id_offset=env_id_offset)
+                  env_id_offset=env_id_offset, cfg=cfg)
     st0 = sc.initial_mdp_state(per_env_levels=per_env_levels)
     if high_index:
         st0["curr_target_index"] = torch.randint(11, 20, (num_envs,), generator=sc.gen)
     orc = ao.AllstepsOracle(sc.cfg, num_envs, sc.env_origins, sc.joint_limits, sc.body_indices,
-                            sc.stone_uniforms(0), intended_regen=intended_regen)
-    mdp = make_cuda(num_envs, seed, intended_regen=intended_regen, env_id_offset=env_id_offset)
+                            sc.stone_uniforms(0), intended_regen=intended_regen, missed_step_height=missed_step)
+    mdp = make_cuda(num_envs, seed, intended_regen=intended_regen, env_id_offset=env_id_offset, cfg=cfg,
+                    missed_step=missed_step is not None)
+    totals_missed = 0
     origins = sc.env_origins.cuda()
     if per_env_levels:
         # levels first, then stones at those levels (oracle: set curriculum, regenerate)
@@ -171,6 +178,11 @@ def run_replay(num_envs, steps, seed, full_bodies=False, layout="contiguous", fa
         assert stats["n_terminated"] == int(o_term.sum())
         assert stats["n_time_out"] == int(o_to.sum())
         assert stats["sum_target_index"] == int(orc.pass1["curr_target_index"].sum())
+        if missed_step is not None:
+            assert stats["n_missed"] == int(orc.missed_step_pass1.sum()), f"step {step} n_missed"
+            totals["missed"] = totals.get("missed", 0) + stats["n_missed"]
+        else:
+            assert stats["n_missed"] == 0
         totals["resets"] += n_reset
         totals["advanced"] += stats["n_advanced"]
         totals["promoted"] += int((orc.curriculum != level_before).any())
@@ -228,6 +240,17 @@ def test_per_env_levels_and_env_id_offset():
 def test_intended_regeneration_extension():
     totals, _, _ = run_replay(768, 10, seed=9, high_index=True, intended_regen=True, per_env_levels=True)
     assert totals["regen"] > 0
+
+
+def test_missed_step_termination_extension():
+    """BASELINE north_star "missed-step termination" (no reference counterpart): AS_FLAG_MISSED_STEP against
+    the oracle's specification of it -- masks bit-exact; off by default (every other replay asserts n_missed == 0)."""
+    # the synthetic swing foot hovers 0.11 m above its stone: 0.12 makes every foot outside the radius a missed step
+    totals, _, _ = run_replay(2048, 8, seed=61, missed_step=0.12)
+    assert totals["missed"] > 1000 and totals["resets"] >= totals["missed"]
+    # at the default height nothing of the synthetic state counts as down: the flag alone changes nothing
+    totals, _, _ = run_replay(1024, 4, seed=62, missed_step=0.05)
+    assert totals["missed"] == 0 and totals["resets"] > 0
 
 
 def test_explicit_stone_uniforms():
@@ -383,7 +406,8 @@ def test_symmetry_functions_match_the_reference_fixture():
     assert out["dones"].shape == (2 * R,) and out["neglogpacs"].shape == (2 * R,) and out["sigmas"].shape == (2 * R, 21)
     assert np.array_equal(bits(out["obses"]), d["rl_games_obs"]) and np.array_equal(bits(out["mus"]), d["rl_games_mus"])
     # an env whose index tensors are not the ones the kernels are built with is refused
-    bad = types.SimpleNamespace(unwrapped=types.SimpleNamespace(**{**base.__dict__,
+    fields = {k: v for k, v in base.__dict__.items() if not k.startswith("_allsteps")}
+    bad = types.SimpleNamespace(unwrapped=types.SimpleNamespace(**{**fields,
                                 "right_body_indices": base.left_body_indices}), device="cuda:0")
     with pytest.raises(ValueError, match="mirror tables"):
         symmetry.get_symmetric_states_rsl_rl(obs, actions, bad)
