@@ -375,6 +375,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->ws.bin = reinterpret_cast<uint8_t*>(base + l.bin_off);
   h->ws.contact_pre = reinterpret_cast<float4*>(base + l.contact_pre_off);
   h->ws.body_dense = reinterpret_cast<float*>(base + l.body_dense_off);
+  h->ws.win_stale = reinterpret_cast<uint32_t*>(base + l.win_stale_off);
   build_mirror_tables(h);
   build_joint_consts(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -382,6 +383,13 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   if (e != cudaSuccess) {
     delete h;
     return cuda_fail(e, "cudaMemsetAsync(workspace)");
+  }
+  // no stone window is valid yet (k_prepare* refreshes the records whose bit is set)
+  if (e == cudaSuccess)
+    e = cudaMemsetAsync(h->ws.win_stale, 0xFF, static_cast<size_t>((num_envs + 31) / 32 * 4), s);
+  if (e != cudaSuccess) {
+    delete h;
+    return cuda_fail(e, "cudaMemsetAsync(win_stale)");
   }
   // initial MDP state of AllstepsEnv.__init__ (ENV:74-78): index 1, right leg swings, everything else zero
   AsMdpState none;
@@ -776,10 +784,10 @@ int as_import_state(AsHandle* h, const AsMdpState* src, void* stream) {
   return check_launch(h, "k_clear_promotion");
 }
 
-// Snapshot layout: [Ctrl | state words, both buffers | stone windows | grid bins | stones (optional)].
+// Snapshot layout: [Ctrl | state words, both buffers | stone windows | grid bins | window-stale bits | stones (optional)].
 namespace {
 struct SnapshotLayout {
-  int64_t ctrl, state, window, bin, stones, total;
+  int64_t ctrl, state, window, bin, stale, stones, total;
 };
 SnapshotLayout snapshot_layout(int64_t n, bool with_stones) {
   const WorkspaceLayout w = workspace_layout(n);
@@ -789,6 +797,7 @@ SnapshotLayout snapshot_layout(int64_t n, bool with_stones) {
   l.state = off;  off += w.stones_off - w.state0_off;
   l.window = off; off += w.reset_ids_off - w.window_off;
   l.bin = off;    off += w.contact_pre_off - w.bin_off;
+  l.stale = off;  off += w.total - w.win_stale_off;
   l.stones = off; off += with_stones ? (w.window_off - w.stones_off) : 0;
   l.total = off;
   return l;
@@ -810,7 +819,8 @@ int as_snapshot(AsHandle* h, void* dst, int32_t include_stones, void* stream) {
   const unsigned char* base = reinterpret_cast<const unsigned char*>(h->ws.ctrl);
   AS_CUDA(cudaMemcpyAsync(d + l.ctrl, base + w.ctrl_off, static_cast<size_t>(l.window - l.ctrl), cudaMemcpyDeviceToDevice, s));
   AS_CUDA(cudaMemcpyAsync(d + l.window, base + w.window_off, static_cast<size_t>(l.bin - l.window), cudaMemcpyDeviceToDevice, s));
-  AS_CUDA(cudaMemcpyAsync(d + l.bin, base + w.bin_off, static_cast<size_t>(l.stones - l.bin), cudaMemcpyDeviceToDevice, s));
+  AS_CUDA(cudaMemcpyAsync(d + l.bin, base + w.bin_off, static_cast<size_t>(l.stale - l.bin), cudaMemcpyDeviceToDevice, s));
+  AS_CUDA(cudaMemcpyAsync(d + l.stale, base + w.win_stale_off, static_cast<size_t>(l.stones - l.stale), cudaMemcpyDeviceToDevice, s));
   if (include_stones)
     AS_CUDA(cudaMemcpyAsync(d + l.stones, base + w.stones_off, static_cast<size_t>(l.total - l.stones), cudaMemcpyDeviceToDevice, s));
   return AS_OK;
@@ -828,7 +838,8 @@ int as_restore(AsHandle* h, const void* src, int32_t include_stones, void* strea
   if (int rc = check_launch(h, "k_restore_ctrl")) return rc;
   AS_CUDA(cudaMemcpyAsync(base + w.state0_off, d + l.state, static_cast<size_t>(l.window - l.state), cudaMemcpyDeviceToDevice, s));
   AS_CUDA(cudaMemcpyAsync(base + w.window_off, d + l.window, static_cast<size_t>(l.bin - l.window), cudaMemcpyDeviceToDevice, s));
-  AS_CUDA(cudaMemcpyAsync(base + w.bin_off, d + l.bin, static_cast<size_t>(l.stones - l.bin), cudaMemcpyDeviceToDevice, s));
+  AS_CUDA(cudaMemcpyAsync(base + w.bin_off, d + l.bin, static_cast<size_t>(l.stale - l.bin), cudaMemcpyDeviceToDevice, s));
+  AS_CUDA(cudaMemcpyAsync(base + w.win_stale_off, d + l.stale, static_cast<size_t>(l.stones - l.stale), cudaMemcpyDeviceToDevice, s));
   if (include_stones)
     AS_CUDA(cudaMemcpyAsync(base + w.stones_off, d + l.stones, static_cast<size_t>(l.total - l.stones), cudaMemcpyDeviceToDevice, s));
   h->pass1_done = false;

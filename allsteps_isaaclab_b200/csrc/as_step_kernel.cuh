@@ -873,6 +873,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       sw.x = pack_state(m.idx, m.leg, m.count, level, ep);
       sw.y = __float_as_uint(m.pot);
       st_out[e] = sw;
+      if (PRE) {
+        // this instantiation never writes windows: tell k_prepare* of the next step which records to refresh
+        const unsigned stale = __ballot_sync(0xffffffffu, win_dirty);
+        if (lane == 0) a.ws.win_stale[e >> 5] = stale;
+      }
       if (!PRE && (win_dirty || !win_valid) && !regen) {  // (a regenerated env's window is written by the regeneration kernel)
         s_prev.w = __int_as_float(m.idx);  // tag
         wrow[0] = s_prev; wrow[1] = s_curr; wrow[2] = s_next;
@@ -1262,12 +1267,12 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
   const AsStateIn& in = a.in;
   const int idx = state_idx(a.ws.state[a.ws.ctrl->parity][e].x);
   const int nxt = min(idx + 1, kS - 1);
-  const float4 w0 = a.ws.window[e * 4];
+  const bool stale = (a.ws.win_stale[e >> 5] >> (e & 31)) & 1u;
   const float* rr = in.contact_right + e * in.contact_right_stride;
   const float* lr = in.contact_left + e * in.contact_left_stride;
   a.ws.contact_pre[e] = make_float4(contact_norm(rr, idx, false), contact_norm(lr, idx, false),
                                     contact_norm(rr, nxt, false), contact_norm(lr, nxt, false));
-  if (__float_as_int(w0.w) != idx) {
+  if (stale) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) refresh_window_entry(a.ws, e, idx, k);
   }
@@ -1296,8 +1301,7 @@ __global__ void __launch_bounds__(256) k_prepare_paired(const __grid_constant__ 
   const bool live = e < a.num_envs;  // both lanes of a pair agree; no early exit, the shuffles below need the warp
   const int half = static_cast<int>(t & 1);
   const int idx = live ? state_idx(a.ws.state[a.ws.ctrl->parity][e].x) : 0;
-  float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (live) w0 = a.ws.window[e * 4];  // (both lanes: one request)
+  const bool stale = live && ((a.ws.win_stale[e >> 5] >> (e & 31)) & 1u);  // (one word per 64 lanes: one request)
   const int o = idx * 3;
   const int k = o & 3;
   const bool has_next = idx < kS - 1;
@@ -1326,7 +1330,6 @@ __global__ void __launch_bounds__(256) k_prepare_paired(const __grid_constant__ 
   rc[8] = r2.x; rc[9] = 0.f; rc[10] = 0.f; rc[11] = 0.f;
   lc[8] = l2.x; lc[9] = 0.f; lc[10] = 0.f; lc[11] = 0.f;
   if (live) {
-    const bool stale = __float_as_int(w0.w) != idx;
     if (stale) {  // lane h rewrites entries 2h, 2h+1 of the record
       refresh_window_entry(a.ws, e, idx, 2 * half);
       refresh_window_entry(a.ws, e, idx, 2 * half + 1);

@@ -8,6 +8,10 @@
 //   5  as 1 with ld.global.cv (volatile, no caching)
 //   6  three scalar ld.global.nc per vector, one lane per env
 //   7  as 1 with ld.global.nc.L2::64B  (explicit 64-byte L2 prefetch size)
+//   8  TMA bulk copies (cp.async.bulk.shared.global), one 16-byte copy per chunk the vector touches, one lane per env
+//   9  TMA bulk copies, one 32-byte copy per vector (the two chunks it can span)
+//  10  cp.async.cg (LDGSTS) 16-byte copies global -> shared, no L2 size hint
+//  11  cp.async.cg 16-byte copies with L2::64B
 // Run under ncu for dram__bytes_read.sum / lts sectors; prints the time per launch itself.
 //
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/gather_probe tools/gather_probe.cu
@@ -80,6 +84,64 @@ __global__ void __launch_bounds__(256) k_single(const float* cr, const float* cl
   out[e] = make_float2(a, b);
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one lane per env; every lane copies the chunk(s) of its two vectors into its own 64-byte slot of shared memory
+template <int V>
+__global__ void __launch_bounds__(256) k_async(const float* cr, const float* cl, const uint8_t* idxs, float2* out, int64_t n) {
+  __shared__ __align__(128) float slot[256][16];   // [0..7] right, [8..15] left
+  __shared__ __align__(8) unsigned long long bar;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = e < n;
+  const int idx = live ? idxs[e] : 0;
+  const int o = idx * 3, k = o & 3;
+  const int chunks = (k >= 2) ? 2 : 1;
+  const uint32_t b = smem_u32(&bar);
+  if (V == 8 || V == 9) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(256) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t bytes = live ? (V == 9 ? 64u : 32u * chunks) : 0u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    if (live) {
+      const float* pr = cr + e * kRow + (o & ~3);
+      const float* pl = cl + e * kRow + (o & ~3);
+      const uint32_t d = smem_u32(&slot[threadIdx.x][0]);
+      const uint32_t sz = V == 9 ? 32u : 16u * chunks;
+      // (variant 9 may read 16 bytes past the vector's last chunk; the probe's rows are padded by the next row)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(pr), "r"(sz), "r"(b) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d + 32), "l"(pl), "r"(sz), "r"(b) : "memory");
+    }
+    uint32_t ok;
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(b), "r"(0) : "memory");
+    } while (!ok);
+  } else {
+    if (live) {
+      const float* pr = cr + e * kRow + (o & ~3);
+      const float* pl = cl + e * kRow + (o & ~3);
+      const uint32_t d = smem_u32(&slot[threadIdx.x][0]);
+      for (int c = 0; c < chunks; ++c) {
+        if (V == 10) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16 * c), "l"(pr + 4 * c) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 32 + 16 * c), "l"(pl + 4 * c) : "memory");
+        } else {
+          asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d + 16 * c), "l"(pr + 4 * c) : "memory");
+          asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d + 32 + 16 * c), "l"(pl + 4 * c) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  if (!live) return;
+  const float* r = &slot[threadIdx.x][0];
+  const float* l = &slot[threadIdx.x][8];
+  out[e] = make_float2(r[k] + r[k + 1] + r[k + 2], l[k] + l[k + 1] + l[k + 2]);
+}
+
 int main(int argc, char** argv) {
   const int64_t n = argc > 1 ? atoll(argv[1]) : (1 << 20);
   const int sets = 3;  // rotate so that nothing survives in L2 (2 x 252 MB per set)
@@ -101,9 +163,12 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  const char* names[8] = {"nc single 1-2x128", "nc paired", "plain paired", "cg paired", "nc no_allocate paired", "cv paired",
-                          "nc single 3x32", "nc L2::64B paired"};
-  for (int v = 0; v < 8; ++v) {
+  const char* names[12] = {"nc single 1-2x128", "nc paired", "plain paired", "cg paired", "nc no_allocate paired", "cv paired",
+                           "nc single 3x32", "nc L2::64B paired", "TMA bulk 16B chunks", "TMA bulk 32B", "cp.async.cg 16B",
+                           "cp.async.cg 16B L2::64B"};
+  const int only = argc > 2 ? atoi(argv[2]) : -1;
+  for (int v = 0; v < 12; ++v) {
+    if (only >= 0 && v != only) continue;
     const unsigned b1 = (unsigned)((n + 255) / 256), b2 = (unsigned)((2 * n + 255) / 256);
     const int reps = 9;
     float ms = 0;
@@ -119,6 +184,10 @@ int main(int argc, char** argv) {
         case 5: k_paired<5><<<b2, 256>>>(cr[s], cl[s], idxs, out, n); break;
         case 6: k_single<6><<<b1, 256>>>(cr[s], cl[s], idxs, out, n); break;
         case 7: k_paired<7><<<b2, 256>>>(cr[s], cl[s], idxs, out, n); break;
+        case 8: k_async<8><<<b1, 256>>>(cr[s], cl[s], idxs, out, n); break;
+        case 9: k_async<9><<<b1, 256>>>(cr[s], cl[s], idxs, out, n); break;
+        case 10: k_async<10><<<b1, 256>>>(cr[s], cl[s], idxs, out, n); break;
+        case 11: k_async<11><<<b1, 256>>>(cr[s], cl[s], idxs, out, n); break;
       }
     }
     CK(cudaEventRecord(e1));
