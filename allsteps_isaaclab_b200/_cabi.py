@@ -113,6 +113,7 @@ SIGNATURES = {
     "as_step_pass1": (C.c_int, [_ptr, C.POINTER(AsStateIn), _ptr, _i64, _ptr, C.POINTER(AsStepOut), _ptr]),
     "as_reset": (C.c_int, [_ptr, _ptr, _ptr, _i64, _ptr, C.POINTER(AsResetOut), _ptr]),
     "as_step_pass2": (C.c_int, [_ptr, C.POINTER(AsStateIn), _ptr, _ptr]),
+    "as_step_no_reset": (C.c_int, [_ptr, _ptr]),
     "as_stats_device_ptr": (C.c_int, [_ptr, C.POINTER(_ptr)]),
     "as_fold_stats": (C.c_int, [_ptr, _ptr]),
     "as_finish_step": (C.c_int, [_ptr, _ptr, _ptr]),

@@ -32,6 +32,8 @@ struct AsHandle {
   bool peer_connected;
   volatile uint32_t* peer_host_error;  // mapped pinned host word the exchange kernel sets when a peer timed out
   bool pass1_done;
+  bool spec_valid;      // as_step_pass1 speculated pass 2 into the other state buffer; as_step_pass2 / as_step_no_reset closes it
+  float* spec_obs;      // the observation buffer that pass 1 wrote
   bool pending_valid;   // a fused step was launched and still needs as_finish_step
   StepArgs pending;     // its arguments: the conditional fix-up re-reads the same inputs
 };
@@ -331,6 +333,10 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModeFused, 0, true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 0, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 0, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 0, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
+  AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 0, true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesPacked));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -345,6 +351,8 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->sm_count = prop.multiProcessorCount;
   h->launches = 0;
   h->pass1_done = false;
+  h->spec_valid = false;
+  h->spec_obs = nullptr;
   h->obs_clip_pass1 = 0.0f;
   std::memset(&h->peer, 0, sizeof(h->peer));
   h->peer_connected = false;
@@ -375,6 +383,8 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->ws.bin = reinterpret_cast<uint8_t*>(base + l.bin_off);
   h->ws.contact_pre = reinterpret_cast<float4*>(base + l.contact_pre_off);
   h->ws.body_dense = reinterpret_cast<float*>(base + l.body_dense_off);
+  h->ws.tail1 = reinterpret_cast<float4*>(base + l.tail1_off);
+  h->ws.pass1_reset = reinterpret_cast<uint8_t*>(base + l.pass1_reset_off);
   h->ws.win_stale = reinterpret_cast<uint32_t*>(base + l.win_stale_off);
   build_mirror_tables(h);
   build_joint_consts(h);
@@ -653,11 +663,38 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   a.ext_episode_length = episode_length;
   h->obs_clip_pass1 = out->obs_clip;  // as_step_pass2 rewrites the same observation buffer: same epilogue
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (int rc = launch_prepare(h, in, s)) return rc;
-  AS_CUDA(launch_step(h, k_step<kModePass1, 2, true>, k_step<kModePass1, 2, false>, a, s, false));
+  bool gather_body = false;
+  if (!(a.dense16 & kDenseBody) && h->num_envs >= kSeparateGatherMinEnvs) {  // (as in as_step_fused)
+    gather_body = true;
+    a.body_from_prepare = 1;
+    a.in.body_pos = h->ws.body_dense;
+    a.in.body_env_stride = 9;
+    a.in.body_row_stride = 3;
+    a.in.right_foot_row = 0;
+    a.in.left_foot_row = 1;
+    a.in.torso_row = 2;
+    a.dense16 |= kDenseBody;
+  }
+  if (int rc = launch_prepare(h, in, s, gather_body)) return rc;
+  const bool dep = h->pdl >= 2 && a.use_pre;
+  a.pdl_wait = dep ? 1 : 0;
+  const bool fast = !a.in.quat_xyzw && !a.out.reward_terms && a.out.obs_clip == 0.0f && a.prefetch_tiles == 0;
+  const bool packed = in->root_pos_stride == AS_ROOT_STATE_DIM && in->root_quat_stride == AS_ROOT_STATE_DIM &&
+                      in->root_lin_vel_stride == AS_ROOT_STATE_DIM && in->root_quat == in->root_pos + 3 &&
+                      in->root_lin_vel == in->root_pos + 7 && (reinterpret_cast<uintptr_t>(in->root_pos) & 15u) == 0;
+  using StepKernel = void (*)(StepArgs);
+  static const StepKernel kFullPre[2][2] = {  // [fast][packed]
+      {k_step<kModePass1, 0, true, false, false, true>, k_step<kModePass1, 0, true, false, true, true>},
+      {k_step<kModePass1, 0, true, true, false, true>, k_step<kModePass1, 0, true, true, true, true>}};
+  const bool pre = a.use_pre && !h->jc.exact_div && h->allow_pre;
+  const StepKernel full = pre ? kFullPre[fast ? 1 : 0][packed ? 1 : 0] : k_step<kModePass1, 2, true>;
+  AS_CUDA(launch_step(h, full, k_step<kModePass1, 2, false>, a, s, dep,
+                      (pre && packed) ? kSmemBytesPacked : kSmemBytes));
   if (int rc = check_launch(h, "k_step<pass1>")) return rc;
   k_fold_pass1<<<1, 128, 0, s>>>(h->ws.ctrl, h->num_envs);
   h->pass1_done = true;
+  h->spec_valid = true;
+  h->spec_obs = out->obs;
   return check_launch(h, "k_fold_pass1");
 }
 
@@ -685,6 +722,7 @@ int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int6
   r.n_ids = n_ids;
   r.ext_episode_length = episode_length;
   r.fused = 0;
+  r.into_other = h->spec_valid ? 1 : 0;  // behind a speculating pass 1 the step continues in the other state buffer
   const int grid = grid_for(n_ids, 8, h->sm_count, 4);
   k_reset_rows<<<grid, 256, 0, s>>>(r);
   return check_launch(h, "k_reset_rows");
@@ -696,15 +734,43 @@ int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
   // (no call-order precondition: the reference runs `_compute_useful_values` at the end of `_reset_idx` whether or
   // not a pass preceded it -- DirectRLEnv.reset() calls `_reset_idx(all ids)` before the first step, DRL:256-279)
   if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->spec_valid) {
+    // pass 1 already ran pass 2 for every env that did not reset: redo the envs that did (from the views as they are
+    // now, after the PhysX writes) and make the speculated state buffer the current one
+    CommitArgs c;
+    std::memset(&c, 0, sizeof(c));
+    c.P = h->params;
+    c.jc = h->jc;
+    c.in = *in;
+    c.ws = h->ws;
+    c.obs = obs;
+    c.obs_clip = h->obs_clip_pass1;
+    c.inv_step_dt = h->inv_step_dt;
+    c.num_envs = h->num_envs;
+    const int grid = grid_for(h->num_envs / 16 + 1, 8, h->sm_count, 8);
+    k_pass2_commit<<<grid, 256, 0, s>>>(c);
+    h->spec_valid = false;
+    return check_launch(h, "k_pass2_commit");
+  }
   AsStepOut out;
   std::memset(&out, 0, sizeof(out));
   out.obs = obs;
   out.obs_clip = h->obs_clip_pass1;
   StepArgs a = make_step_args(h, in, nullptr, 0, &out);
-  if (int rc = launch_prepare(h, in, static_cast<cudaStream_t>(stream))) return rc;
-  AS_CUDA(launch_step(h, k_step<kModePass2, 2, true>, k_step<kModePass2, 2, false>, a, static_cast<cudaStream_t>(stream),
-                      false));
+  if (int rc = launch_prepare(h, in, s)) return rc;
+  AS_CUDA(launch_step(h, k_step<kModePass2, 2, true>, k_step<kModePass2, 2, false>, a, s, false));
   return check_launch(h, "k_step<pass2>");
+}
+
+int as_step_no_reset(AsHandle* h, void* stream) {
+  AS_REQUIRE(h, "handle is null");
+  if (!h->spec_valid) return AS_OK;  // nothing was speculated (no pass 1 since the last pass 2)
+  const int grid = grid_for(h->num_envs * 11, 256 * 4, h->sm_count, 8);
+  k_pass2_revert<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->ws, h->spec_obs, h->obs_clip_pass1,
+                                                                        h->num_envs);
+  h->spec_valid = false;
+  return check_launch(h, "k_pass2_revert");
 }
 
 int as_apply_action(AsHandle* h, const float* actions, int64_t actions_stride, float* efforts, void* stream) {

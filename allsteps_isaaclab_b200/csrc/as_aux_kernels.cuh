@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
     promote_now = static_cast<int>(promotion_rule(P, nr, si, a.num_envs));
   }
   const uint32_t parity = ctrl->parity;
-  uint2* st_cur = a.fused ? a.ws.state[parity ^ 1u] : a.ws.state[parity];  // fused: the step wrote the other buffer
+  // fused: the step wrote the other buffer; 3-call path after a speculating pass 1: so did that pass
+  uint2* st_cur = (a.fused || a.into_other) ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
   float t_lo, t_hi, t_pose, t_pose_m, t_vel_m;  // this lane's joint constants, fetched once
   load_reset_tables(P, lane, t_lo, t_hi, t_pose, t_pose_m, t_vel_m);
 
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
       a.out.root_state[row * AS_ROOT_STATE_DIM + lane] = val;
     }
     if (a.out.reset_ids && lane == 0) a.out.reset_ids[w] = static_cast<int32_t>(e);
+    if (!a.fused && lane == 0) a.ws.reset_ids[w] = static_cast<int32_t>(e);  // (k_pass2_commit walks this list)
     if (!a.fused) {
       uint32_t word = st_cur[e].x;  // same address for all lanes: broadcast
       const int level = min(state_level(word) + promote_now, P.max_level);
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
     }
   }
   if (a.out.n_reset && blockIdx.x == 0 && threadIdx.x == 0) *a.out.n_reset = static_cast<int32_t>(n_reset);
+  if (!a.fused && blockIdx.x == 0 && threadIdx.x == 0) ctrl->n_reset_list = static_cast<uint32_t>(n_reset);
 }
 
 // Stone sequences for all envs (env_ids == null) or a list; level from the packed word (+ pending promotion).
@@ -466,6 +469,124 @@ __global__ void __launch_bounds__(256) k_grid_state(Workspace ws, uint8_t* bins_
       hist_dst[i0] = ws.ctrl->grid_attempts[i0];
       hist_dst[kMaxGridBins + i0] = ws.ctrl->grid_successes[i0];
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 3-call path, pass 2
+// as_step_pass1 ran pass 2 speculatively for every env that did not reset (state in the other buffer, observation
+// rows final).  What is left of ENV:567 when some env did reset:
+//   k_pass2_commit   one warp per env that reset: `_compute_useful_values` + its observation row from the physics
+//                    state as it is AFTER the PhysX writes of ENV:563-565 (general orientation, the body positions the
+//                    simulator reports now, the contact rows scene.reset zeroed), into the other state buffer; the
+//                    last CTA then makes that buffer the current one.
+// and when none did (DRL:360 skips `_reset_idx`):
+//   k_pass2_revert   the observation tails of pass 1 back into the observation rows; the state buffer of pass 1 stays.
+struct CommitArgs {
+  AsParams P;
+  JointConsts jc;
+  AsStateIn in;     // the views as they are after the writes
+  Workspace ws;
+  float* obs;       // (N,59)
+  float obs_clip;
+  float inv_step_dt;
+  int64_t num_envs;
+};
+
+__device__ __forceinline__ float clip_obs(float v, float c) { return c > 0.0f ? (v < -c ? -c : (v > c ? c : v)) : v; }
+
+__global__ void __launch_bounds__(256) k_pass2_commit(const __grid_constant__ CommitArgs a) {
+  __shared__ float s_row[8][20];
+  const AsParams& P = a.P;
+  Ctrl* ctrl = a.ws.ctrl;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t n = ctrl->n_reset_list;
+  uint2* st = a.ws.state[ctrl->parity ^ 1u];  // the buffer pass 1 speculated into and as_reset wrote
+  const bool exact = a.jc.exact_div != 0;
+  const AsStateIn& in = a.in;
+  const float4 jc_l = a.jc.c[lane < kJ ? lane : 0];
+  for (int64_t w = warp; w < n; w += n_warps) {
+    const int64_t e = a.ws.reset_ids[w];
+    const uint2 sw = st[e];
+    Mdp m{state_idx(sw.x), state_leg(sw.x), state_count(sw.x), __uint_as_float(sw.y)};
+    const int level = state_level(sw.x), ep = state_ep(sw.x);
+    // every lane computes the env's scalars (same addresses: broadcast loads); lanes share the row stores
+    const float* rp = in.root_pos + e * in.root_pos_stride;
+    const float* rq = in.root_quat + e * in.root_quat_stride;
+    const float* rv = in.root_lin_vel + e * in.root_lin_vel_stride;
+    const Vec3 p{rp[0], rp[1], rp[2]}, v{rv[0], rv[1], rv[2]};
+    const Quat q = in.quat_xyzw ? Quat{rq[3], rq[0], rq[1], rq[2]} : Quat{rq[0], rq[1], rq[2], rq[3]};
+    const float* body = in.body_pos + e * in.body_env_stride;
+    const float* b_r = body + in.right_foot_row * in.body_row_stride;
+    const float* b_l = body + in.left_foot_row * in.body_row_stride;
+    const float* b_t = body + in.torso_row * in.body_row_stride;
+    const Vec3 rf{b_r[0], b_r[1], b_r[2]}, lf{b_l[0], b_l[1], b_l[2]};
+    const float h = b_t[2] - min_nan(lf.z, rf.z);                       // ENV:281-283
+    float roll, pitch;
+    euler_roll_pitch(q, roll, pitch);                                    // ENV:285
+    const Vec3 vb = rotate_by_inverse(q, v);                             // ENV:293
+    const Quat inv = quat_inverse(q);
+    const float f_r = contact_norm(in.contact_right + e * in.contact_right_stride, m.idx, false);
+    const float f_l = contact_norm(in.contact_left + e * in.contact_left_stride, m.idx, false);
+    const float4* stones = a.ws.stones + e * kS;
+    float4 s_prev = stones[window_slot_stone(m.idx, 0)], s_curr = stones[window_slot_stone(m.idx, 1)],
+           s_next = stones[window_slot_stone(m.idx, 2)];
+    PassOut po{};
+    const FootGeom g = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
+    if (foot_update(P, g, m, po)) {  // (cannot happen on zeroed contact rows; kept general)
+      s_prev = s_curr;
+      s_curr = s_next;
+      s_next = stones[min(m.idx + 1, kS - 1)];
+    }
+    targets_and_potential(P, a.inv_step_dt, exact, p, inv, s_prev, s_curr, s_next, m, po);
+    if (lane == 0) {
+      uint2 out;
+      out.x = pack_state(m.idx, m.leg, m.count, level, ep);
+      out.y = __float_as_uint(m.pot);
+      st[e] = out;
+      atomicOr(&a.ws.win_stale[e >> 5], 1u << (e & 31));  // its stone window is for k_prepare* to refresh
+      float* r = s_row[wib];
+      r[0] = h; r[1] = roll; r[2] = pitch; r[3] = vb.x; r[4] = vb.y; r[5] = vb.z;
+      r[6] = po.contact_r; r[7] = po.contact_l;
+      r[8] = po.tb0.x; r[9] = po.tb0.y; r[10] = po.tb0.z; r[11] = po.tb1.x; r[12] = po.tb1.y; r[13] = po.tb1.z;
+      r[14] = po.tb2.x; r[15] = po.tb2.y; r[16] = po.tb2.z;
+    }
+    __syncwarp();
+    float* row = a.obs + e * kObs;
+    if (lane < 6) row[lane] = clip_obs(s_row[wib][lane], a.obs_clip);                       // ENV:332-335
+    if (lane >= 6 && lane < 17) row[48 + lane - 6] = clip_obs(s_row[wib][lane], a.obs_clip);  // ENV:338-339
+    if (lane < kJ) {
+      const float jp = in.joint_pos[e * in.joint_pos_stride + lane];
+      const float jv = in.joint_vel[e * in.joint_vel_stride + lane];
+      row[6 + lane] = clip_obs(scale_joint(jc_l, jp, exact), a.obs_clip);                  // ENV:336
+      row[6 + kJ + lane] = clip_obs(clamp_nan(jv * P.dof_vel_scale, -5.0f, 5.0f), a.obs_clip);  // ENV:337
+    }
+    __syncwarp();
+  }
+  // the last CTA makes the speculated buffer the current state
+  __shared__ unsigned int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&ctrl->blocks_done2, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    ctrl->parity ^= 1u;
+    ctrl->n_reset_list = 0;
+    ctrl->blocks_done2 = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pass2_revert(Workspace ws, float* __restrict__ obs, float obs_clip,
+                                                      int64_t num_envs) {
+  const int64_t total = num_envs * 11;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e = i / 11;
+    const int c = static_cast<int>(i - e * 11);
+    obs[e * kObs + 48 + c] = clip_obs(reinterpret_cast<const float*>(ws.tail1 + e * 3)[c], obs_clip);
   }
 }
 

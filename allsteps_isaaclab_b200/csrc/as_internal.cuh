@@ -120,13 +120,15 @@ struct Workspace {
   float4* contact_pre;// (N) |F_right|, |F_left| under each foot for the env's CURRENT stone (.x, .y) and for the stone after it
                       // (.z, .w: what pass 2 needs when pass 1 advances the index), gathered by k_prepare*
   float* body_dense;  // (N,3,3) right foot, left foot, torso positions gathered out of a strided body tensor (k_prepare*)
+  float4* tail1;      // (N,3) 3-call path: the observation tail (foot contacts, targets_b: columns 48..58) as pass 1 leaves it
+  uint8_t* pass1_reset;// (N) 3-call path: the env was flagged for reset by pass 1 (terminated | time_out)
   uint32_t* win_stale;// (ceil(N/32)) one bit per env: its stone-window record must be refreshed by k_prepare* (set by the
                       // step kernel instantiation that does not write windows; set for every env of a fresh handle)
 };
 
 struct WorkspaceLayout {
   int64_t ctrl_off, state0_off, state1_off, stones_off, window_off, reset_ids_off, regen_ids_off, regen_info_off,
-      bin_off, contact_pre_off, body_dense_off, win_stale_off, total;
+      bin_off, contact_pre_off, body_dense_off, tail1_off, pass1_reset_off, win_stale_off, total;
 };
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -156,6 +158,10 @@ inline WorkspaceLayout workspace_layout(int64_t n) {
   off = align_up(off + n * 16, 256);
   l.body_dense_off = off;
   off = align_up(off + n * 36, 256);
+  l.tail1_off = off;
+  off = align_up(off + n * 48, 256);
+  l.pass1_reset_off = off;
+  off = align_up(off + n, 256);
   l.win_stale_off = off;
   off = align_up(off + (n + 31) / 32 * 4, 256);
   l.total = off;
@@ -202,6 +208,7 @@ struct ResetArgs {
   int64_t num_envs;
   int64_t env_id_offset;
   int32_t fused;                // 1: state words were already reset by the step kernel, rows go to env's own row
+  int32_t into_other;           // 3-call path behind a speculating pass 1: the reset state words go into the OTHER buffer
 };
 
 }  // namespace as

@@ -558,6 +558,11 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   constexpr bool kNeedActions = MODE != kModePass2;
   constexpr bool kPingPong = MODE == kModeFused || MODE == kModeFixup;
   constexpr bool kStats = MODE == kModeFused || MODE == kModePass1;
+  // 3-call path, pass 1: like the fused step the kernel ASSUMES that some env resets and runs pass 2 (ENV:567) for
+  // the envs that do not -- into the OTHER state buffer and into the observation tile -- while the state and the
+  // observation tail as pass 1 leaves them go to the current state buffer and to ws.tail1.  as_step_pass2 then only
+  // has to flip the buffers and redo the envs that did reset; as_step_no_reset puts the tails back.
+  constexpr bool kSpec = MODE == kModePass1;
 
   // ---------------------------------------------------------------- HBM -> SMEM (TMA bulk where the view allows)
   const uint32_t dense = a.dense16;
@@ -630,7 +635,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   // ---------------------------------------------------------------- MDP role: state word + dependent gathers
   const uint32_t parity = ctrl->parity;
   const uint2* st_in = a.ws.state[parity];
-  uint2* st_out = kPingPong ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
+  uint2* st_out = (kPingPong || kSpec) ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
   const float4* stones = a.ws.stones + e * kS;
   auto stone_at = [&](int i) -> float4 { return ldg64_f4(stones + i); };
   float4* wrow = a.ws.window + e * 4;
@@ -818,8 +823,19 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       }
     }
 
-    if (MODE == kModeFused && active) {
-      if (is_reset) {
+    if (kSpec && active) {
+      uint2 v1;
+      v1.x = pack_state(m.idx, m.leg, m.count, level, ep);
+      v1.y = __float_as_uint(m.pot);
+      a.ws.state[parity][e] = v1;
+      float4* t1 = a.ws.tail1 + e * 3;
+      t1[0] = make_float4(po.contact_r, po.contact_l, po.tb0.x, po.tb0.y);
+      t1[1] = make_float4(po.tb0.z, po.tb1.x, po.tb1.y, po.tb1.z);
+      t1[2] = make_float4(po.tb2.x, po.tb2.y, po.tb2.z, 0.0f);
+      a.ws.pass1_reset[e] = is_reset ? 1 : 0;
+    }
+    if ((MODE == kModeFused || kSpec) && active) {
+      if (MODE == kModeFused && is_reset) {
         mirror = misc->coin[t] != 0;  // drawn by the joint role in its idle time (ordered by the orientation barrier)
         // ---- masked reset, ENV:487-538.  Pass 2 on the post-reset state: identity orientation (vector part +-0),
         // zero velocity, zero contacts (contact_sensor.py:155), stale body positions; so roll = pitch = v_b = 0 and
@@ -846,7 +862,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
         po.tb2 = Vec3{s_next.x - p.x, s_next.y - p.y, s_next.z - p.z};
         po.body_dist = norm2(s_next.x - p.x, s_next.y - p.y);
         m.pot = potential_of(P, a.inv_step_dt, po.body_dist, exact);  // ENV:487-488, then ENV:415-416 in pass 2
-      } else if (!(P.flags & AS_FLAG_SKIP_PASS2)) {
+      } else if (!(P.flags & AS_FLAG_SKIP_PASS2) && !(kSpec && is_reset)) {
         // ---- pass 2 over ALL envs, ENV:567, on unchanged physics: only the foot state machine can
         // change anything.  Assumed to happen; the fix-up kernel undoes the assumption when no env reset.
         if (idx_after_pass1 != idx_before) {  // the current stone changed in pass 1: new contact column
@@ -860,7 +876,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
           geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
         }
         const bool moved = foot_update(P, geom, m, po);
-        adv2 = po.advanced;
+        if (MODE == kModeFused) adv2 = po.advanced;  // (3-call path: counted only if as_step_pass2 commits; left out)
         if (moved) {
           slide_window();
           targets_and_potential(P, a.inv_step_dt, exact, p, inv, s_prev, s_curr, s_next, m, po);
@@ -1383,7 +1399,7 @@ __global__ void __launch_bounds__(kThreads, AS_STEP_MIN_CTAS) k_step(const __gri
   uint32_t phase_root = 0, phase_joint = 0;
   const int tile = FULL ? static_cast<int>(blockIdx.x) : a.tile_base;  // (full tiles start at 0; the ragged launch is one CTA)
   static_assert(!PACKED || FULL, "a packed root tile needs a full tile (its byte count must be a multiple of 16)");
-  static_assert(!PRE || (FULL && MODE == kModeFused), "the prepared path is the full-tile fused step");
+  static_assert(!PRE || (FULL && (MODE == kModeFused || MODE == kModePass1)), "the prepared path needs full tiles");
   process_tile<MODE, FULL, EXACT, FAST, PACKED, PRE>(a, tile, phase_root, phase_joint, smem);
 }
 

@@ -101,6 +101,7 @@ class AllstepsHooksB200:
 
     def _get_dones(self):  # ENV:396-405; the same launch produces the rewards of ENV:347-394
         self.mdp.pass1(self._physics_views(), self.actions, self.buf, episode_length=self.episode_length_buf)
+        self._pass1_open = True  # closed by `_reset_idx` (pass 2) or, when nothing resets, by `_get_observations`
         return self.buf.terminated, self.buf.time_out
 
     def _get_rewards(self) -> torch.Tensor:  # ENV:347-394 (computed against the `terminated` returned above)
@@ -119,8 +120,12 @@ class AllstepsHooksB200:
         self.robot.write_joint_state_to_sim(self.buf.reset_joint_pos[:k], self.buf.reset_joint_vel[:k], None,
                                             env_ids)  # ENV:565
         self.mdp.pass2(self._physics_views(), self.buf)  # ENV:567
+        self._pass1_open = False
 
     def _get_observations(self) -> Dict[str, torch.Tensor]:  # ENV:326-345
+        if getattr(self, "_pass1_open", False):  # DRL:360 skipped `_reset_idx`: no pass 2 this step
+            self.mdp.no_reset()
+            self._pass1_open = False
         return {"policy": self.buf.obs}
 
     # ------------------------------------------------------------------ the reference's public buffers, on demand

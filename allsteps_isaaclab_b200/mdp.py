@@ -312,8 +312,15 @@ class AllstepsMDP:
         self._keepalive = (ids, env_origins)
 
     def pass2(self, views: PhysicsViews, out: StepBuffers):
+        """ENV:567 after the PhysX writes of `_reset_idx`: makes `out.obs` final for a step in which envs reset."""
         _cabi.check(self.lib.as_step_pass2(self.handle, C.byref(views.struct), out.obs.data_ptr(), self._stream()),
                     "as_step_pass2")
+        self._keepalive = (views, out)
+
+    def no_reset(self):
+        """The step's `reset_buf` was empty (DRL:360): no `_reset_idx`, no pass 2 -- makes the observations of `pass1`
+        final.  Exactly one of `pass2` / `no_reset` closes every `pass1`; a no-op when none is open."""
+        _cabi.check(self.lib.as_step_no_reset(self.handle, self._stream()), "as_step_no_reset")
 
     # ------------------------------------------------------------------ action path / symmetry
     def apply_action(self, actions: torch.Tensor, efforts: Optional[torch.Tensor] = None) -> torch.Tensor:

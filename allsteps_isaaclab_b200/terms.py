@@ -69,6 +69,7 @@ class _Binding:
         self.buf.reward_terms.zero_()
         self.mdp.generate_stones(env.scene.env_origins)
         self.epoch = None
+        self.open = False
 
     def views(self, env) -> PhysicsViews:
         robot, left, right = (env.scene[n] for n in self.names)
@@ -87,6 +88,7 @@ class _Binding:
         actions = am.action if am is not None else env.actions
         self.mdp.pass1(self.views(env), actions, self.buf, episode_length=env.episode_length_buf)
         self.epoch = env.common_step_counter
+        self.open = True  # closed by `reset_allsteps` (pass 2) or by the first observation term when nothing resets
 
 
 def binding(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None, **kw) -> _Binding:
@@ -103,6 +105,9 @@ def binding(env, asset_cfg=None, left_sensor_cfg=None, right_sensor_cfg=None, **
 def _obs(env, name: str, ent) -> torch.Tensor:
     b = binding(env, *ent)
     b.ensure_pass1(env)  # no-op when termination/reward terms already ran this step (the usual order)
+    if b.open:  # observations are computed after `_reset_idx` (manager_based_rl_env.py:220-239): nothing reset this step
+        b.mdp.no_reset()
+        b.open = False
     lo, hi = OBS_SLICES[name]
     return b.buf.obs[:, lo:hi]
 
@@ -191,6 +196,7 @@ def reset_allsteps(env, env_ids, write_to_sim: bool = True, asset_cfg=None, left
         robot.write_root_velocity_to_sim(root[:, 7:], env_ids)
         robot.write_joint_state_to_sim(b.buf.reset_joint_pos[:k], b.buf.reset_joint_vel[:k], None, env_ids)
     b.mdp.pass2(b.views(env), b.buf)
+    b.open = False
 
 
 # ---------------------------------------------------------------------------------------------- curriculum

@@ -308,6 +308,8 @@ def time_three_call(torch, wl, origins, steps, warmup, device_reset_list=False):
         if len(ids) > 0:
             mdp.reset(origins, ids, out, episode_length=ep_len)
             mdp.pass2(v, out)
+        else:
+            mdp.no_reset()
 
     def run(n):
         for _ in range(n):

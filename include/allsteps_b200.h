@@ -195,7 +195,7 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
                   const AsStepOut* out, const AsResetOut* reset_out, void* stream);
 
 /* ---- the same step as three calls, for hosts that run PhysX between them --------------------------------
- * pass1:  `_get_dones` + `_get_rewards` (+ observations as they are when nothing resets).
+ * pass1:  `_get_dones` + `_get_rewards`; `obs` is final only after as_step_pass2 or as_step_no_reset (below).
  *         episode_length: optional device int64 (N) owned by DirectRLEnv (already incremented, DRL:351);
  *         NULL = the library keeps and increments its own counter.
  * reset:  `_reset_idx(env_ids)` minus the PhysX writes: promotion rule, MDP state reset, start pose rows.
@@ -210,6 +210,14 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
 int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids,
              int64_t* episode_length, const AsResetOut* compact_out, void* stream);
 int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream);
+/* DRL:360 found no env to reset, so `_reset_idx` -- and with it pass 2 -- does not run this step: the observations of
+ * as_step_pass1 are made final.  (as_step_pass1 works like the fused step: it ASSUMES that some env resets, runs pass 2
+ * for every env that does not on the spot -- their physics cannot change between DRL:354 and ENV:567 -- and leaves the
+ * result in the second state buffer and in `obs`; as_step_pass2 then only redoes the envs that did reset, from the views
+ * as they are after the PhysX writes, and switches buffers.  This call takes the assumption back: observation columns
+ * 48..58 as pass 1 left them, state of pass 1.)  Call it, or as_reset + as_step_pass2, once per as_step_pass1; a no-op
+ * when no pass 1 is open. */
+int as_step_no_reset(AsHandle* h, void* stream);
 
 /* ---- curriculum: ENV:470-479 -----------------------------------------------------------------------------
  * The step kernels leave per-step statistics in the control block; as_finish_step folds them, applies the

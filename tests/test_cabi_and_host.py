@@ -53,9 +53,10 @@ def test_workspace_size_is_monotonic_and_aligned(lib):
         assert b % 256 == 0 and b > prev
         prev = b
     assert lib.as_workspace_bytes(0) == 0
-    # 1M envs: stones 320 B + stone window 64 B + 2 x 8 B state + 2 x 4 B lists + 8 B contact norms + 2 B grid
-    # + 36 B dense body rows (used when the caller's body tensor is strided)
-    assert lib.as_workspace_bytes(1 << 20) < (1 << 20) * 480
+    # 1M envs: stones 320 B + stone window 64 B + 2 x 8 B state + 2 x 4 B lists + 16 B contact norms + 2 B grid
+    # + 36 B dense body rows (used when the caller's body tensor is strided) + 48 B pass-1 observation tails and
+    # 1 B reset flags (3-call path) + 1 bit window-stale flags
+    assert lib.as_workspace_bytes(1 << 20) < (1 << 20) * 520
 
 
 def test_argument_validation_and_loud_failure_without_gpu(lib):

@@ -96,6 +96,9 @@ class OracleMDP:
             episode_length[ids] = 0
         self.launch_count += 1
 
+    def no_reset(self):
+        pass  # (the stand-in's pass 1 leaves the pass-1 observations in place)
+
     def pass2(self, views, buf):
         buf.obs.copy_(self.orc.observations())  # (the oracle's reset ended with its pass 2 on the rows it wrote)
         self.launch_count += 1

@@ -40,6 +40,8 @@ def probe(N, steps=50, sets=4, warmup=10):
             if len(ids):
                 mdp.reset(origins, ids, out, episode_length=ep_len)
                 mdp.pass2(v, out)
+            else:
+                mdp.no_reset()
             wl.j += 1
     else:
         one = wl.step
