@@ -87,7 +87,18 @@ class AsStats(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
-STATS_ADDITIVE_FIELDS = 10  # leading int64 fields that are summed over ranks
+STATS_ADDITIVE_FIELDS = 10  # leading int64 fields that are summed over ranks (AS_NUM_ADDITIVE_STATS)
+MAX_GRID_CELLS = 256
+
+
+class AsExchange(C.Structure):
+    """What shards exchange per step: the statistics and this step's difficulty-grid outcomes (one device record)."""
+    _fields_ = [("stats", AsStats), ("grid_attempts", C.c_uint32 * MAX_GRID_CELLS),
+                ("grid_successes", C.c_uint32 * MAX_GRID_CELLS)]
+
+
+STATS_INT64_WORDS = C.sizeof(AsStats) // 8          # int64 words of the AsStats head of an exchange record
+EXCHANGE_INT64_WORDS = C.sizeof(AsExchange) // 8    # ... of the whole record (grid arrays: two uint32 per word)
 
 
 class AsMdpState(C.Structure):
@@ -125,6 +136,7 @@ SIGNATURES = {
     "as_peer_connect": (C.c_int, [_ptr, _ptr]),
     "as_peer_status": (C.c_int, [_ptr, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64), _ptr]),
     "as_global_stats_device_ptr": (C.c_int, [_ptr, C.POINTER(_ptr)]),
+    "as_exchange_device_ptr": (C.c_int, [_ptr, C.POINTER(_ptr), C.POINTER(_ptr)]),
     "as_export_state": (C.c_int, [_ptr, C.POINTER(AsMdpState), _ptr]),
     "as_export_stone_poses": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "as_import_state": (C.c_int, [_ptr, C.POINTER(AsMdpState), _ptr]),

@@ -32,6 +32,7 @@ struct AsHandle {
   bool peer_connected;
   volatile uint32_t* peer_host_error;  // mapped pinned host word the exchange kernel sets when a peer timed out
   bool pass1_done;
+  bool device_list;     // as_reset took the envs from the list pass 1 compacted on the device (no host round trip)
   bool spec_valid;      // as_step_pass1 speculated pass 2 into the other state buffer; as_step_pass2 / as_step_no_reset closes it
   float* spec_obs;      // the observation buffer that pass 1 wrote
   bool pending_valid;   // a fused step was launched and still needs as_finish_step
@@ -352,6 +353,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->launches = 0;
   h->pass1_done = false;
   h->spec_valid = false;
+  h->device_list = false;
   h->spec_obs = nullptr;
   h->obs_clip_pass1 = 0.0f;
   std::memset(&h->peer, 0, sizeof(h->peer));
@@ -518,12 +520,13 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
                       ragged_kernel, a, s, dep, packed ? kSmemBytesPacked : kSmemBytes));
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
   if (h->ev_stop) AS_CUDA(cudaEventRecord(h->ev_stop, s));
-  if (grid) {  // kernel (c): outcomes into the difficulty histogram, then new bins by inverse-CDF sampling
+  if (grid) {  // kernel (c): new bins by inverse-CDF sampling from the histograms as they stand after the previous
+               // step; this step's outcomes into the step's record (they join the histograms when the step is closed)
     const int g = grid_for(h->num_envs, 256 * 8, h->sm_count, 1);
-    k_grid_hist<<<g, 256, 0, s>>>(h->params, h->ws);
-    if (int rc = check_launch(h, "k_grid_hist")) return rc;
     k_grid_sample<<<g, 256, 0, s>>>(h->params, h->ws, h->env_id_offset);
     if (int rc = check_launch(h, "k_grid_sample")) return rc;
+    k_grid_hist<<<g, 256, 0, s>>>(h->params, h->ws);
+    if (int rc = check_launch(h, "k_grid_hist")) return rc;
   }
   if (regen_enabled) {  // kernel (b): warp-per-env stone regeneration over the compacted list
     ResetArgs r = make_reset_args(h, in->env_origins);
@@ -621,11 +624,18 @@ int as_peer_status(AsHandle* h, int* world, int* rank, int64_t* timeouts, void* 
 
 int as_global_stats_device_ptr(AsHandle* h, AsStats** device_stats) {
   AS_REQUIRE(h && device_stats, "null argument");
-  *device_stats = &h->ws.ctrl->gstats;
+  *device_stats = &h->ws.ctrl->gx.stats;
   return AS_OK;
 }
 
-int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream) {
+int as_exchange_device_ptr(AsHandle* h, AsExchange** local, AsExchange** global) {
+  AS_REQUIRE(h, "handle is null");
+  if (local) *local = reinterpret_cast<AsExchange*>(&h->ws.ctrl->stats);
+  if (global) *global = &h->ws.ctrl->gx;
+  return AS_OK;
+}
+
+int as_finish_step(AsHandle* h, const AsExchange* global_stats, void* stream) {
   AS_REQUIRE(h, "handle is null");
   if (!h->pending_valid) return fail(AS_ERR_STATE, "as_finish_step without a preceding as_step_fused");
   if (int rc = check_peer(h)) {
@@ -637,9 +647,10 @@ int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream) {
   a.global_stats = global_stats;
   if (h->peer_connected && global_stats == nullptr) {
     // fold + sum over the shards through NVLink peer memory, in one small kernel under the step kernel's tail
-    AS_CUDA(launch_dependent(k_peer_exchange, 1u, 128u, 0, s, h->pdl >= 1, h->ws.ctrl, h->peer, h->num_envs));
+    const int cells = (h->params.flags & AS_FLAG_GRID_CURRICULUM) ? static_cast<int>(h->params.grid_bins * h->params.grid_bins) : 0;
+    AS_CUDA(launch_dependent(k_peer_exchange, 1u, 128u, 0, s, h->pdl >= 1, h->ws.ctrl, h->peer, h->num_envs, cells));
     if (int rc = check_launch(h, "k_peer_exchange")) return rc;
-    a.global_stats = &h->ws.ctrl->gstats;
+    a.global_stats = &h->ws.ctrl->gx;
   }
   const int grid = grid_for(a.num_tiles, 1, h->sm_count, 1);
   // programmatic dependent launch: the step kernel releases its dependents as soon as its last wave of CTAs is
@@ -663,6 +674,8 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   a.ext_episode_length = episode_length;
   h->obs_clip_pass1 = out->obs_clip;  // as_step_pass2 rewrites the same observation buffer: same epilogue
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  AS_CUDA(cudaMemsetAsync(&h->ws.ctrl->n_reset_list, 0, sizeof(uint32_t), s));  // pass 1 compacts the flagged envs
+  h->device_list = false;
   bool gather_body = false;
   if (!(a.dense16 & kDenseBody) && h->num_envs >= kSeparateGatherMinEnvs) {  // (as in as_step_fused)
     gather_body = true;
@@ -701,9 +714,16 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
 int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids, int64_t* episode_length,
              const AsResetOut* compact_out, void* stream) {
   AS_REQUIRE(h, "handle is null");
-  AS_REQUIRE(n_ids >= 0 && n_ids <= h->num_envs, "id count out of range");
-  if (n_ids == 0) return AS_OK;  // DRL:360: `_reset_idx` is not entered (an empty id tensor has a null pointer)
-  AS_REQUIRE(env_origins && env_ids, "env_origins/env_ids is null");
+  const bool from_device_list = env_ids == nullptr && n_ids < 0;
+  if (from_device_list) {
+    // "the envs as_step_pass1 flagged": the id list that pass compacted on the device, however many there are
+    if (!h->spec_valid) return fail(AS_ERR_STATE, "as_reset(env_ids = NULL, n_ids < 0) needs a preceding as_step_pass1");
+    AS_REQUIRE(env_origins != nullptr, "env_origins is null");
+  } else {
+    AS_REQUIRE(n_ids >= 0 && n_ids <= h->num_envs, "id count out of range");
+    if (n_ids == 0) return AS_OK;  // DRL:360: `_reset_idx` is not entered (an empty id tensor has a null pointer)
+    AS_REQUIRE(env_origins && env_ids, "env_origins/env_ids is null");
+  }
   if (h->pending_valid) return fail(AS_ERR_STATE, "a fused step is open; close it with as_finish_step");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!h->pass1_done) {
@@ -714,16 +734,19 @@ int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int6
     if (int rc = check_launch(h, "k_prepare_reset")) return rc;
   }
   h->pass1_done = false;  // consumed: a second reset without a pass in between prepares for itself
-  k_decide_promotion<<<1, 32, 0, s>>>(h->params, h->ws.ctrl, nullptr, 1);
+  // (an explicit id list means `_reset_idx` was entered, i.e. some env reset; with the device-side list that is
+  // decided by the count pass 1 folded -- the rule is not evaluated in a step in which nothing resets, DRL:360)
+  k_decide_promotion<<<1, 32, 0, s>>>(h->params, h->ws.ctrl, nullptr, from_device_list ? 0 : 1);
   if (int rc = check_launch(h, "k_decide_promotion")) return rc;
   ResetArgs r = make_reset_args(h, env_origins);
   if (compact_out) r.out = *compact_out;
-  r.env_ids = env_ids;
-  r.n_ids = n_ids;
+  r.env_ids = from_device_list ? h->ws.reset_ids : env_ids;
+  r.n_ids = from_device_list ? -1 : n_ids;
+  h->device_list = from_device_list;
   r.ext_episode_length = episode_length;
   r.fused = 0;
   r.into_other = h->spec_valid ? 1 : 0;  // behind a speculating pass 1 the step continues in the other state buffer
-  const int grid = grid_for(n_ids, 8, h->sm_count, 4);
+  const int grid = grid_for(from_device_list ? h->num_envs / 8 + 1 : n_ids, 8, h->sm_count, 4);
   k_reset_rows<<<grid, 256, 0, s>>>(r);
   return check_launch(h, "k_reset_rows");
 }
@@ -748,6 +771,7 @@ int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
     c.obs_clip = h->obs_clip_pass1;
     c.inv_step_dt = h->inv_step_dt;
     c.num_envs = h->num_envs;
+    c.revert_if_none = h->device_list ? 1 : 0;
     const int grid = grid_for(h->num_envs / 16 + 1, 8, h->sm_count, 8);
     k_pass2_commit<<<grid, 256, 0, s>>>(c);
     h->spec_valid = false;
@@ -950,6 +974,7 @@ int64_t as_sizeof(int32_t which) {
     case 4: return sizeof(AsStats);
     case 5: return sizeof(AsMdpState);
     case 6: return sizeof(AsMirrorJob);
+    case 7: return sizeof(AsExchange);
     default: return -1;
   }
 }

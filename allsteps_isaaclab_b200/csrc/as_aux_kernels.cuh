@@ -118,14 +118,15 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const unsigned long long step = ctrl->step_counter;
-  const int64_t n_reset = a.fused ? 0 : a.n_ids;  // fused: the step kernel already wrote the start-pose rows
+  // fused: the step kernel already wrote the start-pose rows; n_ids < 0: the list pass 1 compacted on the device
+  const int64_t n_reset = a.fused ? 0 : (a.n_ids < 0 ? static_cast<int64_t>(ctrl->n_reset_list) : a.n_ids);
   // promotion decided in THIS step is already in force when stones are regenerated (ENV:471 precedes ENV:500)
   // (3-call path: as_reset ran k_decide_promotion first and left the decision in promote_cur)
   int promote_now;
   if (!a.fused) {
     promote_now = static_cast<int>(ctrl->promote_cur);
   } else if (a.global_stats) {
-    promote_now = static_cast<int>(promotion_decision(P, *a.global_stats));
+    promote_now = static_cast<int>(promotion_decision(P, a.global_stats->stats));
   } else {  // the step kernel's counters are still in the replicated slots (folded by the finish kernel)
     const unsigned nr = slot_sum(ctrl, kCntReset);
     const unsigned si = slot_sum(ctrl, kCntSumIndex);
@@ -360,10 +361,13 @@ __global__ void __launch_bounds__(256) k_import(const __grid_constant__ AsParams
 
 // ------------------------------------------------------------------------------------------------ kernel (c)
 // Grid-curriculum extension (no reference counterpart; specification = oracle/grid_curriculum.py).
+// k_grid_sample: every CTA rebuilds the integer CDF of the bin weights (histograms as they stand after the PREVIOUS
+//                step) with a warp-scan (shuffle) prefix sum, then draws a new bin for each env that reset by
+//                inverse-CDF search with its Philox uniform.
 // k_grid_hist:   shared-memory histogram of this step's episode outcomes over the difficulty grid, flushed with one
-//                atomic per touched bin and CTA.
-// k_grid_sample: every CTA rebuilds the integer CDF of the bin weights with a warp-scan (shuffle) prefix sum, then
-//                draws a new bin for each env that reset by inverse-CDF search with its Philox uniform.
+//                atomic per touched bin and CTA into the step's outcome record (Ctrl::grid_delta_*); the record is
+//                added to the histograms when the step is closed -- after having been summed over all shards by the
+//                peer exchange / the caller's all-reduce when the run is sharded.
 // Both walk the id list the step kernel compacted (ws.regen_ids / ws.regen_info).
 constexpr uint32_t kStreamGrid = 2;
 
@@ -380,9 +384,10 @@ __global__ void __launch_bounds__(256) k_grid_hist(const __grid_constant__ AsPar
     if (ws.regen_info[w] > kS / 2) atomicAdd(&s_succ[b], 1u);
   }
   __syncthreads();
+  // into this step's outcome record: it joins the histograms when the step is closed (summed over shards if sharded)
   for (int i = threadIdx.x; i < kMaxGridBins; i += blockDim.x) {
-    if (s_att[i]) atomicAdd(&ctrl->grid_attempts[i], s_att[i]);
-    if (s_succ[i]) atomicAdd(&ctrl->grid_successes[i], s_succ[i]);
+    if (s_att[i]) atomicAdd(&ctrl->grid_delta_att[i], s_att[i]);
+    if (s_succ[i]) atomicAdd(&ctrl->grid_delta_succ[i], s_succ[i]);
   }
 }
 
@@ -490,6 +495,8 @@ struct CommitArgs {
   float obs_clip;
   float inv_step_dt;
   int64_t num_envs;
+  int32_t revert_if_none;  // device-side reset list: whether any env reset is only known here -- none did: behave as
+                           // k_pass2_revert (DRL:360 would have skipped `_reset_idx`)
 };
 
 __device__ __forceinline__ float clip_obs(float v, float c) { return c > 0.0f ? (v < -c ? -c : (v > c ? c : v)) : v; }
@@ -502,6 +509,16 @@ __global__ void __launch_bounds__(256) k_pass2_commit(const __grid_constant__ Co
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int64_t n = ctrl->n_reset_list;
+  if (n == 0 && a.revert_if_none) {
+    const int64_t total = a.num_envs * 11;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t e = i / 11;
+      const int c = static_cast<int>(i - e * 11);
+      a.obs[e * kObs + 48 + c] = clip_obs(reinterpret_cast<const float*>(a.ws.tail1 + e * 3)[c], a.obs_clip);
+    }
+    return;
+  }
   uint2* st = a.ws.state[ctrl->parity ^ 1u];  // the buffer pass 1 speculated into and as_reset wrote
   const bool exact = a.jc.exact_div != 0;
   const AsStateIn& in = a.in;
@@ -588,6 +605,7 @@ __global__ void __launch_bounds__(256) k_pass2_revert(Workspace ws, float* __res
     const int c = static_cast<int>(i - e * 11);
     obs[e * kObs + 48 + c] = clip_obs(reinterpret_cast<const float*>(ws.tail1 + e * 3)[c], obs_clip);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) ws.ctrl->n_reset_list = 0;
 }
 
 // `_reset_idx` called outside a step (as_reset without a preceding as_step_pass1): the numerator of ENV:471 from the
@@ -622,7 +640,7 @@ __global__ void k_restore_ctrl(Ctrl* ctrl, const Ctrl* saved) {
     ctrl->promote_cur = saved->promote_cur;
     ctrl->step_counter = saved->step_counter;
     ctrl->stats = saved->stats;
-    ctrl->gstats = saved->gstats;
+    ctrl->gx.stats = saved->gx.stats;
     ctrl->last_adv2 = saved->last_adv2;
     ctrl->stats_folded = 0;
     ctrl->blocks_done = ctrl->blocks_done2 = 0;

@@ -1,5 +1,6 @@
 // Internal layout shared by the Allsteps kernels and the C-ABI glue (not part of the public header).
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -78,18 +79,24 @@ struct Ctrl {
   uint32_t stats_folded;  // as_fold_stats already folded this step's counters (the finish kernel must not redo it)
   uint32_t peer_epoch;    // steps closed through the peer exchange (its flag value is peer_epoch + 1, never 0)
   unsigned long long step_counter;
-  AsStats stats;          // folded statistics of the last step (this shard)
+  AsStats stats;          // folded statistics of the last step (this shard) ...
+  unsigned int grid_delta_att[kMaxGridBins];   // ... followed by this step's grid outcomes: together one AsExchange
+  unsigned int grid_delta_succ[kMaxGridBins];
   unsigned int slots[kSlots][kNumCounters];
   float slot_reward[kSlots];
   unsigned int grid_attempts[kMaxGridBins];   // grid curriculum extension: episodes ended per difficulty bin
   unsigned int grid_successes[kMaxGridBins];  // ... of which the env had passed half of the stones
   unsigned long long dbg_t[16];               // -DAS_TIMING builds only: summed clock64() phase durations per CTA
-  AsStats gstats;                             // step counters summed over all shards (peer exchange)
+  AsExchange gx;                              // exchange records summed over all shards (peer exchange)
   unsigned long long peer_timeouts;           // peers that did not deliver within the time limit (sticky: see peer_error)
   uint32_t peer_error;                        // != 0: a peer exchange timed out; the shards may have diverged (AS_ERR_PEER)
   uint32_t step_state;                        // written by the LAST CTA of every fused step kernel: 2 = it closed the step itself
                                               // (statistics folded, promotion decided, parity flipped), 1 = k_fixup_finish has to
 };
+
+static_assert(offsetof(Ctrl, grid_delta_att) == offsetof(Ctrl, stats) + sizeof(AsStats) &&
+                  offsetof(Ctrl, grid_delta_succ) == offsetof(Ctrl, grid_delta_att) + sizeof(unsigned int) * kMaxGridBins,
+              "Ctrl::stats and the grid outcome arrays form one AsExchange");
 
 // Peer exchange buffer of one rank: for each of the two epoch parities one 128-byte slot per sending rank.
 constexpr int kMaxPeers = AS_MAX_PEERS;
@@ -100,7 +107,12 @@ struct PeerSlot {
   unsigned long long pad[5];
 };
 static_assert(sizeof(PeerSlot) == 128, "one slot per 128-byte line");
-constexpr int64_t kPeerBufferBytes = 2 * kMaxPeers * static_cast<int64_t>(sizeof(PeerSlot));
+struct PeerGrid {  // one sender's grid outcomes of a step
+  unsigned int att[kMaxGridBins], succ[kMaxGridBins];
+};
+constexpr int64_t kPeerGridOffset = 2 * kMaxPeers * static_cast<int64_t>(sizeof(PeerSlot));
+constexpr int64_t kPeerBufferBytes = kPeerGridOffset + 2 * kMaxPeers * static_cast<int64_t>(sizeof(PeerGrid));
+static_assert(offsetof(AsExchange, grid_attempts) == sizeof(AsStats), "AsExchange is AsStats + the two grid arrays");
 struct PeerArgs {
   PeerSlot* buf[kMaxPeers];  // buf[r]: rank r's buffer as seen from this GPU (own: local pointer, others: IPC mappings)
   int32_t world, rank;
@@ -179,7 +191,7 @@ struct StepArgs {
   AsStepOut out;
   Workspace ws;
   const int64_t* ext_episode_length;  // 3-call path: DirectRLEnv-owned counter (already incremented), or null
-  const AsStats* global_stats;        // fix-up/finish: statistics summed over ranks, or null
+  const AsExchange* global_stats;     // fix-up/finish: exchange record summed over ranks, or null
   int64_t num_envs;
   int64_t env_id_offset;
   int32_t num_tiles;
@@ -203,7 +215,7 @@ struct ResetArgs {
   const int32_t* env_ids;   // 3-call path: explicit list; fused path: null (uses ws.reset_ids / ws.regen_ids)
   int64_t n_ids;
   int64_t* ext_episode_length;
-  const AsStats* global_stats;
+  const AsExchange* global_stats;
   const float* stone_uniforms;  // optional explicit draws (5,N,S)
   int64_t num_envs;
   int64_t env_id_offset;

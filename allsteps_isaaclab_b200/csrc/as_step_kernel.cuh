@@ -790,10 +790,14 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     if (MODE == kModeFused) {  // the joint role finishes the envs that reset: tell it early which ones they are
       misc->flags[t] = is_reset ? 1u : 0u;
       flags_arrive();
+    }
+    if (MODE == kModeFused || kSpec) {
       // reserve this warp's range of the reset-id list now: the atomic's round trip to L2 (the ids are written at
       // the end) then hides behind pass 1 instead of sitting in front of the hand-off to the joint role
+      // (3-call path: the list lets as_reset take "the envs pass 1 flagged" without a host round trip)
       rmask = __ballot_sync(0xffffffffu, is_reset);
-      if (rmask && a.want_reset_list && lane == __ffs(rmask) - 1) rbase = atomicAdd(&ctrl->n_reset_list, __popc(rmask));
+      if (rmask && (kSpec || a.want_reset_list) && lane == __ffs(rmask) - 1)
+        rbase = atomicAdd(&ctrl->n_reset_list, __popc(rmask));
     }
     bool moved1 = false;
     if (active) {
@@ -908,6 +912,10 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
 #ifdef AS_TIMING
     if (tid == 0) { AS_T(t_m2); AS_TACC(0, t_start, t_m0); AS_TACC(1, t_m0, t_m1); AS_TACC(2, t_m1, t_m2); }
 #endif
+    if (kSpec && rmask) {
+      const unsigned base = __shfl_sync(0xffffffffu, rbase, __ffs(rmask) - 1);
+      if (is_reset) a.ws.reset_ids[base + __popc(rmask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
+    }
     if (MODE == kModeFused) {
       // ---- reset / regeneration id lists (warp ballots)
       if (rmask && a.want_reset_list) {
@@ -1430,70 +1438,113 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 __global__ void __launch_bounds__(128) k_peer_exchange(Ctrl* ctrl, const __grid_constant__ PeerArgs peer,
-                                                       int64_t num_envs) {
+                                                       int64_t num_envs, int grid_cells) {
   __shared__ unsigned int fold[kNumCounters];
+  __shared__ unsigned int s_timeouts;
   asm volatile("griddepcontrol.launch_dependents;");  // the finish kernel may become resident; it waits for us
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the step kernel has completed and flushed
   fold_stats(ctrl, fold, num_envs);
   const int tid = threadIdx.x;
   if (tid == 0) ctrl->stats_folded = 1;
   __syncthreads();
-  if (tid >= 32) return;
   const unsigned long long epoch = static_cast<unsigned long long>(ctrl->peer_epoch) + 1ull;
   const int par = static_cast<int>(epoch & 1ull);
+  auto grid_slot = [&](int owner, int sender) {
+    return reinterpret_cast<PeerGrid*>(reinterpret_cast<unsigned char*>(peer.buf[owner]) + kPeerGridOffset) +
+           par * kMaxPeers + sender;
+  };
+  if (grid_cells > 0) {
+    // this step's difficulty-grid outcomes go first (all threads), the flag that publishes them last (below)
+    for (int r = 0; r < peer.world; ++r) {
+      PeerGrid* dst = grid_slot(r, peer.rank);
+      for (int i = tid; i < grid_cells; i += blockDim.x) {
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&dst->att[i]), "r"(ctrl->grid_delta_att[i]) : "memory");
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&dst->succ[i]), "r"(ctrl->grid_delta_succ[i]) : "memory");
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+  }
   const long long* mine = reinterpret_cast<const long long*>(&ctrl->stats);
   long long got[kPeerCounters];
 #pragma unroll
   for (int k = 0; k < kPeerCounters; ++k) got[k] = 0;
-  bool timed_out = false;
-  if (tid < peer.world) {
-    PeerSlot* dst = peer.buf[tid] + par * kMaxPeers + peer.rank;
-#pragma unroll
-    for (int k = 0; k < kPeerCounters; ++k) {
-      asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(&dst->counters[k]), "l"(mine[k]) : "memory");
-    }
-    st_release_sys_u64(&dst->flag, epoch);  // release: the counters are visible before the flag
-    const PeerSlot* src = peer.buf[peer.rank] + par * kMaxPeers + tid;
-    const unsigned long long t0 = global_timer_ns();
-    while (ld_acquire_sys_u64(&src->flag) != epoch) {
-      if (peer.timeout_ns != 0ull && global_timer_ns() - t0 > peer.timeout_ns) {
-        timed_out = true;
-        break;
-      }
-      __nanosleep(100);
-    }
-    if (!timed_out) {
+  if (tid < 32) {
+    bool timed_out = false;
+    if (tid < peer.world) {
+      PeerSlot* dst = peer.buf[tid] + par * kMaxPeers + peer.rank;
 #pragma unroll
       for (int k = 0; k < kPeerCounters; ++k) {
-        asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(got[k]) : "l"(&src->counters[k]) : "memory");
+        asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(&dst->counters[k]), "l"(mine[k]) : "memory");
+      }
+      st_release_sys_u64(&dst->flag, epoch);  // release: counters (and the grid record) are visible before the flag
+      const PeerSlot* src = peer.buf[peer.rank] + par * kMaxPeers + tid;
+      const unsigned long long t0 = global_timer_ns();
+      while (ld_acquire_sys_u64(&src->flag) != epoch) {
+        if (peer.timeout_ns != 0ull && global_timer_ns() - t0 > peer.timeout_ns) {
+          timed_out = true;
+          break;
+        }
+        __nanosleep(100);
+      }
+      if (!timed_out) {
+#pragma unroll
+        for (int k = 0; k < kPeerCounters; ++k) {
+          asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(got[k]) : "l"(&src->counters[k]) : "memory");
+        }
       }
     }
-  }
-  const unsigned n_to = __popc(__ballot_sync(0xffffffffu, timed_out));
+    const unsigned n_to = __popc(__ballot_sync(0xffffffffu, timed_out));
 #pragma unroll
-  for (int k = 0; k < kPeerCounters; ++k) {
+    for (int k = 0; k < kPeerCounters; ++k) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) got[k] += __shfl_xor_sync(0xffffffffu, got[k], o);
-  }
-  if (tid == 0) {
-    AsStats g = ctrl->stats;  // level, step counter, reward sum: this shard's
-    if (n_to == 0) {
-      long long* gs = reinterpret_cast<long long*>(&g);
-#pragma unroll
-      for (int k = 0; k < kPeerCounters; ++k) gs[k] = got[k];
-    } else {
-      // A peer did not deliver in time.  A sum over some of the shards is never published: this step closes on the
-      // shard's own counters, and the error is STICKY -- ctrl->peer_error on the device, the mapped host word for the
-      // API, which refuses every further step with AS_ERR_PEER (the shards may have promoted differently).
-      ctrl->peer_timeouts += n_to;
-      ctrl->peer_error = 1u;
-      if (peer.host_error) {
-        *reinterpret_cast<volatile uint32_t*>(peer.host_error) = static_cast<uint32_t>(epoch) | 0x80000000u;
-        __threadfence_system();
-      }
+      for (int o = 16; o > 0; o >>= 1) got[k] += __shfl_xor_sync(0xffffffffu, got[k], o);
     }
-    ctrl->gstats = g;
-    ctrl->peer_epoch = static_cast<uint32_t>(epoch == 0xFFFFFFFFull ? 0ull : epoch);
+    if (tid == 0) {
+      s_timeouts = n_to;
+      AsStats g = ctrl->stats;  // level, step counter, reward sum: this shard's
+      if (n_to == 0) {
+        long long* gs = reinterpret_cast<long long*>(&g);
+#pragma unroll
+        for (int k = 0; k < kPeerCounters; ++k) gs[k] = got[k];
+      } else {
+        // A peer did not deliver in time.  A sum over some of the shards is never published: this step closes on the
+        // shard's own record, and the error is STICKY -- ctrl->peer_error on the device, the mapped host word for the
+        // API, which refuses every further step with AS_ERR_PEER (the shards may have promoted differently).
+        ctrl->peer_timeouts += n_to;
+        ctrl->peer_error = 1u;
+        if (peer.host_error) {
+          *reinterpret_cast<volatile uint32_t*>(peer.host_error) = static_cast<uint32_t>(epoch) | 0x80000000u;
+          __threadfence_system();
+        }
+      }
+      ctrl->gx.stats = g;
+      ctrl->peer_epoch = static_cast<uint32_t>(epoch == 0xFFFFFFFFull ? 0ull : epoch);
+    }
+  }
+  __syncthreads();  // every peer's flag has been seen (acquire) by a lane of warp 0: their grid records are readable
+  if (grid_cells > 0) {
+    const bool ok = s_timeouts == 0;
+    for (int i = tid; i < kMaxGridBins; i += blockDim.x) {
+      unsigned int att = 0, succ = 0;
+      if (i < grid_cells) {
+        if (ok) {
+          for (int r = 0; r < peer.world; ++r) {
+            const PeerGrid* src = grid_slot(peer.rank, r);
+            unsigned int x, y;
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(x) : "l"(&src->att[i]) : "memory");
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(y) : "l"(&src->succ[i]) : "memory");
+            att += x;
+            succ += y;
+          }
+        } else {
+          att = ctrl->grid_delta_att[i];
+          succ = ctrl->grid_delta_succ[i];
+        }
+      }
+      ctrl->gx.grid_attempts[i] = att;
+      ctrl->gx.grid_successes[i] = succ;
+    }
   }
 }
 
@@ -1524,7 +1575,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
   if (tid < 32) {
     // "did any env reset" (DRL:359-360) is a property of ALL envs: with a global sum at hand, that one decides
     unsigned n;
-    if (a.global_stats) n = a.global_stats->n_reset > 0 ? 1u : 0u;
+    if (a.global_stats) n = a.global_stats->stats.n_reset > 0 ? 1u : 0u;
     else n = prefolded ? static_cast<unsigned>(ctrl->stats.n_reset) : slot_sum(ctrl, kCntReset);
     if (tid == 0) misc->is_last = n;  // reused as "number of resets this step"
   }
@@ -1552,9 +1603,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_fixup_finish(const __grid_const
   if (misc->is_last == 0) return;
   __threadfence();
   if (!prefolded) fold_stats(ctrl, misc->fold, a.num_envs);
+  if (a.P.flags & AS_FLAG_GRID_CURRICULUM) {
+    // this step's episode outcomes join the difficulty-grid histograms (the sum over all shards when one was handed in)
+    for (int i = tid; i < kMaxGridBins; i += blockDim.x) {
+      ctrl->grid_attempts[i] += a.global_stats ? a.global_stats->grid_attempts[i] : ctrl->grid_delta_att[i];
+      ctrl->grid_successes[i] += a.global_stats ? a.global_stats->grid_successes[i] : ctrl->grid_delta_succ[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < kMaxGridBins; i += blockDim.x) ctrl->grid_delta_att[i] = ctrl->grid_delta_succ[i] = 0u;
+  }
   if (tid == 0) {
     ctrl->stats_folded = 0;
-    const AsStats* g = a.global_stats ? a.global_stats : &ctrl->stats;
+    const AsStats* g = a.global_stats ? &a.global_stats->stats : &ctrl->stats;
     ctrl->promote_cur = promotion_decision(a.P, *g);
     if (a.rows.n_reset) *a.rows.n_reset = static_cast<int32_t>(a.want_reset_list ? ctrl->n_reset_list : ctrl->stats.n_reset);
     ctrl->parity ^= 1u;

@@ -181,6 +181,11 @@ class AllstepsMDP:
         off = stats_ptr.value - self.workspace.data_ptr()
         # device view of the folded step statistics (int64 fields; see _cabi.AsStats)
         self.stats_tensor = self.workspace[off: off + C.sizeof(_cabi.AsStats)].view(torch.int64)
+        # ... and of the whole exchange record it heads (statistics + this step's difficulty-grid outcomes): what a
+        # sharded caller all-reduces -- `exchange_tensor[:10]` and, with the grid curriculum, `exchange_tensor[grid_words]`
+        # (two uint32 counters per int64 word; the sums cannot carry) -- and hands to `finish_step`
+        self.exchange_tensor = self.workspace[off: off + C.sizeof(_cabi.AsExchange)].view(torch.int64)
+        self.grid_words = slice(_cabi.STATS_INT64_WORDS, _cabi.EXCHANGE_INT64_WORDS)
         self._keepalive = None
 
     # ------------------------------------------------------------------ plumbing
@@ -277,6 +282,7 @@ class AllstepsMDP:
         off = ptr.value - self.workspace.data_ptr()
         # device view of the step counters summed over all shards (int64 fields; see _cabi.AsStats)
         self.global_stats_tensor = self.workspace[off: off + C.sizeof(_cabi.AsStats)].view(torch.int64)
+        self.global_exchange_tensor = self.workspace[off: off + C.sizeof(_cabi.AsExchange)].view(torch.int64)
 
     def peer_status(self) -> Dict[str, int]:
         world, rank, timeouts = C.c_int(), C.c_int(), C.c_int64()
@@ -289,8 +295,20 @@ class AllstepsMDP:
         `stats_tensor` so they can be all-reduced over the shards first (promotion on the global mean)."""
         _cabi.check(self.lib.as_fold_stats(self.handle, self._stream()), "as_fold_stats")
 
+    def all_reduce_exchange(self, buf: torch.Tensor, dist, group=None) -> torch.Tensor:
+        """The plain-library route of a sharded step: `buf` (a copy of `exchange_tensor`, made after `fold_stats()`)
+        summed over the ranks where it is additive -- the ten leading counters and, with the grid curriculum, the
+        grid outcomes.  Hand the result to `finish_step`."""
+        dist.all_reduce(buf[:_cabi.STATS_ADDITIVE_FIELDS], group=group)
+        if self.grid_bins:
+            dist.all_reduce(buf[self.grid_words], group=group)
+        return buf
+
     def finish_step(self, global_stats: Optional[torch.Tensor] = None):
-        """Close the fused step: conditional no-reset fix-up, promotion rule (ENV:471-479), counters."""
+        """Close the fused step: conditional no-reset fix-up, promotion rule (ENV:471-479), counters.  global_stats: a
+        device tensor holding an AsExchange summed over the shards (see `all_reduce_exchange`)."""
+        if global_stats is not None and global_stats.numel() * global_stats.element_size() < C.sizeof(_cabi.AsExchange):
+            raise ValueError("global_stats must hold a whole AsExchange record (a copy of mdp.exchange_tensor)")
         _cabi.check(self.lib.as_finish_step(self.handle, _ptr(global_stats), self._stream()), "as_finish_step")
 
     # ------------------------------------------------------------------ 3-call path
@@ -304,8 +322,16 @@ class AllstepsMDP:
                                            _ptr(episode_length), C.byref(out.step_out), self._stream()),
                     "as_step_pass1")
 
-    def reset(self, env_origins: torch.Tensor, env_ids: torch.Tensor, out: StepBuffers,
+    def reset(self, env_origins: torch.Tensor, env_ids: Optional[torch.Tensor], out: StepBuffers,
               episode_length: Optional[torch.Tensor] = None):
+        """`_reset_idx(env_ids)` minus the PhysX writes.  env_ids None: the envs the preceding `pass1` flagged, taken
+        from the id list that pass compacted on the device -- no `.nonzero()`, no host round trip; `out.reset_ids[:n]`
+        / `out.n_reset` (device) name them, rows are in that order."""
+        if env_ids is None:
+            _cabi.check(self.lib.as_reset(self.handle, env_origins.data_ptr(), None, -1, _ptr(episode_length),
+                                          C.byref(out.reset_out), self._stream()), "as_reset")
+            self._keepalive = (env_origins,)
+            return
         ids = env_ids.to(device=self.device, dtype=torch.int32).contiguous()
         _cabi.check(self.lib.as_reset(self.handle, env_origins.data_ptr(), ids.data_ptr(), ids.numel(),
                                       _ptr(episode_length), C.byref(out.reset_out), self._stream()), "as_reset")

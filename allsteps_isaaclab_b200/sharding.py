@@ -12,7 +12,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from ._cabi import STATS_ADDITIVE_FIELDS, AsStats
+from ._cabi import EXCHANGE_INT64_WORDS, STATS_ADDITIVE_FIELDS, STATS_INT64_WORDS, AsStats
 
 STAT_NAMES = [name for name, _ in AsStats._fields_]
 SHARD_ALIGN = 4  # rows: keeps every shard's tiles 16-byte aligned for the TMA bulk copies

@@ -304,6 +304,10 @@ def time_three_call(torch, wl, origins, steps, warmup, device_reset_list=False):
     def one(v, d):
         ep_len.add_(1)
         mdp.pass1(v, d["actions"], out, episode_length=ep_len)
+        if device_reset_list:  # the envs pass 1 flagged, from the list it compacted on the device: no host round trip
+            mdp.reset(origins, None, out, episode_length=ep_len)
+            mdp.pass2(v, out)
+            return
         ids = out.dones.nonzero(as_tuple=False).squeeze(-1)  # DRL:359
         if len(ids) > 0:
             mdp.reset(origins, ids, out, episode_length=ep_len)
@@ -461,7 +465,7 @@ def selfcheck_global_promotion(torch, dist, dev, rank, world, per=8192, steps=10
     peer.connect_peers()
     single = make(N, 0, origins_all, {k: st0[k] for k in keys})  # every rank steps the whole thing: no broadcast needed
     o_p, o_n, o_s = StepBuffers(per, dev), StepBuffers(per, dev), StepBuffers(N, dev)
-    gbuf = torch.zeros_like(nccl.stats_tensor)
+    gbuf = torch.zeros_like(nccl.exchange_tensor)
     gen = torch.Generator(device=dev).manual_seed(seed)  # same sequence on every rank
     ok_pn = ok_single = True
     level0, promotions = 0, 0
@@ -476,9 +480,8 @@ def selfcheck_global_promotion(torch, dist, dev, rank, world, per=8192, steps=10
         peer.step(v_sh, ds["actions"], o_p)
         nccl.step(v_sh, ds["actions"], o_n, finish=False)
         nccl.fold_stats()
-        gbuf.copy_(nccl.stats_tensor)
-        dist.all_reduce(gbuf[:10])
-        nccl.finish_step(gbuf)
+        gbuf.copy_(nccl.exchange_tensor)
+        nccl.finish_step(nccl.all_reduce_exchange(gbuf, dist))
         torch.cuda.synchronize(dev)
         for name in ("obs", "reward", "terminated", "time_out"):
             a, b, c = getattr(o_p, name), getattr(o_n, name), getattr(o_s, name)[sl]
@@ -556,14 +559,15 @@ def main_b200(args):
 
     side = torch.cuda.Stream(dev) if dist is not None else None
     reducer = StatsReducer(dev) if dist is not None else None
-    gbuf = torch.zeros(13, dtype=torch.int64, device=dev)  # a whole AsStats; its first 10 int64 are the additive counters
+    gbuf = [None]  # a whole AsExchange record (statistics + grid outcomes)
 
     def nccl_close(m, v, d, o):  # config-4 semantics through the plain library route (--global-promotion nccl)
+        if gbuf[0] is None:
+            gbuf[0] = torch.zeros_like(m.exchange_tensor)
         m.step(v, d["actions"], o, finish=False)
         m.fold_stats()
-        gbuf.copy_(m.stats_tensor)
-        dist.all_reduce(gbuf[:10])
-        m.finish_step(gbuf)
+        gbuf[0].copy_(m.exchange_tensor)
+        m.finish_step(m.all_reduce_exchange(gbuf[0], dist))
 
     if args.global_promotion and dist is not None:  # the headline workload itself with a global promotion route
         wl, origins = make(N, peers=args.global_promotion == "peer",
@@ -661,7 +665,10 @@ def main_b200(args):
         # ---- BASELINE config 2: 4096 envs, rl_games' default batch scale
         blocks["c2_4096"], w2, o2 = small_block(4096)
         ms_t, l_t = time_three_call(torch, w2, o2, k_small, args.warmup)
-        three = {"4096": {"us_per_step": 1e3 * ms_t / k_small, "kernels_per_step": l_t / k_small}}
+        ms_d, l_d = time_three_call(torch, w2, o2, k_small, args.warmup, device_reset_list=True)
+        three = {"4096": {"us_per_step": 1e3 * ms_t / k_small, "kernels_per_step": l_t / k_small,
+                          "fused_us_per_step": blocks["c2_4096"]["us_per_step_library_calls"],
+                          "device_list_us_per_step": 1e3 * ms_d / k_small, "device_list_kernels_per_step": l_d / k_small}}
         del w2
         # ---- BASELINE config 3: 65536 envs with the pitch x yaw grid curriculum (extension)
         blocks["c3_65536_grid"], w3, _ = small_block(65536, grid_bins=11)
@@ -670,19 +677,26 @@ def main_b200(args):
         w65, o65 = make(65536, seed=99)
         ms_f, _ = time_cycle(torch, w65, k_small, args.warmup)
         ms_t, l_t = time_three_call(torch, w65, o65, k_small, args.warmup)
+        ms_d, l_d = time_three_call(torch, w65, o65, k_small, args.warmup, device_reset_list=True)
         three["65536"] = {"us_per_step": 1e3 * ms_t / k_small, "kernels_per_step": l_t / k_small,
-                          "fused_us_per_step": 1e3 * ms_f / k_small}
+                          "fused_us_per_step": 1e3 * ms_f / k_small,
+                          "device_list_us_per_step": 1e3 * ms_d / k_small, "device_list_kernels_per_step": l_d / k_small}
         del w65
         # ---- the 3-call path at the headline size
         k_big = min(max(args.steps, 40), 200)
         w1m, o1m = make(N, seed=77)
         ms_f, _ = time_cycle(torch, w1m, k_big, args.warmup)
         ms_t, l_t = time_three_call(torch, w1m, o1m, k_big, args.warmup)
+        ms_d, l_d = time_three_call(torch, w1m, o1m, k_big, args.warmup, device_reset_list=True)
         three[str(N)] = {"us_per_step": 1e3 * ms_t / k_big, "kernels_per_step": l_t / k_big,
-                         "fused_us_per_step": 1e3 * ms_f / k_big, "ratio_to_fused": ms_t / ms_f}
-        three["what"] = ("as_step_pass1 -> host .nonzero() of reset_buf (DRL:359, a device->host sync) -> as_reset -> "
-                         "as_step_pass2: the path the DirectRLEnv hooks take when PhysX sits between the writes of "
-                         "ENV:563-565 and pass 2")
+                         "fused_us_per_step": 1e3 * ms_f / k_big, "ratio_to_fused": ms_t / ms_f,
+                         "device_list_us_per_step": 1e3 * ms_d / k_big, "device_list_kernels_per_step": l_d / k_big,
+                         "device_list_ratio_to_fused": ms_d / ms_f}
+        three["what"] = ("us_per_step: as_step_pass1 -> host .nonzero() of reset_buf (DRL:359, a device->host sync, "
+                         "which Isaac Lab's DirectRLEnv.step does itself) -> as_reset(ids) -> as_step_pass2: the path the "
+                         "DirectRLEnv hooks take when PhysX sits between the writes of ENV:563-565 and pass 2.  "
+                         "device_list_us_per_step: the same three calls with as_reset taking the envs pass 1 flagged "
+                         "from the id list it compacted on the device -- no host round trip")
         blocks["three_call"] = three
         del w1m
         torch.cuda.empty_cache()

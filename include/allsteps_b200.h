@@ -164,6 +164,18 @@ typedef struct AsStats {
   int64_t n_missed;      /* AS_FLAG_MISSED_STEP: envs terminated by a missed step (this shard)             */
 } AsStats;
 
+/* What the shards of a sharded run exchange per step: the step statistics (only the leading AS_NUM_ADDITIVE_STATS
+ * int64 fields are summed) followed by this step's difficulty-grid outcomes (AS_FLAG_GRID_CURRICULUM: episodes ended
+ * per bin, and how many of them had passed half of the stones; zero otherwise).  One contiguous device record, so that
+ * the plain-library route is one all-reduce over a byte range. */
+#define AS_NUM_ADDITIVE_STATS 10
+#define AS_MAX_GRID_CELLS 256
+typedef struct AsExchange {
+  AsStats stats;
+  uint32_t grid_attempts[AS_MAX_GRID_CELLS];
+  uint32_t grid_successes[AS_MAX_GRID_CELLS];
+} AsExchange;
+
 typedef struct AsHandle AsHandle;
 
 /* ---- lifetime --------------------------------------------------------------------------------------- */
@@ -200,6 +212,10 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
  *         NULL = the library keeps and increments its own counter.
  * reset:  `_reset_idx(env_ids)` minus the PhysX writes: promotion rule, MDP state reset, start pose rows.
  *         Compact outputs: row i of the AsResetOut buffers belongs to env_ids[i].
+ *         env_ids == NULL with n_ids < 0: "the envs as_step_pass1 just flagged" -- the id list that pass compacted on
+ *         the device (no `.nonzero()` / host round trip as in DRL:359); rows come out in list order, `reset_ids` and
+ *         `n_reset` of AsResetOut say which and how many; when the list is empty the as_step_pass2 that follows acts
+ *         as as_step_no_reset.
  *         Called without a preceding as_step_pass1 (DirectRLEnv.reset() runs `_reset_idx(all ids)` before the first
  *         step, DRL:256-279) it evaluates the promotion rule on the indices as they are and advances the Philox
  *         step counter itself.
@@ -222,16 +238,21 @@ int as_step_no_reset(AsHandle* h, void* stream);
 /* ---- curriculum: ENV:470-479 -----------------------------------------------------------------------------
  * The step kernels leave per-step statistics in the control block; as_finish_step folds them, applies the
  * promotion rule (mean(curr_target_index) > 12 and at least one reset => level+1) for the NEXT step and clears
- * the accumulators.  When envs are sharded, pass `global_stats` = device AsStats summed over ranks (NCCL) to
- * promote on the global mean; NULL = promote on this shard's own envs (what `--distributed` replicas do). */
-int as_stats_device_ptr(AsHandle* h, AsStats** device_stats);
+ * the accumulators.  When envs are sharded, pass `global` = a device AsExchange summed over ranks (NCCL: the first
+ * AS_NUM_ADDITIVE_STATS int64 of `stats` and, with AS_FLAG_GRID_CURRICULUM, the two grid arrays) to promote on the
+ * global mean and to keep every shard's difficulty-grid histograms equal to those of one handle holding all envs;
+ * NULL = this shard's own envs (what `--distributed` replicas do). */
+int as_stats_device_ptr(AsHandle* h, AsStats** device_stats);  /* = the head of the record as_exchange_device_ptr gives */
+/* This shard's exchange record (`local`: statistics folded by as_fold_stats / the finish kernel + this step's grid
+ * outcomes) and the record summed over all shards by the peer-memory exchange (`global`; after as_peer_connect). */
+int as_exchange_device_ptr(AsHandle* h, AsExchange** local, AsExchange** global);
 /* Optional, between as_step_fused and as_finish_step: fold this step's counters into the device AsStats now, so
  * that the caller can all-reduce them and pass the sum to as_finish_step(global_stats) for a promotion decision on
  * the global mean in the same step. */
 int as_fold_stats(AsHandle* h, void* stream);
 /* Closes the step opened by as_step_fused (required once per fused step, on the same stream; the buffers given
  * to as_step_fused must stay alive until then because the conditional no-reset fix-up re-reads them). */
-int as_finish_step(AsHandle* h, const AsStats* global_stats, void* stream);
+int as_finish_step(AsHandle* h, const AsExchange* global, void* stream);
 int as_read_stats(AsHandle* h, AsStats* host_out, void* stream); /* synchronises `stream` */
 
 /* ---- the promotion rule's cross-shard sum over NVLink peer memory (the ONE cross-env dependency of the
@@ -313,7 +334,10 @@ int as_export_stone_poses(AsHandle* h, const int32_t* env_ids, int64_t n_ids, fl
  * With the flag set, every env that resets in as_step_fused has its episode outcome added to a (grid_bins x
  * grid_bins) pitch x yaw difficulty histogram, is assigned a new bin by inverse-CDF sampling, and gets a stone
  * sequence regenerated at that bin's difficulty.  as_grid_state copies the per-env bins (N bytes) and the two
- * histograms (attempts[256] then successes[256], uint32) out of / into the device state; NULL = skip. */
+ * histograms (attempts[256] then successes[256], uint32) out of / into the device state; NULL = skip.
+ * Bins drawn in step t use the histograms as they stand after step t-1; the outcomes of step t are added when the step
+ * is closed (as_finish_step) -- summed over all shards when the step is closed on a global record, so that sharded
+ * runs sample from the same CDF as one handle holding all envs. */
 int as_grid_state(AsHandle* h, uint8_t* bins_dst, const uint8_t* bins_src, uint32_t* hist_dst, const uint32_t* hist_src,
                   void* stream);
 

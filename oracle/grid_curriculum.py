@@ -16,6 +16,10 @@ Definition
   sampling    cdf = inclusive prefix sum of w; u24 = 24-bit uniform; target = (u24 * cdf[-1]) >> 24;
               new bin = first b with cdf[b] > target
   each env that resets is assigned a new bin and its stone sequence is regenerated at that bin's difficulty.
+  order       bins drawn in step t come from the histograms as they stand after step t-1; the outcomes of step t are
+              added afterwards.  (So that a run sharded over several GPUs can sum the step's outcomes over the ranks
+              when it closes the step, off the sampling path, and still sample from exactly the CDF one handle holding
+              all envs would use: the histograms are GLOBAL, every shard keeps an identical copy.)
 """
 from __future__ import annotations
 
@@ -105,11 +109,12 @@ class GridCurriculum:
         self.env_id_offset = env_id_offset
 
     def episode_end(self, env_ids: np.ndarray, index_at_end: np.ndarray, num_stones: int, seed: int, step: int):
-        """Record the outcomes of the envs that reset, then draw their new bins (histogram first, then CDF)."""
-        b = self.bins[env_ids]
-        np.add.at(self.attempts, b, 1)
-        np.add.at(self.successes, b, (index_at_end > num_stones // 2).astype(np.uint32))
+        """Draw the new bins of the envs that reset from the histograms of the previous steps, then record this step's
+        outcomes (see "order" above)."""
+        b = self.bins[env_ids].copy()
         cdf = cdf_of(self.attempts, self.successes)
         u24 = grid_draws(seed, step, env_ids + self.env_id_offset)
         self.bins[env_ids] = sample_bins(cdf, u24)
+        np.add.at(self.attempts, b, 1)
+        np.add.at(self.successes, b, (index_at_end > num_stones // 2).astype(np.uint32))
         return self.bins[env_ids]

@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match_the_library(lib):
     for i, t in enumerate([_cabi.AsParams, _cabi.AsStateIn, _cabi.AsStepOut, _cabi.AsResetOut, _cabi.AsStats,
-                           _cabi.AsMdpState, _cabi.AsMirrorJob]):
+                           _cabi.AsMdpState, _cabi.AsMirrorJob, _cabi.AsExchange]):
         assert C.sizeof(t) == lib.as_sizeof(i), t.__name__
     assert lib.as_sizeof(99) == -1
     assert lib.as_abi_version() == _cabi.ABI_VERSION

@@ -826,8 +826,8 @@ def test_global_promotion_over_shards_and_wrapper_outputs():
                                        sc.body_indices, quat_xyzw=True)
             sh.step(v, dev["actions"][sl], outs[r], finish=False)
             sh.fold_stats()
-        g = shards[0].stats_tensor.clone()
-        g[:10] = shards[0].stats_tensor[:10] + shards[1].stats_tensor[:10]  # what the NCCL all-reduce produces
+        g = shards[0].exchange_tensor.clone()
+        g[:10] = shards[0].exchange_tensor[:10] + shards[1].exchange_tensor[:10]  # what the NCCL all-reduce produces
         for sh in shards:
             sh.finish_step(g)
         torch.cuda.synchronize()
@@ -1192,3 +1192,62 @@ def test_resume_from_a_checkpoint_is_bit_identical():
         after = mdp.export_state()
         for k in before:
             assert torch.equal(before[k], after[k]), k
+
+
+@pytest.mark.parametrize("N,fall", [(3000, 0.03), (40, 0.0), ((1 << 17) + 5, 0.02)])
+def test_three_call_path_with_the_device_side_reset_list(N, fall):
+    """as_reset(env_ids = NULL): the envs pass 1 flagged come from the id list it compacted on the device -- no
+    `.nonzero()` -- and as_step_pass2 decides on the device whether anything reset at all.  Must equal the flow with the
+    host's id tensor (DRL:359) bit for bit, in busy and in quiet steps."""
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+
+    seed = 71
+    sc = Scenario(N, seed=seed, fall_fraction=fall)
+    (host_mdp, dev_mdp), origins, st0 = _twin_mdps(N, seed, sc)
+    out_h, out_d = StepBuffers(N, "cuda:0"), StepBuffers(N, "cuda:0")
+    ep_h = st0["episode_length_buf"].cuda().clone()
+    ep_d = ep_h.clone()
+
+    def writes(keep, ids, out, k):
+        keep["root_pos_w"][ids] = out.reset_root_state[:k, 0:3]
+        keep["root_quat_w"][ids] = out.reset_root_state[:k, 3:7]
+        keep["root_lin_vel_w"][ids] = out.reset_root_state[:k, 7:10]
+        keep["joint_pos"][ids] = out.reset_joint_pos[:k]
+        keep["joint_vel"][ids] = out.reset_joint_vel[:k]
+        keep["force_matrix_right"][ids] = 0.0
+        keep["force_matrix_left"][ids] = 0.0
+
+    quiet = busy = 0
+    for step in range(8):
+        st = host_mdp.export_state()
+        phys = sc.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+        vh, kh = to_views(phys, origins, sc.body_indices)
+        vd, kd = to_views(phys, origins, sc.body_indices)
+        ep_h += 1
+        ep_d += 1
+        host_mdp.pass1(vh, kh["actions"], out_h, episode_length=ep_h)
+        ids = out_h.dones.nonzero().squeeze(-1)
+        if len(ids):
+            host_mdp.reset(origins, ids, out_h, episode_length=ep_h)
+            writes(kh, ids, out_h, len(ids))
+            host_mdp.pass2(vh, out_h)
+            busy += 1
+        else:
+            host_mdp.no_reset()
+            quiet += 1
+        dev_mdp.pass1(vd, kd["actions"], out_d, episode_length=ep_d)
+        dev_mdp.reset(origins, None, out_d, episode_length=ep_d)
+        n = int(out_d.n_reset.item())          # (the test plays PhysX: it needs the rows on the host side)
+        assert n == len(ids)
+        ids_d = out_d.reset_ids[:n].long()
+        assert torch.equal(ids_d.sort().values, ids)
+        writes(kd, ids_d, out_d, n)
+        dev_mdp.pass2(vd, out_d)
+        torch.cuda.synchronize()
+        for name in ("obs", "reward", "terminated", "time_out", "dones"):
+            assert torch.equal(getattr(out_h, name), getattr(out_d, name)), f"step {step}: {name}"
+        assert torch.equal(ep_h, ep_d)
+        a, b = host_mdp.export_state(), dev_mdp.export_state()
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"step {step}: state {k}"
+    assert (quiet > 0) if fall == 0.0 else (busy > 0)

@@ -39,7 +39,7 @@ class OracleMDP:
         self.launch_count = 0      # "launches": calls that would start kernels
         self.counter = 0           # the library's Philox step counter
         self.pass1_done = False
-        self.stats_tensor = torch.zeros(13, dtype=torch.int64)
+        self.stats_tensor = torch.zeros(14, dtype=torch.int64)
         self.orc = None
         OracleMDP.instances.append(self)
 

@@ -63,7 +63,8 @@ def main():
     st0["curr_target_index"] = torch.randint(11, 20, (N,), generator=sc.gen)   # near the promotion threshold
     sl = slice(rank * per, (rank + 1) * per)
     origins = sc.env_origins[sl].to(dev)
-    mdps = [AllstepsMDP(per, device=dev, seed=seed, env_id_offset=rank * per) for _ in range(2)]
+    grid = int(os.environ.get("PEER_CHECK_GRID", "0"))  # B > 0: pitch x yaw grid curriculum with global histograms
+    mdps = [AllstepsMDP(per, device=dev, seed=seed, env_id_offset=rank * per, grid_bins=grid) for _ in range(2)]
     for m in mdps:
         m.generate_stones(origins)
         m.import_state({k: st0[k][sl] for k in ("curr_target_index", "swing_leg", "target_reach_count",
@@ -72,13 +73,20 @@ def main():
     assert peer_mdp.connect_peers() == (world, rank)
     single = None
     if rank == 0:  # ONE handle with all envs: what every shard has to reproduce
-        single = AllstepsMDP(N, device=dev, seed=seed)
+        single = AllstepsMDP(N, device=dev, seed=seed, grid_bins=grid)
         single.generate_stones(sc.env_origins.to(dev))
         single.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
                                                  "episode_length_buf", "potentials")})
         out_single = StepBuffers(N, dev)
     outs = [StepBuffers(per, dev), StepBuffers(per, dev)]
-    g = torch.zeros_like(nccl_mdp.stats_tensor)
+    g = torch.zeros_like(nccl_mdp.exchange_tensor)
+
+    def reduce_record(buf):
+        all_reduce(buf[:10])
+        if grid:
+            all_reduce(buf[nccl_mdp.grid_words])
+        return buf
+
     promotions = 0
     level_before = 0
     for step in range(steps):
@@ -90,9 +98,8 @@ def main():
         views = PhysicsViews.from_dict(d, origins, sc.body_indices)
         nccl_mdp.step(views, d["actions"], outs[0], finish=False)
         nccl_mdp.fold_stats()
-        g.copy_(nccl_mdp.stats_tensor)
-        all_reduce(g[:10])
-        nccl_mdp.finish_step(g)
+        g.copy_(nccl_mdp.exchange_tensor)
+        nccl_mdp.finish_step(reduce_record(g))
         peer_mdp.step(views, d["actions"], outs[1])
         torch.cuda.synchronize()
         if single is not None:
@@ -124,8 +131,26 @@ def main():
         assert torch.equal(peer_mdp.global_stats_tensor[:10], g[:10]), (
             f"rank {rank} step {step}: global counters {peer_mdp.global_stats_tensor[:10].tolist()} vs NCCL "
             f"{g[:10].tolist()}")
+        if grid:  # every shard holds the histograms of ALL envs: equal between the routes and to the single handle's
+            ga, gb = nccl_mdp.grid_state(), peer_mdp.grid_state()
+            assert torch.equal(ga[1], gb[1]) and torch.equal(ga[2], gb[2]) and torch.equal(ga[0], gb[0]), (
+                f"rank {rank} step {step}: grid state differs between the routes")
+            hist = torch.stack((gb[1], gb[2])).cpu()
+            if backend == "nccl":
+                h0 = hist.to(dev)
+                dist.broadcast(h0, src=0)
+                h0 = h0.cpu()
+            else:
+                h0 = hist.clone()
+                dist.broadcast(h0, src=0)
+            assert torch.equal(hist, h0), f"rank {rank} step {step}: histograms differ between the ranks"
+            if single is not None:
+                gs = single.grid_state()
+                assert torch.equal(gs[1], gb[1]) and torch.equal(gs[2], gb[2]), "histograms differ from the single handle's"
+                assert torch.equal(gs[0][sl], gb[0]), "bins differ from the single handle's"
+                assert int(gs[1].sum()) > 0 or step == 0
         level = int(sb["curriculum"].max())
-        promotions += int(level != level_before)
+        promotions += int(level != level_before or grid > 0)
         level_before = level
     status = peer_mdp.peer_status()
     assert status["timeouts"] == 0 and status["world"] == world, status
@@ -148,23 +173,22 @@ def main():
         all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    local_mdp = AllstepsMDP(per, device=dev, seed=seed, env_id_offset=rank * per)
+    local_mdp = AllstepsMDP(per, device=dev, seed=seed, env_id_offset=rank * per, grid_bins=grid)
     local_mdp.generate_stones(origins)
     out_l = StepBuffers(per, dev)
 
     def via_nccl():
         nccl_mdp.step(views, d["actions"], outs[0], finish=False)
         nccl_mdp.fold_stats()
-        g.copy_(nccl_mdp.stats_tensor)
-        all_reduce(g[:10])
-        nccl_mdp.finish_step(g)
+        g.copy_(nccl_mdp.exchange_tensor)
+        nccl_mdp.finish_step(reduce_record(g))
 
     t_local = timed(lambda: local_mdp.step(views, d["actions"], out_l))
     t_nccl = timed(via_nccl)
     t_peer = timed(lambda: peer_mdp.step(views, d["actions"], outs[1]))
     assert peer_mdp.peer_status()["timeouts"] == 0
     if rank == 0:
-        print(f"peer_check OK: world {world} ({backend}), {per} envs per rank, {steps} steps, {promotions} promotions, "
+        print(f"peer_check OK: world {world} ({backend}{', grid %dx%d' % (grid, grid) if grid else ''}), {per} envs per rank, {steps} steps, {promotions} promotions, "
               f"shards == single handle; us/step: shard-local {t_local:.1f}, {backend} all-reduce {t_nccl:.1f}, "
               f"peer-memory exchange {t_peer:.1f}", flush=True)
     dist.destroy_process_group()

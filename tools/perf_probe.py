@@ -36,6 +36,11 @@ def probe(N, steps=50, sets=4, warmup=10):
             v, d = wl.sets[k]
             ep_len.add_(1)
             mdp.pass1(v, d["actions"], out, episode_length=ep_len)
+            if "--device-list" in sys.argv:
+                mdp.reset(origins, None, out, episode_length=ep_len)
+                mdp.pass2(v, out)
+                wl.j += 1
+                return
             ids = out.dones.nonzero(as_tuple=False).squeeze(-1)
             if len(ids):
                 mdp.reset(origins, ids, out, episode_length=ep_len)
