@@ -514,8 +514,8 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   const bool pre = a.use_pre && ex == 0 && h->allow_pre;
   // the last CTA closes the step itself unless somebody else has to see the open step: the cross-shard exchange, an
   // all-reduce the caller announced (AS_STEP_DEFER_FINISH), or the regeneration kernels launched below
-  a.self_finish = (h->allow_self_finish && !h->peer_connected && !regen_enabled &&
-                   !(out->flags & AS_STEP_DEFER_FINISH)) ? 1 : 0;
+  a.self_finish = (h->allow_self_finish && !regen_enabled && !(out->flags & AS_STEP_DEFER_FINISH)) ? 1 : 0;
+  if (h->peer_connected) a.peer = h->peer;  // (world > 0: the closing CTA sums the counters over the shards itself)
   AS_CUDA(launch_step(h, pre ? kFullPre[fast ? 1 : 0][packed ? 1 : 0] : kFull[ex][fast ? 1 : 0][packed ? 1 : 0],
                       ragged_kernel, a, s, dep, packed ? kSmemBytesPacked : kSmemBytes));
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
@@ -523,10 +523,11 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   if (grid) {  // kernel (c): new bins by inverse-CDF sampling from the histograms as they stand after the previous
                // step; this step's outcomes into the step's record (they join the histograms when the step is closed)
     const int g = grid_for(h->num_envs, 256 * 8, h->sm_count, 1);
-    k_grid_sample<<<g, 256, 0, s>>>(h->params, h->ws, h->env_id_offset);
-    if (int rc = check_launch(h, "k_grid_sample")) return rc;
+    // (the outcomes first: they are recorded against the bins the envs WERE playing, which the sampler overwrites)
     k_grid_hist<<<g, 256, 0, s>>>(h->params, h->ws);
     if (int rc = check_launch(h, "k_grid_hist")) return rc;
+    k_grid_sample<<<g, 256, 0, s>>>(h->params, h->ws, h->env_id_offset);
+    if (int rc = check_launch(h, "k_grid_sample")) return rc;
   }
   if (regen_enabled) {  // kernel (b): warp-per-env stone regeneration over the compacted list
     ResetArgs r = make_reset_args(h, in->env_origins);
@@ -645,7 +646,9 @@ int as_finish_step(AsHandle* h, const AsExchange* global_stats, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   StepArgs a = h->pending;  // the fix-up re-reads the inputs of the step it closes
   a.global_stats = global_stats;
-  if (h->peer_connected && global_stats == nullptr) {
+  if (h->peer_connected && global_stats == nullptr && a.self_finish) {
+    a.global_stats = &h->ws.ctrl->gx;  // the step kernel's last CTA exchanged the counters and (normally) closed the step
+  } else if (h->peer_connected && global_stats == nullptr) {
     // fold + sum over the shards through NVLink peer memory, in one small kernel under the step kernel's tail
     const int cells = (h->params.flags & AS_FLAG_GRID_CURRICULUM) ? static_cast<int>(h->params.grid_bins * h->params.grid_bins) : 0;
     AS_CUDA(launch_dependent(k_peer_exchange, 1u, 128u, 0, s, h->pdl >= 1, h->ws.ctrl, h->peer, h->num_envs, cells));
@@ -703,12 +706,10 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   const StepKernel full = pre ? kFullPre[fast ? 1 : 0][packed ? 1 : 0] : k_step<kModePass1, 2, true>;
   AS_CUDA(launch_step(h, full, k_step<kModePass1, 2, false>, a, s, dep,
                       (pre && packed) ? kSmemBytesPacked : kSmemBytes));
-  if (int rc = check_launch(h, "k_step<pass1>")) return rc;
-  k_fold_pass1<<<1, 128, 0, s>>>(h->ws.ctrl, h->num_envs);
-  h->pass1_done = true;
+  h->pass1_done = true;   // (its last CTA folds the statistics and advances the Philox step counter)
   h->spec_valid = true;
   h->spec_obs = out->obs;
-  return check_launch(h, "k_fold_pass1");
+  return check_launch(h, "k_step<pass1>");
 }
 
 int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int64_t n_ids, int64_t* episode_length,
@@ -734,11 +735,10 @@ int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int6
     if (int rc = check_launch(h, "k_prepare_reset")) return rc;
   }
   h->pass1_done = false;  // consumed: a second reset without a pass in between prepares for itself
+  ResetArgs r = make_reset_args(h, env_origins);
   // (an explicit id list means `_reset_idx` was entered, i.e. some env reset; with the device-side list that is
   // decided by the count pass 1 folded -- the rule is not evaluated in a step in which nothing resets, DRL:360)
-  k_decide_promotion<<<1, 32, 0, s>>>(h->params, h->ws.ctrl, nullptr, from_device_list ? 0 : 1);
-  if (int rc = check_launch(h, "k_decide_promotion")) return rc;
-  ResetArgs r = make_reset_args(h, env_origins);
+  r.force_any_reset = from_device_list ? 0 : 1;
   if (compact_out) r.out = *compact_out;
   r.env_ids = from_device_list ? h->ws.reset_ids : env_ids;
   r.n_ids = from_device_list ? -1 : n_ids;

@@ -121,10 +121,14 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
   // fused: the step kernel already wrote the start-pose rows; n_ids < 0: the list pass 1 compacted on the device
   const int64_t n_reset = a.fused ? 0 : (a.n_ids < 0 ? static_cast<int64_t>(ctrl->n_reset_list) : a.n_ids);
   // promotion decided in THIS step is already in force when stones are regenerated (ENV:471 precedes ENV:500)
-  // (3-call path: as_reset ran k_decide_promotion first and left the decision in promote_cur)
   int promote_now;
   if (!a.fused) {
-    promote_now = static_cast<int>(ctrl->promote_cur);
+    // 3-call path: `_reset_idx` opens with the promotion rule (ENV:471-479) on the statistics pass 1 folded; every
+    // warp evaluates it for itself, one thread leaves the decision for the next pass 1 (nobody reads it in here)
+    AsStats s = ctrl->stats;
+    if (a.force_any_reset) s.n_reset = s.n_reset > 0 ? s.n_reset : 1;
+    promote_now = static_cast<int>(promotion_decision(P, s));
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->promote_cur = static_cast<uint32_t>(promote_now);
   } else if (a.global_stats) {
     promote_now = static_cast<int>(promotion_decision(P, a.global_stats->stats));
   } else {  // the step kernel's counters are still in the replicated slots (folded by the finish kernel)
@@ -221,16 +225,6 @@ __global__ void __launch_bounds__(256) k_generate_stones(const __grid_constant__
     stone_draws(a, step, e, gid, lane, u0, u1, u2);
     generate_stones_warp(a.P, lane, difficulty_of_env(a.P, a.ws, e, level), origin, u0, u1, u2, a.ws.stones + e * kS);
     rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, state_idx(st[e].x), lane);
-  }
-}
-
-// 3-call path: `_reset_idx` opens with the promotion rule (ENV:471-479) on the statistics pass 1 folded.
-__global__ void k_decide_promotion(const __grid_constant__ AsParams P, Ctrl* ctrl, const AsStats* global_stats,
-                                   int force_any_reset) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    AsStats s = global_stats ? *global_stats : ctrl->stats;
-    if (force_any_reset) s.n_reset = s.n_reset > 0 ? s.n_reset : 1;
-    ctrl->promote_cur = promotion_decision(P, s);
   }
 }
 

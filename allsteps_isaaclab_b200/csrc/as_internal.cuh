@@ -205,6 +205,7 @@ struct StepArgs {
   uint32_t dense16;                   // per-array "dense and 16-byte aligned" bits (DenseBit), evaluated by the host
   float inv_step_dt;                  // RN(1 / P.step_dt) for the two-FMA quotient of ENV:416 (see JointConsts::exact_div)
   AsResetOut rows;                    // fused: start-pose rows for PhysX, written at the env's own row (optional)
+  PeerArgs peer;                      // fused + self_finish with peers connected: the last CTA exchanges the counters itself
 };
 
 struct ResetArgs {
@@ -221,6 +222,7 @@ struct ResetArgs {
   int64_t env_id_offset;
   int32_t fused;                // 1: state words were already reset by the step kernel, rows go to env's own row
   int32_t into_other;           // 3-call path behind a speculating pass 1: the reset state words go into the OTHER buffer
+  int32_t force_any_reset;      // 3-call path: an explicit id list means `_reset_idx` was entered, i.e. some env reset
 };
 
 }  // namespace as

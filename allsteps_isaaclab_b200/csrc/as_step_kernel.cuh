@@ -426,6 +426,88 @@ __device__ __forceinline__ uint32_t promotion_decision(const AsParams& P, const 
   return promotion_rule(P, s.n_reset, s.sum_target_index, s.n_envs);
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// The cross-shard sum of the ten step counters by ONE warp (lane r talks to rank r): store this shard's counters into
+// OUR slot of rank r's buffer, then the epoch as the flag (release); poll rank r's slot in OUR buffer for the same epoch
+// (acquire) and read its counters; sum over the lanes.  Returns the number of peers that did not deliver in time.
+// Two slots per sender (epoch parity): a rank can run at most one step ahead of a peer that has not yet read, because it
+// cannot close step t+1 without that peer's step-t+1 counters.
+__device__ __forceinline__ unsigned peer_sum_counters_warp(Ctrl* ctrl, const PeerArgs& peer, int lane,
+                                                           long long (&got)[kPeerCounters], unsigned long long& epoch_out) {
+  const unsigned long long epoch = static_cast<unsigned long long>(ctrl->peer_epoch) + 1ull;
+  const int par = static_cast<int>(epoch & 1ull);
+  const long long* mine = reinterpret_cast<const long long*>(&ctrl->stats);
+#pragma unroll
+  for (int k = 0; k < kPeerCounters; ++k) got[k] = 0;
+  bool timed_out = false;
+  if (lane < peer.world) {
+    PeerSlot* dst = peer.buf[lane] + par * kMaxPeers + peer.rank;
+#pragma unroll
+    for (int k = 0; k < kPeerCounters; ++k) {
+      asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(&dst->counters[k]), "l"(mine[k]) : "memory");
+    }
+    st_release_sys_u64(&dst->flag, epoch);  // release: counters (and a grid record stored before) are visible before the flag
+    const PeerSlot* src = peer.buf[peer.rank] + par * kMaxPeers + lane;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u64(&src->flag) != epoch) {
+      if (peer.timeout_ns != 0ull && global_timer_ns() - t0 > peer.timeout_ns) {
+        timed_out = true;
+        break;
+      }
+      __nanosleep(100);
+    }
+    if (!timed_out) {
+#pragma unroll
+      for (int k = 0; k < kPeerCounters; ++k) {
+        asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(got[k]) : "l"(&src->counters[k]) : "memory");
+      }
+    }
+  }
+  const unsigned n_to = __popc(__ballot_sync(0xffffffffu, timed_out));
+#pragma unroll
+  for (int k = 0; k < kPeerCounters; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) got[k] += __shfl_xor_sync(0xffffffffu, got[k], o);
+  }
+  epoch_out = epoch;
+  return n_to;
+}
+
+// Publishes the summed counters as ctrl->gx.stats (lane 0 of the exchanging warp).  A peer that did not deliver in time:
+// a sum over some of the shards is never published -- the step closes on the shard's own record, and the error is
+// STICKY: ctrl->peer_error on the device, the mapped host word for the API, which refuses every further step with
+// AS_ERR_PEER (the shards may have promoted differently).
+__device__ __forceinline__ void peer_publish(Ctrl* ctrl, const PeerArgs& peer, const long long (&got)[kPeerCounters],
+                                             unsigned n_to, unsigned long long epoch) {
+  AsStats g = ctrl->stats;  // level, step counter, reward sum: this shard's
+  if (n_to == 0) {
+    long long* gs = reinterpret_cast<long long*>(&g);
+#pragma unroll
+    for (int k = 0; k < kPeerCounters; ++k) gs[k] = got[k];
+  } else {
+    ctrl->peer_timeouts += n_to;
+    ctrl->peer_error = 1u;
+    if (peer.host_error) {
+      *reinterpret_cast<volatile uint32_t*>(peer.host_error) = static_cast<uint32_t>(epoch) | 0x80000000u;
+      __threadfence_system();
+    }
+  }
+  ctrl->gx.stats = g;
+  ctrl->peer_epoch = static_cast<uint32_t>(epoch == 0xFFFFFFFFull ? 0ull : epoch);
+}
+
 // One-warp version of fold_stats (the last CTA of the fused step kernel folds with the warp that took the ticket).
 __device__ __forceinline__ void fold_stats_warp(Ctrl* ctrl, int64_t num_envs, int lane, unsigned& n_reset_out) {
   unsigned tot[kNumCounters];
@@ -469,26 +551,70 @@ __device__ __forceinline__ void close_step_by_last_cta(const StepArgs& a, Ctrl* 
   __threadfence();
   unsigned state = 1u;
   if (a.self_finish) {
-    const unsigned n_reset = slot_sum(ctrl, kCntReset);
-    if (n_reset > 0 || (a.P.flags & AS_FLAG_SKIP_PASS2)) {
-      unsigned nr;
+    unsigned nr;
+    if (a.peer.world > 0) {
+      // sharded, promotion on the global mean: fold, exchange the ten counters with every peer over NVLink (this warp;
+      // a peer's last CTA answers when ITS step kernel gets there), then decide on the sums -- the exchange and the
+      // finish ride in the step kernel's last CTA instead of two more launches
       fold_stats_warp(ctrl, a.num_envs, lane, nr);
       __syncwarp();
+      __threadfence();
+      long long got[kPeerCounters];
+      unsigned long long ep;
+      const unsigned n_to = peer_sum_counters_warp(ctrl, a.peer, lane, got, ep);
       if (lane == 0) {
-        ctrl->stats_folded = 0;
-        ctrl->promote_cur = promotion_decision(a.P, ctrl->stats);
-        if (a.rows.n_reset) *a.rows.n_reset = static_cast<int32_t>(a.want_reset_list ? ctrl->n_reset_list : nr);
-        ctrl->parity ^= 1u;
-        ctrl->step_counter += 1ull;
-        ctrl->n_reset_list = 0;
-        ctrl->n_regen_list = 0;
+        peer_publish(ctrl, a.peer, got, n_to, ep);
+        ctrl->stats_folded = 1;
       }
-      state = 2u;
+      __syncwarp();
+      const long long global_resets = __shfl_sync(0xffffffffu, n_to == 0 ? got[1] /* AsStats::n_reset */ : static_cast<long long>(nr), 0);
+      if (global_resets > 0 || (a.P.flags & AS_FLAG_SKIP_PASS2)) {
+        if (lane == 0) {
+          ctrl->stats_folded = 0;
+          ctrl->promote_cur = promotion_decision(a.P, ctrl->gx.stats);
+          if (a.rows.n_reset) *a.rows.n_reset = static_cast<int32_t>(a.want_reset_list ? ctrl->n_reset_list : nr);
+          ctrl->parity ^= 1u;
+          ctrl->step_counter += 1ull;
+          ctrl->n_reset_list = 0;
+          ctrl->n_regen_list = 0;
+        }
+        state = 2u;
+      }  // else: nobody reset anywhere -- k_fixup_finish redoes the step without pass 2, on ctrl->gx (already folded)
+    } else {
+      const unsigned n_reset = slot_sum(ctrl, kCntReset);
+      if (n_reset > 0 || (a.P.flags & AS_FLAG_SKIP_PASS2)) {
+        fold_stats_warp(ctrl, a.num_envs, lane, nr);
+        __syncwarp();
+        if (lane == 0) {
+          ctrl->stats_folded = 0;
+          ctrl->promote_cur = promotion_decision(a.P, ctrl->stats);
+          if (a.rows.n_reset) *a.rows.n_reset = static_cast<int32_t>(a.want_reset_list ? ctrl->n_reset_list : nr);
+          ctrl->parity ^= 1u;
+          ctrl->step_counter += 1ull;
+          ctrl->n_reset_list = 0;
+          ctrl->n_regen_list = 0;
+        }
+        state = 2u;
+      }
     }
   }
   if (lane == 0) {
     ctrl->blocks_done = 0;
     ctrl->step_state = state;
+  }
+}
+
+// 3-call path: the last CTA of pass 1 folds its statistics (what k_fold_pass1 did as a launch of its own): consumes the
+// promotion every CTA applied, advances the Philox step counter -- a reset that follows draws at the advanced counter.
+__device__ __forceinline__ void close_pass1_by_last_cta(const StepArgs& a, Ctrl* ctrl, int lane) {
+  __threadfence();
+  unsigned nr;
+  fold_stats_warp(ctrl, a.num_envs, lane, nr);
+  __syncwarp();
+  if (lane == 0) {
+    ctrl->promote_cur = 0;
+    ctrl->step_counter += 1ull;
+    ctrl->blocks_done = 0;
   }
 }
 
@@ -1231,7 +1357,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       for (int w = 0; w < kTile / 32; ++w) rs += misc->wreward[w];
       atomicAdd(&ctrl->slot_reward[slot], rs);
     }
-    if (MODE == kModeFused) {
+    if (MODE == kModeFused || kSpec) {
       // "last CTA closes the step": a ticket per CTA, taken after this CTA's counters are out (fence), by the one
       // thread that has to wait for the bulk store anyway -- the atomic's round trip hides behind that wait
       __syncwarp();
@@ -1249,9 +1375,12 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     if (w3_pending) wrow[3] = s_w3[t];
   }
   if (tid == 0 && b_obs) bulk_wait_read_all();  // shared memory must stay intact until the engine has read it
-  if (MODE == kModeFused && warp == 0) {
+  if ((MODE == kModeFused || kSpec) && warp == 0) {
     const bool last = __shfl_sync(0xffffffffu, ticket, 0) == static_cast<unsigned>(a.num_tiles);
-    if (last) close_step_by_last_cta(a, ctrl, lane);
+    if (last) {
+      if (kSpec) close_pass1_by_last_cta(a, ctrl, lane);
+      else close_step_by_last_cta(a, ctrl, lane);
+    }
   }
 #ifdef AS_TIMING
   if (tid == 0) { AS_T(t_w1); AS_TACC(6, t_w0, t_w1); AS_TACC(7, t_start, t_w1); atomicAdd(&ctrl->dbg_t[15], 1ull); }
@@ -1424,19 +1553,6 @@ __global__ void __launch_bounds__(128) k_fold_early(Ctrl* ctrl, int64_t num_envs
 // fences, then stores the epoch as the flag; it then polls rank r's slot in OUR buffer for the same epoch and reads
 // the counters.  Two slots per sender (epoch parity): a rank can run at most one step ahead of a peer that has not
 // yet read, because it cannot close step t+1 without that peer's step-t+1 counters.
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 __global__ void __launch_bounds__(128) k_peer_exchange(Ctrl* ctrl, const __grid_constant__ PeerArgs peer,
                                                        int64_t num_envs, int grid_cells) {
   __shared__ unsigned int fold[kNumCounters];
@@ -1465,61 +1581,13 @@ __global__ void __launch_bounds__(128) k_peer_exchange(Ctrl* ctrl, const __grid_
     __threadfence_system();
     __syncthreads();
   }
-  const long long* mine = reinterpret_cast<const long long*>(&ctrl->stats);
-  long long got[kPeerCounters];
-#pragma unroll
-  for (int k = 0; k < kPeerCounters; ++k) got[k] = 0;
   if (tid < 32) {
-    bool timed_out = false;
-    if (tid < peer.world) {
-      PeerSlot* dst = peer.buf[tid] + par * kMaxPeers + peer.rank;
-#pragma unroll
-      for (int k = 0; k < kPeerCounters; ++k) {
-        asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(&dst->counters[k]), "l"(mine[k]) : "memory");
-      }
-      st_release_sys_u64(&dst->flag, epoch);  // release: counters (and the grid record) are visible before the flag
-      const PeerSlot* src = peer.buf[peer.rank] + par * kMaxPeers + tid;
-      const unsigned long long t0 = global_timer_ns();
-      while (ld_acquire_sys_u64(&src->flag) != epoch) {
-        if (peer.timeout_ns != 0ull && global_timer_ns() - t0 > peer.timeout_ns) {
-          timed_out = true;
-          break;
-        }
-        __nanosleep(100);
-      }
-      if (!timed_out) {
-#pragma unroll
-        for (int k = 0; k < kPeerCounters; ++k) {
-          asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(got[k]) : "l"(&src->counters[k]) : "memory");
-        }
-      }
-    }
-    const unsigned n_to = __popc(__ballot_sync(0xffffffffu, timed_out));
-#pragma unroll
-    for (int k = 0; k < kPeerCounters; ++k) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) got[k] += __shfl_xor_sync(0xffffffffu, got[k], o);
-    }
+    long long got[kPeerCounters];
+    unsigned long long ep;
+    const unsigned n_to = peer_sum_counters_warp(ctrl, peer, tid, got, ep);
     if (tid == 0) {
       s_timeouts = n_to;
-      AsStats g = ctrl->stats;  // level, step counter, reward sum: this shard's
-      if (n_to == 0) {
-        long long* gs = reinterpret_cast<long long*>(&g);
-#pragma unroll
-        for (int k = 0; k < kPeerCounters; ++k) gs[k] = got[k];
-      } else {
-        // A peer did not deliver in time.  A sum over some of the shards is never published: this step closes on the
-        // shard's own record, and the error is STICKY -- ctrl->peer_error on the device, the mapped host word for the
-        // API, which refuses every further step with AS_ERR_PEER (the shards may have promoted differently).
-        ctrl->peer_timeouts += n_to;
-        ctrl->peer_error = 1u;
-        if (peer.host_error) {
-          *reinterpret_cast<volatile uint32_t*>(peer.host_error) = static_cast<uint32_t>(epoch) | 0x80000000u;
-          __threadfence_system();
-        }
-      }
-      ctrl->gx.stats = g;
-      ctrl->peer_epoch = static_cast<uint32_t>(epoch == 0xFFFFFFFFull ? 0ull : epoch);
+      peer_publish(ctrl, peer, got, n_to, ep);
     }
   }
   __syncthreads();  // every peer's flag has been seen (acquire) by a lane of warp 0: their grid records are readable
@@ -1545,16 +1613,6 @@ __global__ void __launch_bounds__(128) k_peer_exchange(Ctrl* ctrl, const __grid_
       ctrl->gx.grid_attempts[i] = att;
       ctrl->gx.grid_successes[i] = succ;
     }
-  }
-}
-
-// 3-call path: folds the statistics of pass 1, consumes the promotion every CTA applied, advances the counter.
-__global__ void __launch_bounds__(128) k_fold_pass1(Ctrl* ctrl, int64_t num_envs) {
-  __shared__ unsigned int fold[kNumCounters];
-  fold_stats(ctrl, fold, num_envs);
-  if (threadIdx.x == 0) {
-    ctrl->promote_cur = 0;
-    ctrl->step_counter += 1ull;  // a reset that follows draws at the advanced counter
   }
 }
 
