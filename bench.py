@@ -188,6 +188,50 @@ def run_cpu_port(num_envs: int, steps: int, warmup: int, seed: int = 1234, perio
             "threads": torch.get_num_threads()}
 
 
+def run_eager_cuda_port(torch, dev, num_envs: int, steps: int, warmup: int, seed: int = 1234, period: int = 4):
+    """"What users get today": the reference's algorithm as eager torch ops ON THE GPU (the oracle port with CUDA
+    tensors -- about 340 small kernels and the reference's own device->host syncs per pass), same cycle of synthetic
+    states.  Wall time per step (the path synchronises by itself: `.nonzero()`, the camera follow of ENV:323-324)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from scenario import install_mdp_state
+    from allsteps_isaaclab_b200 import synthetic as syn
+    from allsteps_isaaclab_b200.config import AllstepsCfg
+    from oracle import allsteps_oracle as ao
+
+    cfg = AllstepsCfg()
+    with torch.device(dev):
+        origins = syn.env_origins_grid(num_envs, cfg.env_spacing).to(dev)
+        limits = syn.joint_limits_tensor(cfg).to(dev)
+        orc = ao.AllstepsOracle(cfg, num_envs, origins, limits, (0, 1, 2), None)
+        st0 = {k: v.to(dev) for k, v in syn.random_mdp_state(cfg, num_envs, torch.Generator().manual_seed(seed)).items()}
+        install_mdp_state(orc, st0)
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        mirror_u = torch.rand(num_envs, generator=gen, device=dev)
+        noise_u = torch.rand(num_envs, 21, generator=gen, device=dev)
+        keys = ("curr_target_index", "prev_target_index", "next_target_index", "swing_leg", "target_reach_count",
+                "episode_length_buf", "curriculum", "potentials", "old_potentials")
+        snap = {k: getattr(orc, k).clone() for k in keys}
+        pool = []
+        for _ in range(period):
+            phys = syn.random_physics_state(cfg, orc.steps_pos, orc.curr_target_index, orc.swing_leg, gen)
+            pool.append(phys)
+            orc.step(phys, phys["actions"], mirror_u, noise_u, None)
+        times = []
+        for i in range(warmup + steps):
+            if i % period == 0:
+                for k in keys:
+                    setattr(orc, k, snap[k].clone())
+            phys = pool[i % period]
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            orc.step(phys, phys["actions"], mirror_u, noise_u, None)
+            torch.cuda.synchronize(dev)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": num_envs * len(times) / total, "us_per_step": 1e6 * total / len(times), "envs": num_envs}
+
+
 def main_reference(args):
     """The reference arm: the reference's own CPU implementation of the path (it is pure Python/torch and cannot be
     installed on the GPU box, so the bit-identical oracle port stands in -- kind "port"), all host threads, on the
@@ -722,6 +766,19 @@ def main_b200(args):
                                           "positions as a slice of the (N,17,13) body_state_w tensor "
                                           "(articulation_data.py:366-380,430-449)"}
         del wi
+        torch.cuda.empty_cache()
+
+    if extra and rank == 0 and world == 1:
+        # ---- the reference's algorithm as eager torch on this GPU: what an Isaac Lab user gets today
+        try:
+            eager = {str(n): run_eager_cuda_port(torch, dev, n, k, 3) for n, k in ((4096, 30), (N, 8))}
+            for v in eager.values():
+                v["unit"] = UNIT
+            eager["what"] = ("the oracle port (the reference's ops, bit-identical to it on CPU) with CUDA tensors: eager "
+                             "torch kernels + the reference's own host syncs; wall time per step")
+            blocks["eager_torch_cuda"] = eager
+        except Exception as exc:  # a baseline, not the product: never fail the bench on it
+            blocks["eager_torch_cuda"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         torch.cuda.empty_cache()
 
     cpu = None
