@@ -1,0 +1,227 @@
+"""GPU: memory-safety evidence without compute-sanitizer (the tool is closed on the GPU pool -- see
+profiles/r02_sanitizer_note.txt -- so the checks SURVEY section 5 asks of memcheck / racecheck are made by the suite itself):
+
+* guard bands: the workspace and every output buffer of the library sit between 64-KB bands of a byte pattern; after a
+  battery that launches every kernel (all step-kernel modes, ragged and full tiles, prepared instantiations, 3-call path
+  with host and device id lists, regeneration, grid curriculum, action path, mirror, state exchange, snapshot, stone
+  poses) no band byte has changed: no kernel writes outside its buffers;
+* poisoned neighbours: everything in the input tensors that the step must not USE -- angular velocity columns of
+  root_state_w, the 14 other bodies and the velocity columns of body_state_w, every contact column but the current
+  stone's and the next one's -- is NaN; the outputs equal those of the clean run bit for bit: the gathers pick the right
+  floats out of the 16-byte chunks they fetch;
+* unwritten outputs: output buffers start as NaN / 0xFF; after a step every element the call owns is written
+  (no NaN left in obs / reward, masks are 0/1);
+* determinism: the same step sequence twice (eager, and eager vs CUDA-graph replay elsewhere in the suite) gives
+  identical bits -- a data race between CTAs or roles shows as a difference (tools/race_probe.py is the long version).
+"""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from scenario import Scenario
+
+pytestmark = pytest.mark.gpu
+
+BAND = 1 << 16
+PATTERN = 0xA5
+
+
+class Guarded:
+    """A device buffer between two guard bands; `t` is the usable tensor (256-byte aligned)."""
+
+    def __init__(self, shape, dtype, fill=None):
+        n = int(torch.tensor(shape).prod().item()) * torch.empty(0, dtype=dtype).element_size() if len(shape) else 1
+        pad = (256 - n % 256) % 256
+        self.raw = torch.full((BAND + n + pad + BAND,), PATTERN, dtype=torch.uint8, device="cuda")
+        assert self.raw.data_ptr() % 256 == 0
+        self.n = n
+        body = self.raw[BAND:BAND + n]
+        self.t = body.view(dtype).view(*shape)
+        if fill is not None:
+            self.t.fill_(fill) if dtype != torch.bool else body.fill_(0xFF)
+
+    def intact(self):
+        lo = self.raw[:BAND]
+        hi = self.raw[BAND + self.n:]
+        return bool((lo == PATTERN).all()) and bool((hi == PATTERN).all())
+
+
+def guarded_buffers(N, mdp_mod, reward_terms=True):
+    """StepBuffers whose tensors are all guarded."""
+    from allsteps_isaaclab_b200 import _cabi
+    from allsteps_isaaclab_b200.mdp import StepBuffers, _ptr
+
+    g = {
+        "obs": Guarded((N, 59), torch.float32, float("nan")), "reward": Guarded((N,), torch.float32, float("nan")),
+        "terminated": Guarded((N,), torch.bool, 1), "time_out": Guarded((N,), torch.bool, 1),
+        "dones": Guarded((N,), torch.bool, 1),
+        "reward_terms": Guarded((N, 10), torch.float32, float("nan")),
+        "reset_root_state": Guarded((N, 13), torch.float32, 0.0), "reset_joint_pos": Guarded((N, 21), torch.float32, 0.0),
+        "reset_joint_vel": Guarded((N, 21), torch.float32, 0.0), "reset_ids": Guarded((N,), torch.int32, 0),
+        "n_reset": Guarded((1,), torch.int32, 0),
+    }
+    out = StepBuffers(1, "cuda:0", reward_terms=reward_terms)  # shell; its tensors are replaced below
+    for k, v in g.items():
+        setattr(out, k, v.t)
+    if not reward_terms:
+        out.reward_terms = None
+    out.step_out = _cabi.AsStepOut(_ptr(out.obs), _ptr(out.reward), _ptr(out.terminated), _ptr(out.time_out),
+                                   _ptr(out.reward_terms), _ptr(out.dones), 0.0, 0)
+    out.reset_out = _cabi.AsResetOut(_ptr(out.reset_root_state), _ptr(out.reset_joint_pos), _ptr(out.reset_joint_vel),
+                                     _ptr(out.reset_ids), _ptr(out.n_reset))
+    return out, g
+
+
+def guarded_mdp(N, seed, **kw):
+    """AllstepsMDP whose workspace sits between guard bands."""
+    import ctypes as C
+
+    from allsteps_isaaclab_b200 import _cabi
+    from allsteps_isaaclab_b200.mdp import AllstepsMDP
+
+    mdp = AllstepsMDP(N, device="cuda:0", seed=seed, **kw)
+    nbytes = mdp.lib.as_workspace_bytes(N)
+    ws = Guarded((nbytes,), torch.uint8)
+    mdp.lib.as_destroy(mdp.handle)
+    handle = C.c_void_p()
+    _cabi.check(mdp.lib.as_create(C.byref(mdp.params), N, mdp.env_id_offset, 0, ws.t.data_ptr(), nbytes, mdp._stream(),
+                                  C.byref(handle)), "as_create")
+    mdp.handle, mdp.workspace = handle, ws.t
+    sp = C.c_void_p()
+    _cabi.check(mdp.lib.as_stats_device_ptr(handle, C.byref(sp)), "as_stats_device_ptr")
+    off = sp.value - ws.t.data_ptr()
+    mdp.stats_tensor = ws.t[off: off + C.sizeof(_cabi.AsStats)].view(torch.int64)
+    mdp.exchange_tensor = ws.t[off: off + C.sizeof(_cabi.AsExchange)].view(torch.int64)
+    return mdp, ws
+
+
+def _state(sc, mdp, origins, high=True):
+    st0 = sc.initial_mdp_state()
+    if high:
+        st0["curr_target_index"] = torch.randint(9, 20, (sc.N,), generator=sc.gen)
+    mdp.generate_stones(origins)
+    mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                          "episode_length_buf", "potentials")})
+
+
+def _poison_unused(d_isaac, st, N):
+    """NaN into everything the step must not use (the inputs are in Isaac Lab's layout)."""
+    root_state, body_state = d_isaac["_keep"]
+    root_state[:, 10:13] = float("nan")
+    used_rows = torch.zeros(body_state.shape[1], dtype=torch.bool, device="cuda")
+    from allsteps_isaaclab_b200.workload import ISAAC_BODY_ROWS
+
+    used_rows[list(ISAAC_BODY_ROWS)] = True
+    body_state[:, ~used_rows, :] = float("nan")
+    body_state[:, :, 3:] = float("nan")
+    idx = st["curr_target_index"]
+    cols = torch.arange(20, device="cuda")[None, :]
+    # the current stone's column and the next one's are what a step may use (pass 2 looks at the next stone's when
+    # pass 1 advances the index)
+    keep = (cols == idx[:, None]) | (cols == (idx + 1).clamp(max=19)[:, None])
+    for k in ("force_matrix_right", "force_matrix_left"):
+        f = d_isaac[k]
+        f[:, 0][~keep] = float("nan")
+
+
+@pytest.mark.parametrize("N", [300, (1 << 17) + 40])
+def test_guard_bands_poisoned_neighbours_and_unwritten_outputs(N):
+    from allsteps_isaaclab_b200 import symmetry
+    from allsteps_isaaclab_b200 import synthetic as syn
+    from allsteps_isaaclab_b200.mdp import PhysicsViews
+    from allsteps_isaaclab_b200.workload import to_isaac_layout
+
+    seed = 97
+    sc = Scenario(N, seed=seed, fall_fraction=0.05)
+    origins = sc.env_origins.cuda()
+    guards = []
+    results = {}
+    for poisoned in (False, True):
+        mdp, ws = guarded_mdp(N, seed)
+        out, g = guarded_buffers(N, None)
+        guards += [ws] + list(g.values())
+        _state(Scenario(N, seed=seed, fall_fraction=0.05), mdp, origins)
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        rec = []
+        for step in range(4):
+            st = mdp.export_state()
+            d = syn.random_physics_state(sc.cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen,
+                                         fall_fraction=0.05)
+            d, rows = to_isaac_layout(d)
+            if poisoned:
+                _poison_unused(d, st, N)
+            for t in (out.obs, out.reward, out.reward_terms):
+                t.fill_(float("nan"))
+            mdp.step(PhysicsViews.from_dict(d, origins, rows), d["actions"], out)
+            torch.cuda.synchronize()
+            assert not torch.isnan(out.obs).any() and not torch.isnan(out.reward).any(), "an output element was not written"
+            assert not torch.isnan(out.reward_terms).any()
+            for m in (out.terminated, out.time_out, out.dones):
+                assert bool((m.view(torch.uint8) <= 1).all()), "a mask byte was not written"
+            rec.append({k: getattr(out, k).clone() for k in ("obs", "reward", "terminated", "time_out", "dones",
+                                                             "reward_terms")})
+            rec[-1]["state"] = mdp.export_state()
+        results[poisoned] = rec
+        # ---- the rest of the kernels on the guarded workspace
+        ep = torch.zeros(N, dtype=torch.int64, device="cuda")
+        for device_list in (False, True):
+            st = mdp.export_state()
+            d = syn.random_physics_state(sc.cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen,
+                                         fall_fraction=0.05)
+            v = PhysicsViews.from_dict(d, origins)
+            ep += 1
+            mdp.pass1(v, d["actions"], out, episode_length=ep)
+            if device_list:
+                mdp.reset(origins, None, out, episode_length=ep)
+                mdp.pass2(v, out)
+            else:
+                ids = out.dones.nonzero().squeeze(-1)
+                if len(ids):
+                    mdp.reset(origins, ids, out, episode_length=ep)
+                    mdp.pass2(v, out)
+                else:
+                    mdp.no_reset()
+        eff = Guarded((N, 21), torch.float32, 0.0)
+        mdp.apply_action(d["actions"], eff.t)
+        snap = Guarded((int(mdp.lib.as_snapshot_bytes(mdp.handle, 1)),), torch.uint8)
+        mdp.snapshot(True, out=snap.t)
+        mdp.restore(snap.t, True)
+        poses = Guarded((20 * N, 7), torch.float32, 0.0)
+        mdp.export_stone_poses(torch.arange(0, N, 3, device="cuda"), poses.t)
+        symmetry.mirror_batch(mdp, torch.randn(257, 59, device="cuda"), torch.randn(257, 21, device="cuda"))
+        torch.cuda.synchronize()
+        guards += [eff, snap, poses]
+    for a, b in zip(results[False], results[True]):
+        for k in ("obs", "reward", "terminated", "time_out", "dones", "reward_terms"):
+            assert torch.equal(a[k], b[k]), f"{k} changes when the unused neighbours of the inputs are NaN"
+        for k in a["state"]:
+            assert torch.equal(a["state"][k], b["state"][k]), f"state {k} changes when unused inputs are NaN"
+    assert all(gd.intact() for gd in guards), "a kernel wrote outside its buffer (guard band changed)"
+
+
+@pytest.mark.parametrize("kw", [dict(intended_regen=True), dict(grid_bins=6), dict(missed_step=True)])
+def test_guard_bands_extension_kernels(kw):
+    from allsteps_isaaclab_b200 import synthetic as syn
+    from allsteps_isaaclab_b200.mdp import PhysicsViews
+
+    N, seed = 2000, 5
+    sc = Scenario(N, seed=seed, fall_fraction=0.1)
+    origins = sc.env_origins.cuda()
+    runs = []
+    for _ in range(2):  # twice: the two runs must also be bit-identical (determinism)
+        mdp, ws = guarded_mdp(N, seed, **kw)
+        out, g = guarded_buffers(N, None, reward_terms=False)
+        _state(Scenario(N, seed=seed, fall_fraction=0.1), mdp, origins)
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        for step in range(5):
+            st = mdp.export_state()
+            d = syn.random_physics_state(sc.cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen,
+                                         fall_fraction=0.1)
+            mdp.step(PhysicsViews.from_dict(d, origins), d["actions"], out)
+        torch.cuda.synchronize()
+        assert ws.intact() and all(x.intact() for x in g.values())
+        runs.append((out.obs.clone(), mdp.export_state()))
+    assert torch.equal(runs[0][0], runs[1][0])
+    for k in runs[0][1]:
+        assert torch.equal(runs[0][1][k], runs[1][1][k]), k
