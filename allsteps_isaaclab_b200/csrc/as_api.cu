@@ -25,6 +25,8 @@ struct AsHandle {
   float obs_clip_pass1;  // AsStepOut.obs_clip of the last as_step_pass1 (applied by as_step_pass2 too)
   int pdl;             // programmatic dependent launch: >= 1 k_fixup_finish after the step kernel, >= 2 also the step
                        // kernel after the gather kernel (ALLSTEPS_PDL, default 2; 0 = plain stream order)
+  const void* lean_probe_ptr;  // last contact matrix whose memory type was looked up (pinned host => lean k_prepare)
+  bool lean_probe_host;
   int allow_self_finish, allow_pre;  // A/B knobs (ALLSTEPS_SELF_FINISH, ALLSTEPS_PRE; default 1)
   int prefetch_tiles;  // L2 prefetch distance of the step kernel, in 128-env tiles (about one wave of CTAs)
   cudaEvent_t ev_start, ev_stop;  // optional timing hook around k_step<fused>
@@ -93,6 +95,19 @@ int launch_prepare(AsHandle* h, const AsStateIn* in, cudaStream_t s, bool gather
   p.ws = h->ws;
   p.num_envs = h->num_envs;
   p.body_dense = gather_body ? h->ws.body_dense : nullptr;
+  p.stop_frames = h->params.stop_frames;
+  p.contact_epsilon = h->params.contact_epsilon;
+  {
+    // contact matrices in pinned host memory (zero-copy ingest): every load is a PCIe request -- the lean variant
+    if (in->contact_right != h->lean_probe_ptr) {
+      cudaPointerAttributes attr;
+      const cudaError_t e = cudaPointerGetAttributes(&attr, in->contact_right);
+      h->lean_probe_host = e == cudaSuccess && attr.type == cudaMemoryTypeHost;
+      if (e != cudaSuccess) cudaGetLastError();
+      h->lean_probe_ptr = in->contact_right;
+    }
+    p.lean = h->lean_probe_host ? 1 : 0;
+  }
   const bool aligned = ((reinterpret_cast<uintptr_t>(in->contact_right) | reinterpret_cast<uintptr_t>(in->contact_left)) &
                         15u) == 0 && ((in->contact_right_stride | in->contact_left_stride) & 3) == 0;
   if (aligned) {  // two lanes per env: one memory request per force vector
@@ -353,6 +368,8 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->launches = 0;
   h->pass1_done = false;
   h->spec_valid = false;
+  h->lean_probe_ptr = nullptr;
+  h->lean_probe_host = false;
   h->device_list = false;
   h->spec_obs = nullptr;
   h->obs_clip_pass1 = 0.0f;
