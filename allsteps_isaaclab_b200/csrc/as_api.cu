@@ -86,6 +86,19 @@ int num_tiles(int64_t n) { return static_cast<int>((n + kTile - 1) / kTile); }
 // fewer beats the better latency hiding of the separate gather kernel.
 constexpr int64_t kSeparateGatherMinEnvs = 1 << 17;
 
+// Contact matrices in pinned host memory (zero-copy ingest): every load of the gather is a PCIe request, so k_prepare*
+// fetches the current stone's vectors only and the step kernel instantiation with its own gathers is used.
+bool contact_in_host_memory(AsHandle* h, const AsStateIn* in) {
+  if (in->contact_right != h->lean_probe_ptr) {
+    cudaPointerAttributes attr;
+    const cudaError_t e = cudaPointerGetAttributes(&attr, in->contact_right);
+    h->lean_probe_host = e == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (e != cudaSuccess) cudaGetLastError();
+    h->lean_probe_ptr = in->contact_right;
+  }
+  return h->lean_probe_host;
+}
+
 // k_prepare*: contact norms of the current / following stone, stale stone windows, optionally the three body rows out
 // of a strided body tensor (`gather_body`), for batches that are not launch-bound.
 int launch_prepare(AsHandle* h, const AsStateIn* in, cudaStream_t s, bool gather_body = false) {
@@ -95,19 +108,7 @@ int launch_prepare(AsHandle* h, const AsStateIn* in, cudaStream_t s, bool gather
   p.ws = h->ws;
   p.num_envs = h->num_envs;
   p.body_dense = gather_body ? h->ws.body_dense : nullptr;
-  p.stop_frames = h->params.stop_frames;
-  p.contact_epsilon = h->params.contact_epsilon;
-  {
-    // contact matrices in pinned host memory (zero-copy ingest): every load is a PCIe request -- the lean variant
-    if (in->contact_right != h->lean_probe_ptr) {
-      cudaPointerAttributes attr;
-      const cudaError_t e = cudaPointerGetAttributes(&attr, in->contact_right);
-      h->lean_probe_host = e == cudaSuccess && attr.type == cudaMemoryTypeHost;
-      if (e != cudaSuccess) cudaGetLastError();
-      h->lean_probe_ptr = in->contact_right;
-    }
-    p.lean = h->lean_probe_host ? 1 : 0;
-  }
+  p.lean = contact_in_host_memory(h, in) ? 1 : 0;
   const bool aligned = ((reinterpret_cast<uintptr_t>(in->contact_right) | reinterpret_cast<uintptr_t>(in->contact_left)) &
                         15u) == 0 && ((in->contact_right_stride | in->contact_left_stride) & 3) == 0;
   if (aligned) {  // two lanes per env: one memory request per force vector
@@ -528,7 +529,7 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
       {k_step<kModeFused, 0, true, false, false, true>, k_step<kModeFused, 0, true, false, true, true>},
       {k_step<kModeFused, 0, true, true, false, true>, k_step<kModeFused, 0, true, true, true, true>}};
   const StepKernel ragged_kernel = k_step<kModeFused, 2, false>;
-  const bool pre = a.use_pre && ex == 0 && h->allow_pre;
+  const bool pre = a.use_pre && ex == 0 && h->allow_pre && !contact_in_host_memory(h, in);
   // the last CTA closes the step itself unless somebody else has to see the open step: the cross-shard exchange, an
   // all-reduce the caller announced (AS_STEP_DEFER_FINISH), or the regeneration kernels launched below
   a.self_finish = (h->allow_self_finish && !regen_enabled && !(out->flags & AS_STEP_DEFER_FINISH)) ? 1 : 0;
@@ -719,7 +720,7 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   static const StepKernel kFullPre[2][2] = {  // [fast][packed]
       {k_step<kModePass1, 0, true, false, false, true>, k_step<kModePass1, 0, true, false, true, true>},
       {k_step<kModePass1, 0, true, true, false, true>, k_step<kModePass1, 0, true, true, true, true>}};
-  const bool pre = a.use_pre && !h->jc.exact_div && h->allow_pre;
+  const bool pre = a.use_pre && !h->jc.exact_div && h->allow_pre && !contact_in_host_memory(h, in);
   const StepKernel full = pre ? kFullPre[fast ? 1 : 0][packed ? 1 : 0] : k_step<kModePass1, 2, true>;
   AS_CUDA(launch_step(h, full, k_step<kModePass1, 2, false>, a, s, dep,
                       (pre && packed) ? kSmemBytesPacked : kSmemBytes));

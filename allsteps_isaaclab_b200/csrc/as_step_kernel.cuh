@@ -1405,9 +1405,9 @@ struct PrepareArgs {
   int64_t num_envs;
   float* body_dense;  // non-null: gather the body rows
   int32_t lean;       // the contact matrices live in pinned HOST memory (read across PCIe, where every request counts):
-                      // fetch the next stone's vectors only for the envs whose pass 1 can advance the index at all
-  int32_t stop_frames;
-  float contact_epsilon;
+                      // only the current stone's vectors are fetched -- one request per foot and env; the step kernel
+                      // instantiation that can gather for itself then fetches the next stone's for the few envs whose
+                      // pass 1 advances the index
 };
 
 __device__ __forceinline__ void refresh_window_entry(const Workspace& ws, int64_t e, int idx, int slot) {
@@ -1476,37 +1476,9 @@ __global__ void __launch_bounds__(256) k_prepare_paired(const __grid_constant__ 
         r2 = ldg64_f4(rrow + 2);
         l2 = ldg64_f4(lrow + 2);
       }
-    } else if (half == 0 || k >= 2) {  // lean: the current stone's vector only -- one request per foot
+    } else if (half == 0 || k >= 2) {  // lean: the current stone's vector only -- one request per foot (.z/.w unused)
       r = ldg64_f4(rrow + half);
       l = ldg64_f4(lrow + half);
-    }
-  }
-  if (a.lean) {
-    // Pass 1 can advance the index only if the swing foot presses the current stone and the reach counter is one short
-    // of stop_frames (ENV:433-441): only then can pass 2 ask for the next stone's vectors.  Decide that from the
-    // vector just fetched, and fetch the rest (chunk 1 if not there yet, chunk 2 for k = 3) for those envs alone.
-    const uint32_t word = live ? a.ws.state[a.ws.ctrl->parity][e].x : 0u;
-    const float c1x = __shfl_down_sync(0xffffffffu, r.x, 1), c1y = __shfl_down_sync(0xffffffffu, r.y, 1);
-    const float d1x = __shfl_down_sync(0xffffffffu, l.x, 1), d1y = __shfl_down_sync(0xffffffffu, l.y, 1);
-    float fr = 0.f, fl = 0.f;
-    if (k == 0) { fr = norm3(r.x, r.y, r.z); fl = norm3(l.x, l.y, l.z); }
-    else if (k == 1) { fr = norm3(r.y, r.z, r.w); fl = norm3(l.y, l.z, l.w); }
-    else if (k == 2) { fr = norm3(r.z, r.w, c1x); fl = norm3(l.z, l.w, d1x); }
-    else { fr = norm3(r.w, c1x, c1y); fl = norm3(l.w, d1x, d1y); }
-    const bool pressed = (state_leg(word) ? fl : fr) > a.contact_epsilon;
-    bool need = live && half == 0 && has_next && pressed && state_count(word) + 1 >= a.stop_frames;
-    need = __shfl_sync(0xffffffffu, need, threadIdx.x & 30);  // both lanes of the pair
-    if (need) {
-      const float4* rrow = reinterpret_cast<const float4*>(in.contact_right + e * in.contact_right_stride) + (o >> 2);
-      const float4* lrow = reinterpret_cast<const float4*>(in.contact_left + e * in.contact_left_stride) + (o >> 2);
-      if (half == 1 && k < 2) {
-        r = ldg64_f4(rrow + 1);
-        l = ldg64_f4(lrow + 1);
-      }
-      if (half == 0 && k == 3) {
-        r2 = ldg64_f4(rrow + 2);
-        l2 = ldg64_f4(lrow + 2);
-      }
     }
   }
   // the six floats as f[k .. k+5] of the concatenation chunk0 (even lane) | chunk1 (odd lane) | chunk2 (even lane)
