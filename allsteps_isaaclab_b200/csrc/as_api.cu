@@ -764,9 +764,10 @@ int as_reset(AsHandle* h, const float* env_origins, const int32_t* env_ids, int6
   r.ext_episode_length = episode_length;
   r.fused = 0;
   r.into_other = h->spec_valid ? 1 : 0;  // behind a speculating pass 1 the step continues in the other state buffer
-  const int grid = grid_for(from_device_list ? h->num_envs / 8 + 1 : n_ids, 8, h->sm_count, 4);
-  k_reset_rows<<<grid, 256, 0, s>>>(r);
-  return check_launch(h, "k_reset_rows");
+  // (four envs per warp; with the device-side list the count is only known on the device: sized for a tenth of the envs)
+  const int grid = grid_for(from_device_list ? h->num_envs / 10 + 1 : n_ids, 32, h->sm_count, 3);
+  k_reset_list<<<grid, 256, 0, s>>>(r);
+  return check_launch(h, "k_reset_list");
 }
 
 int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
@@ -790,7 +791,7 @@ int as_step_pass2(AsHandle* h, const AsStateIn* in, float* obs, void* stream) {
     c.inv_step_dt = h->inv_step_dt;
     c.num_envs = h->num_envs;
     c.revert_if_none = h->device_list ? 1 : 0;
-    const int grid = grid_for(h->num_envs / 16 + 1, 8, h->sm_count, 8);
+    const int grid = grid_for(h->num_envs / 10 + 1, 32, h->sm_count, 3);
     k_pass2_commit<<<grid, 256, 0, s>>>(c);
     h->spec_valid = false;
     return check_launch(h, "k_pass2_commit");

@@ -111,7 +111,7 @@ __device__ __forceinline__ void stone_draws(const ResetArgs& a, unsigned long lo
 //              PhysX rows are written at the env's own row of full-size buffers.
 //   fused = 0: explicit `env_ids` (3-call path): also resets the MDP word and the DirectRLEnv episode counter,
 //              decides regeneration, writes compact rows.
-__global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ ResetArgs a) {
+__global__ void __launch_bounds__(256, 3) k_reset_list(const __grid_constant__ ResetArgs a) {
   const AsParams& P = a.P;
   Ctrl* ctrl = a.ws.ctrl;
   const int lane = threadIdx.x & 31;
@@ -139,56 +139,112 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
   const uint32_t parity = ctrl->parity;
   // fused: the step wrote the other buffer; 3-call path after a speculating pass 1: so did that pass
   uint2* st_cur = (a.fused || a.into_other) ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
-  float t_lo, t_hi, t_pose, t_pose_m, t_vel_m;  // this lane's joint constants, fetched once
-  load_reset_tables(P, lane, t_lo, t_hi, t_pose, t_pose_m, t_vel_m);
-
-  for (int64_t w = warp; w < n_reset; w += n_warps) {
-    const int64_t e = a.fused ? a.ws.reset_ids[w] : a.env_ids[w];
-    const int64_t row = a.fused ? e : w;
-    const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
-    const uint4 b0 = philox_block(P.seed, step, kStreamReset, gid, 0);
-    const bool mirror = u32_to_unit(b0.x) > 0.5f;  // ENV:518
-    const float ox = a.env_origins[e * 3], oy = a.env_origins[e * 3 + 1], oz = a.env_origins[e * 3 + 2];
-    if (lane < kJ) {
-      const float u = philox_uniform(P.seed, step, kStreamReset, gid, 1 + lane);
-      if (a.out.joint_pos)
-        a.out.joint_pos[row * kJ + lane] = reset_joint_value(P, mirror ? t_pose_m : t_pose, t_lo, t_hi, u);
-      if (a.out.joint_vel) a.out.joint_vel[row * kJ + lane] = mirror ? t_vel_m : 0.0f;
-    }
-    if (a.out.root_state && lane < AS_ROOT_STATE_DIM) {
-      const float z = mirror ? -0.0f : 0.0f;
-      float val = 0.0f;
-      if (lane == 0) val = P.default_root_pos[0] + ox;
-      else if (lane == 1) val = P.default_root_pos[1] + oy;
-      else if (lane == 2) val = P.default_root_pos[2] + oz;
-      else if (lane == 3) val = 1.0f;
-      else if (lane <= 6) val = z;
-      a.out.root_state[row * AS_ROOT_STATE_DIM + lane] = val;
-    }
-    if (a.out.reset_ids && lane == 0) a.out.reset_ids[w] = static_cast<int32_t>(e);
-    if (!a.fused && lane == 0) a.ws.reset_ids[w] = static_cast<int32_t>(e);  // (k_pass2_commit walks this list)
-    if (!a.fused) {
-      uint32_t word = st_cur[e].x;  // same address for all lanes: broadcast
-      const int level = min(state_level(word) + promote_now, P.max_level);
-      const bool regen = (P.flags & AS_FLAG_INTENDED_REGEN) && state_idx(word) > kS / 2;
-      __syncwarp();
-      if (lane == 0) {
+  // Explicit id list (3-call path).  FOUR envs per warp, eight lanes each: a reset env is a chain of dependent loads
+  // (id -> state word -> origins -> stones) with a little arithmetic in between, so a warp per env leaves the kernel
+  // latency-bound at a few thousand resident warps; four independent chains per warp quadruple the loads in flight.
+  const int grp = lane >> 3, g = lane & 7;
+  for (int64_t w0 = warp * 4; w0 < n_reset; w0 += n_warps * 4) {
+    const int64_t w = w0 + grp;
+    const bool have = w < n_reset;
+    int64_t e = 0;
+    int level = 0;
+    bool regen = false;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (have) {
+      e = a.env_ids[w];
+      const int64_t row = w;
+      const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
+      const uint32_t word = st_cur[e].x;
+      ox = a.env_origins[e * 3];
+      oy = a.env_origins[e * 3 + 1];
+      oz = a.env_origins[e * 3 + 2];
+      const uint4 b0 = philox_block(P.seed, step, kStreamReset, gid, 0);
+      const bool mirror = u32_to_unit(b0.x) > 0.5f;  // ENV:518
+      for (int j = g; j < kJ; j += 8) {
+        float lo, hi, pose, pose_m, vel_m;
+        load_reset_tables(P, j, lo, hi, pose, pose_m, vel_m);
+        const float u = philox_uniform(P.seed, step, kStreamReset, gid, 1 + j);
+        if (a.out.joint_pos) a.out.joint_pos[row * kJ + j] = reset_joint_value(P, mirror ? pose_m : pose, lo, hi, u);
+        if (a.out.joint_vel) a.out.joint_vel[row * kJ + j] = mirror ? vel_m : 0.0f;
+      }
+      if (a.out.root_state) {
+        const float z = mirror ? -0.0f : 0.0f;
+        for (int c = g; c < AS_ROOT_STATE_DIM; c += 8) {
+          float val = 0.0f;
+          if (c == 0) val = P.default_root_pos[0] + ox;
+          else if (c == 1) val = P.default_root_pos[1] + oy;
+          else if (c == 2) val = P.default_root_pos[2] + oz;
+          else if (c == 3) val = 1.0f;
+          else if (c <= 6) val = z;
+          a.out.root_state[row * AS_ROOT_STATE_DIM + c] = val;
+        }
+      }
+      level = min(state_level(word) + promote_now, P.max_level);
+      regen = (P.flags & AS_FLAG_INTENDED_REGEN) && state_idx(word) > kS / 2;
+      if (g == 0) {
+        if (a.out.reset_ids) a.out.reset_ids[w] = static_cast<int32_t>(e);
+        a.ws.reset_ids[w] = static_cast<int32_t>(e);  // (k_pass2_commit walks this list)
         uint2 sw;
         sw.x = pack_state(1, mirror ? 1 : 0, 0, state_level(word), 0);  // ENV:487-494,538; DRL:584
         sw.y = __float_as_uint(0.0f);
         st_cur[e] = sw;
         if (a.ext_episode_length) a.ext_episode_length[e] = 0;
       }
-      if (regen) {
-        float u0, u1, u2;
-        stone_draws(a, step, e, gid, lane, u0, u1, u2);
-        generate_stones_warp(P, lane, difficulty_of_env(P, a.ws, e, level), Vec3{ox, oy, oz}, u0, u1, u2,
-                             a.ws.stones + e * kS);
-        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->stats.n_regenerated), 1ull);
-      }
-      rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, 1, lane);
+    }
+    // regeneration takes the whole warp (one stone per lane): the groups that need it take turns
+    const unsigned rmask = __ballot_sync(kFullMask, have && regen);
+    for (int q = 0; q < 4; ++q) {
+      if (!((rmask >> (q * 8)) & 1u)) continue;
+      const int64_t eq = __shfl_sync(kFullMask, e, q * 8);
+      const int lq = __shfl_sync(kFullMask, level, q * 8);
+      const Vec3 org{__shfl_sync(kFullMask, ox, q * 8), __shfl_sync(kFullMask, oy, q * 8),
+                     __shfl_sync(kFullMask, oz, q * 8)};
+      float u0, u1, u2;
+      stone_draws(a, step, eq, static_cast<uint32_t>(eq + a.env_id_offset), lane, u0, u1, u2);
+      generate_stones_warp(P, lane, difficulty_of_env(P, a.ws, eq, lq), org, u0, u1, u2, a.ws.stones + eq * kS);
+      if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->stats.n_regenerated), 1ull);
+    }
+    __syncwarp();
+    if (have && g < 4) {  // the env restarts at index 1: its stone window
+      float4 v = a.ws.stones[e * kS + window_slot_stone(1, g)];
+      if (g == 0) v.w = __int_as_float(1);
+      a.ws.window[e * 4 + g] = v;
     }
   }
+  if (a.out.n_reset && blockIdx.x == 0 && threadIdx.x == 0) *a.out.n_reset = static_cast<int32_t>(n_reset);
+  if (!a.fused && blockIdx.x == 0 && threadIdx.x == 0) ctrl->n_reset_list = static_cast<uint32_t>(n_reset);
+}
+
+
+// fused = 1: regeneration of the stone rows of the envs the step kernel listed (one warp per env).
+__global__ void __launch_bounds__(256, 4) k_reset_rows(const __grid_constant__ ResetArgs a) {
+  const AsParams& P = a.P;
+  Ctrl* ctrl = a.ws.ctrl;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const unsigned long long step = ctrl->step_counter;
+  // fused: the step kernel already wrote the start-pose rows; n_ids < 0: the list pass 1 compacted on the device
+  const int64_t n_reset = a.fused ? 0 : (a.n_ids < 0 ? static_cast<int64_t>(ctrl->n_reset_list) : a.n_ids);
+  // promotion decided in THIS step is already in force when stones are regenerated (ENV:471 precedes ENV:500)
+  int promote_now;
+  if (!a.fused) {
+    // 3-call path: `_reset_idx` opens with the promotion rule (ENV:471-479) on the statistics pass 1 folded; every
+    // warp evaluates it for itself, one thread leaves the decision for the next pass 1 (nobody reads it in here)
+    AsStats s = ctrl->stats;
+    if (a.force_any_reset) s.n_reset = s.n_reset > 0 ? s.n_reset : 1;
+    promote_now = static_cast<int>(promotion_decision(P, s));
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->promote_cur = static_cast<uint32_t>(promote_now);
+  } else if (a.global_stats) {
+    promote_now = static_cast<int>(promotion_decision(P, a.global_stats->stats));
+  } else {  // the step kernel's counters are still in the replicated slots (folded by the finish kernel)
+    const unsigned nr = slot_sum(ctrl, kCntReset);
+    const unsigned si = slot_sum(ctrl, kCntSumIndex);
+    promote_now = static_cast<int>(promotion_rule(P, nr, si, a.num_envs));
+  }
+  const uint32_t parity = ctrl->parity;
+  // fused: the step wrote the other buffer; 3-call path after a speculating pass 1: so did that pass
+  uint2* st_cur = (a.fused || a.into_other) ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
   if (a.fused) {
     const int64_t n_regen = ctrl->n_regen_list;
     for (int64_t w = warp; w < n_regen; w += n_warps) {
@@ -202,8 +258,6 @@ __global__ void __launch_bounds__(256) k_reset_rows(const __grid_constant__ Rese
       rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, 1, lane);  // a reset env restarts at index 1
     }
   }
-  if (a.out.n_reset && blockIdx.x == 0 && threadIdx.x == 0) *a.out.n_reset = static_cast<int32_t>(n_reset);
-  if (!a.fused && blockIdx.x == 0 && threadIdx.x == 0) ctrl->n_reset_list = static_cast<uint32_t>(n_reset);
 }
 
 // Stone sequences for all envs (env_ids == null) or a list; level from the packed word (+ pending promotion).
@@ -496,7 +550,7 @@ struct CommitArgs {
 __device__ __forceinline__ float clip_obs(float v, float c) { return c > 0.0f ? (v < -c ? -c : (v > c ? c : v)) : v; }
 
 __global__ void __launch_bounds__(256) k_pass2_commit(const __grid_constant__ CommitArgs a) {
-  __shared__ float s_row[8][20];
+  __shared__ float s_row[8][4][20];
   const AsParams& P = a.P;
   Ctrl* ctrl = a.ws.ctrl;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -516,62 +570,70 @@ __global__ void __launch_bounds__(256) k_pass2_commit(const __grid_constant__ Co
   uint2* st = a.ws.state[ctrl->parity ^ 1u];  // the buffer pass 1 speculated into and as_reset wrote
   const bool exact = a.jc.exact_div != 0;
   const AsStateIn& in = a.in;
-  const float4 jc_l = a.jc.c[lane < kJ ? lane : 0];
-  for (int64_t w = warp; w < n; w += n_warps) {
-    const int64_t e = a.ws.reset_ids[w];
-    const uint2 sw = st[e];
-    Mdp m{state_idx(sw.x), state_leg(sw.x), state_count(sw.x), __uint_as_float(sw.y)};
-    const int level = state_level(sw.x), ep = state_ep(sw.x);
-    // every lane computes the env's scalars (same addresses: broadcast loads); lanes share the row stores
-    const float* rp = in.root_pos + e * in.root_pos_stride;
-    const float* rq = in.root_quat + e * in.root_quat_stride;
-    const float* rv = in.root_lin_vel + e * in.root_lin_vel_stride;
-    const Vec3 p{rp[0], rp[1], rp[2]}, v{rv[0], rv[1], rv[2]};
-    const Quat q = in.quat_xyzw ? Quat{rq[3], rq[0], rq[1], rq[2]} : Quat{rq[0], rq[1], rq[2], rq[3]};
-    const float* body = in.body_pos + e * in.body_env_stride;
-    const float* b_r = body + in.right_foot_row * in.body_row_stride;
-    const float* b_l = body + in.left_foot_row * in.body_row_stride;
-    const float* b_t = body + in.torso_row * in.body_row_stride;
-    const Vec3 rf{b_r[0], b_r[1], b_r[2]}, lf{b_l[0], b_l[1], b_l[2]};
-    const float h = b_t[2] - min_nan(lf.z, rf.z);                       // ENV:281-283
-    float roll, pitch;
-    euler_roll_pitch(q, roll, pitch);                                    // ENV:285
-    const Vec3 vb = rotate_by_inverse(q, v);                             // ENV:293
-    const Quat inv = quat_inverse(q);
-    const float f_r = contact_norm(in.contact_right + e * in.contact_right_stride, m.idx, false);
-    const float f_l = contact_norm(in.contact_left + e * in.contact_left_stride, m.idx, false);
-    const float4* stones = a.ws.stones + e * kS;
-    float4 s_prev = stones[window_slot_stone(m.idx, 0)], s_curr = stones[window_slot_stone(m.idx, 1)],
-           s_next = stones[window_slot_stone(m.idx, 2)];
-    PassOut po{};
-    const FootGeom g = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
-    if (foot_update(P, g, m, po)) {  // (cannot happen on zeroed contact rows; kept general)
-      s_prev = s_curr;
-      s_curr = s_next;
-      s_next = stones[min(m.idx + 1, kS - 1)];
-    }
-    targets_and_potential(P, a.inv_step_dt, exact, p, inv, s_prev, s_curr, s_next, m, po);
-    if (lane == 0) {
-      uint2 out;
-      out.x = pack_state(m.idx, m.leg, m.count, level, ep);
-      out.y = __float_as_uint(m.pot);
-      st[e] = out;
-      atomicOr(&a.ws.win_stale[e >> 5], 1u << (e & 31));  // its stone window is for k_prepare* to refresh
-      float* r = s_row[wib];
-      r[0] = h; r[1] = roll; r[2] = pitch; r[3] = vb.x; r[4] = vb.y; r[5] = vb.z;
-      r[6] = po.contact_r; r[7] = po.contact_l;
-      r[8] = po.tb0.x; r[9] = po.tb0.y; r[10] = po.tb0.z; r[11] = po.tb1.x; r[12] = po.tb1.y; r[13] = po.tb1.z;
-      r[14] = po.tb2.x; r[15] = po.tb2.y; r[16] = po.tb2.z;
+  // four envs per warp, eight lanes each (see k_reset_rows: independent load chains per warp)
+  const int grp = lane >> 3, g = lane & 7;
+  for (int64_t w0 = warp * 4; w0 < n; w0 += n_warps * 4) {
+    const int64_t w = w0 + grp;
+    const bool have = w < n;
+    int64_t e = 0;
+    if (have) {
+      e = a.ws.reset_ids[w];
+      const uint2 sw = st[e];
+      Mdp m{state_idx(sw.x), state_leg(sw.x), state_count(sw.x), __uint_as_float(sw.y)};
+      const int level = state_level(sw.x), ep = state_ep(sw.x);
+      // every lane of the group computes the env's scalars (same addresses: broadcast loads)
+      const float* rp = in.root_pos + e * in.root_pos_stride;
+      const float* rq = in.root_quat + e * in.root_quat_stride;
+      const float* rv = in.root_lin_vel + e * in.root_lin_vel_stride;
+      const Vec3 p{rp[0], rp[1], rp[2]}, v{rv[0], rv[1], rv[2]};
+      const Quat q = in.quat_xyzw ? Quat{rq[3], rq[0], rq[1], rq[2]} : Quat{rq[0], rq[1], rq[2], rq[3]};
+      const float* body = in.body_pos + e * in.body_env_stride;
+      const float* b_r = body + in.right_foot_row * in.body_row_stride;
+      const float* b_l = body + in.left_foot_row * in.body_row_stride;
+      const float* b_t = body + in.torso_row * in.body_row_stride;
+      const Vec3 rf{b_r[0], b_r[1], b_r[2]}, lf{b_l[0], b_l[1], b_l[2]};
+      const float4* stones = a.ws.stones + e * kS;
+      float4 s_prev = stones[window_slot_stone(m.idx, 0)], s_curr = stones[window_slot_stone(m.idx, 1)],
+             s_next = stones[window_slot_stone(m.idx, 2)];
+      const float f_r = contact_norm(in.contact_right + e * in.contact_right_stride, m.idx, false);
+      const float f_l = contact_norm(in.contact_left + e * in.contact_left_stride, m.idx, false);
+      const float h = b_t[2] - min_nan(lf.z, rf.z);                       // ENV:281-283
+      float roll, pitch;
+      euler_roll_pitch(q, roll, pitch);                                    // ENV:285
+      const Vec3 vb = rotate_by_inverse(q, v);                             // ENV:293
+      const Quat inv = quat_inverse(q);
+      PassOut po{};
+      const FootGeom gm = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
+      if (foot_update(P, gm, m, po)) {  // (cannot happen on zeroed contact rows; kept general)
+        s_prev = s_curr;
+        s_curr = s_next;
+        s_next = stones[min(m.idx + 1, kS - 1)];
+      }
+      targets_and_potential(P, a.inv_step_dt, exact, p, inv, s_prev, s_curr, s_next, m, po);
+      if (g == 0) {
+        uint2 out;
+        out.x = pack_state(m.idx, m.leg, m.count, level, ep);
+        out.y = __float_as_uint(m.pot);
+        st[e] = out;
+        atomicOr(&a.ws.win_stale[e >> 5], 1u << (e & 31));  // its stone window is for k_prepare* to refresh
+        float* r = s_row[wib][grp];
+        r[0] = h; r[1] = roll; r[2] = pitch; r[3] = vb.x; r[4] = vb.y; r[5] = vb.z;
+        r[6] = po.contact_r; r[7] = po.contact_l;
+        r[8] = po.tb0.x; r[9] = po.tb0.y; r[10] = po.tb0.z; r[11] = po.tb1.x; r[12] = po.tb1.y; r[13] = po.tb1.z;
+        r[14] = po.tb2.x; r[15] = po.tb2.y; r[16] = po.tb2.z;
+      }
     }
     __syncwarp();
-    float* row = a.obs + e * kObs;
-    if (lane < 6) row[lane] = clip_obs(s_row[wib][lane], a.obs_clip);                       // ENV:332-335
-    if (lane >= 6 && lane < 17) row[48 + lane - 6] = clip_obs(s_row[wib][lane], a.obs_clip);  // ENV:338-339
-    if (lane < kJ) {
-      const float jp = in.joint_pos[e * in.joint_pos_stride + lane];
-      const float jv = in.joint_vel[e * in.joint_vel_stride + lane];
-      row[6 + lane] = clip_obs(scale_joint(jc_l, jp, exact), a.obs_clip);                  // ENV:336
-      row[6 + kJ + lane] = clip_obs(clamp_nan(jv * P.dof_vel_scale, -5.0f, 5.0f), a.obs_clip);  // ENV:337
+    if (have) {
+      float* row = a.obs + e * kObs;
+      for (int c = g; c < 17; c += 8)   // ENV:332-335 (columns 0..5) and ENV:338-339 (columns 48..58)
+        row[c < 6 ? c : 48 + c - 6] = clip_obs(s_row[wib][grp][c], a.obs_clip);
+      for (int j = g; j < kJ; j += 8) {
+        const float jp = in.joint_pos[e * in.joint_pos_stride + j];
+        const float jv = in.joint_vel[e * in.joint_vel_stride + j];
+        row[6 + j] = clip_obs(scale_joint(a.jc.c[j], jp, exact), a.obs_clip);                     // ENV:336
+        row[6 + kJ + j] = clip_obs(clamp_nan(jv * P.dof_vel_scale, -5.0f, 5.0f), a.obs_clip);     // ENV:337
+      }
     }
     __syncwarp();
   }
