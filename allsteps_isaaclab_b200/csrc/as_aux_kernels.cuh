@@ -80,6 +80,46 @@ __device__ __forceinline__ void generate_stones_warp(const AsParams& P, int lane
   if (lane < kS) out_row[lane] = make_float4(x + origin.x, y + origin.y, z + origin.z, phi);  // ENV:111
 }
 
+// The same for one env by ONE thread: the twenty stones in sequence, the four cumulative sums as running double
+// accumulators (the additions happen in the same order, so the results are those of the warp version bit for bit).
+// `draw(k, s)`: uniform k (0 dr, 1 dphi, 2 dtheta) of stone s.  Used where many envs regenerate at once (the
+// reset-heavy configuration): a thread per env keeps thousands of independent chains in flight where a warp per env
+// spends its time in 4 x 20 dependent shuffle steps with 12 idle lanes.
+template <typename Draw>
+__device__ __forceinline__ void generate_stones_thread(const AsParams& P, const Difficulty& D, const Vec3& origin,
+                                                       Draw draw, float4* out_row, float4* window_row) {
+  const float deg2rad = 0.017453292519943295f;
+  const float half_pi = 1.5707963705062866f;
+  const float yaw_lo = (P.yaw_range_deg[0] * D.ratio_yaw) * deg2rad, yaw_hi = (P.yaw_range_deg[1] * D.ratio_yaw) * deg2rad;
+  const float pit_lo = (P.pitch_range_deg[0] * D.ratio_pitch) * deg2rad + half_pi;
+  const float pit_hi = (P.pitch_range_deg[1] * D.ratio_pitch) * deg2rad + half_pi;
+  double phi_acc = 0.0, x = 0.0, y = 0.0, z = 0.0;
+#pragma unroll 1
+  for (int s = 0; s < kS; ++s) {
+    float dr = torch_lerp(P.dist_lower, D.dist_upper, draw(0, s));   // ENV:137
+    float dphi = torch_lerp(yaw_lo, yaw_hi, draw(1, s));             // ENV:138
+    float dth = torch_lerp(pit_lo, pit_hi, draw(2, s));              // ENV:139
+    if (s == 0) {                                                    // ENV:144-146
+      dr = 0.0f; dphi = 0.0f; dth = half_pi;
+    } else if (s <= 2) {                                             // ENV:148-150
+      dr = P.init_step_separation; dphi = 0.0f; dth = half_pi;
+    }
+    phi_acc += static_cast<double>(dphi);                            // ENV:155
+    const float phi = static_cast<float>(phi_acc);
+    const float st = sinf(dth), ct = cosf(dth);
+    x += static_cast<double>((dr * st) * cosf(phi));                 // ENV:157,165
+    y += static_cast<double>((dr * st) * sinf(phi));                 // ENV:158,166
+    z += static_cast<double>(dr * ct);                               // ENV:159,167
+    float4 v = make_float4(static_cast<float>(x) + origin.x, static_cast<float>(y) + origin.y,
+                           static_cast<float>(z) + origin.z, phi);   // ENV:111
+    out_row[s] = v;
+    if (s < 4) {  // the env restarts at index 1: window = stones 0..3, tagged
+      if (s == 0) v.w = __int_as_float(1);
+      window_row[s] = v;
+    }
+  }
+}
+
 // Rebuilds one env's stone window from its stone row (lanes 0..3); call after the row was (re)written.
 __device__ __forceinline__ void rebuild_window_warp(const float4* stone_row, float4* window_row, int idx, int lane) {
   __syncwarp();
@@ -247,15 +287,31 @@ __global__ void __launch_bounds__(256, 4) k_reset_rows(const __grid_constant__ R
   uint2* st_cur = (a.fused || a.into_other) ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
   if (a.fused) {
     const int64_t n_regen = ctrl->n_regen_list;
-    for (int64_t w = warp; w < n_regen; w += n_warps) {
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t n_threads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t w = tid; w < n_regen; w += n_threads) {  // one THREAD per env (generate_stones_thread)
       const int64_t e = a.ws.regen_ids[w];
       const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
       const int level = min(state_level(st_cur[e].x) + promote_now, P.max_level);
       const Vec3 origin{a.env_origins[e * 3], a.env_origins[e * 3 + 1], a.env_origins[e * 3 + 2]};
-      float u0, u1, u2;
-      stone_draws(a, step, e, gid, lane, u0, u1, u2);
-      generate_stones_warp(P, lane, difficulty_of_env(P, a.ws, e, level), origin, u0, u1, u2, a.ws.stones + e * kS);
-      rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, 1, lane);  // a reset env restarts at index 1
+      const Difficulty D = difficulty_of_env(P, a.ws, e, level);
+      if (a.stone_uniforms) {
+        const int64_t plane = a.num_envs * kS;
+        const float* tab = a.stone_uniforms + e * kS;
+        generate_stones_thread(P, D, origin, [&](int k, int s) { return tab[k * plane + s]; }, a.ws.stones + e * kS,
+                               a.ws.window + e * 4);
+      } else {
+        // draw k * S + s is component s & 3 of Philox block 5 k + (s >> 2): three blocks serve four stones
+        uint4 blk[3];
+        int have = -1;
+        generate_stones_thread(P, D, origin, [&](int k, int s) {
+          if ((s >> 2) != have) {
+            have = s >> 2;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) blk[q] = philox_block(P.seed, step, kStreamStones, gid, static_cast<uint32_t>(5 * q + have));
+          }
+          return u32_to_unit(lane_of(blk[k], s & 3)); }, a.ws.stones + e * kS, a.ws.window + e * 4);
+      }
     }
   }
 }
