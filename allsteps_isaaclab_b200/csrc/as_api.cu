@@ -27,6 +27,7 @@ struct AsHandle {
                        // kernel after the gather kernel (ALLSTEPS_PDL, default 2; 0 = plain stream order)
   const void* lean_probe_ptr;  // last contact matrix whose memory type was looked up (pinned host => lean k_prepare)
   bool lean_probe_host;
+  int64_t prepare_min_envs;  // from this many envs on the scattered reads of a step go to k_prepare*
   int allow_self_finish, allow_pre;  // A/B knobs (ALLSTEPS_SELF_FINISH, ALLSTEPS_PRE; default 1)
   int prefetch_tiles;  // L2 prefetch distance of the step kernel, in 128-env tiles (about one wave of CTAs)
   cudaEvent_t ev_start, ev_stop;  // optional timing hook around k_step<fused>
@@ -83,8 +84,9 @@ int check_peer(const AsHandle* h) {
 int num_tiles(int64_t n) { return static_cast<int>((n + kTile - 1) / kTile); }
 
 // Below this batch size the step is launch-latency bound (working set in L2, a handful of CTAs per SM): one launch
-// fewer beats the better latency hiding of the separate gather kernel.
-constexpr int64_t kSeparateGatherMinEnvs = 1 << 17;
+// fewer beats the better latency hiding of the separate gather kernel (measured, us per step with / without k_prepare*:
+// 32 768 envs 22.1 / 22.0, 65 536 envs 25.9 / 27.6, 131 072 envs 40.9 / 47.5, 524 288 envs 107 / 130).
+constexpr int64_t kSeparateGatherMinEnvsDefault = 1 << 16;  // (ALLSTEPS_PREPARE_MIN_ENVS overrides: tuning knob)
 
 // Contact matrices in pinned host memory (zero-copy ingest): every load of the gather is a PCIe request, so k_prepare*
 // fetches the current stone's vectors only and the step kernel instantiation with its own gathers is used.
@@ -102,7 +104,7 @@ bool contact_in_host_memory(AsHandle* h, const AsStateIn* in) {
 // k_prepare*: contact norms of the current / following stone, stale stone windows, optionally the three body rows out
 // of a strided body tensor (`gather_body`), for batches that are not launch-bound.
 int launch_prepare(AsHandle* h, const AsStateIn* in, cudaStream_t s, bool gather_body = false) {
-  if (h->num_envs < kSeparateGatherMinEnvs) return AS_OK;
+  if (h->num_envs < h->prepare_min_envs) return AS_OK;
   PrepareArgs p;
   p.in = *in;
   p.ws = h->ws;
@@ -238,7 +240,7 @@ StepArgs make_step_args(AsHandle* h, const AsStateIn* in, const float* actions, 
   if (dense(actions, actions_stride, kJ)) bits |= kDenseAct;
   if (out && dense(out->obs, kObs, kObs)) bits |= kDenseObs;
   a.dense16 = bits;
-  a.use_pre = h->num_envs >= kSeparateGatherMinEnvs ? 1 : 0;
+  a.use_pre = h->num_envs >= h->prepare_min_envs ? 1 : 0;
   a.prefetch_tiles = h->prefetch_tiles;
   return a;
 }
@@ -386,6 +388,8 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
     h->prefetch_tiles = pf ? std::atoi(pf) : 0;
     const char* pdl = std::getenv("ALLSTEPS_PDL");
     h->pdl = pdl ? std::atoi(pdl) : 2;
+    const char* pm = std::getenv("ALLSTEPS_PREPARE_MIN_ENVS");
+    h->prepare_min_envs = pm ? std::atoll(pm) : kSeparateGatherMinEnvsDefault;
     const char* sf = std::getenv("ALLSTEPS_SELF_FINISH");
     h->allow_self_finish = sf ? std::atoi(sf) : 1;
     const char* pre = std::getenv("ALLSTEPS_PRE");
@@ -489,7 +493,7 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   a.want_reset_list = (reset_out && reset_out->reset_ids) ? 1 : 0;
   if (want_rows) a.rows = *reset_out;  // start-pose rows are written by the step kernel itself
   bool gather_body = false;
-  if (!(a.dense16 & kDenseBody) && h->num_envs >= kSeparateGatherMinEnvs) {
+  if (!(a.dense16 & kDenseBody) && h->num_envs >= h->prepare_min_envs) {
     // The three body rows the task reads (12 bytes each out of Isaac Lab's (N,B,13) body_state_w) are scattered
     // reads like the contact vectors: k_prepare* gathers them into a dense (N,3,3) array, which the step kernel (and
     // the fix-up, which re-reads the inputs) then takes by bulk copy.
@@ -698,7 +702,7 @@ int as_step_pass1(AsHandle* h, const AsStateIn* in, const float* actions, int64_
   AS_CUDA(cudaMemsetAsync(&h->ws.ctrl->n_reset_list, 0, sizeof(uint32_t), s));  // pass 1 compacts the flagged envs
   h->device_list = false;
   bool gather_body = false;
-  if (!(a.dense16 & kDenseBody) && h->num_envs >= kSeparateGatherMinEnvs) {  // (as in as_step_fused)
+  if (!(a.dense16 & kDenseBody) && h->num_envs >= h->prepare_min_envs) {  // (as in as_step_fused)
     gather_body = true;
     a.body_from_prepare = 1;
     a.in.body_pos = h->ws.body_dense;
