@@ -460,6 +460,8 @@ __global__ void __launch_bounds__(256) k_import(const __grid_constant__ AsParams
       if (k == 0) v.w = __int_as_float(idx);
       ws.window[e * 4 + k] = v;
     }
+    // ... of every env, so no record is stale any more (a warp's 32 consecutive envs share one word of the bit mask)
+    if ((e & 31) == 0) ws.win_stale[e >> 5] = 0u;
   }
 }
 
