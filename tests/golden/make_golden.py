@@ -8,6 +8,8 @@ allsteps_replay_n64.npz   16 consecutive MDP steps of 64 envs through the refere
 stones_levels.npz         `_generate_foot_steps_allsteps` at curriculum levels 0..9 for given uniforms.
 mirror_symmetry.npz       `get_symmetric_states_rl_games` / `get_symmetric_states_rsl_rl` (ENV:570-660) on random
                           observation / action / mu batches (incl. -0.0, inf and NaN entries).
+stone_poses_view.npz      what `RigidObjectCollection.write_object_pose_to_sim` (rigid_object_collection.py:271-301)
+                          hands to `root_physx_view.set_transforms` for the stone egress of ENV:119-120.
 math_helpers.npz          euler_xyz_from_quat / quat_rotate_inverse / subtract_frame_transforms / scale_transform /
                           unscale_transform of the reference's utils/math.py on random inputs.
 """
@@ -172,6 +174,18 @@ def mirror_symmetry(rows=96, seed=31):
             "rsl_rl_obs": as_bits(o3), "rsl_rl_actions": as_bits(a3), "actions_only": as_bits(n2)}
 
 
+def stone_poses_view(num_envs=96, seed=43):
+    from oracle import ref_rigid_collection as rc
+
+    g = torch.Generator().manual_seed(seed)
+    steps_pos = 5.0 * torch.randn(num_envs, 20, 3, generator=g)
+    env_ids = torch.randperm(num_envs, generator=g)[:31].sort().values
+    poses, view_ids = rc.reference_stone_pose_write(steps_pos, env_ids)
+    poses_all, view_ids_all = rc.reference_stone_pose_write(steps_pos, torch.arange(num_envs))
+    return {"steps_pos": steps_pos.numpy(), "env_ids": env_ids.numpy(), "view_ids": view_ids.numpy(),
+            "rows": poses[view_ids].numpy(), "view_ids_all": view_ids_all.numpy(), "poses_all": poses_all.numpy()}
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "needs the reference checkout under /root/reference"
     torch.set_num_threads(1)
@@ -182,6 +196,7 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "stones_levels.npz"), **stones_levels())
     np.savez_compressed(os.path.join(HERE, "math_helpers.npz"), **math_helpers())
     np.savez_compressed(os.path.join(HERE, "mirror_symmetry.npz"), **mirror_symmetry())
+    np.savez_compressed(os.path.join(HERE, "stone_poses_view.npz"), **stone_poses_view())
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -82,3 +82,26 @@ def test_cuda_stones_match_reference_at_every_level():
     st = mdp.export_state()
     _close(st["steps_pos"], d["pos_local"], "stone positions")
     _close(st["steps_dphi"], d["dphi"], "cumulative yaw")
+
+
+def test_stone_pose_egress_equals_the_reference_method():
+    """`as_export_stone_poses` against what the reference's own
+    `RigidObjectCollection.write_object_pose_to_sim` (rigid_object_collection.py:271-301, executed unmodified by
+    tests/golden/make_golden.py through oracle/ref_rigid_collection.py) hands to `root_physx_view.set_transforms` for
+    the stone write of ENV:119-120: the same index list and, at those indices, the same x,y,z,w pose rows."""
+    from allsteps_isaaclab_b200.mdp import AllstepsMDP
+
+    d = gu.load("stone_poses_view.npz")
+    steps_pos = gu.t(d["steps_pos"]).cuda()
+    N = steps_pos.shape[0]
+    mdp = AllstepsMDP(N, device="cuda:0", seed=1)
+    mdp.import_state({"steps_pos": steps_pos, "steps_dphi": torch.zeros(N, 20)})
+    env_ids = gu.t(d["env_ids"]).cuda()
+    poses, view_ids = mdp.export_stone_poses(env_ids)
+    torch.cuda.synchronize()
+    assert torch.equal(view_ids.cpu().long(), gu.t(d["view_ids"]))
+    assert torch.equal(poses[view_ids.long()].cpu(), gu.t(d["rows"]))
+    poses, view_ids = mdp.export_stone_poses()
+    torch.cuda.synchronize()
+    assert torch.equal(view_ids.cpu().long(), gu.t(d["view_ids_all"]))
+    assert torch.equal(poses.cpu(), gu.t(d["poses_all"]))

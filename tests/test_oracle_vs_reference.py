@@ -159,3 +159,24 @@ def test_symmetric_states_port_equals_the_live_reference_functions():
     fresh = mg.mirror_symmetry()
     for k in fresh:
         assert np.array_equal(fresh[k], d[k]), k
+
+
+def test_stone_pose_fixture_is_what_the_live_reference_writes():
+    """tests/golden/stone_poses_view.npz against a fresh execution of the reference's
+    RigidObjectCollection.write_object_pose_to_sim (oracle/ref_rigid_collection.py), plus the closed form the CUDA
+    kernel implements: view row s*N + e = (x, y, z, 0, 0, 0, 1), index list object-major."""
+    import numpy as np
+
+    import golden_util as gu
+    from oracle import ref_rigid_collection as rc
+
+    d = gu.load("stone_poses_view.npz")
+    steps_pos, env_ids = gu.t(d["steps_pos"]), gu.t(d["env_ids"])
+    poses, view_ids = rc.reference_stone_pose_write(steps_pos, env_ids)
+    assert np.array_equal(view_ids.numpy(), d["view_ids"]) and np.array_equal(poses[view_ids].numpy(), d["rows"])
+    N, S = steps_pos.shape[:2]
+    want_ids = (torch.arange(S).unsqueeze(1) * N + env_ids).flatten()
+    assert torch.equal(view_ids, want_ids)
+    rows = poses[view_ids].reshape(S, len(env_ids), 7)
+    assert torch.equal(rows[..., :3], steps_pos[env_ids].transpose(0, 1))
+    assert torch.equal(rows[..., 3:], torch.tensor([0.0, 0.0, 0.0, 1.0]).expand(S, len(env_ids), 4))
