@@ -1079,6 +1079,35 @@ def test_peer_exchange_world_of_one_equals_the_plain_step():
         levels.add(int(b["curriculum"].max()))
     assert len(levels) > 1, "no promotion happened"
     assert peer.peer_status() == {"world": 1, "rank": 0, "timeouts": 0}
+    # quiet steps: nobody resets anywhere, so the exchanging CTA leaves the step open and the fix-up kernel redoes it
+    # without pass 2 on the exchanged record -- and with the grid curriculum the exchange runs as a kernel of its own
+    for kw, n_quiet in ((dict(), 40), (dict(grid_bins=4), 40)):
+        scq = Scenario(n_quiet, seed=seed + 1, fall_fraction=0.0)
+        originsq = scq.env_origins.cuda()
+        twins = [make_cuda(n_quiet, seed, **kw) for _ in range(2)]
+        st0q = scq.initial_mdp_state()
+        for m in twins:
+            m.generate_stones(originsq)
+            m.import_state({k: st0q[k] for k in ("curr_target_index", "swing_leg", "target_reach_count", "potentials")})
+        twins[1].connect_self()
+        quiet = 0
+        for step in range(8):
+            st = twins[0].export_state()
+            phys = scq.physics(st["steps_pos"].cpu(), st["curr_target_index"].cpu(), st["swing_leg"].cpu())
+            phys["root_lin_vel_w"] *= 0.1
+            views, keep = to_views(phys, originsq, scq.body_indices)
+            o = [StepBuffers(n_quiet, "cuda:0"), StepBuffers(n_quiet, "cuda:0")]
+            twins[0].step(views, keep["actions"], o[0])
+            twins[1].step(views, keep["actions"], o[1])
+            torch.cuda.synchronize()
+            quiet += int(int(o[0].n_reset.item()) == 0)
+            for name in ("obs", "reward", "terminated", "time_out"):
+                assert torch.equal(getattr(o[0], name), getattr(o[1], name)), f"{kw} quiet step {step}: {name}"
+            a, b = twins[0].export_state(), twins[1].export_state()
+            for k in a:
+                assert torch.equal(a[k], b[k]), f"{kw} quiet step {step}: state {k}"
+        assert quiet > 0
+        assert twins[1].peer_status()["timeouts"] == 0
 
 
 def test_programmatic_launch_chain_changes_nothing(monkeypatch):
