@@ -337,6 +337,25 @@ def time_kernel_only(torch, wl, steps):
     return sum(ms) / len(ms), ms[len(ms) // 2]
 
 
+def time_per_step(torch, wl, steps):
+    """Every step between its own pair of CUDA events (median and p5 / p95 of the step time)."""
+    dev = wl.mdp.device
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    wl.rewind()
+    for _ in range(3):
+        wl.step()
+    torch.cuda.synchronize(dev)
+    ev[0].record()
+    for i in range(steps):
+        wl.step()
+        ev[i + 1].record()
+    torch.cuda.synchronize(dev)
+    us = sorted(1e3 * ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+    pick = lambda q: us[min(len(us) - 1, int(q * len(us)))]  # noqa: E731
+    return {"p5": pick(0.05), "p50": pick(0.5), "p95": pick(0.95), "steps": steps,
+            "note": "one CUDA-event pair per step; the steps that start a cycle include the state rewind"}
+
+
 def time_three_call(torch, wl, origins, steps, warmup, device_reset_list=False):
     """DRL:351-375 as the DirectRLEnv hooks run it under PhysX: as_step_pass1, the host's `.nonzero()` on reset_buf
     (DRL:359, a device->host sync), as_reset on those ids, as_step_pass2.  (No PhysX here: pass 2 sees unchanged
@@ -632,6 +651,7 @@ def main_b200(args):
         ms_total, launches = time_cycle(torch, wl, args.steps, args.warmup, dist, stats_hook)
         # the dominant kernel alone (rank-local, timed by events on its stream), same clock record
         k_avg, k_med = time_kernel_only(torch, wl, min(args.steps, 200))
+        step_us = time_per_step(torch, wl, min(max(args.steps, 50), 200))
     ms_total = reduce_max(ms_total)
     ms_step = ms_total / args.steps
     value = N * world * args.steps / (ms_total * 1e-3)
@@ -827,6 +847,7 @@ def main_b200(args):
                                     "algorithmic_bytes_per_env_step": b_kernel,
                                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None}},
             "cpu_baseline": cpu,
+            "step_us": step_us,
             "clocks": clocks.summary(),
             "step_stats": {k: stats[k] for k in ("n_reset", "n_terminated", "n_time_out", "n_advanced", "level")},
             **blocks,
