@@ -190,6 +190,56 @@ __device__ __forceinline__ float4 ldg64_f4(const float4* p) {
   asm("ld.global.nc.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
+// The same for data that is read exactly once (the contact matrices): the lines are also marked "evict first" in L2, so
+// that the gather's fills do not push out what the step kernel is about to read (state words, contact records, stone
+// windows written / touched by the same kernel).  Measured at 1 M envs (profiles/r02_experiments.txt): no hints 188.5 us
+// per step; this + "evict last" on the contact record 185.3; + "evict last" on the step kernel's state-word store (the
+// next k_prepare* reads it first thing; AS_HINT_STATE) 184.0-184.4; "evict last" on the window refresh (AS_HINT_WINDOW)
+// helps at 262 144 envs (62.5 against 64.3) and costs at 1 M (187.7), off.  -D...=0 / 1 build the variants.
+#ifndef AS_GATHER_EVICT_FIRST
+#define AS_GATHER_EVICT_FIRST 1
+#endif
+#ifndef AS_HINT_WINDOW
+#define AS_HINT_WINDOW 0
+#endif
+#ifndef AS_HINT_STATE
+#define AS_HINT_STATE 1
+#endif
+
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg64_once_f4(const float4* p, uint64_t pol) {
+#if AS_GATHER_EVICT_FIRST
+  float4 r;
+  asm("ld.global.nc.L2::cache_hint.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+  return r;
+#else
+  return ldg64_f4(p);
+#endif
+}
+__device__ __forceinline__ void st_keep_f4(float4* p, const float4& v, uint64_t pol) {
+#if AS_GATHER_EVICT_FIRST
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ void st_keep_u2(uint2* p, const uint2& v, uint64_t pol) {
+#if AS_GATHER_EVICT_FIRST
+  asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+#else
+  *p = v;
+#endif
+}
 __device__ __forceinline__ float ldg64_f(const float* p) {
   float r;
   asm("ld.global.nc.L2::64B.f32 %0, [%1];" : "=f"(r) : "l"(p));
@@ -1018,7 +1068,12 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       uint2 sw;
       sw.x = pack_state(m.idx, m.leg, m.count, level, ep);
       sw.y = __float_as_uint(m.pot);
+#if AS_HINT_STATE
+      if (PRE) st_keep_u2(st_out + e, sw, policy_evict_last());  // (k_prepare* of the next step reads it first thing)
+      else st_out[e] = sw;
+#else
       st_out[e] = sw;
+#endif
       if (PRE) {
         // this instantiation never writes windows: tell k_prepare* of the next step which records to refresh
         const unsigned stale = __ballot_sync(0xffffffffu, win_dirty);
@@ -1413,7 +1468,11 @@ struct PrepareArgs {
 __device__ __forceinline__ void refresh_window_entry(const Workspace& ws, int64_t e, int idx, int slot) {
   float4 v = ldg64_f4(ws.stones + e * kS + window_slot_stone(idx, slot));
   if (slot == 0) v.w = __int_as_float(idx);  // tag
+#if AS_HINT_WINDOW
+  st_keep_f4(ws.window + e * 4 + slot, v, policy_evict_last());  // (read by the step kernel in a moment)
+#else
   ws.window[e * 4 + slot] = v;
+#endif
 }
 
 // One lane per env (rows that are not 16-byte aligned).
@@ -1463,18 +1522,19 @@ __global__ void __launch_bounds__(256) k_prepare_paired(const __grid_constant__ 
   const int k = o & 3;
   const bool has_next = idx < kS - 1;
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f), l = r, r2 = r, l2 = r;
+  const uint64_t once = policy_evict_first(), keep = policy_evict_last();
   if (live) {
     const float4* rrow = reinterpret_cast<const float4*>(in.contact_right + e * in.contact_right_stride) + (o >> 2);
     const float4* lrow = reinterpret_cast<const float4*>(in.contact_left + e * in.contact_left_stride) + (o >> 2);
     if (!a.lean) {
       // chunk 1 is needed unless the row ends with this stone's vector (idx = S-1 has k = 1: inside chunk 0)
       if (half == 0 || has_next || k >= 2) {
-        r = ldg64_f4(rrow + half);
-        l = ldg64_f4(lrow + half);
+        r = ldg64_once_f4(rrow + half, once);
+        l = ldg64_once_f4(lrow + half, once);
       }
       if (half == 0 && k == 3 && has_next) {  // floats 3..8: the tail of the second vector sits in a third chunk
-        r2 = ldg64_f4(rrow + 2);
-        l2 = ldg64_f4(lrow + 2);
+        r2 = ldg64_once_f4(rrow + 2, once);
+        l2 = ldg64_once_f4(lrow + 2, once);
       }
     } else if (half == 0 || k >= 2) {  // lean: the current stone's vector only -- one request per foot (.z/.w unused)
       r = ldg64_f4(rrow + half);
@@ -1516,7 +1576,7 @@ __global__ void __launch_bounds__(256) k_prepare_paired(const __grid_constant__ 
   const float f_r = norm3(v[0], v[1], v[2]), f_l = norm3(u[0], u[1], u[2]);  // ENV:421-424
   const float f_r2 = has_next ? norm3(v[3], v[4], v[5]) : f_r;
   const float f_l2 = has_next ? norm3(u[3], u[4], u[5]) : f_l;
-  a.ws.contact_pre[e] = make_float4(f_r, f_l, f_r2, f_l2);
+  st_keep_f4(a.ws.contact_pre + e, make_float4(f_r, f_l, f_r2, f_l2), keep);  // read by the step kernel in a moment
 }
 
 #ifndef AS_STEP_MIN_CTAS
