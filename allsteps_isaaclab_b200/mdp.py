@@ -299,10 +299,9 @@ class AllstepsMDP:
         """The plain-library route of a sharded step: `buf` (a copy of `exchange_tensor`, made after `fold_stats()`)
         summed over the ranks where it is additive -- the ten leading counters and, with the grid curriculum, the
         grid outcomes.  Hand the result to `finish_step`."""
-        dist.all_reduce(buf[:_cabi.STATS_ADDITIVE_FIELDS], group=group)
-        if self.grid_bins:
-            dist.all_reduce(buf[self.grid_words], group=group)
-        return buf
+        from .sharding import all_reduce_exchange
+
+        return all_reduce_exchange(buf, bool(self.grid_bins), group)
 
     def finish_step(self, global_stats: Optional[torch.Tensor] = None):
         """Close the fused step: conditional no-reset fix-up, promotion rule (ENV:471-479), counters.  global_stats: a

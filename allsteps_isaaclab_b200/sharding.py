@@ -29,6 +29,21 @@ def shard_range(global_envs: int, rank: int, world: int, align: int = SHARD_ALIG
     return start, stop
 
 
+def all_reduce_exchange(buf: torch.Tensor, with_grid: bool, group=None) -> torch.Tensor:
+    """Sum an `AsExchange` record (int64 view: `AllstepsMDP.exchange_tensor` copied after `fold_stats()`) over the ranks
+    where it is additive: the ten leading step counters and -- `with_grid` -- the step's difficulty-grid outcomes (two
+    uint32 counters per int64 word; counts of one step cannot carry from the low half into the high one).  Level, step
+    counter, reward sum and the missed-step counter stay this shard's.  NCCL on the GPUs, gloo in the CPU tests."""
+    import torch.distributed as dist
+
+    if buf.numel() < EXCHANGE_INT64_WORDS or buf.dtype != torch.int64:
+        raise ValueError(f"an exchange record is {EXCHANGE_INT64_WORDS} int64 words")
+    dist.all_reduce(buf[:STATS_ADDITIVE_FIELDS], group=group)
+    if with_grid:
+        dist.all_reduce(buf[STATS_INT64_WORDS:EXCHANGE_INT64_WORDS], group=group)
+    return buf
+
+
 class StatsReducer:
     """Sums the additive head of `AsStats` over ranks (async, off the step path) and applies the promotion rule."""
 

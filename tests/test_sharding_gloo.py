@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from allsteps_isaaclab_b200.sharding import STAT_NAMES, StatsReducer, shard_range
+from allsteps_isaaclab_b200 import _cabi
+from allsteps_isaaclab_b200.sharding import STAT_NAMES, StatsReducer, all_reduce_exchange, shard_range
 
 
 def test_shard_ranges_partition_the_env_ids():
@@ -49,7 +50,22 @@ def _worker(rank, world, port, q):
         m_all, n_all = philox.reset_tables(9, 5, np.arange(n_global))
         m_loc, n_loc = philox.reset_tables(9, 5, np.arange(lo, hi))
         ok_philox = np.array_equal(m_loc, m_all[lo:hi]) and np.array_equal(n_loc, n_all[lo:hi])
-        q.put((rank, g, red.promotes(g), ok_philox, int(idx.sum())))
+        # the exchange record of a sharded step closed through the all-reduce route (statistics + grid outcomes)
+        rec = torch.zeros(_cabi.EXCHANGE_INT64_WORDS, dtype=torch.int64)
+        rec[:len(STAT_NAMES)] = local
+        grid = rec[_cabi.STATS_INT64_WORDS:].view(torch.int32)          # attempts[256] then successes[256], uint32
+        grid[3] = 5 + rank
+        grid[256 + 3] = 2 + rank
+        grid[255] = 70000 * (rank + 1)                                   # a high half next to a low half: no carry
+        both = all_reduce_exchange(rec.clone(), with_grid=True)
+        head_only = all_reduce_exchange(rec.clone(), with_grid=False)
+        g2 = both[_cabi.STATS_INT64_WORDS:].view(torch.int32)
+        ok_record = (int(g2[3]) == 11 and int(g2[256 + 3]) == 5 and int(g2[255]) == 210000 and int(g2[254]) == 0
+                     and int(both[STAT_NAMES.index("level")]) == 7
+                     and int(both[STAT_NAMES.index("n_envs")]) == n_global
+                     and torch.equal(head_only[_cabi.STATS_INT64_WORDS:], rec[_cabi.STATS_INT64_WORDS:])
+                     and torch.equal(head_only[:10], both[:10]))
+        q.put((rank, g, red.promotes(g), ok_philox and ok_record, int(idx.sum())))
     finally:
         dist.destroy_process_group()
 
