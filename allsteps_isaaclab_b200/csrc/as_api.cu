@@ -111,6 +111,7 @@ int launch_prepare(AsHandle* h, const AsStateIn* in, cudaStream_t s, bool gather
   p.num_envs = h->num_envs;
   p.body_dense = gather_body ? h->ws.body_dense : nullptr;
   p.lean = contact_in_host_memory(h, in) ? 1 : 0;
+  p.stop_frames = h->params.stop_frames;
   const bool aligned = ((reinterpret_cast<uintptr_t>(in->contact_right) | reinterpret_cast<uintptr_t>(in->contact_left)) &
                         15u) == 0 && ((in->contact_right_stride | in->contact_left_stride) & 3) == 0;
   if (aligned) {  // two lanes per env: one memory request per force vector

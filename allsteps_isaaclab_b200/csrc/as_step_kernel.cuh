@@ -1463,6 +1463,7 @@ struct PrepareArgs {
                       // only the current stone's vectors are fetched -- one request per foot and env; the step kernel
                       // instantiation that can gather for itself then fetches the next stone's for the few envs whose
                       // pass 1 advances the index
+  int32_t stop_frames;  // ENV:56: pass 1 can advance the index only if the reach counter is one short of this
 };
 
 __device__ __forceinline__ void refresh_window_entry(const Workspace& ws, int64_t e, int idx, int slot) {
@@ -1481,13 +1482,17 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= a.num_envs) return;
   const AsStateIn& in = a.in;
-  const int idx = state_idx(a.ws.state[a.ws.ctrl->parity][e].x);
+  const uint32_t word = a.ws.state[a.ws.ctrl->parity][e].x;
+  const int idx = state_idx(word);
   const int nxt = min(idx + 1, kS - 1);
   const bool stale = (a.ws.win_stale[e >> 5] >> (e & 31)) & 1u;
   const float* rr = in.contact_right + e * in.contact_right_stride;
   const float* lr = in.contact_left + e * in.contact_left_stride;
+  // (the next stone's vectors only where pass 1 can advance the index at all: reach counter one short of stop_frames)
+  const bool want_next = state_count(word) + 1 >= a.stop_frames;
   a.ws.contact_pre[e] = make_float4(contact_norm(rr, idx, false), contact_norm(lr, idx, false),
-                                    contact_norm(rr, nxt, false), contact_norm(lr, nxt, false));
+                                    want_next ? contact_norm(rr, nxt, false) : 0.0f,
+                                    want_next ? contact_norm(lr, nxt, false) : 0.0f);
   if (stale) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) refresh_window_entry(a.ws, e, idx, k);
@@ -1516,11 +1521,15 @@ __global__ void __launch_bounds__(256) k_prepare_paired(const __grid_constant__ 
   const int64_t e = t >> 1;
   const bool live = e < a.num_envs;  // both lanes of a pair agree; no early exit, the shuffles below need the warp
   const int half = static_cast<int>(t & 1);
-  const int idx = live ? state_idx(a.ws.state[a.ws.ctrl->parity][e].x) : 0;
+  const uint32_t word = live ? a.ws.state[a.ws.ctrl->parity][e].x : 0u;
+  const int idx = state_idx(word);
   const bool stale = live && ((a.ws.win_stale[e >> 5] >> (e & 31)) & 1u);  // (one word per 64 lanes: one request)
   const int o = idx * 3;
   const int k = o & 3;
-  const bool has_next = idx < kS - 1;
+  // The next stone's vectors are needed only if pass 1 can advance the index at all (ENV:433-441: the reach counter is
+  // one short of stop_frames) -- known from the state word alone, before any contact data: most envs fetch the 12 bytes
+  // of the current stone only, which straddle a 64-byte fill boundary half as often as the 24 bytes of both stones.
+  const bool has_next = idx < kS - 1 && state_count(word) + 1 >= a.stop_frames;
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f), l = r, r2 = r, l2 = r;
   const uint64_t once = policy_evict_first(), keep = policy_evict_last();
   if (live) {
