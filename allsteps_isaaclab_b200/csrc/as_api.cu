@@ -29,6 +29,7 @@ struct AsHandle {
   bool lean_probe_host;
   int64_t prepare_min_envs;  // from this many envs on the scattered reads of a step go to k_prepare*
   int allow_self_finish, allow_pre;  // A/B knobs (ALLSTEPS_SELF_FINISH, ALLSTEPS_PRE; default 1)
+  int regen_mode;      // shape of the regeneration kernel: 0 = by list length, 1 = warp per env, 2 = thread per env (ALLSTEPS_REGEN_MODE)
   int prefetch_tiles;  // L2 prefetch distance of the step kernel, in 128-env tiles (about one wave of CTAs)
   cudaEvent_t ev_start, ev_stop;  // optional timing hook around k_step<fused>
   PeerArgs peer;        // world > 0 after as_peer_create; buf[] complete after as_peer_connect
@@ -86,6 +87,7 @@ int num_tiles(int64_t n) { return static_cast<int>((n + kTile - 1) / kTile); }
 // Below this batch size the step is launch-latency bound (working set in L2, a handful of CTAs per SM): one launch
 // fewer beats the better latency hiding of the separate gather kernel (measured, us per step with / without k_prepare*:
 // 32 768 envs 22.1 / 22.0, 65 536 envs 25.9 / 27.6, 131 072 envs 40.9 / 47.5, 524 288 envs 107 / 130).
+constexpr int64_t kRegenByWarpMaxEnvs = 1 << 15;  // k_reset_rows: a warp per env up to this batch size (profiles/r02_experiments.txt, 12)
 constexpr int64_t kSeparateGatherMinEnvsDefault = 1 << 16;  // (ALLSTEPS_PREPARE_MIN_ENVS overrides: tuning knob)
 
 // Contact matrices in pinned host memory (zero-copy ingest): every load of the gather is a PCIe request, so k_prepare*
@@ -395,6 +397,8 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
     h->allow_self_finish = sf ? std::atoi(sf) : 1;
     const char* pre = std::getenv("ALLSTEPS_PRE");
     h->allow_pre = pre ? std::atoi(pre) : 1;
+    const char* rm = std::getenv("ALLSTEPS_REGEN_MODE");
+    h->regen_mode = rm ? std::atoi(rm) : 0;
   }
   unsigned char* base = static_cast<unsigned char*>(workspace);
   h->ws.ctrl = reinterpret_cast<Ctrl*>(base + l.ctrl_off);
@@ -543,20 +547,17 @@ int as_step_fused(AsHandle* h, const AsStateIn* in, const float* actions, int64_
                       ragged_kernel, a, s, dep, packed ? kSmemBytesPacked : kSmemBytes));
   if (int rc = check_launch(h, "k_step<fused>")) return rc;
   if (h->ev_stop) AS_CUDA(cudaEventRecord(h->ev_stop, s));
-  if (grid) {  // kernel (c): new bins by inverse-CDF sampling from the histograms as they stand after the previous
-               // step; this step's outcomes into the step's record (they join the histograms when the step is closed)
-    const int g = grid_for(h->num_envs, 256 * 8, h->sm_count, 1);
-    // (the outcomes first: they are recorded against the bins the envs WERE playing, which the sampler overwrites)
-    k_grid_hist<<<g, 256, 0, s>>>(h->params, h->ws);
-    if (int rc = check_launch(h, "k_grid_hist")) return rc;
-    k_grid_sample<<<g, 256, 0, s>>>(h->params, h->ws, h->env_id_offset);
-    if (int rc = check_launch(h, "k_grid_sample")) return rc;
-  }
-  if (regen_enabled) {  // kernel (b): warp-per-env stone regeneration over the compacted list
+  if (regen_enabled) {
+    // kernels (b) + (c) over the compacted list: the grid curriculum's outcome record and new bins (sampled from the
+    // histograms as they stand after the previous step; this step's outcomes join them when the step is closed) and
+    // the stone rows.  A programmatic dependent of the step kernel: launch and prologue hide under its last wave.
     ResetArgs r = make_reset_args(h, in->env_origins);
     r.fused = 1;
-    const int grid = grid_for(h->num_envs, 64, h->sm_count, 8);
-    k_reset_rows<<<grid, 256, 0, s>>>(r);
+    // shape of the kernel: a warp per env for small batches, a thread per env for large ones (ALLSTEPS_REGEN_MODE: 1 / 2)
+    const bool by_warp = h->regen_mode == 1 || (h->regen_mode == 0 && h->num_envs <= kRegenByWarpMaxEnvs);
+    const int grid_ctas = grid_for(h->num_envs, 64, h->sm_count, 8);
+    AS_CUDA(launch_dependent(by_warp ? k_reset_rows<true> : k_reset_rows<false>, static_cast<unsigned>(grid_ctas), 256u, 0, s,
+                             h->pdl >= 1, r));
     if (int rc = check_launch(h, "k_reset_rows")) return rc;
   }
   h->pending = a;

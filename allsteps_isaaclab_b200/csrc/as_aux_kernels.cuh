@@ -1,6 +1,8 @@
 // Kernels (b) and (c) plus the small adapters around the fused step:
-//   k_reset_rows      warp-per-env reset: start-pose rows for PhysX (ENV:505-565) from the same Philox draws the
-//                     step kernel used, and stone-sequence regeneration (ENV:106-174) for the compacted id lists
+//   k_reset_list      3-call path: start-pose rows for PhysX (ENV:505-565) from the same Philox draws the step kernel
+//                     uses, MDP words, stone regeneration for an explicit / device-compacted id list
+//   k_reset_rows      fused path: grid-curriculum turnover + stone-sequence regeneration (ENV:106-174) for the envs the
+//                     step kernel listed
 //   k_generate_stones stone sequences for all / listed envs (init, ENV:71)
 //   k_apply_action    ENV:257-274
 //   k_mirror_rows     ENV:570-660 (mirror-symmetry augmentation)
@@ -256,45 +258,119 @@ __global__ void __launch_bounds__(256, 3) k_reset_list(const __grid_constant__ R
 }
 
 
-// fused = 1: regeneration of the stone rows of the envs the step kernel listed (one warp per env).
+// ------------------------------------------------------------------------------------------------ kernels (b) + (c)
+// Behind the fused step: everything that happens to the envs the step kernel listed for regeneration, in ONE launch.
+//   (c) grid-curriculum extension (no reference counterpart; specification = oracle/grid_curriculum.py): the outcome of
+//       the episode that just ended is recorded against the bin the env WAS playing -- a shared-memory histogram per
+//       CTA, flushed with one atomic per touched bin into the step's outcome record (Ctrl::grid_delta_*), which joins
+//       the histograms when the step is closed, summed over the shards first when the run is sharded -- and the env
+//       draws its new bin by inverse-CDF search in the integer CDF of the bin weights (histograms as they stand after
+//       the PREVIOUS step; every CTA rebuilds the CDF with a shuffle scan).
+//   (b) the stone row (ENV:106-174) and the stone window of the env, at the new difficulty.
+// Two shapes of the same arithmetic (bit-identical: same draws, same order of the additions), chosen by the host from
+// the batch size: one WARP per env for small batches, where the list is a few hundred envs and the kernel is pure
+// latency -- the twenty stones' draws, interpolations and sines run side by side -- and one THREAD per env for large
+// ones, where thousands of independent chains in flight beat 4 x 20 dependent shuffle steps with 12 idle lanes
+// (BASELINE config 5: 257 000 of 1 M envs regenerate per step).
+constexpr uint32_t kStreamGrid = 2;
+
+__device__ __forceinline__ unsigned int grid_weight(unsigned int a, unsigned int s) {
+  if (a == 0) return 256u;  // unvisited bins are tried
+  const unsigned long long A = a, S = s;
+  return 1u + static_cast<unsigned int>((1024ull * S * (A - S)) / (A * A + 1ull));  // peaks at a 50 % success rate
+}
+
+template <bool BY_WARP>
 __global__ void __launch_bounds__(256, 4) k_reset_rows(const __grid_constant__ ResetArgs a) {
+  __shared__ unsigned int s_cdf[kMaxGridBins], s_att[kMaxGridBins], s_succ[kMaxGridBins];
+  __shared__ unsigned int s_warp_tot[8];
+  asm volatile("griddepcontrol.launch_dependents;");  // the finish kernel may become resident; it waits for us
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the step kernel has completed: its id lists are final
   const AsParams& P = a.P;
   Ctrl* ctrl = a.ws.ctrl;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp_in_cta = t >> 5;
+  const int64_t n_regen = ctrl->n_regen_list;
+  const int64_t n_threads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t n_warps = n_threads >> 5;
+  // (block-uniform: CTAs without a list entry leave before the first barrier)
+  if (static_cast<int64_t>(blockIdx.x) * (BY_WARP ? blockDim.x >> 5 : blockDim.x) >= n_regen) return;
+  const bool grid = (P.flags & AS_FLAG_GRID_CURRICULUM) != 0;
+  const int nb = static_cast<int>(P.grid_bins * P.grid_bins);
+  if (grid) {
+    // inclusive prefix sum of the bin weights: shuffle scan inside each warp, then the warp totals
+    unsigned int v = t < nb ? grid_weight(__ldcg(&ctrl->grid_attempts[t]), __ldcg(&ctrl->grid_successes[t])) : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int up = __shfl_up_sync(kFullMask, v, o);
+      if (lane >= o) v += up;
+    }
+    if (lane == 31) s_warp_tot[warp_in_cta] = v;
+    s_att[t] = 0u;
+    s_succ[t] = 0u;
+    __syncthreads();
+    unsigned int base = 0;
+    for (int w = 0; w < warp_in_cta; ++w) base += s_warp_tot[w];
+    s_cdf[t] = v + base;
+    __syncthreads();
+  }
   const unsigned long long step = ctrl->step_counter;
-  // fused: the step kernel already wrote the start-pose rows; n_ids < 0: the list pass 1 compacted on the device
-  const int64_t n_reset = a.fused ? 0 : (a.n_ids < 0 ? static_cast<int64_t>(ctrl->n_reset_list) : a.n_ids);
+  // outcome of list entry w (env e) against the bin it played, then the new bin of the env
+  auto grid_turnover = [&](int64_t w, int64_t e) -> int {
+    const int b0 = a.ws.bin[e];
+    if (BY_WARP) {  // a short list spread over many CTAs: straight into the step's outcome record
+      atomicAdd(&ctrl->grid_delta_att[b0], 1u);
+      if (a.ws.regen_info[w] > kS / 2) atomicAdd(&ctrl->grid_delta_succ[b0], 1u);
+    } else {
+      atomicAdd(&s_att[b0], 1u);
+      if (a.ws.regen_info[w] > kS / 2) atomicAdd(&s_succ[b0], 1u);
+    }
+    const unsigned long long total = s_cdf[nb - 1];
+    const uint4 blk = philox_block(P.seed, step, kStreamGrid, static_cast<uint32_t>(e + a.env_id_offset), 0);
+    const unsigned long long target = (static_cast<unsigned long long>(blk.x >> 8) * total) >> 24;
+    int lo = 0, hi = nb - 1;  // first bin with cdf > target
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_cdf[mid] > target) hi = mid; else lo = mid + 1;
+    }
+    a.ws.bin[e] = static_cast<uint8_t>(lo);
+    return lo;
+  };
   // promotion decided in THIS step is already in force when stones are regenerated (ENV:471 precedes ENV:500)
   int promote_now;
-  if (!a.fused) {
-    // 3-call path: `_reset_idx` opens with the promotion rule (ENV:471-479) on the statistics pass 1 folded; every
-    // warp evaluates it for itself, one thread leaves the decision for the next pass 1 (nobody reads it in here)
-    AsStats s = ctrl->stats;
-    if (a.force_any_reset) s.n_reset = s.n_reset > 0 ? s.n_reset : 1;
-    promote_now = static_cast<int>(promotion_decision(P, s));
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->promote_cur = static_cast<uint32_t>(promote_now);
-  } else if (a.global_stats) {
+  if (a.global_stats) {
     promote_now = static_cast<int>(promotion_decision(P, a.global_stats->stats));
   } else {  // the step kernel's counters are still in the replicated slots (folded by the finish kernel)
     const unsigned nr = slot_sum(ctrl, kCntReset);
     const unsigned si = slot_sum(ctrl, kCntSumIndex);
     promote_now = static_cast<int>(promotion_rule(P, nr, si, a.num_envs));
   }
-  const uint32_t parity = ctrl->parity;
-  // fused: the step wrote the other buffer; 3-call path after a speculating pass 1: so did that pass
-  uint2* st_cur = (a.fused || a.into_other) ? a.ws.state[parity ^ 1u] : a.ws.state[parity];
-  if (a.fused) {
-    const int64_t n_regen = ctrl->n_regen_list;
-    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t n_threads = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t w = tid; w < n_regen; w += n_threads) {  // one THREAD per env (generate_stones_thread)
+  const uint2* st_cur = a.ws.state[ctrl->parity ^ 1u];  // (the step wrote the other buffer)
+  if (BY_WARP) {
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + t) >> 5;
+    for (int64_t w = warp; w < n_regen; w += n_warps) {
       const int64_t e = a.ws.regen_ids[w];
-      const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
+      int bin = 0;
+      if (grid) {
+        if (lane == 0) bin = grid_turnover(w, e);
+        bin = __shfl_sync(kFullMask, bin, 0);
+      }
       const int level = min(state_level(st_cur[e].x) + promote_now, P.max_level);
       const Vec3 origin{a.env_origins[e * 3], a.env_origins[e * 3 + 1], a.env_origins[e * 3 + 2]};
-      const Difficulty D = difficulty_of_env(P, a.ws, e, level);
+      const Difficulty D = grid ? difficulty_of_bin(P, bin) : difficulty_of_level(P, level);
+      float u0, u1, u2;
+      stone_draws(a, step, e, static_cast<uint32_t>(e + a.env_id_offset), lane, u0, u1, u2);
+      generate_stones_warp(P, lane, D, origin, u0, u1, u2, a.ws.stones + e * kS);
+      rebuild_window_warp(a.ws.stones + e * kS, a.ws.window + e * 4, 1, lane);  // the env restarts at index 1
+    }
+  } else {
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + t;
+    for (int64_t w = tid; w < n_regen; w += n_threads) {
+      const int64_t e = a.ws.regen_ids[w];
+      const uint32_t gid = static_cast<uint32_t>(e + a.env_id_offset);
+      const int bin = grid ? grid_turnover(w, e) : 0;
+      const int level = min(state_level(st_cur[e].x) + promote_now, P.max_level);
+      const Vec3 origin{a.env_origins[e * 3], a.env_origins[e * 3 + 1], a.env_origins[e * 3 + 2]};
+      const Difficulty D = grid ? difficulty_of_bin(P, bin) : difficulty_of_level(P, level);
       if (a.stone_uniforms) {
         const int64_t plane = a.num_envs * kS;
         const float* tab = a.stone_uniforms + e * kS;
@@ -313,6 +389,11 @@ __global__ void __launch_bounds__(256, 4) k_reset_rows(const __grid_constant__ R
           return u32_to_unit(lane_of(blk[k], s & 3)); }, a.ws.stones + e * kS, a.ws.window + e * 4);
       }
     }
+  }
+  if (grid && !BY_WARP) {
+    __syncthreads();
+    if (s_att[t]) atomicAdd(&ctrl->grid_delta_att[t], s_att[t]);
+    if (s_succ[t]) atomicAdd(&ctrl->grid_delta_succ[t], s_succ[t]);
   }
 }
 
@@ -462,81 +543,6 @@ __global__ void __launch_bounds__(256) k_import(const __grid_constant__ AsParams
     }
     // ... of every env, so no record is stale any more (a warp's 32 consecutive envs share one word of the bit mask)
     if ((e & 31) == 0) ws.win_stale[e >> 5] = 0u;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ kernel (c)
-// Grid-curriculum extension (no reference counterpart; specification = oracle/grid_curriculum.py).
-// k_grid_sample: every CTA rebuilds the integer CDF of the bin weights (histograms as they stand after the PREVIOUS
-//                step) with a warp-scan (shuffle) prefix sum, then draws a new bin for each env that reset by
-//                inverse-CDF search with its Philox uniform.
-// k_grid_hist:   shared-memory histogram of this step's episode outcomes over the difficulty grid, flushed with one
-//                atomic per touched bin and CTA into the step's outcome record (Ctrl::grid_delta_*); the record is
-//                added to the histograms when the step is closed -- after having been summed over all shards by the
-//                peer exchange / the caller's all-reduce when the run is sharded.
-// Both walk the id list the step kernel compacted (ws.regen_ids / ws.regen_info).
-constexpr uint32_t kStreamGrid = 2;
-
-__global__ void __launch_bounds__(256) k_grid_hist(const __grid_constant__ AsParams P, Workspace ws) {
-  __shared__ unsigned int s_att[kMaxGridBins], s_succ[kMaxGridBins];
-  Ctrl* ctrl = ws.ctrl;
-  for (int i = threadIdx.x; i < kMaxGridBins; i += blockDim.x) s_att[i] = s_succ[i] = 0;
-  __syncthreads();
-  const int64_t n = ctrl->n_regen_list;
-  for (int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; w < n;
-       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int b = ws.bin[ws.regen_ids[w]];
-    atomicAdd(&s_att[b], 1u);
-    if (ws.regen_info[w] > kS / 2) atomicAdd(&s_succ[b], 1u);
-  }
-  __syncthreads();
-  // into this step's outcome record: it joins the histograms when the step is closed (summed over shards if sharded)
-  for (int i = threadIdx.x; i < kMaxGridBins; i += blockDim.x) {
-    if (s_att[i]) atomicAdd(&ctrl->grid_delta_att[i], s_att[i]);
-    if (s_succ[i]) atomicAdd(&ctrl->grid_delta_succ[i], s_succ[i]);
-  }
-}
-
-__device__ __forceinline__ unsigned int grid_weight(unsigned int a, unsigned int s) {
-  if (a == 0) return 256u;  // unvisited bins are tried
-  const unsigned long long A = a, S = s;
-  return 1u + static_cast<unsigned int>((1024ull * S * (A - S)) / (A * A + 1ull));  // peaks at a 50 % success rate
-}
-
-__global__ void __launch_bounds__(256) k_grid_sample(const __grid_constant__ AsParams P, Workspace ws,
-                                                     int64_t env_id_offset) {
-  __shared__ unsigned int s_cdf[kMaxGridBins];
-  __shared__ unsigned int s_warp_tot[8];
-  Ctrl* ctrl = ws.ctrl;
-  const int nb = static_cast<int>(P.grid_bins * P.grid_bins);
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  // inclusive prefix sum of the weights: shuffle scan inside each warp, then the warp totals
-  unsigned int v = t < nb ? grid_weight(__ldcg(&ctrl->grid_attempts[t]), __ldcg(&ctrl->grid_successes[t])) : 0u;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int up = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v += up;
-  }
-  if (lane == 31) s_warp_tot[warp] = v;
-  __syncthreads();
-  unsigned int base = 0;
-  for (int w = 0; w < warp; ++w) base += s_warp_tot[w];
-  s_cdf[t] = v + base;
-  __syncthreads();
-  const unsigned long long total = s_cdf[nb - 1];
-  const unsigned long long step = ctrl->step_counter;
-  const int64_t n = ctrl->n_regen_list;
-  for (int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + t; w < n;
-       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t e = ws.regen_ids[w];
-    const uint4 blk = philox_block(P.seed, step, kStreamGrid, static_cast<uint32_t>(e + env_id_offset), 0);
-    const unsigned long long target = (static_cast<unsigned long long>(blk.x >> 8) * total) >> 24;
-    int lo = 0, hi = nb - 1;  // first bin with cdf > target
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (s_cdf[mid] > target) hi = mid; else lo = mid + 1;
-    }
-    ws.bin[e] = static_cast<uint8_t>(lo);
   }
 }
 

@@ -237,7 +237,10 @@ def test_per_env_levels_and_env_id_offset():
     assert totals["resets"] > 0
 
 
-def test_intended_regeneration_extension():
+@pytest.mark.parametrize("regen_mode", ["1", "2"])
+def test_intended_regeneration_extension(regen_mode, monkeypatch):
+    # k_reset_rows regenerates with one warp per env (short lists) or one thread per env (long lists): both shapes
+    monkeypatch.setenv("ALLSTEPS_REGEN_MODE", regen_mode)
     totals, _, _ = run_replay(768, 10, seed=9, high_index=True, intended_regen=True, per_env_levels=True)
     assert totals["regen"] > 0
 
@@ -582,9 +585,12 @@ def test_cuda_graph_replay_is_identical_to_eager_steps():
         assert mdps[0].read_stats()["step_counter"] == mdps[1].read_stats()["step_counter"]
 
 
-def test_grid_curriculum_extension():
+@pytest.mark.parametrize("regen_mode", ["0", "1", "2"])
+def test_grid_curriculum_extension(regen_mode, monkeypatch):
     """Kernel (c): difficulty histogram + inverse-CDF bin sampling + regeneration at the bin's difficulty.  No
-    reference counterpart: checked bit for bit against its specification, oracle/grid_curriculum.py."""
+    reference counterpart: checked bit for bit against its specification, oracle/grid_curriculum.py.  (regen_mode:
+    the shape of k_reset_rows -- chosen by list length, one warp per env, one thread per env.)"""
+    monkeypatch.setenv("ALLSTEPS_REGEN_MODE", regen_mode)
     from allsteps_isaaclab_b200.mdp import StepBuffers
     from oracle import allsteps_oracle as ao
     from oracle import grid_curriculum as gc

@@ -16,7 +16,9 @@ def probe(N, steps=50, sets=4, warmup=10):
     dev = torch.device("cuda:0")
     origins = syn.env_origins_grid(N, cfg.env_spacing).to(dev)
     c5 = "--c5" in sys.argv  # BASELINE config 5: ~half of the envs reset per step, stones regenerated
-    mdp = AllstepsMDP(N, device=dev, seed=1, skip_pass2=("--skip-pass2" in sys.argv), intended_regen=c5)
+    grid = "--grid" in sys.argv  # BASELINE config 3: 11 x 11 pitch x yaw grid curriculum (extension)
+    mdp = AllstepsMDP(N, device=dev, seed=1, skip_pass2=("--skip-pass2" in sys.argv), intended_regen=c5,
+                      grid_bins=11 if grid else 0)
     mdp.generate_stones(origins)
     st0 = syn.random_mdp_state(cfg, N, torch.Generator().manual_seed(1))
     mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
@@ -25,7 +27,7 @@ def probe(N, steps=50, sets=4, warmup=10):
     out = StepBuffers(N, dev, reset_rows=("--no-rows" not in sys.argv))
     # every input set is generated from the MDP state it meets; the state is rewound when the cycle restarts
     wl = ChainedWorkload(mdp, origins, out, sets, 1234, cfg, layout="isaac" if isaac else "dense",
-                         fall_fraction=0.3 if c5 else 0.02, stones_change=c5)
+                         fall_fraction=0.3 if c5 else 0.02, stones_change=c5 or grid)
     pool = wl.sets
     l0 = mdp.launch_count
     if "--three-call" in sys.argv:
