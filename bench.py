@@ -736,7 +736,7 @@ def main_b200(args):
         del w2
         # ---- BASELINE config 3: 65536 envs with the pitch x yaw grid curriculum (extension)
         blocks["c3_65536_grid"], w3, _ = small_block(65536, grid_bins=11)
-        blocks["c3_65536_grid"]["bound"] = "launch latency (5 launches; working set is L2 resident)"
+        blocks["c3_65536_grid"]["bound"] = "launch latency (4 dependent launches: k_prepare, k_step, k_reset_rows with the grid turnover, k_fixup_finish; working set is L2 resident)"
         del w3
         w65, o65 = make(65536, seed=99)
         ms_f, _ = time_cycle(torch, w65, k_small, args.warmup)
