@@ -114,6 +114,7 @@ int launch_prepare(AsHandle* h, const AsStateIn* in, cudaStream_t s, bool gather
   p.body_dense = gather_body ? h->ws.body_dense : nullptr;
   p.lean = contact_in_host_memory(h, in) ? 1 : 0;
   p.stop_frames = h->params.stop_frames;
+  p.contact_epsilon = h->params.contact_epsilon;
   const bool aligned = ((reinterpret_cast<uintptr_t>(in->contact_right) | reinterpret_cast<uintptr_t>(in->contact_left)) &
                         15u) == 0 && ((in->contact_right_stride | in->contact_left_stride) & 3) == 0;
   if (aligned) {  // two lanes per env: one memory request per force vector
@@ -410,7 +411,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   h->ws.regen_ids = reinterpret_cast<int32_t*>(base + l.regen_ids_off);
   h->ws.regen_info = reinterpret_cast<uint8_t*>(base + l.regen_info_off);
   h->ws.bin = reinterpret_cast<uint8_t*>(base + l.bin_off);
-  h->ws.contact_pre = reinterpret_cast<float4*>(base + l.contact_pre_off);
+  h->ws.contact_pre = reinterpret_cast<uint8_t*>(base + l.contact_pre_off);
   h->ws.body_dense = reinterpret_cast<float*>(base + l.body_dense_off);
   h->ws.tail1 = reinterpret_cast<float4*>(base + l.tail1_off);
   h->ws.pass1_reset = reinterpret_cast<uint8_t*>(base + l.pass1_reset_off);

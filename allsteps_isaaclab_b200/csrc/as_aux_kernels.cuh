@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(256) k_pass2_commit(const __grid_constant__ Co
       const Vec3 vb = rotate_by_inverse(q, v);                             // ENV:293
       const Quat inv = quat_inverse(q);
       PassOut po{};
-      const FootGeom gm = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
+      const FootGeom gm = foot_geometry(P, rf, lf, f_r > P.contact_epsilon, f_l > P.contact_epsilon, s_curr);
       if (foot_update(P, gm, m, po)) {  // (cannot happen on zeroed contact rows; kept general)
         s_prev = s_curr;
         s_curr = s_next;

@@ -129,8 +129,8 @@ struct Workspace {
   int32_t* regen_ids; // (N)
   uint8_t* regen_info;// (N) curr_target_index at the end of the episode, parallel to regen_ids (grid curriculum)
   uint8_t* bin;       // (N) difficulty-grid bin of each env (grid curriculum extension)
-  float4* contact_pre;// (N) |F_right|, |F_left| under each foot for the env's CURRENT stone (.x, .y) and for the stone after it
-                      // (.z, .w: what pass 2 needs when pass 1 advances the index), gathered by k_prepare*
+  uint8_t* contact_pre;// (N) ENV:425 evaluated by k_prepare*: bit 0 / 1 = the right / left foot presses on the env's CURRENT stone
+                      // (|F| > contact_epsilon), bit 2 / 3 = on the stone after it (what pass 2 needs when pass 1 advances)
   float* body_dense;  // (N,3,3) right foot, left foot, torso positions gathered out of a strided body tensor (k_prepare*)
   float4* tail1;      // (N,3) 3-call path: the observation tail (foot contacts, targets_b: columns 48..58) as pass 1 leaves it
   uint8_t* pass1_reset;// (N) 3-call path: the env was flagged for reset by pass 1 (terminated | time_out)
@@ -167,7 +167,7 @@ inline WorkspaceLayout workspace_layout(int64_t n) {
   l.bin_off = off;
   off = align_up(off + n, 256);
   l.contact_pre_off = off;
-  off = align_up(off + n * 16, 256);
+  off = align_up(off + n, 256);
   l.body_dense_off = off;
   off = align_up(off + n * 36, 256);
   l.tail1_off = off;

@@ -233,6 +233,13 @@ __device__ __forceinline__ void st_keep_f4(float4* p, const float4& v, uint64_t 
   *p = v;
 #endif
 }
+__device__ __forceinline__ void st_keep_u8(uint8_t* p, unsigned v, uint64_t pol) {
+#if AS_GATHER_EVICT_FIRST
+  asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+#else
+  *p = static_cast<uint8_t>(v);
+#endif
+}
 __device__ __forceinline__ void st_keep_u2(uint2* p, const uint2& v, uint64_t pol) {
 #if AS_GATHER_EVICT_FIRST
   asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
@@ -293,11 +300,11 @@ struct PassOut {
   Vec3 tb0, tb1, tb2;          // targets_b rows (prev, curr, next), ENV:302-316
 };
 
-__device__ __forceinline__ FootGeom foot_geometry(const AsParams& P, const Vec3& rf, const Vec3& lf, float force_r,
-                                                  float force_l, const float4& s_curr) {
+__device__ __forceinline__ FootGeom foot_geometry(const AsParams& P, const Vec3& rf, const Vec3& lf, bool press_r,
+                                                  bool press_l, const float4& s_curr) {
   FootGeom g;
-  g.press_r = force_r > P.contact_epsilon;  // ENV:425
-  g.press_l = force_l > P.contact_epsilon;
+  g.press_r = press_r;  // ENV:425: |F| > 1e-4 on the current stone (evaluated where the force vector is read)
+  g.press_l = press_l;
   g.d_r = norm2(rf.x - s_curr.x, rf.y - s_curr.y);  // ENV:431
   g.d_l = norm2(lf.x - s_curr.x, lf.y - s_curr.y);
   return g;
@@ -804,7 +811,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
       if (kNeedActions && (dense & kDenseAct)) bulk_prefetch_l2(a.actions + penv0 * kJ, kTile * kJ * 4);
       bulk_prefetch_l2(a.ws.state[ctrl->parity] + penv0, kTile * 8);
       bulk_prefetch_l2(a.ws.window + penv0 * 4, kTile * 64);
-      if (a.use_pre) bulk_prefetch_l2(a.ws.contact_pre + penv0, kTile * 8);
+      if (a.use_pre) bulk_prefetch_l2(a.ws.contact_pre + penv0, kTile);
     }
   }
 
@@ -824,7 +831,7 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
   float4 s_prev = make_float4(0, 0, 0, 0), s_curr = s_prev, s_next = s_prev;
   bool win_valid = false, win_dirty = false, w3_pending = false;
   float4* s_w3 = reinterpret_cast<float4*>(smem + kOffW3);
-  float f_r = 0.0f, f_l = 0.0f, f_r_next = 0.0f, f_l_next = 0.0f;
+  bool f_r = false, f_l = false, f_r_next = false, f_l_next = false;  // ENV:425 for the current / the following stone
   const float* cr_row = nullptr;
   const float* cl_row = nullptr;
   if (!joint_role && active) {
@@ -848,15 +855,15 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
     }
     cr_row = a.in.contact_right + e * a.in.contact_right_stride;
     cl_row = a.in.contact_left + e * a.in.contact_left_stride;
-    if (PRE || a.use_pre) {  // |F| of the current (and the following) stone under each foot, gathered by k_prepare* just before
-      const float4 pre = a.ws.contact_pre[e];
-      f_r = pre.x;
-      f_l = pre.y;
-      f_r_next = pre.z;
-      f_l_next = pre.w;
+    if (PRE || a.use_pre) {  // "foot presses on the current (the following) stone", evaluated by k_prepare* just before
+      const unsigned pre = a.ws.contact_pre[e];
+      f_r = pre & 1u;
+      f_l = pre & 2u;
+      f_r_next = pre & 4u;
+      f_l_next = pre & 8u;
     } else {  // small batches are launch-bound: the gathers stay in this kernel and a launch is saved
-      f_r = contact_norm(cr_row, m.idx, contact_aligned);
-      f_l = contact_norm(cl_row, m.idx, contact_aligned);
+      f_r = contact_norm(cr_row, m.idx, contact_aligned) > P.contact_epsilon;
+      f_l = contact_norm(cl_row, m.idx, contact_aligned) > P.contact_epsilon;
     }
     win_valid = PRE || __float_as_int(w0.w) == m.idx;
     if (win_valid) {
@@ -1050,8 +1057,8 @@ __device__ __forceinline__ void process_tile(const StepArgs& a, int tile, uint32
             f_r = f_r_next;
             f_l = f_l_next;
           } else {
-            f_r = contact_norm(cr_row, m.idx, contact_aligned);
-            f_l = contact_norm(cl_row, m.idx, contact_aligned);
+            f_r = contact_norm(cr_row, m.idx, contact_aligned) > P.contact_epsilon;
+            f_l = contact_norm(cl_row, m.idx, contact_aligned) > P.contact_epsilon;
           }
           geom = foot_geometry(P, rf, lf, f_r, f_l, s_curr);
         }
@@ -1464,6 +1471,7 @@ struct PrepareArgs {
                       // instantiation that can gather for itself then fetches the next stone's for the few envs whose
                       // pass 1 advances the index
   int32_t stop_frames;  // ENV:56: pass 1 can advance the index only if the reach counter is one short of this
+  float contact_epsilon;  // ENV:425
 };
 
 __device__ __forceinline__ void refresh_window_entry(const Workspace& ws, int64_t e, int idx, int slot) {
@@ -1490,9 +1498,11 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
   const float* lr = in.contact_left + e * in.contact_left_stride;
   // (the next stone's vectors only where pass 1 can advance the index at all: reach counter one short of stop_frames)
   const bool want_next = state_count(word) + 1 >= a.stop_frames;
-  a.ws.contact_pre[e] = make_float4(contact_norm(rr, idx, false), contact_norm(lr, idx, false),
-                                    want_next ? contact_norm(rr, nxt, false) : 0.0f,
-                                    want_next ? contact_norm(lr, nxt, false) : 0.0f);
+  const float eps = a.contact_epsilon;
+  a.ws.contact_pre[e] = static_cast<uint8_t>(
+      (contact_norm(rr, idx, false) > eps ? 1u : 0u) | (contact_norm(lr, idx, false) > eps ? 2u : 0u) |
+      ((want_next && contact_norm(rr, nxt, false) > eps) ? 4u : 0u) |
+      ((want_next && contact_norm(lr, nxt, false) > eps) ? 8u : 0u));
   if (stale) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) refresh_window_entry(a.ws, e, idx, k);
@@ -1585,7 +1595,10 @@ __global__ void __launch_bounds__(256) k_prepare_paired(const __grid_constant__ 
   const float f_r = norm3(v[0], v[1], v[2]), f_l = norm3(u[0], u[1], u[2]);  // ENV:421-424
   const float f_r2 = has_next ? norm3(v[3], v[4], v[5]) : f_r;
   const float f_l2 = has_next ? norm3(u[3], u[4], u[5]) : f_l;
-  st_keep_f4(a.ws.contact_pre + e, make_float4(f_r, f_l, f_r2, f_l2), keep);  // read by the step kernel in a moment
+  // ENV:425 evaluated here: four bits per env instead of four floats (16 -> 1 byte written here and read by the step)
+  const float eps = a.contact_epsilon;
+  st_keep_u8(a.ws.contact_pre + e, (f_r > eps ? 1u : 0u) | (f_l > eps ? 2u : 0u) | (f_r2 > eps ? 4u : 0u) | (f_l2 > eps ? 8u : 0u),
+             keep);  // read by the step kernel in a moment
 }
 
 #ifndef AS_STEP_MIN_CTAS
