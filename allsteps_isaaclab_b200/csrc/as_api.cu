@@ -365,6 +365,7 @@ int as_create(const AsParams* params, int64_t num_envs, int64_t env_id_offset, i
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_step<kModePass2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   AS_CUDA(cudaFuncSetAttribute(k_fixup_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  AS_CUDA(cudaFuncSetAttribute(k_mirror_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kMirrorSmemBytes));
   AsHandle* h = new (std::nothrow) AsHandle();
   AS_REQUIRE(h != nullptr, "out of host memory");
   h->params = *params;
@@ -832,39 +833,54 @@ int as_apply_action(AsHandle* h, const float* actions, int64_t actions_stride, f
   return check_launch(h, "k_apply_action");
 }
 
-int as_mirror_rows(AsHandle* h, const float* in, float* out, int64_t rows, int32_t kind, void* stream) {
-  AS_REQUIRE(h && in && out, "null argument");
-  AS_REQUIRE(rows >= 0, "negative row count");
-  AS_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (observations) or 1 (actions)");
-  if (rows == 0) return AS_OK;
-  const MirrorTable& t = kind == 0 ? h->mirror_obs : h->mirror_act;
-  const int grid = grid_for(rows * t.dim, 256 * 4, h->sm_count, 8);
-  k_mirror_rows<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, in, out, rows);
-  return check_launch(h, "k_mirror_rows");
-}
-
 int as_mirror_batch(AsHandle* h, const AsMirrorJob* jobs, int32_t n_jobs, void* stream) {
   AS_REQUIRE(h && jobs, "null argument");
   AS_REQUIRE(n_jobs >= 1 && n_jobs <= 4, "1..4 jobs per launch");
   MirrorJobs mj;
   std::memset(&mj, 0, sizeof(mj));
-  int64_t most = 0;
+  int64_t most_tiles = 0, most_tail = 0;
   for (int i = 0; i < n_jobs; ++i) {
     AS_REQUIRE(jobs[i].in && jobs[i].out, "job with a null pointer");
     AS_REQUIRE(jobs[i].rows >= 0, "negative row count");
     AS_REQUIRE(jobs[i].kind == 0 || jobs[i].kind == 1, "kind must be 0 (observations) or 1 (actions / mus)");
+    const int64_t dim = jobs[i].kind == 0 ? kObs : kJ;
+    AS_REQUIRE(jobs[i].rows * dim < (1ll << 40), "too many rows");
     mj.in[i] = jobs[i].in;
     mj.out[i] = jobs[i].out;
     mj.rows[i] = jobs[i].rows;
     mj.kind[i] = jobs[i].kind;
-    const int64_t items = jobs[i].rows * (jobs[i].kind == 0 ? kObs : kJ);
-    most = items > most ? items : most;
+    // full tiles go through shared memory by TMA bulk copies: both halves of the output and the input on 16-byte
+    // boundaries (torch allocations are; a row count that is a multiple of 4 puts the lower half on one too)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(jobs[i].in) | reinterpret_cast<uintptr_t>(jobs[i].out)) & 15u) == 0 &&
+                         ((jobs[i].rows * dim * 4) & 15) == 0;
+    const int64_t tiles = aligned ? jobs[i].rows / kMirrorRows : 0;
+    AS_REQUIRE(tiles < (1ll << 30), "too many rows");
+    mj.tiles[i] = static_cast<int32_t>(tiles);
+    const int64_t tail_items = (jobs[i].rows - tiles * kMirrorRows) * dim;
+    most_tiles = tiles > most_tiles ? tiles : most_tiles;
+    most_tail = tail_items > most_tail ? tail_items : most_tail;
   }
   mj.n = n_jobs;
-  if (most == 0) return AS_OK;
-  const dim3 grid(static_cast<unsigned>(grid_for(most, 256 * 4, h->sm_count, 8)), static_cast<unsigned>(n_jobs));
-  k_mirror_batch<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->mirror_obs, h->mirror_act, mj);
+  if (most_tiles == 0 && most_tail == 0) return AS_OK;
+  const int tail_blocks = most_tail ? grid_for(most_tail, 256 * 4, h->sm_count, 8) : 0;
+  const dim3 grid(static_cast<unsigned>(most_tiles + tail_blocks), static_cast<unsigned>(n_jobs));
+  k_mirror_batch<<<grid, 256, kMirrorSmemBytes, static_cast<cudaStream_t>(stream)>>>(h->mirror_obs, h->mirror_act, mj,
+                                                                                     tail_blocks);
   return check_launch(h, "k_mirror_batch");
+}
+
+int as_mirror_rows(AsHandle* h, const float* in, float* out, int64_t rows, int32_t kind, void* stream) {
+  AS_REQUIRE(h && in && out, "null argument");
+  AS_REQUIRE(rows >= 0, "negative row count");
+  AS_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (observations) or 1 (actions)");
+  if (rows == 0) return AS_OK;
+  AsMirrorJob job;
+  std::memset(&job, 0, sizeof(job));
+  job.in = in;
+  job.out = out;
+  job.rows = rows;
+  job.kind = kind;
+  return as_mirror_batch(h, &job, 1, stream);
 }
 
 int as_export_state(AsHandle* h, const AsMdpState* dst, void* stream) {

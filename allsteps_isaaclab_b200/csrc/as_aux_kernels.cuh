@@ -5,7 +5,7 @@
 //                     step kernel listed
 //   k_generate_stones stone sequences for all / listed envs (init, ENV:71)
 //   k_apply_action    ENV:257-274
-//   k_mirror_rows     ENV:570-660 (mirror-symmetry augmentation)
+//   k_mirror_batch    ENV:570-660 (mirror-symmetry augmentation; 128-row tiles through shared memory by TMA bulk copies)
 //   k_export / k_import  packed state <-> the reference's int64/fp32 buffers
 #pragma once
 #include "as_internal.cuh"
@@ -444,11 +444,21 @@ struct MirrorTable {
 
 // ENV:570-660: rows [0,R) copy, rows [R,2R) = +-in[r][src[c]].  The sign is applied as a NEGATION (`-x`, what
 // ENV:593,634 do), not as a product with -1: the two differ in the bits they give a NaN.
+//
+// A pure copy: every input element is read once and written twice.  Full tiles of kMirrorRows rows travel through
+// shared memory with three TMA bulk copies -- rows in, the same buffer straight out again as the upper half, and the
+// permuted / negated tile as the lower half -- so that neither half costs a second global read or a scattered access.
+// The rows behind the last full tile, and tensors whose rows do not sit on 16-byte boundaries, take the element loop.
+constexpr int kMirrorRows = 128;
+constexpr int kMirrorSmemBytes = 2 * kMirrorRows * AS_OBS_DIM * 4;
+
+// rows [row0, rows) of the job, element by element
 __device__ __forceinline__ void mirror_rows_body(const MirrorTable& t, const float* __restrict__ in,
-                                                 float* __restrict__ out, int64_t rows) {
+                                                 float* __restrict__ out, int64_t rows, int64_t row0, int block,
+                                                 int n_blocks) {
   const int64_t total = rows * t.dim;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  for (int64_t i = row0 * t.dim + static_cast<int64_t>(block) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(n_blocks) * blockDim.x) {
     const int64_t r = i / t.dim;
     const int c = static_cast<int>(i - r * t.dim);
     out[i] = in[i];
@@ -456,27 +466,74 @@ __device__ __forceinline__ void mirror_rows_body(const MirrorTable& t, const flo
     out[total + i] = t.sign[c] < 0.0f ? -v : v;
   }
 }
-__global__ void __launch_bounds__(256) k_mirror_rows(const __grid_constant__ MirrorTable t,
-                                                     const float* __restrict__ in, float* __restrict__ out,
-                                                     int64_t rows) {
-  mirror_rows_body(t, in, out, rows);
+
+template <int DIM>
+__device__ __forceinline__ void mirror_tile(const MirrorTable& t, const float* __restrict__ in, float* __restrict__ out,
+                                            int64_t rows, int64_t tile, unsigned char* smem, uint64_t* mbar,
+                                            int* s_src) {
+  constexpr uint32_t kBytes = kMirrorRows * DIM * 4;  // (a multiple of 16 for both row widths)
+  float* a = reinterpret_cast<float*>(smem);
+  float* b = reinterpret_cast<float*>(smem + kBytes);
+  const int tid = threadIdx.x;
+  const int64_t off = tile * kMirrorRows * DIM;
+  const uint32_t bar = smem_u32(mbar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_arrive_expect_tx(bar, kBytes);
+    bulk_g2s(smem_u32(a), in + off, kBytes, bar);
+  }
+  // (source column, with the sign in the top bit) out of the constant bank, where a warp's 32 different columns would
+  // be 32 serialised reads
+  if (tid < DIM) s_src[tid] = t.src[tid] | (t.sign[tid] < 0.0f ? (1 << 30) : 0);
+  __syncthreads();
+  mbar_wait(bar, 0);
+  if (tid == 0) {  // upper half: the rows as they came
+    bulk_s2g(out + off, smem_u32(a), kBytes);
+    bulk_commit();
+  }
+  for (int i = tid; i < kMirrorRows * DIM; i += blockDim.x) {
+    const int r = i / DIM, c = i - r * DIM;
+    const int sc = s_src[c];
+    const float v = a[r * DIM + (sc & 0xffff)];
+    b[i] = (sc >> 30) ? -v : v;
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (tid == 0) {  // lower half: the mirrored rows
+    bulk_s2g(out + rows * DIM + off, smem_u32(b), kBytes);
+    bulk_commit();
+    bulk_wait_read_all();
+  }
 }
 
-// The three tensors A2CAgentSymmetry.play_steps mirrors (obses, actions, mus: learning/a2c_ppo_mirroring.py:32-34)
-// in ONE launch: blockIdx.y picks the job.
 struct MirrorJobs {
   const float* in[4];
   float* out[4];
   int64_t rows[4];
-  int32_t kind[4];  // 0 observations (dim 59), 1 actions / mus (dim 21)
+  int32_t kind[4];   // 0 observations (dim 59), 1 actions / mus (dim 21)
+  int32_t tiles[4];  // full tiles that go through shared memory (0: the whole job takes the element loop)
   int32_t n;
 };
+// The tensors A2CAgentSymmetry.play_steps mirrors (obses, actions, mus: learning/a2c_ppo_mirroring.py:32-34) in ONE
+// launch: blockIdx.y picks the job; blockIdx.x < tiles: one tile; the CTAs behind share the remaining rows.
 __global__ void __launch_bounds__(256) k_mirror_batch(const __grid_constant__ MirrorTable t_obs,
                                                       const __grid_constant__ MirrorTable t_act,
-                                                      const __grid_constant__ MirrorJobs jobs) {
+                                                      const __grid_constant__ MirrorJobs jobs, int tail_blocks) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  __shared__ int s_src[AS_OBS_DIM];
   const int j = blockIdx.y;
   if (j >= jobs.n) return;
-  mirror_rows_body(jobs.kind[j] == 0 ? t_obs : t_act, jobs.in[j], jobs.out[j], jobs.rows[j]);
+  const MirrorTable& t = jobs.kind[j] == 0 ? t_obs : t_act;
+  const int tiles = jobs.tiles[j];
+  const int blk = blockIdx.x;
+  if (blk < tiles) {
+    if (jobs.kind[j] == 0) mirror_tile<AS_OBS_DIM>(t, jobs.in[j], jobs.out[j], jobs.rows[j], blk, smem, &mbar, s_src);
+    else mirror_tile<AS_NUM_JOINTS>(t, jobs.in[j], jobs.out[j], jobs.rows[j], blk, smem, &mbar, s_src);
+  } else if (blk < tiles + tail_blocks) {
+    mirror_rows_body(t, jobs.in[j], jobs.out[j], jobs.rows[j], static_cast<int64_t>(tiles) * kMirrorRows, blk - tiles,
+                     tail_blocks);
+  }
 }
 
 __global__ void __launch_bounds__(256) k_export(const __grid_constant__ AsParams P, Workspace ws, AsMdpState dst,

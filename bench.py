@@ -356,6 +356,48 @@ def time_per_step(torch, wl, steps):
             "note": "one CUDA-event pair per step; the steps that start a cycle include the state rewind"}
 
 
+def time_mirror(torch, mdp, cfg, rows, iters, peak):
+    """the mirror-symmetry augmentation of `A2CAgentSymmetry.play_steps`
+    (learning/a2c_ppo_mirroring.py:32-34 -> ENV:611-660) on `rows` = horizon x envs rows: vstack((x, mirrored(x))) for
+    obses (rows,59), actions and mus (rows,21) -- one launch of k_mirror_batch against the reference's own torch ops
+    (clone + three fancy-index assignments + vstack per tensor) run eagerly on the same GPU."""
+    from allsteps_isaaclab_b200 import symmetry
+    from oracle import allsteps_oracle as ao  # (baseline leg only)
+
+    dev = mdp.device
+    g = torch.Generator(device=dev).manual_seed(5)
+    obs = torch.randn(rows, 59, device=dev, generator=g)
+    act = torch.randn(rows, 21, device=dev, generator=g)
+    mus = torch.randn(rows, 21, device=dev, generator=g)
+    tabs = (cfg.right_joint_indices, cfg.left_joint_indices, cfg.negation_joint_indices)
+
+    def ours():
+        return symmetry.mirror_batch(mdp, obs, act, mus)
+
+    def eager():
+        return (ao.symmetric_states(obs, *tabs, "obs"), ao.symmetric_states(act, *tabs, "actions"),
+                ao.symmetric_states(mus, *tabs, "actions"))
+
+    same = all(torch.equal(a, b) for a, b in zip(ours(), eager()))
+    res = {}
+    for name, f, n in (("k_mirror_batch", ours, iters), ("eager_torch", eager, max(3, iters // 4))):
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            f()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        res[name] = e0.elapsed_time(e1) / n * 1e3
+    b_alg = rows * (59 + 21 + 21) * 4 * 3  # every input element read once, written twice
+    return {"rows": rows, "us": res["k_mirror_batch"], "eager_torch_us": res["eager_torch"],
+            "speedup_vs_eager_torch": res["eager_torch"] / res["k_mirror_batch"],
+            "algorithmic_GBps": b_alg / (res["k_mirror_batch"] * 1e-6) / 1e9,
+            "roofline_frac": b_alg / (res["k_mirror_batch"] * 1e-6) / 1e9 / peak, "bit_identical_to_eager_torch": same}
+
+
 def time_three_call(torch, wl, origins, steps, warmup, device_reset_list=False):
     """DRL:351-375 as the DirectRLEnv hooks run it under PhysX: as_step_pass1, the host's `.nonzero()` on reset_buf
     (DRL:359, a device->host sync), as_reset on those ids, as_step_pass2.  (No PhysX here: pass 2 sees unchanged
@@ -786,6 +828,18 @@ def main_b200(args):
                                           "positions as a slice of the (N,17,13) body_state_w tensor "
                                           "(articulation_data.py:366-380,430-449)"}
         del wi
+        torch.cuda.empty_cache()
+
+    if extra and rank == 0 and world == 1:
+        # ---- mirror-symmetry augmentation of a PPO rollout (horizon 32)
+        m_f1 = AllstepsMDP(4096, device=dev, seed=3)
+        blocks["f1_mirror"] = {"32x4096": time_mirror(torch, m_f1, m_f1.cfg, 32 * 4096, 200, peak),
+                               "32x65536": time_mirror(torch, m_f1, m_f1.cfg, 32 * 65536, 40, peak),
+                               "what": "vstack((x, mirrored(x))) of obses (rows,59), actions and mus (rows,21) of "
+                                       "A2CAgentSymmetry.play_steps: 1212 algorithmic bytes per row (read once, "
+                                       "written twice), output buffers allocated inside the timed call like the "
+                                       "reference's"}
+        del m_f1
         torch.cuda.empty_cache()
 
     if extra and rank == 0 and world == 1:

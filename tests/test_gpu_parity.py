@@ -377,6 +377,43 @@ def test_action_path_and_mirror_rows():
           "mirrored actions")
 
 
+@pytest.mark.parametrize("rows", [4 * 128, 3 * 128 + 44, 1029, 127, 32 * 4096])
+def test_mirror_kernel_tiles_and_tails(rows):
+    """k_mirror_batch moves full 128-row tiles through shared memory (TMA bulk copies) and the rest element by element:
+    whole tiles, tiles + a tail, a row count that puts the lower half off a 16-byte boundary (element loop for
+    everything), fewer rows than a tile, a rollout-sized batch; and inputs that are not 16-byte aligned.  Against the
+    oracle's restatement of ENV:570-660 (pinned to the live reference), bit for bit incl. NaN / -0.0 / inf entries."""
+    from allsteps_isaaclab_b200 import symmetry
+    from oracle import allsteps_oracle as ao
+
+    mdp = make_cuda(64, 3)
+    cfg = mdp.cfg
+    tabs = (cfg.right_joint_indices, cfg.left_joint_indices, cfg.negation_joint_indices)
+    g = torch.Generator().manual_seed(rows)
+    obs = torch.randn(rows, 59, generator=g)
+    act = torch.randn(rows, 21, generator=g)
+    mus = torch.randn(rows, 21, generator=g)
+    for t in (obs, act, mus):
+        flat = t.view(-1)
+        flat[::97] = float("nan")
+        flat[5::101] = -0.0
+        flat[7::103] = float("inf")
+    bits = lambda t: t.detach().cpu().contiguous().numpy().view(np.uint32)  # noqa: E731
+    want = (ao.symmetric_states(obs, *tabs, "obs"), ao.symmetric_states(act, *tabs, "actions"),
+            ao.symmetric_states(mus, *tabs, "actions"))
+    l0 = mdp.launch_count
+    got = symmetry.mirror_batch(mdp, obs.cuda(), act.cuda(), mus.cuda())
+    assert mdp.launch_count == l0 + 1
+    for w, o in zip(want, got):
+        assert np.array_equal(bits(o), bits(w))
+    assert np.array_equal(bits(mdp.mirror_rows(obs.cuda(), "obs")), bits(want[0]))
+    # a view that starts 4 bytes into an allocation: no bulk copies possible, same result
+    pad = torch.empty(rows * 59 + 1, device="cuda")
+    view = pad[1:].view(rows, 59)
+    view.copy_(obs)
+    assert np.array_equal(bits(mdp.mirror_rows(view, "obs")), bits(want[0]))
+
+
 def test_symmetry_functions_match_the_reference_fixture():
     """the drop-ins with the reference's signatures (ENV:570, ENV:611) and the play_steps-shaped call
     (learning/a2c_ppo_mirroring.py:20-40) against outputs of the reference's own functions (mirror_symmetry.npz),
