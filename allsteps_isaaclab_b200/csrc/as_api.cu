@@ -827,9 +827,15 @@ int as_step_no_reset(AsHandle* h, void* stream) {
 int as_apply_action(AsHandle* h, const float* actions, int64_t actions_stride, float* efforts, void* stream) {
   AS_REQUIRE(h && actions && efforts, "null argument");
   AS_REQUIRE(actions_stride >= kJ, "actions stride too small");
-  const int grid = grid_for(h->num_envs * kJ, 256 * 4, h->sm_count, 8);
-  k_apply_action<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->params, h->ws, actions, actions_stride,
-                                                                       efforts, h->num_envs);
+  // full tiles by TMA bulk copies: dense rows on 16-byte boundaries (a tile is 128 x 84 bytes)
+  const bool bulk = actions_stride == kJ &&
+                    ((reinterpret_cast<uintptr_t>(actions) | reinterpret_cast<uintptr_t>(efforts)) & 15u) == 0;
+  const int tiles = bulk ? static_cast<int>(h->num_envs / kTile) : 0;
+  const int64_t tail_items = (h->num_envs - static_cast<int64_t>(tiles) * kTile) * kJ;
+  const int tail_blocks = tail_items ? grid_for(tail_items, 256 * 4, h->sm_count, 8) : 0;
+  const int tile_blocks = (tiles + kActionTilesPerCta - 1) / kActionTilesPerCta;
+  k_apply_action<<<tile_blocks + tail_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->params, h->ws, actions, actions_stride, efforts, h->num_envs, tiles, tile_blocks, tail_blocks);
   return check_launch(h, "k_apply_action");
 }
 

@@ -419,15 +419,61 @@ __global__ void __launch_bounds__(256) k_generate_stones(const __grid_constant__
   }
 }
 
-// ENV:257-274: efforts = gain[level] * gear * clamp(action)
+// ENV:257-274: efforts = gain[level] * gear * clamp(action).  Runs four times per env step (decimation, CFG:55), a pure
+// stream of 84 bytes in and 84 bytes out per env: full 128-env tiles are brought in by one TMA bulk copy, scaled in
+// place in shared memory (the env's gain from its state word, the gears from a shared copy of the table -- out of the
+// constant bank a warp's 21 different joints would be 21 serialised reads) and sent out by one bulk copy; the envs
+// behind the last full tile, and action views that are strided or not on a 16-byte boundary, take the element loop
+// (the CTAs behind the tile CTAs).
+constexpr int kActionTilesPerCta = 4;  // all four loads are issued up front: 43 KB in flight per CTA, five CTAs per SM
 __global__ void __launch_bounds__(256) k_apply_action(const __grid_constant__ AsParams P, Workspace ws,
                                                       const float* __restrict__ actions, int64_t stride,
-                                                      float* __restrict__ efforts, int64_t num_envs) {
-  const int64_t total = num_envs * kJ;
-  const uint2* st = ws.state[ws.ctrl->parity];
+                                                      float* __restrict__ efforts, int64_t num_envs, int tiles,
+                                                      int tile_blocks, int tail_blocks) {
+  __shared__ __align__(128) float s_act[kActionTilesPerCta][kTile * kJ];
+  __shared__ float s_gain[kActionTilesPerCta][kTile];
+  __shared__ float s_gear[kJ];
+  __shared__ uint64_t mbar[kActionTilesPerCta];
+  const uint2* __restrict__ st = ws.state[ws.ctrl->parity];
   const int pending = static_cast<int>(ws.ctrl->promote_cur);
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  const int tid = threadIdx.x;
+  if (static_cast<int>(blockIdx.x) < tile_blocks) {
+    constexpr uint32_t kBytes = kTile * kJ * 4;
+    const int tile0 = blockIdx.x * kActionTilesPerCta;
+    const int n_sub = min(kActionTilesPerCta, tiles - tile0);
+    const int64_t env0 = static_cast<int64_t>(tile0) * kTile;
+    if (tid == 0) {
+      for (int k = 0; k < n_sub; ++k) {
+        const uint32_t bar = smem_u32(&mbar[k]);
+        mbar_init(bar, 1);
+        mbar_arrive_expect_tx(bar, kBytes);
+        bulk_g2s(smem_u32(s_act[k]), actions + (env0 + k * kTile) * kJ, kBytes, bar);
+      }
+    }
+    for (int i = tid; i < n_sub * kTile; i += blockDim.x)
+      (&s_gain[0][0])[i] = P.applied_gain[min(state_level(st[env0 + i].x) + pending, P.max_level)];
+    if (tid < kJ) s_gear[tid] = P.joint_gears[tid];
+    __syncthreads();
+    for (int k = 0; k < n_sub; ++k) {
+      mbar_wait(smem_u32(&mbar[k]), 0);
+      for (int i = tid; i < kTile * kJ; i += blockDim.x) {
+        const int e = i / kJ, j = i - e * kJ;
+        s_act[k][i] = (s_gain[k][e] * s_gear[j]) * clamp_nan(s_act[k][i], -1.0f, 1.0f);
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        bulk_s2g(efforts + (env0 + k * kTile) * kJ, smem_u32(s_act[k]), kBytes);
+        bulk_commit();
+      }
+    }
+    if (tid == 0) bulk_wait_read_all();
+    return;
+  }
+  const int64_t first = static_cast<int64_t>(tiles) * kTile * kJ;
+  const int64_t total = num_envs * kJ;
+  for (int64_t i = first + static_cast<int64_t>(blockIdx.x - tile_blocks) * blockDim.x + tid; i < total;
+       i += static_cast<int64_t>(tail_blocks) * blockDim.x) {
     const int64_t e = i / kJ;
     const int j = static_cast<int>(i - e * kJ);
     const int level = min(state_level(st[e].x) + pending, P.max_level);

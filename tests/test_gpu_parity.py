@@ -365,8 +365,16 @@ def test_action_path_and_mirror_rows():
     orc.clamp_actions(actions)
     mdp = make_cuda(N, 4)
     mdp.import_state({"curriculum": levels})
-    eff = mdp.apply_action(actions.cuda())
+    eff = mdp.apply_action(actions.cuda())  # 777 envs: six 128-env tiles by TMA bulk copies + 9 envs element by element
     close(eff, orc.joint_efforts(), "joint efforts")
+    # a strided (N,32) view and a view 4 bytes into an allocation take the element loop: same bits
+    wide = torch.zeros(N, 32, device="cuda")
+    wide[:, :21] = actions.cuda()
+    exact(mdp.apply_action(wide[:, :21]), eff, "efforts from a strided action view")
+    pad = torch.empty(N * 21 + 1, device="cuda")
+    off = pad[1:].view(N, 21)
+    off.copy_(actions)
+    exact(mdp.apply_action(off), eff, "efforts from a misaligned action view")
     # mirror augmentation, ENV:570-660: against the oracle's restatement (pinned to the live reference functions in
     # tests/test_oracle_vs_reference.py and to tests/golden/mirror_symmetry.npz)
     cfg = sc.cfg
