@@ -398,6 +398,28 @@ def time_mirror(torch, mdp, cfg, rows, iters, peak):
             "roofline_frac": b_alg / (res["k_mirror_batch"] * 1e-6) / 1e9 / peak, "bit_identical_to_eager_torch": same}
 
 
+def time_action(torch, dev, n, iters, peak):
+    """ENV:257-274 (clamp, gain[level] * gear * action), called `decimation` = 4 times per env
+    step: 84 bytes in + 84 bytes out per env; six rotating buffer pairs (1 GB at 1 M envs: nothing survives in L2)."""
+    from allsteps_isaaclab_b200.mdp import AllstepsMDP
+
+    m = AllstepsMDP(n, device=dev, seed=3)
+    sets = [(-1.5 + 3.0 * torch.rand(n, 21, device=dev), torch.empty(n, 21, device=dev)) for _ in range(6)]
+    for a, e in sets:
+        m.apply_action(a, e)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        a, e = sets[i % len(sets)]
+        m.apply_action(a, e)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    us = e0.elapsed_time(e1) / iters * 1e3
+    return {"envs": n, "us_per_call": us, "algorithmic_GBps": n * 168 / (us * 1e-6) / 1e9,
+            "roofline_frac": n * 168 / (us * 1e-6) / 1e9 / peak}
+
+
 def time_three_call(torch, wl, origins, steps, warmup, device_reset_list=False):
     """DRL:351-375 as the DirectRLEnv hooks run it under PhysX: as_step_pass1, the host's `.nonzero()` on reset_buf
     (DRL:359, a device->host sync), as_reset on those ids, as_step_pass2.  (No PhysX here: pass 2 sees unchanged
@@ -840,6 +862,12 @@ def main_b200(args):
                                        "written twice), output buffers allocated inside the timed call like the "
                                        "reference's"}
         del m_f1
+        torch.cuda.empty_cache()
+        # ---- the action path
+        blocks["f2_action"] = {"1048576": time_action(torch, dev, N, 120, peak),
+                               "4096": time_action(torch, dev, 4096, 300, peak),
+                               "what": "as_apply_action per call (Isaac Lab makes `decimation` = 4 calls per env step); "
+                                       "4096 envs: the host's launch path, not the kernel"}
         torch.cuda.empty_cache()
 
     if extra and rank == 0 and world == 1:
