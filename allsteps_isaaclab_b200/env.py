@@ -95,11 +95,19 @@ class AllstepsHooksB200:
     # ------------------------------------------------------------------ the six hooks
     def _pre_physics_step(self, actions: torch.Tensor):  # ENV:257-268 (the clamp is applied inside the kernels)
         self.actions = actions.to(torch.float32)
+        self._efforts_valid = False
 
     def _apply_action(self):  # ENV:270-274
-        self.robot.set_joint_effort_target(self.mdp.apply_action(self.actions))
+        # DirectRLEnv.step calls this `decimation` = 4 times per env step (DRL:333-349) with the same actions and the
+        # same curriculum levels -- both change only outside that loop (`_pre_physics_step`, `_reset_idx`): the
+        # efforts are computed by the first call and handed out again by the other three
+        if not getattr(self, "_efforts_valid", False):
+            self._efforts = self.mdp.apply_action(self.actions, getattr(self, "_efforts", None))
+            self._efforts_valid = True
+        self.robot.set_joint_effort_target(self._efforts)
 
     def _get_dones(self):  # ENV:396-405; the same launch produces the rewards of ENV:347-394
+        self._efforts_valid = False  # (levels can change from here on)
         self.mdp.pass1(self._physics_views(), self.actions, self.buf, episode_length=self.episode_length_buf)
         self._pass1_open = True  # closed by `_reset_idx` (pass 2) or, when nothing resets, by `_get_observations`
         return self.buf.terminated, self.buf.time_out
@@ -110,6 +118,7 @@ class AllstepsHooksB200:
     def _reset_idx(self, env_ids: Optional[torch.Tensor]):  # ENV:469-567
         if env_ids is None or len(env_ids) == self.num_envs:
             env_ids = self.robot._ALL_INDICES
+        self._efforts_valid = False
         self.robot.reset(env_ids)
         super()._reset_idx(env_ids)  # scene.reset (contact rows -> 0) and episode_length_buf[env_ids] = 0, DRL:563-584
         self.mdp.reset(self.scene.env_origins, env_ids, self.buf)
