@@ -74,12 +74,9 @@ class AllstepsHooksB200:
     # ------------------------------------------------------------------ views of the PhysX-side tensors
     def _physics_views(self) -> PhysicsViews:
         d = self.robot.data
-        return PhysicsViews(root_pos_w=d.root_pos_w, root_quat_w=d.root_quat_w, root_lin_vel_w=d.root_lin_vel_w,
-                            body_pos_w=d.body_pos_w, joint_pos=d.joint_pos, joint_vel=d.joint_vel,
-                            force_matrix_right=self.sensor_right.data.force_matrix_w,
-                            force_matrix_left=self.sensor_left.data.force_matrix_w,
-                            env_origins=self.scene.env_origins,
-                            body_rows=(self.foot_indices[0], self.foot_indices[1], self.torso_index))
+        t = (d.root_pos_w, d.root_quat_w, d.root_lin_vel_w, d.body_pos_w, d.joint_pos, d.joint_vel,
+             self.sensor_right.data.force_matrix_w, self.sensor_left.data.force_matrix_w, self.scene.env_origins)
+        return PhysicsViews.cached(self, t, (self.foot_indices[0], self.foot_indices[1], self.torso_index))
 
     # ------------------------------------------------------------------ ENV:106-123
     def _generate_foot_steps(self, env_ids: Optional[torch.Tensor] = None):

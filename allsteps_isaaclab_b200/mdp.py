@@ -90,6 +90,23 @@ class PhysicsViews:
         self.num_envs = N
         self.device = root_pos_w.device
 
+    _FIELDS = ("root_pos_w", "root_quat_w", "root_lin_vel_w", "body_pos_w", "joint_pos", "joint_vel",
+               "force_matrix_right", "force_matrix_left", "env_origins")
+
+    @classmethod
+    def cached(cls, holder, tensors: tuple, body_rows, quat_xyzw: bool = False) -> "PhysicsViews":
+        """The views of `tensors` (in `_FIELDS` order), rebuilt -- struct and validation -- only when an address,
+        stride, shape or dtype changed since the last call with this `holder`.  Isaac Lab's data properties hand out
+        fresh views of persistent PhysX-side buffers on every access; the hooks ask for them two or three times a step."""
+        key = tuple((t.data_ptr(), t.stride(), t.shape, t.dtype) for t in tensors) + (tuple(body_rows), quat_xyzw)
+        v = getattr(holder, "_as_views", None)
+        if v is None or holder._as_views_key != key:
+            v = cls(**dict(zip(cls._FIELDS, tensors)), body_rows=body_rows, quat_xyzw=quat_xyzw)
+            holder._as_views, holder._as_views_key = v, key
+        else:
+            v.tensors = dict(zip(cls._FIELDS, tensors))  # (keep THESE tensor objects alive while kernels run)
+        return v
+
     @classmethod
     def from_dict(cls, d: Dict[str, torch.Tensor], env_origins, body_rows=(0, 1, 2), quat_xyzw=False) -> "PhysicsViews":
         return cls(root_pos_w=d["root_pos_w"], root_quat_w=d["root_quat_w"], root_lin_vel_w=d["root_lin_vel_w"],
@@ -190,6 +207,11 @@ class AllstepsMDP:
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self) -> int:
+        # (the raw handle of torch's current stream on this device: the private accessor is an order of magnitude
+        # cheaper than building a torch.cuda.Stream object on every library call)
+        raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        if raw is not None:
+            return raw(self.device.index if self.device.index is not None else torch.cuda.current_device())
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def __del__(self):

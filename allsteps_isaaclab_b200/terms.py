@@ -74,10 +74,9 @@ class _Binding:
     def views(self, env) -> PhysicsViews:
         robot, left, right = (env.scene[n] for n in self.names)
         d = robot.data
-        return PhysicsViews(root_pos_w=d.root_pos_w, root_quat_w=d.root_quat_w, root_lin_vel_w=d.root_lin_vel_w,
-                            body_pos_w=d.body_pos_w, joint_pos=d.joint_pos, joint_vel=d.joint_vel,
-                            force_matrix_right=right.data.force_matrix_w, force_matrix_left=left.data.force_matrix_w,
-                            env_origins=env.scene.env_origins, body_rows=self.body_rows)
+        t = (d.root_pos_w, d.root_quat_w, d.root_lin_vel_w, d.body_pos_w, d.joint_pos, d.joint_vel,
+             right.data.force_matrix_w, left.data.force_matrix_w, env.scene.env_origins)
+        return PhysicsViews.cached(self, t, self.body_rows)
 
     def ensure_pass1(self, env):
         """Pass 1 of the env step in progress, once.  Before the first step (`common_step_counter == 0`: the shape
