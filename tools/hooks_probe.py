@@ -58,7 +58,7 @@ def main():
         pr.enable()
         loop(100)
         pr.disable()
-        pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+        pstats.Stats(pr).sort_stats("tottime").print_stats(28)
 
 
 main()
