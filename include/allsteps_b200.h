@@ -275,12 +275,18 @@ int as_peer_status(AsHandle* h, int* world, int* rank, int64_t* timeouts, void* 
 int as_global_stats_device_ptr(AsHandle* h, AsStats** device_stats);
 
 /* ---- action path: ENV:257-274 `_pre_physics_step` + `_apply_action` --------------------------------------
- * efforts[n,j] = applied_gain[level[n]] * joint_gears[j] * clamp(actions[n,j], -1, 1) */
+ * efforts[n,j] = applied_gain[level[n]] * joint_gears[j] * clamp(actions[n,j], -1, 1)
+ * Any row stride >= 21 and any 4-byte aligned address is accepted; dense rows (stride 21) with `actions` and `efforts`
+ * on 16-byte boundaries take the bulk-copy path (full 128-env tiles through shared memory), everything else an element
+ * loop with the same results.  Isaac Lab calls `_apply_action` `decimation` times per env step with unchanged inputs:
+ * one call per env step is enough. */
 int as_apply_action(AsHandle* h, const float* actions, int64_t actions_stride, float* efforts, void* stream);
 
 /* ---- mirror-symmetry augmentation: ENV:570-660 `get_symmetric_states_*` ----------------------------------
  * out (2*rows, dim): rows [0,rows) = copy of `in`, rows [rows, 2*rows) = mirrored.  kind: 0 = observations
- * (dim 59), 1 = actions / mus (dim 21). */
+ * (dim 59), 1 = actions / mus (dim 21).  `in` and `out` on 16-byte boundaries and a row count that is a multiple of 4
+ * take the bulk-copy path (128-row tiles through shared memory: every element read once, written twice); other
+ * shapes / alignments an element loop with the same results. */
 int as_mirror_rows(AsHandle* h, const float* in, float* out, int64_t rows, int32_t kind, void* stream);
 /* The same for up to four tensors in ONE launch -- what A2CAgentSymmetry.play_steps does to `obses`, `actions` and
  * `mus` every PPO epoch (learning/a2c_ppo_mirroring.py:32-38 -> get_symmetric_states_rl_games, ENV:611-660). */
