@@ -127,7 +127,7 @@ def _poison_unused(d_isaac, st, N):
 
 @pytest.mark.parametrize("N", [300, (1 << 17) + 40])
 def test_guard_bands_poisoned_neighbours_and_unwritten_outputs(N):
-    from allsteps_isaaclab_b200 import symmetry
+    from allsteps_isaaclab_b200 import _cabi, symmetry
     from allsteps_isaaclab_b200 import synthetic as syn
     from allsteps_isaaclab_b200.mdp import PhysicsViews
     from allsteps_isaaclab_b200.workload import to_isaac_layout
@@ -190,8 +190,17 @@ def test_guard_bands_poisoned_neighbours_and_unwritten_outputs(N):
         poses = Guarded((20 * N, 7), torch.float32, 0.0)
         mdp.export_stone_poses(torch.arange(0, N, 3, device="cuda"), poses.t)
         symmetry.mirror_batch(mdp, torch.randn(257, 59, device="cuda"), torch.randn(257, 21, device="cuda"))
+        # the tiled path of the mirror kernel (TMA bulk stores of whole 128-row tiles + a 12-row tail) into guarded outputs
+        R = 4 * 128 + 12
+        m_obs, m_act = Guarded((2 * R, 59), torch.float32, 0.0), Guarded((2 * R, 21), torch.float32, 0.0)
+        x_obs, x_act = torch.randn(R, 59, device="cuda"), torch.randn(R, 21, device="cuda")
+        for src, dst, kind in ((x_obs, m_obs, 0), (x_act, m_act, 1)):
+            _cabi.check(mdp.lib.as_mirror_rows(mdp.handle, src.data_ptr(), dst.t.data_ptr(), R, kind, mdp._stream()),
+                        "as_mirror_rows")
         torch.cuda.synchronize()
-        guards += [eff, snap, poses]
+        assert torch.equal(m_obs.t[:R], x_obs) and torch.equal(m_obs.t, mdp.mirror_rows(x_obs, "obs"))
+        assert torch.equal(m_act.t, mdp.mirror_rows(x_act, "actions"))
+        guards += [eff, snap, poses, m_obs, m_act]
     for a, b in zip(results[False], results[True]):
         for k in ("obs", "reward", "terminated", "time_out", "dones", "reward_terms"):
             assert torch.equal(a[k], b[k]), f"{k} changes when the unused neighbours of the inputs are NaN"
