@@ -135,18 +135,18 @@ class AllstepsHooksB200:
         return {"policy": self.buf.obs}
 
     # ------------------------------------------------------------------ the reference's public buffers, on demand
-    def _state(self) -> Dict[str, torch.Tensor]:
-        return self.mdp.export_state()
+    def _state(self, field: str) -> torch.Tensor:
+        return self.mdp.export_state((field,))[field]  # (only the buffer that was asked for is materialised)
 
-    curr_target_index = property(lambda self: self._state()["curr_target_index"])
-    prev_target_index = property(lambda self: self._state()["prev_target_index"])
-    next_target_index = property(lambda self: self._state()["next_target_index"])
-    swing_leg = property(lambda self: self._state()["swing_leg"])
-    target_reach_count = property(lambda self: self._state()["target_reach_count"])
-    curriculum = property(lambda self: self._state()["curriculum"])
-    potentials = property(lambda self: self._state()["potentials"])
-    steps_pos = property(lambda self: self._state()["steps_pos"])
-    steps_dphi = property(lambda self: self._state()["steps_dphi"])
+    curr_target_index = property(lambda self: self._state("curr_target_index"))
+    prev_target_index = property(lambda self: self._state("prev_target_index"))
+    next_target_index = property(lambda self: self._state("next_target_index"))
+    swing_leg = property(lambda self: self._state("swing_leg"))
+    target_reach_count = property(lambda self: self._state("target_reach_count"))
+    curriculum = property(lambda self: self._state("curriculum"))
+    potentials = property(lambda self: self._state("potentials"))
+    steps_pos = property(lambda self: self._state("steps_pos"))
+    steps_dphi = property(lambda self: self._state("steps_dphi"))
 
 
 class _StandaloneBase:

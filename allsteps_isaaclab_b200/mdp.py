@@ -8,7 +8,7 @@ streams only; every number is produced by the CUDA library behind include/allste
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional
+from typing import Dict, Optional, Tuple
 
 import torch
 
@@ -392,22 +392,29 @@ class AllstepsMDP:
         return out
 
     # ------------------------------------------------------------------ state in the reference's layouts
-    def export_state(self) -> Dict[str, torch.Tensor]:
+    _STATE_FIELDS = ("curr_target_index", "swing_leg", "target_reach_count", "episode_length_buf", "curriculum",
+                     "potentials", "steps_pos", "steps_dphi")
+
+    def export_state(self, fields: Optional[Tuple[str, ...]] = None) -> Dict[str, torch.Tensor]:
+        """The MDP state in the reference's own buffers (ENV:48,74-78, DRL:179).  `fields`: only these (default all;
+        `prev_target_index` / `next_target_index` come with `curr_target_index`) -- the 320-byte stone rows are the
+        bulk of a full export, a caller that logs one counter per step should not pay for them."""
         N, dev = self.num_envs, self.device
-        i64 = lambda: torch.empty(N, dtype=torch.int64, device=dev)  # noqa: E731
-        d = {
-            "curr_target_index": i64(), "swing_leg": i64(), "target_reach_count": i64(),
-            "episode_length_buf": i64(), "curriculum": i64(),
-            "potentials": torch.empty(N, dtype=torch.float32, device=dev),
-            "steps_pos": torch.empty(N, NUM_STONES, 3, dtype=torch.float32, device=dev),
-            "steps_dphi": torch.empty(N, NUM_STONES, dtype=torch.float32, device=dev),
-        }
-        st = _cabi.AsMdpState(_ptr(d["curr_target_index"]), _ptr(d["swing_leg"]), _ptr(d["target_reach_count"]),
-                              _ptr(d["episode_length_buf"]), _ptr(d["curriculum"]), _ptr(d["potentials"]),
-                              _ptr(d["steps_pos"]), _ptr(d["steps_dphi"]))
+        want = set(self._STATE_FIELDS if fields is None else fields)
+        if want & {"prev_target_index", "next_target_index"}:
+            want.add("curr_target_index")
+        unknown = want - set(self._STATE_FIELDS) - {"prev_target_index", "next_target_index"}
+        if unknown:
+            raise KeyError(f"unknown state fields: {sorted(unknown)}")
+        shapes = {"potentials": ((N,), torch.float32), "steps_pos": ((N, NUM_STONES, 3), torch.float32),
+                  "steps_dphi": ((N, NUM_STONES), torch.float32)}
+        d = {k: torch.empty(*shapes.get(k, ((N,), torch.int64))[0], dtype=shapes.get(k, ((N,), torch.int64))[1], device=dev)
+             for k in self._STATE_FIELDS if k in want}
+        st = _cabi.AsMdpState(*[_ptr(d.get(k)) for k in self._STATE_FIELDS])
         _cabi.check(self.lib.as_export_state(self.handle, C.byref(st), self._stream()), "as_export_state")
-        d["prev_target_index"] = torch.clamp(d["curr_target_index"] - 1, 0, NUM_STONES - 1)  # ENV:76
-        d["next_target_index"] = torch.clamp(d["curr_target_index"] + 1, 0, NUM_STONES - 1)  # ENV:77
+        if "curr_target_index" in d:
+            d["prev_target_index"] = torch.clamp(d["curr_target_index"] - 1, 0, NUM_STONES - 1)  # ENV:76
+            d["next_target_index"] = torch.clamp(d["curr_target_index"] + 1, 0, NUM_STONES - 1)  # ENV:77
         return d
 
     def export_stone_poses(self, env_ids: Optional[torch.Tensor] = None, view_poses: Optional[torch.Tensor] = None):

@@ -62,7 +62,7 @@ class ChainedWorkload:
         adv, rst = [], []
         self._step_fn = close_step
         for _ in range(self.period):
-            st = mdp.export_state()
+            st = mdp.export_state(("steps_pos", "curr_target_index", "swing_leg"))
             d = syn.random_physics_state(self.cfg, st["steps_pos"], st["curr_target_index"], st["swing_leg"], gen,
                                          fall_fraction=fall_fraction)
             del st

@@ -353,6 +353,22 @@ def test_three_call_path_matches_oracle(N, fall, layout, steps):
         assert n_quiet > 0, "the quiet case is there to exercise as_step_no_reset"
 
 
+def test_export_state_of_selected_fields():
+    """`export_state(fields)` materialises only what is asked for (the env properties of the hooks use it), with the
+    same values as the full export."""
+    mdp = make_cuda(500, 5)
+    mdp.generate_stones(torch.zeros(500, 3, device="cuda"))
+    full = mdp.export_state()
+    one = mdp.export_state(("potentials",))
+    assert set(one) == {"potentials"} and torch.equal(one["potentials"], full["potentials"])
+    some = mdp.export_state(("next_target_index", "steps_dphi"))
+    assert set(some) == {"curr_target_index", "prev_target_index", "next_target_index", "steps_dphi"}
+    for k, v in some.items():
+        assert torch.equal(v, full[k]), k
+    with pytest.raises(KeyError):
+        mdp.export_state(("no_such_buffer",))
+
+
 def test_action_path_and_mirror_rows():
     from oracle import allsteps_oracle as ao
 
