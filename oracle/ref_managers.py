@@ -120,3 +120,30 @@ def load_managers():
             del sys.modules[k]
         sys.modules.update(saved)
     return _loaded
+
+
+def load_rl_env_methods():
+    """`ManagerBasedRLEnv.step` and `ManagerBasedRLEnv._reset_idx` of the reference (manager_based_rl_env.py:153-239,
+    347-392) as plain functions of `self`: the two method bodies are compiled from the reference's own source text --
+    unmodified but for the argument / return annotations, which name types of modules that cannot be imported here
+    (`gymnasium`, the simulator) -- so that a test can let the REFERENCE decide the order in which the managers are
+    called around a step, instead of replaying that order by hand."""
+    import ast
+
+    import torch
+
+    path = os.path.join(_ISAACLAB, "envs", "manager_based_rl_env.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "ManagerBasedRLEnv")
+    out = {}
+    for node in cls.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("step", "_reset_idx"):
+            node.returns = None
+            for a in node.args.args:
+                a.annotation = None
+            ns = {"torch": torch}
+            exec(compile(ast.fix_missing_locations(ast.Module(body=[node], type_ignores=[])), path, "exec"), ns)
+            out[node.name] = ns[node.name]
+    assert set(out) == {"step", "_reset_idx"}, "reference layout changed"
+    return out

@@ -253,3 +253,113 @@ def test_reference_managers_drive_the_terms(monkeypatch):
         obs_man.compute()
         assert mdp.launch_count == before
     assert n_reset > 0
+
+
+class _Quiet:
+    """Manager / simulator stand-ins that the Allsteps task does not use (actions are applied by PhysX, nothing is
+    recorded, there are no commands): every method is a no-op, `reset` returns an empty log."""
+
+    active_terms: list = []
+
+    def __getattr__(self, name):
+        if name == "reset":
+            return lambda *a, **k: {}
+        if name in ("has_gui", "has_rtx_sensors"):
+            return lambda: False
+        return lambda *a, **k: None
+
+
+def test_the_reference_step_function_drives_the_terms(monkeypatch):
+    """The same replay, but the ORDER of the manager calls is not restated here: the bodies of the reference's own
+    `ManagerBasedRLEnv.step` and `_reset_idx` (manager_based_rl_env.py:153-239,347-392, compiled from its source by
+    oracle/ref_managers.load_rl_env_methods) run on an env object that carries the reference's managers built on our
+    term configuration.  Physics is the scene stand-in's `update()`: it installs the next synthetic state at the last
+    of the `decimation` sub-steps."""
+    from allsteps_isaaclab_b200 import manager_cfg, terms
+    from oracle import allsteps_oracle as ao
+    from oracle import ref_managers
+    from scenario import Scenario, install_mdp_state
+
+    M = ref_managers.load_managers()
+    methods = ref_managers.load_rl_env_methods()
+    N, seed = 80, 23
+    sc = Scenario(N, seed=seed, full_bodies=True)
+    OracleMDP.body_rows = sc.body_indices
+    OracleMDP.instances.clear()
+    monkeypatch.setattr(terms, "AllstepsMDP", OracleMDP)
+    st0 = sc.initial_mdp_state()
+    direct = ao.AllstepsOracle(sc.cfg, N, sc.env_origins, sc.joint_limits, sc.body_indices, sc.stone_uniforms(0))
+    install_mdp_state(direct, st0)
+    phys = sc.physics(direct.steps_pos, direct.curr_target_index, direct.swing_leg)
+    scene, robot, left, right = _world(sc, phys, M)
+
+    class Env:  # what `step` / `_reset_idx` touch on `self`
+        step = methods["step"]
+        _reset_idx = methods["_reset_idx"]
+
+    env = Env()
+    env.num_envs, env.device, env.scene = N, "cpu", scene
+    env.common_step_counter, env._sim_step_counter = 0, 0
+    env.step_dt, env.physics_dt = sc.cfg.step_dt, sc.cfg.step_dt / 4
+    env.max_episode_length_s = sc.cfg.episode_length_s
+    env.episode_length_buf = st0["episode_length_buf"].clone()
+    env.extras = {}
+    env.cfg = types.SimpleNamespace(decimation=4, rerender_on_reset=False, sim=types.SimpleNamespace(render_interval=4))
+    env.sim = _Quiet()
+    env.recorder_manager = _Quiet()
+    env.command_manager = _Quiet()
+
+    class Actions(_Quiet):  # ActionManager: `process_action` keeps the raw actions the terms read (`.action`)
+        action = torch.zeros(N, 21)
+
+        def process_action(self, a):
+            self.action = a
+
+    env.action_manager = Actions()
+    pending = {}
+
+    def scene_update(dt=None):  # the last sub-step of the physics loop brings the step's synthetic state
+        env._substeps = getattr(env, "_substeps", 0) + 1
+        if env._substeps % 4 == 0:
+            world = {k: v.clone() for k, v in pending["phys"].items()}
+            robot.load_physics(world)
+            left.data.force_matrix_w = world["force_matrix_left"]
+            right.data.force_matrix_w = world["force_matrix_right"]
+
+    scene.update = scene_update
+    scene.write_data_to_sim = lambda: None
+
+    cfgs = manager_cfg.build_manager_cfgs(M)
+    terms.binding(env, seed=seed)
+    mdp = OracleMDP.instances[0]
+    env.observation_manager = M.ObservationManager(cfgs["observations"], env)
+    env.reward_manager = M.RewardManager(cfgs["rewards"], env)
+    env.termination_manager = M.TerminationManager(cfgs["terminations"], env)
+    env.event_manager = M.EventManager(cfgs["events"], env)
+    env.curriculum_manager = M.CurriculumManager(cfgs["curriculum"], env)
+    assert mdp.counter == 0 and not mdp.pass1_done, "building the managers must not step the MDP"
+
+    # the stand-in's oracle starts from the same mid-episode state as the directly stepped one; its Philox step counter
+    # is what the library's would be after the initial reset of a real run
+    mdp.orc.load_physics(mdp._load(terms.binding(env).views(env)))
+    install_mdp_state(mdp.orc, st0)
+    mdp.counter = 1
+
+    n_reset = 0
+    for step in range(8):
+        phys = sc.physics(direct.steps_pos, direct.curr_target_index, direct.swing_leg)
+        m, n = sc.reset_uniforms(step + 2)
+        o_obs, o_rew, o_term, o_to, o_ids = direct.step(phys, phys["actions"], m, n, None)
+        pending["phys"] = phys
+        obs, rew, terminated, time_outs, extras = env.step(phys["actions"].clone())
+        assert env._sim_step_counter == 4 * (step + 1) and env.common_step_counter == step + 1
+        assert torch.equal(terminated, o_term) and torch.equal(time_outs, o_to), f"step {step}"
+        assert torch.allclose(rew, o_rew, rtol=1e-6, atol=1e-6), f"step {step}"
+        assert torch.equal(obs["policy"], o_obs), f"step {step}"
+        assert torch.equal(env.episode_length_buf, direct.episode_length_buf), f"step {step}"
+        if len(o_ids):
+            n_reset += len(o_ids)
+            assert torch.equal(robot.rec.calls["joint_state"][2], o_ids)
+            assert torch.equal(robot.rec.calls["joint_state"][0], direct.reset_writes["joint_pos"])
+            assert "Curriculum/allsteps_level/level" in extras["log"]
+    assert n_reset > 0
