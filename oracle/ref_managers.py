@@ -122,28 +122,37 @@ def load_managers():
     return _loaded
 
 
-def load_rl_env_methods():
-    """`ManagerBasedRLEnv.step` and `ManagerBasedRLEnv._reset_idx` of the reference (manager_based_rl_env.py:153-239,
-    347-392) as plain functions of `self`: the two method bodies are compiled from the reference's own source text --
-    unmodified but for the argument / return annotations, which name types of modules that cannot be imported here
-    (`gymnasium`, the simulator) -- so that a test can let the REFERENCE decide the order in which the managers are
-    called around a step, instead of replaying that order by hand."""
+def load_env_methods(rel_path: str, class_name: str, names):
+    """Methods of a reference env class as plain functions of `self`: the bodies are compiled from the reference's own
+    source text -- unmodified but for the argument / return annotations, which name types of modules that cannot be
+    imported here (`gymnasium`, the simulator) -- so that a test can let the REFERENCE decide the order of the calls
+    around a step instead of replaying that order by hand."""
     import ast
 
     import torch
 
-    path = os.path.join(_ISAACLAB, "envs", "manager_based_rl_env.py")
+    path = os.path.join(_ISAACLAB, rel_path)
     with open(path) as f:
         tree = ast.parse(f.read())
-    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "ManagerBasedRLEnv")
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name)
     out = {}
     for node in cls.body:
-        if isinstance(node, ast.FunctionDef) and node.name in ("step", "_reset_idx"):
+        if isinstance(node, ast.FunctionDef) and node.name in names:
             node.returns = None
-            for a in node.args.args:
+            for a in node.args.args + node.args.kwonlyargs:
                 a.annotation = None
             ns = {"torch": torch}
             exec(compile(ast.fix_missing_locations(ast.Module(body=[node], type_ignores=[])), path, "exec"), ns)
             out[node.name] = ns[node.name]
-    assert set(out) == {"step", "_reset_idx"}, "reference layout changed"
+    assert set(out) == set(names), "reference layout changed"
     return out
+
+
+def load_rl_env_methods():
+    """`ManagerBasedRLEnv.step` and `._reset_idx` (manager_based_rl_env.py:153-239, 347-392)."""
+    return load_env_methods(os.path.join("envs", "manager_based_rl_env.py"), "ManagerBasedRLEnv", ("step", "_reset_idx"))
+
+
+def load_direct_env_methods():
+    """`DirectRLEnv.reset`, `.step` and `._reset_idx` (direct_rl_env.py:256-294, 296-383, 563-584)."""
+    return load_env_methods(os.path.join("envs", "direct_rl_env.py"), "DirectRLEnv", ("reset", "step", "_reset_idx"))

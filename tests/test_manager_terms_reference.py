@@ -3,7 +3,9 @@ driven by the reference's UNMODIFIED managers (oracle/ref_managers.py loads isaa
 configurations pass `ManagerBase._resolve_common_term_cfg` (manager_base.py:219-298), the ObservationManager's
 construction-time shape probe (observation_manager.py:411) steps nothing, and a replay in ManagerBasedRLEnv.step order
 (manager_based_rl_env.py:203-239, `_reset_idx` :347-392) through ObservationManager / RewardManager /
-TerminationManager / EventManager / CurriculumManager reproduces the reference MDP step.
+TerminationManager / EventManager / CurriculumManager reproduces the reference MDP step.  Two more tests hand the order
+of the calls to the reference as well: the bodies of its `ManagerBasedRLEnv.step` / `_reset_idx` drive the terms (B2), and
+the bodies of its `DirectRLEnv.reset` / `step` / `_reset_idx` drive the six hooks of `env.py` (B1).
 
 There is no GPU here, so the CUDA handle behind the terms is replaced (monkeypatched module attribute, test only) by a
 stand-in with the same methods that serves the CPU oracle's numbers: what is under test is the term layer -- signatures,
@@ -98,6 +100,11 @@ class OracleMDP:
 
     def no_reset(self):
         pass  # (the stand-in's pass 1 leaves the pass-1 observations in place)
+
+    def apply_action(self, actions, efforts=None):
+        self.orc.clamp_actions(actions)
+        self.launch_count += 1
+        return self.orc.joint_efforts()
 
     def pass2(self, views, buf):
         buf.obs.copy_(self.orc.observations())  # (the oracle's reset ended with its pass 2 on the rows it wrote)
@@ -362,4 +369,105 @@ def test_the_reference_step_function_drives_the_terms(monkeypatch):
             assert torch.equal(robot.rec.calls["joint_state"][2], o_ids)
             assert torch.equal(robot.rec.calls["joint_state"][0], direct.reset_writes["joint_pos"])
             assert "Curriculum/allsteps_level/level" in extras["log"]
+    assert n_reset > 0
+
+
+def test_the_reference_direct_rl_env_step_drives_the_hooks(monkeypatch):
+    """B1 the same way: the bodies of the reference's own `DirectRLEnv.reset`, `.step` and `._reset_idx`
+    (direct_rl_env.py:256-294,296-383,563-584) run on an env whose six hooks are `AllstepsHooksB200` -- the order of
+    `_pre_physics_step` / 4 x `_apply_action` / `_get_dones` / `_get_rewards` / `_reset_idx` / `_get_observations`, the
+    `.nonzero()`, the counters and `super()._reset_idx` are the reference's, not a restatement.  (CPU: the handle behind
+    the hooks is the stand-in over the oracle; the hooks on the real handle are compared in tests/test_gpu_faces.py.)"""
+    from allsteps_isaaclab_b200 import env as env_mod
+    from oracle import allsteps_oracle as ao
+    from oracle import ref_managers
+    from scenario import Scenario, install_mdp_state
+
+    methods = ref_managers.load_direct_env_methods()
+    N, seed = 72, 31
+    sc = Scenario(N, seed=seed, full_bodies=True)
+    OracleMDP.body_rows = sc.body_indices
+    OracleMDP.instances.clear()
+    monkeypatch.setattr(env_mod, "AllstepsMDP", OracleMDP)
+    st0 = sc.initial_mdp_state()
+    direct = ao.AllstepsOracle(sc.cfg, N, sc.env_origins, sc.joint_limits, sc.body_indices, sc.stone_uniforms(0))
+    phys = sc.physics(direct.steps_pos, direct.curr_target_index, direct.swing_leg)
+    scene, robot, left, right = _world(sc, phys, None)
+
+    class RefDirectRLEnv:  # the reference's driver, nothing else
+        reset, step, _reset_idx = methods["reset"], methods["step"], methods["_reset_idx"]
+
+    class Env(env_mod.AllstepsHooksB200, RefDirectRLEnv):
+        pass
+
+    env = Env()
+    env.robot, env.sensor_left, env.sensor_right, env.scene = robot, left, right, scene
+    env.num_envs, env.device = N, "cpu"
+    env.common_step_counter, env._sim_step_counter = 0, 0
+    env.step_dt, env.physics_dt = sc.cfg.step_dt, sc.cfg.step_dt / 4
+    env.episode_length_buf = torch.zeros(N, dtype=torch.long)  # DRL:179-182
+    env.reset_terminated = torch.zeros(N, dtype=torch.bool)
+    env.reset_time_outs = torch.zeros(N, dtype=torch.bool)
+    env.reset_buf = torch.zeros(N, dtype=torch.bool)
+    env.extras = {}
+    env.cfg = types.SimpleNamespace(decimation=4, rerender_on_reset=False, wait_for_textures=False, events=None,
+                                    action_noise_model=None, observation_noise_model=None,
+                                    sim=types.SimpleNamespace(render_interval=4))
+    env.sim = _Quiet()
+    pending = {}
+    calls = []
+
+    def scene_update(dt=None):
+        env._substeps = getattr(env, "_substeps", 0) + 1
+        if env._substeps % 4 == 0 and "phys" in pending:
+            world = {k: v.clone() for k, v in pending["phys"].items()}
+            robot.load_physics(world)
+            left.data.force_matrix_w = world["force_matrix_left"]
+            right.data.force_matrix_w = world["force_matrix_right"]
+
+    scene.update = scene_update
+    scene.write_data_to_sim = lambda: calls.append("write_data_to_sim")
+    env._init_allsteps_b200(sc.cfg, seed)
+    mdp = OracleMDP.instances[0]
+    assert torch.equal(mdp.orc.steps_pos, direct.steps_pos), "stones generated by the hook (ENV:71)"
+
+    # ---- DirectRLEnv.reset(): `_reset_idx(all ids)` before any step, then the observations
+    fresh = ao.AllstepsOracle(sc.cfg, N, sc.env_origins, sc.joint_limits, sc.body_indices, sc.stone_uniforms(0))
+    m, n = sc.reset_uniforms(1)
+    fresh.load_physics(phys)
+    fresh.reset_rows(torch.arange(N), m, n)
+    mdp.orc.load_physics(mdp._load(env._physics_views()))
+    obs, extras = env.reset()
+    assert torch.equal(obs["policy"], fresh.observations()), "observations of the initial reset"
+    assert torch.equal(robot.rec.calls["joint_state"][0], fresh.reset_writes["joint_pos"])
+    assert int(env.episode_length_buf.abs().sum()) == 0 and mdp.counter == 1
+
+    # ---- steps from a mid-episode state
+    install_mdp_state(direct, st0)
+    install_mdp_state(mdp.orc, st0)
+    env.episode_length_buf[:] = st0["episode_length_buf"]
+    n_reset = 0
+    for step in range(8):
+        phys = sc.physics(direct.steps_pos, direct.curr_target_index, direct.swing_leg)
+        m, n = sc.reset_uniforms(step + 2)
+        direct.clamp_actions(phys["actions"])
+        o_eff = direct.joint_efforts().clone()  # ENV:270-274 at the levels the step starts with
+        o_obs, o_rew, o_term, o_to, o_ids = direct.step(phys, phys["actions"], m, n, None)
+        pending["phys"] = phys
+        before = mdp.launch_count
+        obs, rew, terminated, time_outs, extras = env.step(phys["actions"].clone())
+        assert env._sim_step_counter == 4 * (step + 1) and env.common_step_counter == step + 1
+        assert torch.equal(terminated, o_term) and torch.equal(time_outs, o_to), f"step {step}"
+        assert torch.equal(env.reset_buf, o_term | o_to)
+        assert torch.allclose(rew, o_rew, rtol=1e-6, atol=1e-6), f"step {step}"
+        assert torch.equal(obs["policy"], o_obs), f"step {step}"
+        assert torch.equal(env.episode_length_buf, direct.episode_length_buf), f"step {step}"
+        # four `_apply_action` calls of the decimation loop: one launch, the efforts of the levels BEFORE this step's reset
+        assert torch.allclose(robot.rec.calls["joint_effort_target"][0], o_eff, rtol=1e-6, atol=1e-6), f"step {step}"
+        # launches: efforts 1 + pass 1 + (reset + pass 2 | nothing)
+        assert mdp.launch_count - before == (4 if len(o_ids) else 2), f"step {step}"
+        if len(o_ids):
+            n_reset += len(o_ids)
+            assert torch.equal(robot.rec.calls["joint_state"][2], o_ids)
+            assert torch.equal(robot.rec.calls["joint_state"][0], direct.reset_writes["joint_pos"])
     assert n_reset > 0
