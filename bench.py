@@ -724,7 +724,7 @@ def main_b200(args):
     stats = mdp.read_stats()
 
     peak, peak_src = measured_peaks()
-    # k_step<fused> moves everything except the 24 B/env of contact vectors, which k_contact_gather fetches for it
+    # k_step<fused> moves everything except the 24 B/env of contact vectors, which k_prepare* fetches for it
     b_kernel = B_ALG - 24
     achieved_kernel = N * b_kernel / (k_avg * 1e-3) / 1e9
     achieved_step = N * B_ALG / (ms_step * 1e-3) / 1e9
@@ -751,7 +751,7 @@ def main_b200(args):
                         f"{world} GPU(s).  Under Isaac Lab the state is device resident; this leg is synthetic.",
                "note": "pinned host buffers; H2D of step t+1 and D2H of step t-1 overlap the kernel of step t; in "
                        "zero_copy_contact_matrices the (N,1,20,3) contact tensors stay in pinned host memory and "
-                       "k_contact_gather_paired reads the current stone's vectors through PCIe"}
+                       "k_prepare_paired reads the current stone's vectors through PCIe"}
 
     blocks = {}
     extra = not args.no_extra_blocks
@@ -921,7 +921,7 @@ def main_b200(args):
                          "traffic": traffic["dram_bytes_per_step"] if traffic and "dram_bytes_per_step" in traffic
                          else None,
                          "what": "whole step (SURVEY 8d): 652 algorithmic bytes per env-step over ms_per_step; "
-                                 "kernels k_contact_gather_paired + k_step<fused> + k_fixup_finish",
+                                 "kernels k_prepare_paired + k_step<fused> + k_fixup_finish",
                          "algorithmic_bytes_per_env_step": B_ALG, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved_step / 8000.0,
                          "kernel": {"name": "as::k_step<fused>", "achieved": achieved_kernel,
