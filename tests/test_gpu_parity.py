@@ -245,6 +245,14 @@ def test_intended_regeneration_extension(regen_mode, monkeypatch):
     assert totals["regen"] > 0
 
 
+def test_long_replay_over_whole_episodes():
+    """A soak: 1200 consecutive steps of 192 envs against the oracle, state compared after every step -- longer than an
+    episode (900 steps), so every env times out or falls and restarts several times, the episode counters run their
+    whole range and the promotion rule is evaluated on every reset."""
+    totals, _, _ = run_replay(192, 1200, seed=123, fall_fraction=0.004)
+    assert totals["resets"] > 400 and totals["advanced"] > 10000
+
+
 def test_missed_step_termination_extension():
     """BASELINE north_star "missed-step termination" (no reference counterpart): AS_FLAG_MISSED_STEP against
     the oracle's specification of it -- masks bit-exact; off by default (every other replay asserts n_missed == 0)."""
