@@ -291,6 +291,7 @@ def test_explicit_stone_uniforms():
 
 
 @pytest.mark.parametrize("N,fall,layout,steps", [(1536, 0.02, "contiguous", 8), (48, 0.0, "contiguous", 12),
+                                                 (160, 0.004, "contiguous", 1000),  # a soak: longer than an episode
                                                  ((1 << 17) + 37, 0.02, "contiguous", 4),
                                                  (1 << 17, 0.02, "isaac", 3)])
 def test_three_call_path_matches_oracle(N, fall, layout, steps):
