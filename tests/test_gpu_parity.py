@@ -1080,6 +1080,77 @@ def test_nan_inputs_propagate_like_torch():
         exact(st["target_reach_count"], orc.target_reach_count, f"step {step} count")
 
 
+def test_extreme_magnitudes_propagate_like_torch():
+    """Infinities, values near the top of the float range and denormals in the physics state: overflowing norms
+    (inf), inf - inf (NaN), denormal contact forces against the 1e-4 threshold, a zero / denormal quaternion through
+    MATH:81-92's normalisation -- masks bit-exact, NaN and inf in the same places, finite values within tolerance.
+    (Not covered, documented in as_math.cuh: quotients whose operands overflow or leave 2^+-60 -- a quaternion norm, a
+    joint position, a distance of that size: the branch-free divisions give NaN where IEEE division gives 0 or inf;
+    observations and rewards only, never a mask.)"""
+    from allsteps_isaaclab_b200.mdp import StepBuffers
+    from oracle import allsteps_oracle as ao
+
+    N, seed = 512, 37
+    sc = Scenario(N, seed=seed, fall_fraction=0.0)
+    st0 = sc.initial_mdp_state()
+    orc = ao.AllstepsOracle(sc.cfg, N, sc.env_origins, sc.joint_limits, sc.body_indices, sc.stone_uniforms(0))
+    mdp = make_cuda(N, seed)
+    origins = sc.env_origins.cuda()
+    mdp.generate_stones(origins)
+    install_mdp_state(orc, st0)
+    mdp.import_state({k: st0[k] for k in ("curr_target_index", "swing_leg", "target_reach_count",
+                                          "episode_length_buf", "potentials")})
+    mdp.import_state({"steps_pos": orc.steps_pos, "steps_dphi": orc.steps_dphi})
+    out = StepBuffers(N, "cuda:0")
+    inf, big, tiny = float("inf"), 3.0e38, 1.0e-41
+    for step in range(3):
+        phys = sc.physics(orc.steps_pos, orc.curr_target_index, orc.swing_leg)
+        phys["root_lin_vel_w"][3] = torch.tensor([big, big, 0.0])      # the speed overflows to inf: so_fast
+        phys["root_lin_vel_w"][4, 1] = -inf
+        phys["root_pos_w"][5, 0] = 1.0e15                                # far away, inside 2^+-60
+        phys["root_pos_w"][6, 2] = -inf                                  # died; inf - inf further down
+        phys["root_quat_w"][7] = torch.tensor([tiny, 0.0, 0.0, 0.0])     # a denormal quaternion: clamp(norm, 1e-9)
+        phys["root_quat_w"][8] = 0.0
+        phys["root_quat_w"][9] = torch.tensor([1.0e15, -2.0e15, 3.0e15, 1.0e15])  # far from unit, inside 2^+-60
+        phys["joint_vel"][10, 3] = inf
+        phys["joint_vel"][11, 4] = tiny
+        phys["joint_pos"][12, 6] = -1.0e15
+        phys["actions"][13, 0] = inf                                     # clamped to 1
+        phys["actions"][14, 1] = -inf
+        phys["body_pos_w"][15, sc.body_indices[2], 2] = inf              # torso height
+        phys["body_pos_w"][16, sc.body_indices[0], :2] = big             # right foot far away
+        for k in ("force_matrix_right", "force_matrix_left"):
+            idx = orc.curr_target_index
+            phys[k][17, 0, idx[17]] = torch.tensor([tiny, tiny, tiny])   # denormal force: no contact
+            phys[k][18, 0, idx[18]] = torch.tensor([big, big, big])      # the norm overflows: contact
+            phys[k][19, 0, idx[19]] = torch.tensor([0.0, 0.0, inf])
+            phys[k][20, 0, idx[20]] = torch.tensor([7.0e-5, 7.0e-5, 0.0])  # |F| = 0.99e-4, just under the threshold
+            phys[k][21, 0, idx[21]] = torch.tensor([7.2e-5, 7.2e-5, 0.0])  # just over
+        mirror_u, noise_u = sc.reset_uniforms(step)
+        o_obs, o_rew, o_term, o_to, o_ids = orc.step(phys, phys["actions"], mirror_u, noise_u, sc.stone_uniforms(step))
+        views, keep = to_views(phys, origins, sc.body_indices)
+        mdp.step(views, keep["actions"], out)
+        torch.cuda.synchronize()
+        exact(out.terminated, o_term, f"step {step} terminated")
+        exact(out.time_out, o_to, f"step {step} time_out")
+        for name, got, want in (("obs", out.obs.cpu(), o_obs), ("reward", out.reward.cpu(), o_rew)):
+            gn, wn = torch.isnan(got), torch.isnan(want)
+            assert torch.equal(gn, wn), f"step {step}: NaN pattern of {name} differs at {(gn != wn).nonzero()[:8].tolist()}"
+            gi, wi = torch.isinf(got), torch.isinf(want)
+            assert torch.equal(gi, wi), f"step {step}: inf pattern of {name} differs at {(gi != wi).nonzero()[:8].tolist()}"
+            assert torch.equal(got[wi], want[wi]), f"step {step}: sign of an infinity in {name}"
+            ok = ~(wn | wi)
+            z = torch.zeros_like(got)
+            if name == "obs":
+                close_obs(torch.where(ok, got, z), torch.where(ok, want, z), f"step {step} obs")
+            else:
+                close(got[ok], want[ok], f"step {step} reward")
+        st = mdp.export_state()
+        exact(st["curr_target_index"], orc.curr_target_index, f"step {step} idx")
+        exact(st["target_reach_count"], orc.target_reach_count, f"step {step} count")
+        exact(st["swing_leg"], orc.swing_leg, f"step {step} leg")
+
+
 def test_stone_poses_in_physx_view_layout():
     """as_export_stone_poses against a torch restatement of the reference egress: ENV:119-120 builds (N,S,7) w,x,y,z
     poses, RigidObjectCollection.write_object_pose_to_sim (rigid_object_collection.py:295-301) scatters them into
